@@ -1,0 +1,234 @@
+"""ctypes binding of oracle/_ref/libjxl_ref_harness.so (the UNMODIFIED reference,
+built by oracle/build_ref.py).  TEST INFRASTRUCTURE ONLY: importable from tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+Never imported by the product package `libjxl_b200`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+SO = HERE / "_ref" / "libjxl_ref_harness.so"
+
+
+class RefFrameInfo(C.Structure):
+    _fields_ = [
+        ("xsize", C.c_int32), ("ysize", C.c_int32),
+        ("xsize_blocks", C.c_int32), ("ysize_blocks", C.c_int32),
+        ("xsize_groups", C.c_int32), ("ysize_groups", C.c_int32),
+        ("num_groups", C.c_int32), ("ac_is16", C.c_int32),
+        ("cmap_xsize", C.c_int32), ("cmap_ysize", C.c_int32),
+        ("gab", C.c_int32), ("epf_iters", C.c_int32),
+        ("inv_global_scale", C.c_float), ("global_scale_float", C.c_float),
+        ("x_dm_multiplier", C.c_float), ("b_dm_multiplier", C.c_float),
+        ("quant_biases", C.c_float * 4),
+        ("cfl_base_x", C.c_float), ("cfl_base_b", C.c_float), ("cfl_color_scale", C.c_float),
+        ("gab_weights", C.c_float * 6),
+        ("epf_sharp_lut", C.c_float * 8),
+        ("epf_channel_scale", C.c_float * 3),
+        ("epf_quant_mul", C.c_float), ("epf_pass0_sigma_scale", C.c_float),
+        ("epf_pass2_sigma_scale", C.c_float), ("epf_border_sad_mul", C.c_float),
+        ("inverse_opsin_matrix", C.c_float * 9),
+        ("opsin_biases", C.c_float * 4),
+        ("opsin_biases_cbrt", C.c_float * 4),
+        ("dequant_table_floats", C.c_int32),
+        ("dequant_offsets", C.c_int32 * 81),
+    ]
+
+
+PLANE_AC_STRATEGY, PLANE_RAW_QUANT, PLANE_SHARPNESS, PLANE_YTOX, PLANE_YTOB = 0, 1, 2, 3, 4
+PLANE_DC, PLANE_SIGMA, PLANE_DEQUANT, PLANE_COEFFS, PLANE_DECODED = 5, 6, 7, 8, 9
+
+STAGE_GAB, STAGE_EPF0, STAGE_EPF1, STAGE_EPF2, STAGE_XYB = 1, 2, 4, 8, 16
+
+_lib = None
+
+
+def available() -> bool:
+    return SO.exists()
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not SO.exists():
+            raise RuntimeError(f"{SO} missing: run `python oracle/build_ref.py` where /root/reference exists")
+        L = C.CDLL(str(SO))
+        L.ref_frame_open.restype = C.c_void_p
+        L.ref_frame_open.argtypes = [C.c_char_p, C.c_size_t, C.c_int]
+        L.ref_frame_close.argtypes = [C.c_void_p]
+        L.ref_frame_info.argtypes = [C.c_void_p, C.POINTER(RefFrameInfo)]
+        L.ref_frame_get_plane.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.ref_frame_render.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.ref_encode_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_uint8)),
+                                      C.POINTER(C.c_size_t)]
+        L.ref_decode_linear_f32.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ref_runner_create.restype = C.c_void_p
+        L.ref_runner_create.argtypes = [C.c_int]
+        L.ref_runner_destroy.argtypes = [C.c_void_p]
+        L.ref_free.argtypes = [C.c_void_p]
+        L.ref_transform_to_pixels.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.ref_transform_from_pixels.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.ref_llf_from_dc.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        _lib = L
+    return _lib
+
+
+def encode_rgb8(img: np.ndarray, distance: float = 1.0, effort: int = 7, gaborish: int = -1,
+                epf: int = -1, threads: int | None = None) -> bytes:
+    """cjxl-equivalent through the public JxlEncoder API; returns a bare codestream."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w, c = img.shape
+    assert c == 3
+    out = C.POINTER(C.c_uint8)()
+    n = C.c_size_t()
+    rc = lib().ref_encode_rgb8(img.ctypes.data, w, h, distance, effort, gaborish, epf,
+                               threads or os.cpu_count() or 1, C.byref(out), C.byref(n))
+    if rc:
+        raise RuntimeError(f"ref_encode_rgb8 failed rc={rc}")
+    data = C.string_at(out, n.value)
+    lib().ref_free(out)
+    return data
+
+
+class Runner:
+    def __init__(self, threads: int):
+        self.threads = threads
+        self.h = lib().ref_runner_create(threads)
+
+    def close(self):
+        if self.h:
+            lib().ref_runner_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+def decode_linear_f32(data: bytes, threads: int = 1, out: np.ndarray | None = None,
+                      runner: Runner | None = None) -> np.ndarray:
+    """Full reference decode (public API) -> (H, W, 3) linear sRGB float32."""
+    w, h = C.c_int(), C.c_int()
+    if out is None:
+        rc = lib().ref_decode_linear_f32(data, len(data), runner.h if runner else None, threads,
+                                         None, 0, C.byref(w), C.byref(h))
+        if rc:
+            raise RuntimeError(f"ref_decode_linear_f32 (probe) rc={rc}")
+        out = np.empty((h.value, w.value, 3), np.float32)
+    rc = lib().ref_decode_linear_f32(data, len(data), runner.h if runner else None, threads,
+                                     out.ctypes.data, out.size, C.byref(w), C.byref(h))
+    if rc:
+        raise RuntimeError(f"ref_decode_linear_f32 rc={rc}")
+    return out
+
+
+@dataclass
+class FrameDump:
+    """Everything the hot path consumes, as the reference decoder produced it."""
+    info: RefFrameInfo
+    ac_strategy: np.ndarray   # u8  (yb, xb)
+    raw_quant: np.ndarray     # i32 (yb, xb)
+    sharpness: np.ndarray     # u8  (yb, xb)
+    ytox: np.ndarray          # i8  (cmy, cmx)
+    ytob: np.ndarray          # i8
+    dc: np.ndarray            # f32 (3, yb, xb)
+    sigma: np.ndarray | None  # f32 (yb+4, xb+4) inverse sigma, reference-computed
+    dequant: np.ndarray       # f32 (table,)
+    dequant_offsets: np.ndarray  # i32 (27, 3)
+    coeffs: np.ndarray        # i16|i32 (3, num_groups, 65536)
+    decoded: np.ndarray       # f32 (H, W, 3) reference decode, linear sRGB
+
+
+class Frame:
+    """A frame opened with the reference's FrameDecoder, coefficients retained."""
+
+    def __init__(self, data: bytes, threads: int = 1):
+        self.h = lib().ref_frame_open(data, len(data), threads)
+        if not self.h:
+            raise RuntimeError("ref_frame_open failed (frame not eligible for the hot path?)")
+        self.info = RefFrameInfo()
+        lib().ref_frame_info(self.h, C.byref(self.info))
+
+    def close(self):
+        if self.h:
+            lib().ref_frame_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _plane(self, which: int, shape, dtype) -> np.ndarray:
+        a = np.empty(shape, dtype)
+        rc = lib().ref_frame_get_plane(self.h, which, a.ctypes.data, a.nbytes)
+        if rc:
+            raise RuntimeError(f"ref_frame_get_plane({which}) rc={rc}")
+        return a
+
+    def dump(self) -> FrameDump:
+        i = self.info
+        yb, xb = i.ysize_blocks, i.xsize_blocks
+        sigma = None
+        if i.epf_iters > 0:
+            sigma = self._plane(PLANE_SIGMA, (yb + 4, xb + 4), np.float32)
+        return FrameDump(
+            info=i,
+            ac_strategy=self._plane(PLANE_AC_STRATEGY, (yb, xb), np.uint8),
+            raw_quant=self._plane(PLANE_RAW_QUANT, (yb, xb), np.int32),
+            sharpness=self._plane(PLANE_SHARPNESS, (yb, xb), np.uint8),
+            ytox=self._plane(PLANE_YTOX, (i.cmap_ysize, i.cmap_xsize), np.int8),
+            ytob=self._plane(PLANE_YTOB, (i.cmap_ysize, i.cmap_xsize), np.int8),
+            dc=self._plane(PLANE_DC, (3, yb, xb), np.float32),
+            sigma=sigma,
+            dequant=self._plane(PLANE_DEQUANT, (i.dequant_table_floats,), np.float32),
+            dequant_offsets=np.array(list(i.dequant_offsets), np.int32).reshape(27, 3),
+            coeffs=self._plane(PLANE_COEFFS, (3, i.num_groups, 65536),
+                               np.int16 if i.ac_is16 else np.int32),
+            decoded=self._plane(PLANE_DECODED, (i.ysize, i.xsize, 3), np.float32),
+        )
+
+    def render(self, stage_mask: int = -1, reps: int = 1, want_output: bool = True):
+        """Hot path only (reference code) from the retained coefficients.
+        Returns (planar f32 (3,H,W) or None, [seconds per rep])."""
+        i = self.info
+        out = np.empty((3, i.ysize, i.xsize), np.float32) if want_output else None
+        secs = (C.c_double * max(reps, 1))()
+        rc = lib().ref_frame_render(self.h, stage_mask, out.ctypes.data if want_output else None,
+                                    reps, secs)
+        if rc:
+            raise RuntimeError(f"ref_frame_render rc={rc}")
+        return out, list(secs)
+
+
+def transform_to_pixels(strategy: int, coeffs: np.ndarray, rows: int, cols: int) -> np.ndarray:
+    coeffs = np.ascontiguousarray(coeffs, np.float32).ravel()
+    px = np.zeros((rows, cols), np.float32)
+    rc = lib().ref_transform_to_pixels(strategy, coeffs.ctypes.data, coeffs.size, px.ctypes.data, cols)
+    if rc:
+        raise RuntimeError(f"ref_transform_to_pixels rc={rc}")
+    return px
+
+
+def transform_from_pixels(strategy: int, pixels: np.ndarray) -> np.ndarray:
+    pixels = np.ascontiguousarray(pixels, np.float32)
+    rows, cols = pixels.shape
+    co = np.zeros(rows * cols, np.float32)
+    rc = lib().ref_transform_from_pixels(strategy, pixels.ctypes.data, cols, co.ctypes.data, co.size)
+    if rc:
+        raise RuntimeError(f"ref_transform_from_pixels rc={rc}")
+    return co
+
+
+def llf_from_dc(strategy: int, dc: np.ndarray, block: np.ndarray) -> np.ndarray:
+    dc = np.ascontiguousarray(dc, np.float32)
+    block = np.ascontiguousarray(block, np.float32).ravel().copy()
+    rc = lib().ref_llf_from_dc(strategy, dc.ctypes.data, dc.shape[1], block.ctypes.data, block.size)
+    if rc:
+        raise RuntimeError(f"ref_llf_from_dc rc={rc}")
+    return block

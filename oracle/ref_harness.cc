@@ -1,0 +1,664 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, loaded by, or called from the
+// product library (libjxl_b200/csrc).  See oracle/README.md.
+//
+// A thin C ABI over the UNMODIFIED reference (libjxl 0.13.0 compiled by
+// oracle/build_ref.py from /root/reference) so that tests and bench.py can
+//   (1) manufacture VarDCT bitstreams (public JxlEncoder API),
+//   (2) run the reference decoder end to end (public JxlDecoder API) -> linear
+//       sRGB float pixels: the image-level oracle and the "full decode" CPU
+//       baseline,
+//   (3) open a frame with the reference's own FrameDecoder and keep the
+//       entropy-decoded quantized coefficients + every side-info plane the hot
+//       path consumes: exactly the hand-off SURVEY.md §8(b) describes,
+//   (4) re-run ONLY the hot path (DecodeGroupForRoundtrip + the reference
+//       render-pipeline stages) from those coefficients: stage-by-stage golden
+//       images for the C restatement, and the transform-only CPU baseline,
+//   (5) call the function-level facade the reference's own ac_strategy_test
+//       uses (TransformToPixels / LowestFrequenciesFromDC).
+//
+// This file is OUR code; it only #includes reference headers.
+// Flow of (3) mirrors jxl::DecodeFrame (lib/jxl/dec_frame.cc:82-133) with the
+// sections fed in two ProcessSections calls so that accumulate-mode coefficient
+// storage (lib/jxl/dec_group.cc:219,335-338) can be switched on in between.
+
+#include <jxl/decode.h>
+#include <jxl/encode.h>
+#include <jxl/thread_parallel_runner.h>
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "lib/jxl/ac_strategy.h"
+#include "lib/jxl/base/data_parallel.h"
+#include "lib/jxl/base/span.h"
+#include "lib/jxl/chroma_from_luma.h"
+#include "lib/jxl/color_encoding_internal.h"
+#include "lib/jxl/dct_util.h"
+#include "lib/jxl/dec_bit_reader.h"
+#include "lib/jxl/dec_cache.h"
+#include "lib/jxl/dec_frame.h"
+#include "lib/jxl/dec_group.h"
+#include "lib/jxl/dec_transforms_testonly.h"
+#include "lib/jxl/enc_transforms.h"
+#include "lib/jxl/epf.h"
+#include "lib/jxl/fields.h"
+#include "lib/jxl/frame_header.h"
+#include "lib/jxl/headers.h"
+#include "lib/jxl/image.h"
+#include "lib/jxl/image_bundle.h"
+#include "lib/jxl/image_metadata.h"
+#include "lib/jxl/loop_filter.h"
+#include "lib/jxl/memory_manager_internal.h"
+#include "lib/jxl/passes_state.h"
+#include "lib/jxl/quant_weights.h"
+#include "lib/jxl/quantizer.h"
+#include "lib/jxl/render_pipeline/render_pipeline.h"
+#include "lib/jxl/render_pipeline/stage_epf.h"
+#include "lib/jxl/render_pipeline/stage_gaborish.h"
+#include "lib/jxl/render_pipeline/stage_write.h"
+#include "lib/jxl/render_pipeline/stage_xyb.h"
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+double NowSec() {
+  using namespace std::chrono;
+  return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct Runner {
+  explicit Runner(int threads) {
+    opaque = JxlThreadParallelRunnerCreate(nullptr, threads < 1 ? 1 : threads);
+  }
+  ~Runner() { JxlThreadParallelRunnerDestroy(opaque); }
+  void* opaque;
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// (1) encoder
+// ---------------------------------------------------------------------------
+REF_API void ref_free(void* p) { free(p); }
+
+// gaborish / epf: -1 keeps the encoder default for the distance
+// (lib/jxl/enc_frame.cc:316-341).  Output: bare codestream, malloc'd.
+REF_API int ref_encode_rgb8(const uint8_t* rgb, int w, int h, float distance,
+                            int effort, int gaborish, int epf, int threads,
+                            uint8_t** out, size_t* out_size) {
+  Runner runner(threads);
+  JxlEncoder* enc = JxlEncoderCreate(nullptr);
+  if (!enc) return 1;
+  int rc = 0;
+  std::vector<uint8_t> buf(1 << 20);
+  do {
+    if (JxlEncoderSetParallelRunner(enc, JxlThreadParallelRunner,
+                                    runner.opaque) != JXL_ENC_SUCCESS) { rc = 2; break; }
+    JxlEncoderUseContainer(enc, JXL_FALSE);
+    JxlBasicInfo info;
+    JxlEncoderInitBasicInfo(&info);
+    info.xsize = w;
+    info.ysize = h;
+    info.bits_per_sample = 8;
+    info.exponent_bits_per_sample = 0;
+    info.num_color_channels = 3;
+    info.num_extra_channels = 0;
+    info.alpha_bits = 0;
+    info.uses_original_profile = JXL_FALSE;
+    if (JxlEncoderSetBasicInfo(enc, &info) != JXL_ENC_SUCCESS) { rc = 3; break; }
+    JxlColorEncoding ce;
+    JxlColorEncodingSetToSRGB(&ce, JXL_FALSE);
+    if (JxlEncoderSetColorEncoding(enc, &ce) != JXL_ENC_SUCCESS) { rc = 4; break; }
+    JxlEncoderFrameSettings* fs = JxlEncoderFrameSettingsCreate(enc, nullptr);
+    JxlEncoderSetFrameDistance(fs, distance);
+    JxlEncoderFrameSettingsSetOption(fs, JXL_ENC_FRAME_SETTING_EFFORT, effort);
+    if (gaborish >= 0)
+      JxlEncoderFrameSettingsSetOption(fs, JXL_ENC_FRAME_SETTING_GABORISH, gaborish);
+    if (epf >= 0)
+      JxlEncoderFrameSettingsSetOption(fs, JXL_ENC_FRAME_SETTING_EPF, epf);
+    JxlPixelFormat pf = {3, JXL_TYPE_UINT8, JXL_NATIVE_ENDIAN, 0};
+    if (JxlEncoderAddImageFrame(fs, &pf, rgb, static_cast<size_t>(w) * h * 3) !=
+        JXL_ENC_SUCCESS) { rc = 5; break; }
+    JxlEncoderCloseInput(enc);
+    size_t pos = 0;
+    for (;;) {
+      uint8_t* next = buf.data() + pos;
+      size_t avail = buf.size() - pos;
+      JxlEncoderStatus st = JxlEncoderProcessOutput(enc, &next, &avail);
+      pos = next - buf.data();
+      if (st == JXL_ENC_NEED_MORE_OUTPUT) { buf.resize(buf.size() * 2); continue; }
+      if (st != JXL_ENC_SUCCESS) rc = 6;
+      break;
+    }
+    if (rc) break;
+    *out = static_cast<uint8_t*>(malloc(pos));
+    memcpy(*out, buf.data(), pos);
+    *out_size = pos;
+  } while (false);
+  JxlEncoderDestroy(enc);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------
+// (2) full reference decode through the public API -> interleaved linear sRGB f32
+// (same output djxl --color_space=RGB_D65_SRG_Rel_Lin produces)
+// `runner_opaque` may be NULL (a runner with `threads` workers is made).
+// ---------------------------------------------------------------------------
+REF_API void* ref_runner_create(int threads) {
+  return JxlThreadParallelRunnerCreate(nullptr, threads < 1 ? 1 : threads);
+}
+REF_API void ref_runner_destroy(void* r) { JxlThreadParallelRunnerDestroy(r); }
+
+REF_API int ref_decode_linear_f32(const uint8_t* jxl, size_t n, void* runner_opaque,
+                                  int threads, float* out, size_t out_floats,
+                                  int* w, int* h) {
+  std::unique_ptr<Runner> own;
+  if (!runner_opaque) { own.reset(new Runner(threads)); runner_opaque = own->opaque; }
+  JxlDecoder* dec = JxlDecoderCreate(nullptr);
+  if (!dec) return 1;
+  int rc = 0;
+  JxlPixelFormat pf = {3, JXL_TYPE_FLOAT, JXL_NATIVE_ENDIAN, 0};
+  do {
+    if (JxlDecoderSetParallelRunner(dec, JxlThreadParallelRunner, runner_opaque) !=
+        JXL_DEC_SUCCESS) { rc = 2; break; }
+    JxlDecoderSubscribeEvents(dec, JXL_DEC_BASIC_INFO | JXL_DEC_COLOR_ENCODING |
+                                       JXL_DEC_FULL_IMAGE);
+    JxlDecoderSetInput(dec, jxl, n);
+    JxlDecoderCloseInput(dec);
+    for (;;) {
+      JxlDecoderStatus st = JxlDecoderProcessInput(dec);
+      if (st == JXL_DEC_BASIC_INFO) {
+        JxlBasicInfo info;
+        JxlDecoderGetBasicInfo(dec, &info);
+        *w = info.xsize;
+        *h = info.ysize;
+      } else if (st == JXL_DEC_COLOR_ENCODING) {
+        JxlColorEncoding ce;
+        JxlColorEncodingSetToLinearSRGB(&ce, JXL_FALSE);
+        if (JxlDecoderSetOutputColorProfile(dec, &ce, nullptr, 0) != JXL_DEC_SUCCESS) {
+          rc = 3; break;
+        }
+      } else if (st == JXL_DEC_NEED_IMAGE_OUT_BUFFER) {
+        size_t need = 0;
+        JxlDecoderImageOutBufferSize(dec, &pf, &need);
+        if (!out) { rc = -1; break; }  // size query only
+        if (need > out_floats * sizeof(float)) { rc = 4; break; }
+        JxlDecoderSetImageOutBuffer(dec, &pf, out, need);
+      } else if (st == JXL_DEC_FULL_IMAGE) {
+        continue;
+      } else if (st == JXL_DEC_SUCCESS) {
+        break;
+      } else { rc = 10 + static_cast<int>(st); break; }
+    }
+  } while (false);
+  JxlDecoderDestroy(dec);
+  return rc == -1 ? 0 : rc;
+}
+
+// ---------------------------------------------------------------------------
+// (3) frame opened with reference internals, coefficients retained
+// ---------------------------------------------------------------------------
+namespace {
+using namespace jxl;
+
+struct RefFrame {
+  JxlMemoryManager mm;
+  CodecMetadata metadata;
+  std::unique_ptr<PassesDecoderState> dec_state;
+  std::unique_ptr<ImageBundle> decoded;
+  std::unique_ptr<FrameHeader> frame_header;
+  void* runner = nullptr;
+  std::unique_ptr<ThreadPool> pool;
+  // int32 copy of the coefficients for DecodeGroupForRoundtrip
+  // (GetBlockFromEncoder requires k32: lib/jxl/dec_group.cc:668).
+  std::vector<std::unique_ptr<ACImage>> ac32;
+  // what the entropy decoder produced (int16 or int32, per dec_frame.cc:417-431)
+  std::unique_ptr<ACImage> stored;
+  bool is16 = false;
+  uint32_t passes_shift_backup[kMaxNumPasses];
+  ~RefFrame() {
+    pool.reset();
+    if (runner) JxlThreadParallelRunnerDestroy(runner);
+  }
+};
+
+Status OpenImpl(RefFrame* f, const uint8_t* data, size_t n) {
+  JXL_RETURN_IF_ERROR(MemoryManagerInit(&f->mm, nullptr));
+  if (n < 2 || data[0] != 0xff || data[1] != kCodestreamMarker)
+    return JXL_FAILURE("not a bare codestream");
+  BitReader br(Bytes(data + 2, n - 2));
+  Status ok = [&]() -> Status {
+    JXL_RETURN_IF_ERROR(Bundle::Read(&br, &f->metadata.size));
+    JXL_RETURN_IF_ERROR(Bundle::Read(&br, &f->metadata.m));
+    f->metadata.transform_data.nonserialized_xyb_encoded = f->metadata.m.xyb_encoded;
+    JXL_RETURN_IF_ERROR(Bundle::Read(&br, &f->metadata.transform_data));
+    if (f->metadata.m.color_encoding.WantICC()) return JXL_FAILURE("ICC unsupported");
+    if (f->metadata.m.have_preview) return JXL_FAILURE("preview unsupported");
+    JXL_RETURN_IF_ERROR(br.JumpToByteBoundary());
+    return true;
+  }();
+  size_t hdr_bytes = br.TotalBitsConsumed() / kBitsPerByte;
+  Status closed = br.Close();
+  JXL_RETURN_IF_ERROR(ok);
+  JXL_RETURN_IF_ERROR(closed);
+  const uint8_t* frame_start = data + 2 + hdr_bytes;
+  size_t frame_size = n - 2 - hdr_bytes;
+
+  f->dec_state = jxl::make_unique<PassesDecoderState>(&f->mm);
+  JXL_RETURN_IF_ERROR(f->dec_state->output_encoding_info.SetFromMetadata(f->metadata));
+  // linear sRGB output, like djxl --color_space=RGB_D65_SRG_Rel_Lin
+  JXL_RETURN_IF_ERROR(f->dec_state->output_encoding_info.MaybeSetColorEncoding(
+      ColorEncoding::LinearSRGB(false)));
+  f->decoded = jxl::make_unique<ImageBundle>(&f->mm, &f->metadata.m);
+
+  FrameDecoder fd(f->dec_state.get(), f->metadata, f->pool.get(),
+                  /*use_slow_rendering_pipeline=*/false);
+  BitReader fr(Bytes(frame_start, frame_size));
+  Status st = [&]() -> Status {
+    JXL_RETURN_IF_ERROR(fd.InitFrame(&fr, f->decoded.get(), /*is_preview=*/false));
+    JXL_RETURN_IF_ERROR(fd.InitFrameOutput());
+    return true;
+  }();
+  size_t header_bytes = fr.TotalBitsConsumed() / kBitsPerByte;
+  Status c2 = fr.Close();
+  JXL_RETURN_IF_ERROR(st);
+  JXL_RETURN_IF_ERROR(c2);
+  f->frame_header = jxl::make_unique<FrameHeader>(&f->metadata);
+  *f->frame_header = fd.GetFrameHeader();
+  const FrameHeader& fh = *f->frame_header;
+  if (fh.encoding != FrameEncoding::kVarDCT) return JXL_FAILURE("not VarDCT");
+  if (!fh.chroma_subsampling.Is444()) return JXL_FAILURE("not 444");
+  if (fh.upsampling != 1) return JXL_FAILURE("upsampling");
+  if (fh.flags & (FrameHeader::kPatches | FrameHeader::kSplines | FrameHeader::kNoise))
+    return JXL_FAILURE("image features present");
+  if (fh.passes.num_passes != 1) return JXL_FAILURE("multi-pass");
+  const FrameDimensions fdim = fh.ToFrameDimensions();
+  if (fdim.num_groups < 2) return JXL_FAILURE("single-section frame");
+
+  Status close_ok = true;
+  std::vector<std::unique_ptr<BitReader>> readers;
+  std::vector<FrameDecoder::SectionInfo> early, late;
+  {
+    std::vector<std::unique_ptr<BitReaderScopedCloser>> closers;
+    size_t pos = header_bytes;
+    size_t index = 0;
+    const size_t ac_global_id = fdim.num_dc_groups + 1;
+    for (auto toc : fd.Toc()) {
+      if (pos + toc.size > frame_size) return JXL_FAILURE("truncated");
+      auto r = jxl::make_unique<BitReader>(Bytes(frame_start + pos, toc.size));
+      FrameDecoder::SectionInfo si{r.get(), toc.id, index++};
+      (toc.id <= ac_global_id ? early : late).push_back(si);
+      closers.emplace_back(jxl::make_unique<BitReaderScopedCloser>(*r, close_ok));
+      readers.emplace_back(std::move(r));
+      pos += toc.size;
+    }
+    std::vector<FrameDecoder::SectionStatus> status(early.size());
+    JXL_RETURN_IF_ERROR(fd.ProcessSections(early.data(), early.size(), status.data()));
+    for (auto s : status) JXL_RETURN_IF_ERROR(s == FrameDecoder::kDone);
+    // Switch on accumulate-mode storage: every group's coefficients land in
+    // dec_state->coefficients->PlaneRow(c, group, offset).
+    f->is16 = f->dec_state->coefficients->Type() == ACType::k16;
+    if (f->is16) {
+      JXL_ASSIGN_OR_RETURN(f->dec_state->coefficients,
+                           ACImageT<int16_t>::Make(&f->mm, kGroupDim * kGroupDim,
+                                                   fdim.num_groups));
+    } else {
+      JXL_ASSIGN_OR_RETURN(f->dec_state->coefficients,
+                           ACImageT<int32_t>::Make(&f->mm, kGroupDim * kGroupDim,
+                                                   fdim.num_groups));
+    }
+    f->dec_state->coefficients->ZeroFill();
+    status.assign(late.size(), FrameDecoder::kSkipped);
+    JXL_RETURN_IF_ERROR(fd.ProcessSections(late.data(), late.size(), status.data()));
+    for (auto s : status) JXL_RETURN_IF_ERROR(s == FrameDecoder::kDone);
+  }
+  JXL_RETURN_IF_ERROR(close_ok);
+  JXL_RETURN_IF_ERROR(fd.FinalizeFrame());
+  // all 27 dequant matrices available to the exporter
+  JXL_RETURN_IF_ERROR(f->dec_state->shared_storage.matrices.EnsureComputed(
+      &f->mm, (1u << AcStrategy::kNumValidStrategies) - 1));
+
+  // int32 copy for the roundtrip entry point
+  JXL_ASSIGN_OR_RETURN(auto ac32, ACImageT<int32_t>::Make(&f->mm, kGroupDim * kGroupDim,
+                                                         fdim.num_groups));
+  for (size_t c = 0; c < 3; c++) {
+    for (size_t g = 0; g < fdim.num_groups; g++) {
+      int32_t* dst = ac32->PlaneRow(c, g, 0).ptr32;
+      if (f->is16) {
+        const int16_t* src = f->dec_state->coefficients->PlaneRow(c, g, 0).ptr16;
+        for (size_t k = 0; k < kGroupDim * kGroupDim; k++) dst[k] = src[k];
+      } else {
+        memcpy(dst, f->dec_state->coefficients->PlaneRow(c, g, 0).ptr32,
+               sizeof(int32_t) * kGroupDim * kGroupDim);
+      }
+    }
+  }
+  f->ac32.emplace_back(std::move(ac32));
+  // Leave the decoder state in non-accumulate mode (empty k32 image) so that
+  // DecodeGroupForRoundtrip reads only from `ac32` (dec_group.cc:219,343-355).
+  f->stored = std::move(f->dec_state->coefficients);
+  f->dec_state->coefficients = jxl::make_unique<ACImageT<int32_t>>();
+  return true;
+}
+
+}  // namespace
+
+struct RefFrameInfo {
+  int32_t xsize, ysize, xsize_blocks, ysize_blocks;
+  int32_t xsize_groups, ysize_groups, num_groups, ac_is16;
+  int32_t cmap_xsize, cmap_ysize;           // 64x64-px tiles
+  int32_t gab, epf_iters;
+  float inv_global_scale, global_scale_float;  // Quantizer::InvGlobalScale / Scale
+  float x_dm_multiplier, b_dm_multiplier;
+  float quant_biases[4];
+  float cfl_base_x, cfl_base_b, cfl_color_scale;  // YtoXRatio = base + f*scale
+  float gab_weights[6];                     // x1 x2 y1 y2 b1 b2
+  float epf_sharp_lut[8];
+  float epf_channel_scale[3];
+  float epf_quant_mul, epf_pass0_sigma_scale, epf_pass2_sigma_scale, epf_border_sad_mul;
+  float inverse_opsin_matrix[9];            // already x 255/intensity_target
+  float opsin_biases[4];                    // "neg_bias" (3 used)
+  float opsin_biases_cbrt[4];
+  int32_t dequant_table_floats;             // 2056*64*3
+  int32_t dequant_offsets[27 * 3];          // float offset of Matrix(kind,c)
+};
+
+REF_API void* ref_frame_open(const uint8_t* jxl, size_t n, int threads) {
+  auto* f = new RefFrame();
+  f->runner = JxlThreadParallelRunnerCreate(nullptr, threads < 1 ? 1 : threads);
+  f->pool.reset(new ThreadPool(JxlThreadParallelRunner, f->runner));
+  Status st = OpenImpl(f, jxl, n);
+  if (!st) {
+    delete f;
+    return nullptr;
+  }
+  return f;
+}
+REF_API void ref_frame_close(void* h) { delete static_cast<RefFrame*>(h); }
+
+REF_API int ref_frame_info(void* h, RefFrameInfo* o) {
+  auto* f = static_cast<RefFrame*>(h);
+  const PassesSharedState& sh = *f->dec_state->shared;
+  const FrameDimensions& d = sh.frame_dim;
+  const LoopFilter& lf = f->frame_header->loop_filter;
+  memset(o, 0, sizeof(*o));
+  o->xsize = d.xsize; o->ysize = d.ysize;
+  o->xsize_blocks = d.xsize_blocks; o->ysize_blocks = d.ysize_blocks;
+  o->xsize_groups = d.xsize_groups; o->ysize_groups = d.ysize_groups;
+  o->num_groups = d.num_groups; o->ac_is16 = f->is16;
+  o->cmap_xsize = sh.cmap.ytox_map.xsize(); o->cmap_ysize = sh.cmap.ytox_map.ysize();
+  o->gab = lf.gab; o->epf_iters = lf.epf_iters;
+  o->inv_global_scale = sh.quantizer.InvGlobalScale();
+  o->global_scale_float = sh.quantizer.Scale();
+  o->x_dm_multiplier = f->dec_state->x_dm_multiplier;
+  o->b_dm_multiplier = f->dec_state->b_dm_multiplier;
+  const OpsinParams& op = f->dec_state->output_encoding_info.opsin_params;
+  memcpy(o->quant_biases, op.quant_biases, sizeof(o->quant_biases));
+  const ColorCorrelation& cc = sh.cmap.base();
+  o->cfl_base_x = cc.GetBaseCorrelationX();
+  o->cfl_base_b = cc.GetBaseCorrelationB();
+  o->cfl_color_scale = cc.YtoXRatio(1) - cc.YtoXRatio(0);
+  // exact color_scale_: 1.0f / color_factor_ (chroma_from_luma.h:77-79)
+  o->cfl_color_scale = 1.0f / static_cast<uint32_t>(cc.GetColorFactor());
+  o->gab_weights[0] = lf.gab_x_weight1; o->gab_weights[1] = lf.gab_x_weight2;
+  o->gab_weights[2] = lf.gab_y_weight1; o->gab_weights[3] = lf.gab_y_weight2;
+  o->gab_weights[4] = lf.gab_b_weight1; o->gab_weights[5] = lf.gab_b_weight2;
+  memcpy(o->epf_sharp_lut, lf.epf_sharp_lut, sizeof(o->epf_sharp_lut));
+  memcpy(o->epf_channel_scale, lf.epf_channel_scale, sizeof(o->epf_channel_scale));
+  o->epf_quant_mul = lf.epf_quant_mul;
+  o->epf_pass0_sigma_scale = lf.epf_pass0_sigma_scale;
+  o->epf_pass2_sigma_scale = lf.epf_pass2_sigma_scale;
+  o->epf_border_sad_mul = lf.epf_border_sad_mul;
+  for (int i = 0; i < 9; i++) o->inverse_opsin_matrix[i] = op.inverse_opsin_matrix[i * 4];
+  memcpy(o->opsin_biases, op.opsin_biases, sizeof(o->opsin_biases));
+  memcpy(o->opsin_biases_cbrt, op.opsin_biases_cbrt, sizeof(o->opsin_biases_cbrt));
+  const float* base = sh.matrices.Matrix(AcStrategyType::DCT, 0);
+  for (int k = 0; k < 27; k++)
+    for (int c = 0; c < 3; c++) {
+      const float* p = sh.matrices.Matrix(static_cast<AcStrategyType>(k), c);
+      if (p < base) base = p;
+    }
+  o->dequant_table_floats = DequantMatrices::kSumRequiredXy * kDCTBlockSize * 3;
+  for (int k = 0; k < 27; k++)
+    for (int c = 0; c < 3; c++)
+      o->dequant_offsets[k * 3 + c] =
+          sh.matrices.Matrix(static_cast<AcStrategyType>(k), c) - base;
+  return 0;
+}
+
+// plane ids for ref_frame_get_plane
+enum {
+  REF_PLANE_AC_STRATEGY = 0,  // u8  [ysize_blocks][xsize_blocks]  (type<<1)|first
+  REF_PLANE_RAW_QUANT = 1,    // i32 [ysize_blocks][xsize_blocks]
+  REF_PLANE_SHARPNESS = 2,    // u8  [ysize_blocks][xsize_blocks]
+  REF_PLANE_YTOX = 3,         // i8  [cmap_ysize][cmap_xsize]
+  REF_PLANE_YTOB = 4,         // i8
+  REF_PLANE_DC = 5,           // f32 [3][ysize_blocks][xsize_blocks]
+  REF_PLANE_SIGMA = 6,        // f32 [ysize_blocks+4][xsize_blocks+4] (inv sigma)
+  REF_PLANE_DEQUANT = 7,      // f32 [dequant_table_floats]
+  REF_PLANE_COEFFS = 8,       // i16|i32 [3][num_groups][65536]
+  REF_PLANE_DECODED = 9,      // f32 [ysize][xsize][3] reference decode (linear sRGB)
+};
+
+REF_API int ref_frame_get_plane(void* h, int which, void* out, size_t out_bytes) {
+  auto* f = static_cast<RefFrame*>(h);
+  const PassesSharedState& sh = *f->dec_state->shared;
+  const FrameDimensions& d = sh.frame_dim;
+  const size_t xb = d.xsize_blocks, yb = d.ysize_blocks;
+  auto need = [&](size_t b) { return b <= out_bytes; };
+  switch (which) {
+    case REF_PLANE_AC_STRATEGY: {
+      if (!need(xb * yb)) return 2;
+      uint8_t* o = static_cast<uint8_t*>(out);
+      for (size_t y = 0; y < yb; y++) {
+        AcStrategyRow row = sh.ac_strategy.ConstRow(y);
+        for (size_t x = 0; x < xb; x++) {
+          AcStrategy a = row[x];
+          o[y * xb + x] = (a.RawStrategy() << 1) | (a.IsFirstBlock() ? 1 : 0);
+        }
+      }
+      return 0;
+    }
+    case REF_PLANE_RAW_QUANT: {
+      if (!need(xb * yb * 4)) return 2;
+      for (size_t y = 0; y < yb; y++)
+        memcpy(static_cast<int32_t*>(out) + y * xb, sh.raw_quant_field.ConstRow(y), xb * 4);
+      return 0;
+    }
+    case REF_PLANE_SHARPNESS: {
+      if (!need(xb * yb)) return 2;
+      for (size_t y = 0; y < yb; y++)
+        memcpy(static_cast<uint8_t*>(out) + y * xb, sh.epf_sharpness.ConstRow(y), xb);
+      return 0;
+    }
+    case REF_PLANE_YTOX:
+    case REF_PLANE_YTOB: {
+      const ImageSB& m = which == REF_PLANE_YTOX ? sh.cmap.ytox_map : sh.cmap.ytob_map;
+      if (!need(m.xsize() * m.ysize())) return 2;
+      for (size_t y = 0; y < m.ysize(); y++)
+        memcpy(static_cast<int8_t*>(out) + y * m.xsize(), m.ConstRow(y), m.xsize());
+      return 0;
+    }
+    case REF_PLANE_DC: {
+      if (!need(3 * xb * yb * 4)) return 2;
+      for (size_t c = 0; c < 3; c++)
+        for (size_t y = 0; y < yb; y++)
+          memcpy(static_cast<float*>(out) + (c * yb + y) * xb, sh.dc->ConstPlaneRow(c, y),
+                 xb * 4);
+      return 0;
+    }
+    case REF_PLANE_SIGMA: {
+      const ImageF& s = f->dec_state->sigma;
+      if (s.xsize() == 0) return 3;
+      if (!need((xb + 4) * (yb + 4) * 4)) return 2;
+      for (size_t y = 0; y < yb + 4; y++)
+        memcpy(static_cast<float*>(out) + y * (xb + 4), s.ConstRow(y), (xb + 4) * 4);
+      return 0;
+    }
+    case REF_PLANE_DEQUANT: {
+      RefFrameInfo info;
+      ref_frame_info(h, &info);
+      if (!need(static_cast<size_t>(info.dequant_table_floats) * 4)) return 2;
+      const float* base = sh.matrices.Matrix(AcStrategyType::DCT, 0) - info.dequant_offsets[0];
+      memcpy(out, base, static_cast<size_t>(info.dequant_table_floats) * 4);
+      return 0;
+    }
+    case REF_PLANE_COEFFS: {
+      const size_t per = kGroupDim * kGroupDim;
+      const size_t es = f->is16 ? 2 : 4;
+      if (!need(3 * d.num_groups * per * es)) return 2;
+      for (size_t c = 0; c < 3; c++)
+        for (size_t g = 0; g < d.num_groups; g++) {
+          uint8_t* dst = static_cast<uint8_t*>(out) + (c * d.num_groups + g) * per * es;
+          if (f->is16) memcpy(dst, f->stored->PlaneRow(c, g, 0).ptr16, per * es);
+          else memcpy(dst, f->stored->PlaneRow(c, g, 0).ptr32, per * es);
+        }
+      return 0;
+    }
+    case REF_PLANE_DECODED: {
+      if (!need(static_cast<size_t>(d.xsize) * d.ysize * 3 * 4)) return 2;
+      const Image3F& img = *f->decoded->color();
+      float* o = static_cast<float*>(out);
+      for (size_t y = 0; y < d.ysize; y++)
+        for (size_t c = 0; c < 3; c++) {
+          const float* r = img.ConstPlaneRow(c, y);
+          for (size_t x = 0; x < d.xsize; x++) o[(y * d.xsize + x) * 3 + c] = r[x];
+        }
+      return 0;
+    }
+  }
+  return 1;
+}
+
+// ---------------------------------------------------------------------------
+// (4) hot path only, from the retained coefficients, with the reference's own
+// code: DecodeGroupForRoundtrip (lib/jxl/dec_group.cc:820-841) feeding a
+// pipeline made of the requested subset of the reference stages.  Loop
+// structure follows RoundtripImage (lib/jxl/enc_adaptive_quantization.cc:840-915).
+// stage_mask bits: 1 gab, 2 epf0, 4 epf1, 8 epf2, 16 xyb->linear.  -1 = the
+// frame's own chain (gab/epf per its LoopFilter) + xyb.
+// out: planar f32 [3][ysize][xsize] (may be NULL when only timing).
+// reps: number of timed repetitions; seconds[] gets each repetition's time.
+// ---------------------------------------------------------------------------
+REF_API int ref_frame_render(void* h, int stage_mask, float* out, int reps, double* seconds) {
+  auto* f = static_cast<RefFrame*>(h);
+  PassesDecoderState* ds = f->dec_state.get();
+  const FrameHeader& fh = *f->frame_header;
+  const LoopFilter& lf = fh.loop_filter;
+  const FrameDimensions& d = ds->shared->frame_dim;
+  if (stage_mask < 0) {
+    stage_mask = 16 | (lf.gab ? 1 : 0);
+    if (lf.epf_iters >= 3) stage_mask |= 2;
+    if (lf.epf_iters >= 1) stage_mask |= 4;
+    if (lf.epf_iters >= 2) stage_mask |= 8;
+  }
+  if ((stage_mask & 14) && lf.epf_iters == 0) return 7;  // no sigma image
+  for (int rep = 0; rep < (reps < 1 ? 1 : reps); rep++) {
+    Image3F result;
+    double t0 = NowSec();
+    Status st = [&]() -> Status {
+      RenderPipeline::Builder builder(&f->mm, 3);
+      if (stage_mask & 1) JXL_RETURN_IF_ERROR(builder.AddStage(GetGaborishStage(lf)));
+      if (stage_mask & 2)
+        JXL_RETURN_IF_ERROR(builder.AddStage(GetEPFStage(lf, ds->sigma, EpfStage::Zero)));
+      if (stage_mask & 4)
+        JXL_RETURN_IF_ERROR(builder.AddStage(GetEPFStage(lf, ds->sigma, EpfStage::One)));
+      if (stage_mask & 8)
+        JXL_RETURN_IF_ERROR(builder.AddStage(GetEPFStage(lf, ds->sigma, EpfStage::Two)));
+      if (stage_mask & 16)
+        JXL_RETURN_IF_ERROR(builder.AddStage(GetXYBStage(ds->output_encoding_info)));
+      JXL_RETURN_IF_ERROR(builder.AddStage(GetWriteToImage3FStage(&f->mm, &result)));
+      JXL_ASSIGN_OR_RETURN(ds->render_pipeline, std::move(builder).Finalize(d));
+      if (getenv("REF_DEBUG")) fprintf(stderr, "pipeline built\n");
+      AlignedArray<GroupDecCache> caches;
+      const auto init = [&](size_t num_threads) -> Status {
+        JXL_RETURN_IF_ERROR(ds->render_pipeline->PrepareForThreads(num_threads, false));
+        JXL_ASSIGN_OR_RETURN(caches, AlignedArray<GroupDecCache>::Create(&f->mm, num_threads));
+        return true;
+      };
+      const auto group = [&](uint32_t g, size_t thread) -> Status {
+        RenderPipelineInput input = ds->render_pipeline->GetInputBuffers(g, thread);
+        Status s1 = DecodeGroupForRoundtrip(fh, f->ac32, g, ds, &caches[thread],
+                                            thread, input, nullptr, nullptr);
+        if (!s1 && getenv("REF_DEBUG")) fprintf(stderr, "DecodeGroupForRoundtrip failed g=%u\n", g);
+        JXL_RETURN_IF_ERROR(s1);
+        Status s2 = input.Done();
+        if (!s2 && getenv("REF_DEBUG")) fprintf(stderr, "Done failed g=%u\n", g);
+        JXL_RETURN_IF_ERROR(s2);
+        return true;
+      };
+      JXL_RETURN_IF_ERROR(RunOnPool(f->pool.get(), 0, d.num_groups, init, group, "hot path"));
+      return true;
+    }();
+    double t1 = NowSec();
+    if (!st) return 1;
+    if (seconds) seconds[rep] = t1 - t0;
+    if (out && rep == 0) {
+      if (result.xsize() != d.xsize || result.ysize() != d.ysize) return 5;
+      for (size_t c = 0; c < 3; c++)
+        for (size_t y = 0; y < d.ysize; y++)
+          memcpy(out + (c * d.ysize + y) * d.xsize, result.ConstPlaneRow(c, y),
+                 d.xsize * sizeof(float));
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// (5) function-level facade (lib/jxl/dec_transforms_testonly.h:20-30), the
+// same entry points ac_strategy_test.cc drives for all 27 strategies.
+// coeffs: `size` floats in the reference coefficient layout (clobbered copy);
+// pixels: rows x cols floats with the given stride.
+// ---------------------------------------------------------------------------
+REF_API int ref_transform_to_pixels(int strategy, const float* coeffs, size_t ncoeff,
+                                    float* pixels, size_t stride) {
+  JxlMemoryManager mm;
+  if (!MemoryManagerInit(&mm, nullptr)) return 1;
+  auto mem = AlignedMemory::Create(&mm, (ncoeff + 5 * AcStrategy::kMaxCoeffArea) * sizeof(float));
+  if (!mem.ok()) return 2;
+  AlignedMemory m = std::move(mem).value_();
+  float* c = m.address<float>();
+  float* scratch = c + ncoeff;
+  memcpy(c, coeffs, ncoeff * sizeof(float));
+  TransformToPixels(static_cast<AcStrategyType>(strategy), c, pixels, stride, scratch);
+  return 0;
+}
+
+REF_API int ref_transform_from_pixels(int strategy, const float* pixels, size_t stride,
+                                      float* coeffs, size_t ncoeff) {
+  JxlMemoryManager mm;
+  if (!MemoryManagerInit(&mm, nullptr)) return 1;
+  auto mem = AlignedMemory::Create(&mm, (ncoeff + 5 * AcStrategy::kMaxCoeffArea) * sizeof(float));
+  if (!mem.ok()) return 2;
+  AlignedMemory m = std::move(mem).value_();
+  float* c = m.address<float>();
+  float* scratch = c + ncoeff;
+  TransformFromPixels(static_cast<AcStrategyType>(strategy), pixels, stride, c, scratch);
+  memcpy(coeffs, c, ncoeff * sizeof(float));
+  return 0;
+}
+
+// dc: cov_y x cov_x window (stride dc_stride); llf: top-left of a coefficient
+// block of the strategy (written with row stride max(cov)*8 by the reference).
+REF_API int ref_llf_from_dc(int strategy, const float* dc, size_t dc_stride, float* block,
+                            size_t ncoeff) {
+  JxlMemoryManager mm;
+  if (!MemoryManagerInit(&mm, nullptr)) return 1;
+  auto mem = AlignedMemory::Create(&mm, (ncoeff + 5 * AcStrategy::kMaxCoeffArea) * sizeof(float));
+  if (!mem.ok()) return 2;
+  AlignedMemory m = std::move(mem).value_();
+  float* c = m.address<float>();
+  float* scratch = c + ncoeff;
+  memcpy(c, block, ncoeff * sizeof(float));
+  LowestFrequenciesFromDC(static_cast<AcStrategyType>(strategy), dc, dc_stride, c, scratch);
+  memcpy(block, c, ncoeff * sizeof(float));
+  return 0;
+}
+
+REF_API const char* ref_version() { return "libjxl 0.13.0 (reference, oracle/_ref)"; }
