@@ -1,0 +1,192 @@
+/* jxl_b200.h -- C ABI of the B200-native JPEG XL VarDCT decode transform pipeline.
+ *
+ * Drop-in boundary.  libjxl keeps parsing headers and running the
+ * ANS entropy decoder on the host under its own JxlParallelRunner
+ * (lib/include/jxl/parallel_runner.h:127-129); instead of dequantising and
+ * inverse-transforming each varblock on the CPU it hands the *quantised
+ * coefficient groups + side information* to this library, which runs
+ *
+ *   dequant + chroma-from-luma + LLF-from-DC + variable-size IDCT   (replaces lib/jxl/dec_group.cc:431-450,
+ *                                                                    dec_transforms-inl.h, dct-inl.h)
+ *   Gaborish                                                        (replaces render_pipeline/stage_gaborish.cc:56-100)
+ *   EPF pass 0 / 1 / 2 (+ sigma)                                    (replaces render_pipeline/stage_epf.cc, epf.cc:39-133)
+ *   XYB -> linear RGB                                               (replaces render_pipeline/stage_xyb.cc:78-98,
+ *                                                                    dec_xyb-inl.h:38-86)
+ *
+ * as hand-written sm_100a CUDA kernels and returns the finished frame.
+ *
+ * Conventions: plain C, caller-owned pointers, no exceptions, every entry point
+ * returns 0 on success or a JXLGPU_ERR_* code (the same "0 / non-zero" contract
+ * as JxlParallelRetCode, parallel_runner.h:52-63) so that the host can fall back
+ * to its CPU path (jxl::Status false) on any failure.  One frame in flight per
+ * context.  Thread-safety: jxlgpu_submit_group may be called concurrently from
+ * the runner's worker threads with distinct `thread_id` (< num_host_threads);
+ * everything else is single-threaded per context, matching who calls what in
+ * FrameDecoder (dec_frame.cc:573-735: frame_begin after ProcessACGlobal,
+ * submit_group from ProcessACGroup, frame_finish from FinalizeFrame).
+ */
+#ifndef JXL_B200_H_
+#define JXL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define JXLGPU_API __attribute__((visibility("default")))
+#else
+#define JXLGPU_API
+#endif
+
+#define JXLGPU_ABI_VERSION 1
+
+enum {
+  JXLGPU_OK = 0,
+  JXLGPU_ERR_INVALID_ARGUMENT = 1,
+  JXLGPU_ERR_UNSUPPORTED = 2,   /* frame not eligible: host must use its CPU path */
+  JXLGPU_ERR_NO_DEVICE = 3,     /* CUDA device / driver missing: never a silent CPU fallback */
+  JXLGPU_ERR_CUDA = 4,
+  JXLGPU_ERR_OUT_OF_MEMORY = 5,
+  JXLGPU_ERR_STATE = 6          /* call out of order (e.g. submit before frame_begin) */
+};
+
+/* Coefficient storage type, = jxl::ACType (lib/jxl/dct_util.h:41): libjxl picks
+ * int16 when max_num_bits_ac < 16 (dec_frame.cc:417-431), int32 otherwise and
+ * always int32 on the encoder-roundtrip caller (dec_group.cc:668). */
+enum { JXLGPU_AC_INT16 = 0, JXLGPU_AC_INT32 = 1 };
+
+/* Output pixel layouts. */
+enum {
+  JXLGPU_OUT_RGB_F32 = 0,       /* interleaved linear RGB float32, what JxlDecoderSetImageOutBuffer
+                                   delivers for {3, JXL_TYPE_FLOAT} (decode.h:1021, types.h:80-104) */
+  JXLGPU_OUT_PLANAR_F32 = 1     /* 3 planes [c][y][x]; also used for intermediate-stage taps */
+};
+
+/* Stage selection bits for jxlgpu_frame.stage_mask (0 = derive from gab/epf_iters,
+ * i.e. the order PassesDecoderState::PreparePipeline builds, dec_cache.cc:151-170). */
+enum {
+  JXLGPU_STAGE_GAB = 1,
+  JXLGPU_STAGE_EPF0 = 2,
+  JXLGPU_STAGE_EPF1 = 4,
+  JXLGPU_STAGE_EPF2 = 8,
+  JXLGPU_STAGE_XYB = 16,
+  JXLGPU_STAGE_EXPLICIT = 1u << 31 /* set to make stage_mask authoritative (test taps) */
+};
+
+#define JXLGPU_NUM_STRATEGIES 27   /* AcStrategy::kNumValidStrategies, ac_strategy.h:93-94 */
+#define JXLGPU_GROUP_DIM 256       /* kGroupDim, frame_dimensions.h:25 */
+#define JXLGPU_GROUP_COEFFS 65536  /* coefficients per group and channel */
+
+typedef struct jxlgpu_ctx jxlgpu_ctx;
+
+typedef struct jxlgpu_config {
+  uint32_t abi_version;       /* JXLGPU_ABI_VERSION */
+  int32_t device;             /* CUDA device ordinal */
+  uint32_t num_host_threads;  /* upper bound of thread_id in submit_group (one upload stream each) */
+  uint32_t flags;             /* reserved, 0 */
+} jxlgpu_config;
+
+/* Everything the hot path reads, as it sits in PassesSharedState / PassesDecoderState
+ * after ProcessACGlobal (passes_state.h:48-96, dec_cache.h:86-188).  All plane
+ * pointers are HOST pointers here (copied during frame_begin); strides in elements. */
+typedef struct jxlgpu_frame {
+  /* geometry: FrameDimensions (frame_dimensions.h:34-60) */
+  uint32_t xsize, ysize;                /* true image size = mirror boundary of the filters */
+  uint32_t xsize_blocks, ysize_blocks;  /* ceil(size/8) */
+  uint32_t ac_type;                     /* JXLGPU_AC_* */
+  /* row band rendered by this context, in AC-group rows (multi-GPU sharding, §8e).
+   * band_ny_groups == 0 means the whole frame. Output rows are relative to the band. */
+  uint32_t band_y0_groups, band_ny_groups;
+
+  /* per 8x8-block planes [ysize_blocks][xsize_blocks] */
+  const uint8_t* ac_strategy;   size_t ac_strategy_stride;  /* (type<<1)|is_first, ac_strategy.h:187-198 */
+  const int32_t* raw_quant;     size_t raw_quant_stride;    /* valid at first blocks; [1,256] */
+  const uint8_t* epf_sharpness; size_t epf_sharpness_stride;/* 0..7; may be NULL when epf_iters==0 */
+  /* per 64x64-px tile chroma-from-luma factors (chroma_from_luma.h:135-136) */
+  const int8_t* ytox_map; const int8_t* ytob_map; size_t cmap_stride;
+  /* dequantised, smoothed DC, 3 planes [ysize_blocks][xsize_blocks] (compressed_dc.cc:128-300) */
+  const float* dc[3];           size_t dc_stride;
+
+  /* DequantMatrices table (quant_weights.h:364-367): matrix of strategy k, channel c starts
+   * at dequant_table[dequant_offsets[3*k+c]] and has 64*covered_blocks entries. */
+  const float* dequant_table;   size_t dequant_table_floats;
+  uint32_t dequant_offsets[3 * JXLGPU_NUM_STRATEGIES];
+
+  /* scalars of DequantBlock (dec_group.cc:155-181) */
+  float inv_global_scale;       /* Quantizer::InvGlobalScale() */
+  float quant_scale;            /* Quantizer::Scale() (sigma, epf.cc:44,69) */
+  float x_dm_multiplier, b_dm_multiplier;  /* dec_cache.h:161-162 */
+  float quant_biases[4];        /* OpsinParams::quant_biases */
+  float cfl_base_x, cfl_base_b; /* ColorCorrelation base_correlation_{x,b} */
+  float cfl_color_scale;        /* 1 / color_factor (chroma_from_luma.h:51-57) */
+
+  /* LoopFilter (loop_filter.h:20-70) */
+  uint32_t gab;
+  float gab_weights[6];         /* x1 x2 y1 y2 b1 b2 (unnormalised, as in the bitstream) */
+  uint32_t epf_iters;
+  float epf_sharp_lut[8];
+  float epf_channel_scale[3];
+  float epf_quant_mul, epf_pass0_sigma_scale, epf_pass2_sigma_scale, epf_border_sad_mul;
+
+  /* OpsinParams (dec_xyb.h:28-34); matrix row-major, already x 255/intensity_target */
+  float inverse_opsin_matrix[9];
+  float opsin_biases[3];
+  float opsin_biases_cbrt[3];
+
+  uint32_t out_format;          /* JXLGPU_OUT_* */
+  uint32_t stage_mask;          /* 0, or JXLGPU_STAGE_EXPLICIT | bits */
+} jxlgpu_frame;
+
+JXLGPU_API uint32_t jxlgpu_abi_version(void);
+JXLGPU_API const char* jxlgpu_error_string(int code);
+/* Last CUDA error text recorded by this context (for logs). */
+JXLGPU_API const char* jxlgpu_last_error(const jxlgpu_ctx* ctx);
+
+JXLGPU_API int jxlgpu_create(jxlgpu_ctx** ctx, const jxlgpu_config* config);
+JXLGPU_API void jxlgpu_destroy(jxlgpu_ctx* ctx);
+
+/* Starts a frame: validates eligibility, (re)sizes device buffers, uploads side info.
+ * Replaces the per-frame setup in DecodeGroupImpl (dec_group.cc:183-228). */
+JXLGPU_API int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* frame);
+
+/* One entropy-decoded AC group: coeff[c] points at `ncoeff` quantised coefficients of
+ * channel c (X, Y, B) in libjxl's ACImage order -- varblocks in raster order of their
+ * first block, each 64*covered_blocks long (dec_group.cc:335-359).  Asynchronous H2D on
+ * the stream of `thread_id`; the host buffers may be reused as soon as the call returns
+ * only if they are NOT pinned (they are staged); pinned buffers must stay valid until
+ * frame_finish.  Replaces dec_group.cc:431-450 + RenderPipelineInput::Done(). */
+JXLGPU_API int jxlgpu_submit_group(jxlgpu_ctx* ctx, uint32_t group_idx, size_t thread_id,
+                                   const void* const coeff[3], size_t ncoeff);
+
+/* Runs the kernels for every submitted group of the band and copies the band's pixels to
+ * `out` (host; row stride in bytes).  out == NULL keeps the result on the device
+ * (jxlgpu_device_output).  Replaces LowMemoryRenderPipeline::ProcessBuffers + the write
+ * stage for the in-scope stages (low_memory_render_pipeline.cc:832-934). */
+JXLGPU_API int jxlgpu_frame_finish(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes);
+
+/* ---- device-resident entry points (bench / multi-GPU plumbing; pointers are DEVICE) ---- */
+
+/* Use coefficient planes that already live in HBM: dev_coeff[c] = [num_groups][65536]
+ * elements of the frame's ac_type.  Marks every group as submitted. */
+JXLGPU_API int jxlgpu_set_device_coefficients(jxlgpu_ctx* ctx, const void* const dev_coeff[3]);
+/* Enqueue the whole hot path on `cuda_stream` (a cudaStream_t, 0 = context stream) writing
+ * the band to dev_out (device pointer or NULL for the context's own buffer). No host sync. */
+JXLGPU_API int jxlgpu_render_device(jxlgpu_ctx* ctx, void* dev_out, size_t out_stride_bytes,
+                                    void* cuda_stream);
+/* Context-owned output buffer of the last render (device pointer) and its row stride. */
+JXLGPU_API int jxlgpu_device_output(jxlgpu_ctx* ctx, void** dev_ptr, size_t* stride_bytes);
+/* Post-IDCT XYB planes [3][ysize_blocks*8][xsize_blocks*8] (device pointer): halo exchange
+ * between bands and stage taps. */
+JXLGPU_API int jxlgpu_device_xyb(jxlgpu_ctx* ctx, float** dev_ptr, size_t* plane_stride_floats,
+                                 size_t* row_stride_floats);
+JXLGPU_API int jxlgpu_synchronize(jxlgpu_ctx* ctx);
+/* Number of kernel launches issued by this context since creation (bench "gpu_launches"). */
+JXLGPU_API uint64_t jxlgpu_launch_count(const jxlgpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JXL_B200_H_ */

@@ -99,13 +99,13 @@ def write_config_headers() -> None:
             f"#endif\n")
 
 
-def obj_path(src: Path) -> Path:
+def obj_path(src: Path, variant: str) -> Path:
     h = hashlib.sha1(str(src).encode()).hexdigest()[:10]
-    return OBJ / f"{src.stem}_{h}.o"
+    return OBJ / variant / f"{src.stem}_{h}.o"
 
 
-def compile_one(src: Path, extra: list[str]) -> Path:
-    o = obj_path(src)
+def compile_one(src: Path, extra: list[str], variant: str) -> Path:
+    o = obj_path(src, variant)
     if o.exists() and o.stat().st_mtime >= src.stat().st_mtime:
         return o
     if src.suffix == ".c":
@@ -118,12 +118,32 @@ def compile_one(src: Path, extra: list[str]) -> Path:
     return o
 
 
+# Two builds of the same sources:
+#   default : the reference's own flags (GCC default -ffp-contract=fast lets the
+#             compiler fuse Mul+Add pairs of the Highway code into FMAs on its own,
+#             so low-order bits are compiler dependent) -> CPU baseline timing and
+#             image-level oracle.
+#   strict  : adds -ffp-contract=off, i.e. FMAs exactly where the source says
+#             MulAdd/NegMulAdd -> bit-exact pin for oracle/jxl_oracle.c.
+VARIANTS = {"default": ("libjxl_ref_harness.so", []),
+            "strict": ("libjxl_ref_harness_strict.so", ["-ffp-contract=off"])}
+
+
 def main() -> int:
     if not REF.exists():
         print(f"[build_ref] {REF} not present: keeping prebuilt oracle/_ref as is")
         return 0 if (OUT / "libjxl_ref_harness.so").exists() else 1
-    OBJ.mkdir(parents=True, exist_ok=True)
     write_config_headers()
+    for variant in VARIANTS:
+        rc = build_variant(variant)
+        if rc:
+            return rc
+    return 0
+
+
+def build_variant(variant: str) -> int:
+    so_name, vflags = VARIANTS[variant]
+    (OBJ / variant).mkdir(parents=True, exist_ok=True)
     lists = parse_lists()
     srcs: list[tuple[Path, list[str]]] = []
     for key in ("JPEGXL_INTERNAL_BASE_SOURCES", "JPEGXL_INTERNAL_DEC_SOURCES",
@@ -144,6 +164,8 @@ def main() -> int:
         for f in sorted((REF / "third_party/brotli/c" / sub).glob("*.c")):
             srcs.append((f, []))
     skdefs = ["-DSKCMS_DISABLE_HSW", "-DSKCMS_DISABLE_SKX", "-Wno-psabi"]
+    srcs = [(s_, e_ + vflags) for s_, e_ in srcs]
+    skdefs = skdefs + vflags
     srcs.append((REF / "third_party/skcms/skcms.cc", skdefs))
     srcs.append((REF / "third_party/skcms/src/skcms_TransformBaseline.cc", skdefs))
     # de-duplicate (enc_transforms.cc is already in the ENC list)
@@ -153,21 +175,21 @@ def main() -> int:
             seen.add(s)
             uniq.append((s, e))
     jobs = int(os.environ.get("JOBS", os.cpu_count() or 4))
-    print(f"[build_ref] compiling {len(uniq)} reference sources with {jobs} jobs")
+    print(f"[build_ref] [{variant}] compiling {len(uniq)} reference sources with {jobs} jobs")
     objs = []
     with cf.ThreadPoolExecutor(jobs) as ex:
-        futs = [ex.submit(compile_one, s, e) for s, e in uniq]
+        futs = [ex.submit(compile_one, s, e, variant) for s, e in uniq]
         for i, f in enumerate(futs):
             objs.append(f.result())
             if (i + 1) % 40 == 0:
                 print(f"[build_ref]   {i + 1}/{len(uniq)}")
-    lib = OUT / "libjxl_ref.a"
+    lib = OUT / f"libjxl_ref_{variant}.a"
     if lib.exists():
         lib.unlink()
     subprocess.check_call(["ar", "rcs", str(lib), *map(str, objs)])
     harness = HERE / "ref_harness.cc"
-    so = OUT / "libjxl_ref_harness.so"
-    cmd = ["g++", *CXXFLAGS, *COMMON_DEFS, *includes(), "-shared", str(harness),
+    so = OUT / so_name
+    cmd = ["g++", *CXXFLAGS, *vflags, *COMMON_DEFS, *includes(), "-shared", str(harness),
            "-Wl,--whole-archive", str(lib), "-Wl,--no-whole-archive",
            "-Wl,--exclude-libs,ALL", "-lpthread", "-lm", "-o", str(so)]
     cmd.remove("-w")

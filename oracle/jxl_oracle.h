@@ -1,0 +1,32 @@
+/* jxl_oracle.h -- CPU restatement of the reference hot path. TEST INFRASTRUCTURE ONLY
+ * (see jxl_oracle.c). Takes the very same jxlgpu_frame description the product ABI takes. */
+#ifndef JXL_ORACLE_H_
+#define JXL_ORACLE_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../include/jxl_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+int jxo_covered_blocks_x(int strategy);
+int jxo_covered_blocks_y(int strategy);
+/* jxl::TransformToPixels (dec_transforms-inl.h:456-689); coeffs are not modified. */
+int jxo_transform_to_pixels(int strategy, const float* coeffs, float* pixels, size_t stride);
+/* jxl::LowestFrequenciesFromDC (dec_transforms-inl.h:691-818); writes the LLF corner of block. */
+int jxo_llf_from_dc(int strategy, const float* dc, size_t dc_stride, float* block);
+/* ComputeScaledDCT<rows,cols> (dct-inl.h:349-371). */
+int jxo_scaled_dct(int rows, int cols, const float* px, size_t stride, float* out);
+/* AdjustQuantBias (quantizer-inl.h:35-67); rcp_mode 0 exact reciprocal, 1 host rcpss. */
+float jxo_adjust_quant_bias(int c, int32_t q, const float* biases, int rcp_mode);
+uint32_t jxo_effective_stage_mask(const jxlgpu_frame* f);
+/* ComputeSigma (epf.cc:39-133): (ysize_blocks+4) x (xsize_blocks+4) inverse sigmas. */
+void jxo_compute_sigma(const jxlgpu_frame* f, float* sigma);
+/* Whole frame: coeff[c] = [num_groups][65536] host planes of f->ac_type.
+ * out: xsize*ysize*3 floats in f->out_format. Returns 0 on success. */
+int jxo_render_frame(const jxlgpu_frame* f, const void* const coeff[3], int rcp_mode, float* out);
+#ifdef __cplusplus
+}
+#endif
+#endif

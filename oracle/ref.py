@@ -14,6 +14,9 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 SO = HERE / "_ref" / "libjxl_ref_harness.so"
+# Same sources built with -ffp-contract=off (FMA only where the source says MulAdd):
+# the bit-exact pin for oracle/jxl_oracle.c.  Select with use_variant("strict").
+SO_STRICT = HERE / "_ref" / "libjxl_ref_harness_strict.so"
 
 
 class RefFrameInfo(C.Structure):
@@ -46,19 +49,27 @@ PLANE_DC, PLANE_SIGMA, PLANE_DEQUANT, PLANE_COEFFS, PLANE_DECODED = 5, 6, 7, 8, 
 
 STAGE_GAB, STAGE_EPF0, STAGE_EPF1, STAGE_EPF2, STAGE_XYB = 1, 2, 4, 8, 16
 
-_lib = None
+_libs: dict = {}
+_variant = "default"
 
 
-def available() -> bool:
-    return SO.exists()
+def available(variant: str = "default") -> bool:
+    return (SO if variant == "default" else SO_STRICT).exists()
+
+
+def use_variant(variant: str) -> None:
+    """'default' = the reference's own build flags; 'strict' = + -ffp-contract=off."""
+    global _variant
+    assert variant in ("default", "strict")
+    _variant = variant
 
 
 def lib():
-    global _lib
-    if _lib is None:
-        if not SO.exists():
-            raise RuntimeError(f"{SO} missing: run `python oracle/build_ref.py` where /root/reference exists")
-        L = C.CDLL(str(SO))
+    if _variant not in _libs:
+        so = SO if _variant == "default" else SO_STRICT
+        if not so.exists():
+            raise RuntimeError(f"{so} missing: run `python oracle/build_ref.py` where /root/reference exists")
+        L = C.CDLL(str(so))
         L.ref_frame_open.restype = C.c_void_p
         L.ref_frame_open.argtypes = [C.c_char_p, C.c_size_t, C.c_int]
         L.ref_frame_close.argtypes = [C.c_void_p]
@@ -77,8 +88,8 @@ def lib():
         L.ref_transform_to_pixels.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.ref_transform_from_pixels.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.ref_llf_from_dc.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
-        _lib = L
-    return _lib
+        _libs[_variant] = L
+    return _libs[_variant]
 
 
 def encode_rgb8(img: np.ndarray, distance: float = 1.0, effort: int = 7, gaborish: int = -1,
