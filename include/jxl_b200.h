@@ -185,6 +185,13 @@ JXLGPU_API int jxlgpu_device_xyb(jxlgpu_ctx* ctx, float** dev_ptr, size_t* plane
 JXLGPU_API int jxlgpu_synchronize(jxlgpu_ctx* ctx);
 /* Number of kernel launches issued by this context since creation (bench "gpu_launches"). */
 JXLGPU_API uint64_t jxlgpu_launch_count(const jxlgpu_ctx* ctx);
+/* Per-kernel device times of the LAST render (ms): plan, small IDCT, large IDCT, filter.
+ * Measured with CUDA events recorded on the launch stream; enable before rendering. */
+JXLGPU_API int jxlgpu_set_profiling(jxlgpu_ctx* ctx, int enable);
+JXLGPU_API int jxlgpu_kernel_times(jxlgpu_ctx* ctx, float ms[4]);
+/* Page-locked host memory for coefficient / output staging (truly asynchronous copies). */
+JXLGPU_API void* jxlgpu_alloc_pinned(size_t bytes);
+JXLGPU_API void jxlgpu_free_pinned(void* p);
 
 #ifdef __cplusplus
 }

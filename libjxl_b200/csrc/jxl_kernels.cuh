@@ -1,0 +1,1109 @@
+// jxl_kernels.cuh -- sm_100a kernels of the JPEG XL VarDCT decode transform pipeline.
+//
+// Written from scratch for Blackwell; the arithmetic contract (operation order,
+// explicit FMAs) is the reference's, cited per function as /root/reference paths:
+//   dequant + CfL            lib/jxl/dec_group.cc:115-181, lib/jxl/quantizer-inl.h:35-67
+//   LLF from DC              lib/jxl/dec_transforms-inl.h:35-64,691-818
+//   1-D (I)DCT recursion     lib/jxl/dct-inl.h:45-232   (Perera-Liu radix-2)
+//   2-D transforms, specials lib/jxl/dct-inl.h:349-397, lib/jxl/dec_transforms-inl.h:66-689
+//   sigma                    lib/jxl/epf.cc:39-133
+//   Gaborish / EPF / XYB     lib/jxl/render_pipeline/stage_{gaborish,epf,xyb}.cc, dec_xyb-inl.h:38-86
+//
+// This translation unit is compiled with -fmad=false: the compiler never fuses a
+// multiply and an add on its own; fmaf() appears exactly where the reference's
+// AVX2 path has MulAdd / NegMulAdd, which makes results bit-identical to
+// oracle/jxl_oracle.c (rcp_mode 0).
+//
+// Thread mapping (B200: 148 SMs, 32-wide warps):
+//   plan kernel   one CTA (1024 thr) per 256x256 AC group: block-scan of varblock sizes ->
+//                 per-block coefficient offsets, per-strategy work lists, sigma plane.
+//   small IDCT    one warp per "warp item" = 32/W varblocks of one strategy (W = 8,16,32 lanes
+//                 per varblock); lane = vertical frequency in pass 1, pixel column in pass 2;
+//                 1-D transforms live entirely in registers, one smem transpose in between.
+//   large IDCT    one CTA per varblock with a 64..256 side: pass 1 row transforms, pass 2
+//                 column transforms through the (exclusively owned) output plane region.
+//   filter        one CTA per 64x32 output tile (+halo), all enabled stages fused through two
+//                 shared-memory ping-pong tiles, XYB->RGB in the epilogue.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define JXT_CONST __device__ __constant__ const
+#include "jxl_tables.h"
+
+namespace jxlb {
+
+constexpr float kSqrt2 = 1.41421356237f;  // lib/jxl/dct_scales.h:15
+constexpr int kNumStrategies = 27;
+constexpr int kFirstLarge = 18;           // strategies >= 18 have a 64+ side
+
+// AcStrategy geometry (lib/jxl/ac_strategy.h:148-173)
+__host__ __device__ constexpr int covered_x(int s) {
+  constexpr int k[27] = {1, 1, 1, 1, 2, 4, 1, 2, 1, 4, 2, 4, 1, 1, 1, 1, 1, 1, 8, 4, 8, 16, 8, 16, 32, 16, 32};
+  return k[s];
+}
+__host__ __device__ constexpr int covered_y(int s) {
+  constexpr int k[27] = {1, 1, 1, 1, 2, 4, 2, 1, 4, 1, 4, 2, 1, 1, 1, 1, 1, 1, 8, 8, 4, 16, 16, 8, 32, 32, 16};
+  return k[s];
+}
+
+struct FrameDev {
+  uint32_t xsize, ysize, xb, yb, xg, yg;
+  uint32_t ac_is32;
+  uint32_t stage_mask;       // JXLGPU_STAGE_* bits actually run
+  uint32_t out_format;
+  uint32_t band_y0, band_y1; // pixel rows [band_y0, band_y1) rendered by the filter kernel
+  uint32_t need_y0, need_y1; // pixel rows of post-IDCT data the band's filters read (band +- halo)
+  uint32_t plan_g0;          // first AC group handled by the plan kernel (band sharding)
+  // side info (device)
+  const uint8_t* acs;
+  const int32_t* quant;
+  const uint8_t* sharp;
+  const int8_t* ytox;
+  const int8_t* ytob;
+  uint32_t cmap_stride;
+  const float* dc;           // 3 planes [yb][xb]
+  const float* dq;           // dequant table
+  uint32_t dq_off[3 * kNumStrategies];
+  const void* coeff[3];      // [num_groups][65536]
+  // produced by the plan kernel
+  uint16_t* coeff_off;       // [yb][xb] offset/64 of the varblock inside its group (first blocks)
+  float* sigma;              // [yb][xb] inverse sigma
+  uint32_t* list;            // work lists, entry = (aby << 16) | abx
+  uint32_t* counts;          // [27]
+  uint32_t list_base[kNumStrategies];
+  // planes
+  float* xyb;                // 3 planes [yb*8][xb*8]
+  size_t plane_stride, row_stride;
+  // scalars
+  float inv_global_scale, quant_scale, x_dm, b_dm;
+  float qbias[4];
+  float cfl_base_x, cfl_base_b, cfl_scale;
+  float gab_w[9];            // normalised: w0,w1,w2 per channel
+  float epf_sharp_lut[8];
+  float epf_scale[3];
+  float epf_quant_mul, epf_sm[3], epf_border_mul;  // epf_sm[pass]: sigma multiplier of pass 0/1/2
+  float opsin_m[9], opsin_bias[3], opsin_cbrt[3];
+};
+
+// ---------------------------------------------------------------------------
+// 1-D transforms in registers
+// ---------------------------------------------------------------------------
+// IDCT1DImpl<N> (dct-inl.h:191-232): even/odd split, BTranspose, butterflies.
+template <int N>
+__device__ __forceinline__ void idct1d(float* v) {
+  if constexpr (N == 1) {
+    return;
+  } else if constexpr (N == 2) {
+    const float a = v[0], b = v[1];
+    v[0] = a + b;
+    v[1] = a - b;
+  } else {
+    constexpr int H = N / 2;
+    float e[H], o[H];
+#pragma unroll
+    for (int i = 0; i < H; i++) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+    idct1d<H>(e);
+#pragma unroll
+    for (int i = H - 1; i > 0; i--) o[i] = o[i] + o[i - 1];
+    o[0] = o[0] * kSqrt2;
+    idct1d<H>(o);
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      const float w = JXT_WC[H - 2 + i];
+      v[i] = fmaf(w, o[i], e[i]);
+      v[N - 1 - i] = fmaf(-w, o[i], e[i]);
+    }
+  }
+}
+
+// DCT1DImpl<N> (dct-inl.h:158-189), unscaled.
+template <int N>
+__device__ __forceinline__ void dct1d(float* v) {
+  if constexpr (N == 1) {
+    return;
+  } else if constexpr (N == 2) {
+    const float a = v[0], b = v[1];
+    v[0] = a + b;
+    v[1] = a - b;
+  } else {
+    constexpr int H = N / 2;
+    float t0[H], t1[H];
+#pragma unroll
+    for (int i = 0; i < H; i++) t0[i] = v[i] + v[N - 1 - i];
+    dct1d<H>(t0);
+#pragma unroll
+    for (int i = 0; i < H; i++) t1[i] = (v[i] - v[N - 1 - i]) * JXT_WC[H - 2 + i];
+    dct1d<H>(t1);
+    t1[0] = fmaf(t1[0], kSqrt2, t1[1]);
+#pragma unroll
+    for (int i = 1; i + 1 < H; i++) t1[i] = t1[i] + t1[i + 1];
+#pragma unroll
+    for (int i = 0; i < H; i++) { v[2 * i] = t0[i]; v[2 * i + 1] = t1[i]; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// dequantisation (dec_group.cc:115-181, quantizer-inl.h:35-67)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float adjust_quant_bias(int q, float bias_c, float bias3) {
+  const float fq = (float)q;
+  const float a = fabsf(fq);
+  if (a < 1.125f) return a > 0.0f ? copysignf(bias_c, fq) : 0.0f;
+  return fmaf(-bias3, __frcp_rn(fq), fq);
+}
+
+template <bool I32>
+__device__ __forceinline__ int load_q(const void* p, size_t i) {
+  if constexpr (I32) return __ldg(reinterpret_cast<const int32_t*>(p) + i);
+  else return (int)__ldg(reinterpret_cast<const int16_t*>(p) + i);
+}
+
+struct VarblockCtx {
+  uint32_t abx, aby;
+  size_t cbase;      // element index of coefficient 0 in the channel plane
+  float sx, sy, sb;  // scaled dequant multipliers
+  float x_cc, b_cc;
+};
+
+__device__ __forceinline__ VarblockCtx make_ctx(const FrameDev& P, uint32_t entry) {
+  VarblockCtx v;
+  v.abx = entry & 0xffffu;
+  v.aby = entry >> 16;
+  const size_t bi = (size_t)v.aby * P.xb + v.abx;
+  const uint32_t g = (v.aby >> 5) * P.xg + (v.abx >> 5);
+  v.cbase = (size_t)g * 65536u + (size_t)P.coeff_off[bi] * 64u;
+  const float s = P.inv_global_scale / (float)P.quant[bi];
+  v.sx = s * P.x_dm;
+  v.sy = s;
+  v.sb = s * P.b_dm;
+  const size_t ti = (size_t)(v.aby >> 3) * P.cmap_stride + (v.abx >> 3);
+  v.x_cc = P.cfl_base_x + (float)P.ytox[ti] * P.cfl_scale;
+  v.b_cc = P.cfl_base_b + (float)P.ytob[ti] * P.cfl_scale;
+  return v;
+}
+
+// dequantised coefficient i (index inside the varblock) of channel c
+template <bool I32>
+__device__ __forceinline__ float dequant(const FrameDev& P, const VarblockCtx& v, int kind, int c,
+                                         uint32_t i) {
+  const int qy = load_q<I32>(P.coeff[1], v.cbase + i);
+  const float y_mul = __ldg(P.dq + P.dq_off[3 * kind + 1] + i) * v.sy;
+  const float dy = adjust_quant_bias(qy, P.qbias[1], P.qbias[3]) * y_mul;
+  if (c == 1) return dy;
+  const int qc = load_q<I32>(P.coeff[c], v.cbase + i);
+  const float c_mul = __ldg(P.dq + P.dq_off[3 * kind + c] + i) * (c == 0 ? v.sx : v.sb);
+  const float dc_ = adjust_quant_bias(qc, P.qbias[c], P.qbias[3]) * c_mul;
+  return fmaf(c == 0 ? v.x_cc : v.b_cc, dy, dc_);
+}
+
+// ---------------------------------------------------------------------------
+// plan kernel: one CTA (1024 threads) per AC group
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) plan_kernel(const __grid_constant__ FrameDev P, int want_sigma) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t local_count[kNumStrategies];
+  __shared__ uint32_t local_base[kNumStrategies];
+  const uint32_t t = threadIdx.x;
+  const uint32_t g = blockIdx.x + P.plan_g0;
+  const uint32_t gx = g % P.xg, gy = g / P.xg;
+  const uint32_t abx = gx * 32 + (t & 31), aby = gy * 32 + (t >> 5);
+  const bool valid = abx < P.xb && aby < P.yb;
+  if (t < kNumStrategies) local_count[t] = 0;
+  const size_t bi = (size_t)aby * P.xb + abx;
+  const uint32_t raw = valid ? P.acs[bi] : 0u;
+  const bool first = valid && (raw & 1u);
+  const int s = raw >> 1;
+  const uint32_t area = first ? (uint32_t)(covered_x(s) * covered_y(s)) : 0u;
+  // exclusive scan of `area` in raster order (dec_group.cc:221,335-359: running offset)
+  uint32_t incl = area;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((t & 31) >= (uint32_t)d) incl += n;
+  }
+  if ((t & 31) == 31) warp_sums[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    uint32_t w = warp_sums[t];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, w, d);
+      if (t >= (uint32_t)d) w += n;
+    }
+    warp_sums[t] = w;
+  }
+  __syncthreads();
+  const uint32_t off = incl - area + ((t >> 5) ? warp_sums[(t >> 5) - 1] : 0u);
+  uint32_t rank = 0;
+  // band sharding: only varblocks that intersect the rows this band's filters read are listed
+  const bool wanted = first && (aby * 8u < P.need_y1) && ((aby + (uint32_t)covered_y(s)) * 8u > P.need_y0);
+  if (first) P.coeff_off[bi] = (uint16_t)off;
+  if (wanted) rank = atomicAdd(&local_count[s], 1u);
+  __syncthreads();
+  if (t < kNumStrategies && local_count[t]) local_base[t] = atomicAdd(&P.counts[t], local_count[t]);
+  __syncthreads();
+  if (wanted) {
+    P.list[P.list_base[s] + local_base[s] + rank] = (aby << 16) | abx;
+    if (want_sigma) {
+      // ComputeSigma (epf.cc:39-133)
+      const float kInvSigmaNum = -1.1715728752538099024f;
+      const float sigma_quant = P.epf_quant_mul / (P.quant_scale * (float)P.quant[bi] * kInvSigmaNum);
+      for (int iy = 0; iy < covered_y(s); iy++)
+        for (int ix = 0; ix < covered_x(s); ix++) {
+          const size_t bj = (size_t)(aby + iy) * P.xb + abx + ix;
+          float sg = sigma_quant * P.epf_sharp_lut[P.sharp[bj]];
+          sg = fminf(-1e-4f, sg);
+          P.sigma[bj] = 1.0f / sg;
+        }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// LLF from DC for multi-block DCTs (dec_transforms-inl.h:35-64): forward
+// cy x cx DCT of the DC window, rescaled. Cooperative: `nl` lanes/threads with
+// index l; t0/out are shared scratch of cy*cx floats; sync() separates phases.
+// Result: out[j*cx + k] = LLF value of (vertical freq j, horizontal freq k).
+// ---------------------------------------------------------------------------
+template <int CY, int CX, typename Sync>
+__device__ __forceinline__ void llf_from_dc(const float* dc, size_t dc_stride, int l, float* t0,
+                                            float* out, Sync sync) {
+  if (l < CX) {
+    float col[CY];
+#pragma unroll
+    for (int y = 0; y < CY; y++) col[y] = __ldg(dc + (size_t)y * dc_stride + l);
+    dct1d<CY>(col);
+#pragma unroll
+    for (int y = 0; y < CY; y++) t0[y * CX + l] = (1.0f / CY) * col[y];
+  }
+  sync();
+  if (l < CY) {
+    float row[CX];
+#pragma unroll
+    for (int x = 0; x < CX; x++) row[x] = t0[l * CX + x];
+    dct1d<CX>(row);
+    const float sy = JXT_RESAMPLE[CY - 1 + l];
+#pragma unroll
+    for (int x = 0; x < CX; x++) {
+      const float v = (1.0f / CX) * row[x];
+      const float sx = JXT_RESAMPLE[CX - 1 + x];
+      // multiplication order of ReinterpretingDCT: first-index scale first
+      out[l * CX + x] = (CY < CX) ? (v * sy) * sx : (v * sx) * sy;
+    }
+  }
+  sync();
+}
+
+struct WarpSync {
+  __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+struct BlockSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+// ---------------------------------------------------------------------------
+// small IDCT: plain DCTs with R, C <= 32 (ComputeScaledIDCT<R,C>, dct-inl.h:376-397)
+// W = max(R,C) lanes per varblock. sm: per-warp scratch (>= 32/W * (R*(C+1) + 2*CY*CX) floats).
+// ---------------------------------------------------------------------------
+template <int R, int C, bool I32>
+__device__ __forceinline__ void small_dct_item(const FrameDev& P, int kind, uint32_t first_entry_idx,
+                                               uint32_t count, float* sm) {
+  constexpr int W = R > C ? R : C;
+  constexpr int SLOTS = 32 / W;
+  constexpr int CY = R / 8, CX = C / 8;
+  constexpr int TS = R * (C + 1);             // transpose buffer per slot
+  constexpr int SLOT_FLOATS = TS + 2 * CY * CX;
+  const int lane = threadIdx.x & 31;
+  const int slot = lane / W, l = lane % W;
+  const uint32_t eidx = first_entry_idx + slot;
+  const bool active = eidx < count;
+  float* T = sm + slot * SLOT_FLOATS;
+  float* llf = T + TS;
+  float* llf_tmp = llf + CY * CX;
+  VarblockCtx vb;
+  if (active) vb = make_ctx(P, P.list[P.list_base[kind] + eidx]);
+  else vb = VarblockCtx{};
+#pragma unroll 1
+  for (int c = 0; c < 3; c++) {
+    // ---- LLF (cooperative inside the slot) ----
+    if constexpr (CY * CX > 1) {
+      const float* dcp = P.dc + (size_t)c * P.yb * P.xb + (active ? (size_t)vb.aby * P.xb + vb.abx : 0);
+      llf_from_dc<CY, CX>(dcp, P.xb, active ? l : 1000, llf_tmp, llf, WarpSync());
+    }
+    // ---- pass 1: lane j = vertical frequency, IDCT over horizontal frequency k ----
+    float v[C];
+    if (active && l < R) {
+#pragma unroll
+      for (int k = 0; k < C; k++) {
+        const uint32_t i = (R >= C) ? (uint32_t)(k * R + l) : (uint32_t)(l * C + k);
+        v[k] = dequant<I32>(P, vb, kind, c, i);
+      }
+      if constexpr (CY * CX > 1) {
+        if (l < CY) {
+#pragma unroll
+          for (int k = 0; k < CX; k++) v[k] = llf[l * CX + k];
+        }
+      } else {
+        if (l == 0) v[0] = __ldg(P.dc + (size_t)c * P.yb * P.xb + (size_t)vb.aby * P.xb + vb.abx);
+      }
+      idct1d<C>(v);
+#pragma unroll
+      for (int x = 0; x < C; x++) T[l * (C + 1) + x] = v[x];
+    }
+    __syncwarp();
+    // ---- pass 2: lane x = pixel column, IDCT over vertical frequency ----
+    if (active && l < C) {
+      float u[R];
+#pragma unroll
+      for (int j = 0; j < R; j++) u[j] = T[j * (C + 1) + l];
+      idct1d<R>(u);
+      float* out = P.xyb + (size_t)c * P.plane_stride + (size_t)vb.aby * 8 * P.row_stride + vb.abx * 8 + l;
+#pragma unroll
+      for (int y = 0; y < R; y++) out[(size_t)y * P.row_stride] = u[y];
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// small IDCT: the 8x8 specials (dec_transforms-inl.h:66-93,399-581). 8 lanes per block,
+// 4 blocks per warp. Per slot scratch: co[64] coefficients, tmp[64], px[64] pixels.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void hadamard4(float b00, float b01, float b10, float b11, float* dcs) {
+  dcs[0] = b00 + b01 + b10 + b11;
+  dcs[1] = b00 + b01 - b10 - b11;
+  dcs[2] = b00 - b01 + b10 - b11;
+  dcs[3] = b00 - b01 - b10 + b11;
+}
+
+template <bool I32>
+__device__ __forceinline__ void special_item(const FrameDev& P, int kind, uint32_t first_entry_idx,
+                                             uint32_t count, float* sm) {
+  const int lane = threadIdx.x & 31;
+  const int slot = lane >> 3, l = lane & 7;
+  const uint32_t eidx = first_entry_idx + slot;
+  const bool active = eidx < count;
+  // Inactive slots (tail of a list) run the same instruction stream on scratch data so that
+  // every __syncwarp() is reached by all 32 lanes; only their loads and stores are masked.
+  float* co = sm + slot * 200;   // 200 = 3*64 + 8 pad: slot bases fall on different banks
+  float* tmp = co + 64;
+  float* px = co + 128;
+  VarblockCtx vb;
+  if (active) vb = make_ctx(P, P.list[P.list_base[kind] + eidx]);
+  else vb = VarblockCtx{};
+#pragma unroll 1
+  for (int c = 0; c < 3; c++) {
+    if (active) {
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        const uint32_t i = (uint32_t)(t * 8 + l);
+        co[i] = dequant<I32>(P, vb, kind, c, i);
+      }
+    }
+    __syncwarp();
+    if (active && l == 0)  // LowestFrequenciesFromDC: llf[0] = dc[0]
+      co[0] = __ldg(P.dc + (size_t)c * P.yb * P.xb + (size_t)vb.aby * P.xb + vb.abx);
+    __syncwarp();
+    {
+      switch (kind) {
+        case 1: {  // IDENTITY (dec_transforms-inl.h:463-499)
+          if (l < 4) {
+            const int y = l >> 1, x = l & 1;
+            float dcs[4];
+            hadamard4(co[0], co[1], co[8], co[9], dcs);
+            const float block_dc = dcs[y * 2 + x];
+            float residual_sum = 0.0f;
+#pragma unroll
+            for (int iy = 0; iy < 4; iy++)
+#pragma unroll
+              for (int ix = 0; ix < 4; ix++) {
+                if (ix == 0 && iy == 0) continue;
+                residual_sum += co[(y + iy * 2) * 8 + x + ix * 2];
+              }
+            const float p11 = block_dc - residual_sum * (1.0f / 16);
+#pragma unroll
+            for (int iy = 0; iy < 4; iy++)
+#pragma unroll
+              for (int ix = 0; ix < 4; ix++) {
+                if (ix == 1 && iy == 1) continue;
+                px[(y * 4 + iy) * 8 + x * 4 + ix] = co[(y + iy * 2) * 8 + x + ix * 2] + p11;
+              }
+            px[(4 * y + 1) * 8 + 4 * x + 1] = p11;
+            px[(y * 4) * 8 + x * 4] = co[(y + 2) * 8 + x + 2] + p11;
+          }
+          break;
+        }
+        case 2: {  // DCT2X2 (569-581): IDCT2TopBlock<2>, <4>, <8> in place
+#pragma unroll
+          for (int S = 2; S <= 8; S *= 2) {
+            const int n = S / 2;
+            float r[2][4];
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+              const int item = l + it * 8;
+              if (item < n * n) {
+                const int y = item / n, x = item % n;
+                const float c00 = co[y * 8 + x], c01 = co[y * 8 + n + x];
+                const float c10 = co[(y + n) * 8 + x], c11 = co[(y + n) * 8 + n + x];
+                r[it][0] = c00 + c01 + c10 + c11;
+                r[it][1] = c00 + c01 - c10 - c11;
+                r[it][2] = c00 - c01 + c10 - c11;
+                r[it][3] = c00 - c01 - c10 + c11;
+              }
+            }
+            __syncwarp();
+            float* dst = (S == 8) ? px : co;
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+              const int item = l + it * 8;
+              if (item < n * n) {
+                const int y = item / n, x = item % n;
+                dst[(y * 2) * 8 + x * 2] = r[it][0];
+                dst[(y * 2) * 8 + x * 2 + 1] = r[it][1];
+                dst[(y * 2 + 1) * 8 + x * 2] = r[it][2];
+                dst[(y * 2 + 1) * 8 + x * 2 + 1] = r[it][3];
+              }
+            }
+            __syncwarp();
+          }
+          break;
+        }
+        case 3: {  // DCT4X4 (541-568)
+          float dcs[4];
+          hadamard4(co[0], co[1], co[8], co[9], dcs);
+#pragma unroll
+          for (int it = 0; it < 2; it++) {  // pass 1: (sub-block, j)
+            const int sub = (l >> 2) + 2 * it, j = l & 3;
+            const int y = sub >> 1, x = sub & 1;
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = co[(y + k * 2) * 8 + x + j * 2];
+            if (j == 0) v[0] = dcs[sub];
+            idct1d<4>(v);
+#pragma unroll
+            for (int xx = 0; xx < 4; xx++) tmp[sub * 16 + j * 4 + xx] = v[xx];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 2; it++) {  // pass 2: (sub-block, column)
+            const int sub = (l >> 2) + 2 * it, xx = l & 3;
+            const int y = sub >> 1, x = sub & 1;
+            float u[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) u[j] = tmp[sub * 16 + j * 4 + xx];
+            idct1d<4>(u);
+#pragma unroll
+            for (int yy = 0; yy < 4; yy++) px[(4 * y + yy) * 8 + 4 * x + xx] = u[yy];
+          }
+          break;
+        }
+        case 12: {  // DCT4X8 (520-540): two 4-row halves
+          const float b0 = co[0], b1 = co[8];
+          {
+            const int half = l >> 2, j = l & 3;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = co[(half + j * 2) * 8 + k];
+            if (j == 0) v[0] = half ? (b0 - b1) : (b0 + b1);
+            idct1d<8>(v);
+#pragma unroll
+            for (int x = 0; x < 8; x++) tmp[half * 32 + j * 8 + x] = v[x];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            float u[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) u[j] = tmp[half * 32 + j * 8 + l];
+            idct1d<4>(u);
+#pragma unroll
+            for (int yy = 0; yy < 4; yy++) px[(4 * half + yy) * 8 + l] = u[yy];
+          }
+          break;
+        }
+        case 13: {  // DCT8X4 (500-519): two 4-column halves
+          const float b0 = co[0], b1 = co[8];
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = co[(half + k * 2) * 8 + l];
+            if (l == 0) v[0] = half ? (b0 - b1) : (b0 + b1);
+            idct1d<4>(v);
+#pragma unroll
+            for (int xx = 0; xx < 4; xx++) tmp[half * 32 + l * 4 + xx] = v[xx];
+          }
+          __syncwarp();
+          {
+            const int half = l >> 2, xx = l & 3;
+            float u[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) u[j] = tmp[half * 32 + j * 4 + xx];
+            idct1d<8>(u);
+#pragma unroll
+            for (int yy = 0; yy < 8; yy++) px[yy * 8 + half * 4 + xx] = u[yy];
+          }
+          break;
+        }
+        default: {  // AFV0..3 (399-454)
+          const int afv_kind = kind - 14;
+          const int afv_x = afv_kind & 1, afv_y = afv_kind >> 1;
+          const float b00 = co[0], b01 = co[1], b10 = co[8];
+          const float dcs0 = (b00 + b10 + b01) * 4.0f;
+          const float dcs1 = (b00 + b10 - b01);
+          const float dcs2 = b00 - b10;
+          // (a) AFVIDCT4x4: two of the 16 outputs per lane
+#pragma unroll
+          for (int it = 0; it < 2; it++) {
+            const int i = l + 8 * it;
+            float p = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const float cf = (j == 0) ? dcs0 : co[(j >> 2) * 2 * 8 + (j & 3) * 2];
+              p = fmaf(cf, JXT_AFV_BASIS[j][i], p);
+            }
+            const int r = i >> 2, cc = i & 3;
+            const int iy = afv_y ? 3 - r : r, ix = afv_x ? 3 - cc : cc;
+            px[(iy + afv_y * 4) * 8 + afv_x * 4 + ix] = p;
+          }
+          // (b) 4x4 IDCT of the (odd column) interleave, (c) 4x8 IDCT of the odd rows: pass 1
+          if (l < 4) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = co[k * 2 * 8 + l * 2 + 1];
+            if (l == 0) v[0] = dcs1;
+            idct1d<4>(v);
+#pragma unroll
+            for (int xx = 0; xx < 4; xx++) tmp[l * 4 + xx] = v[xx];
+          } else {
+            const int j = l - 4;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = co[(1 + j * 2) * 8 + k];
+            if (j == 0) v[0] = dcs2;
+            idct1d<8>(v);
+#pragma unroll
+            for (int x = 0; x < 8; x++) tmp[16 + j * 8 + x] = v[x];
+          }
+          __syncwarp();
+          if (l < 4) {
+            float u[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) u[j] = tmp[j * 4 + l];
+            idct1d<4>(u);
+#pragma unroll
+            for (int yy = 0; yy < 4; yy++) px[(afv_y * 4 + yy) * 8 + (afv_x == 1 ? 0 : 4) + l] = u[yy];
+          }
+          {
+            float u[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) u[j] = tmp[16 + j * 8 + l];
+            idct1d<4>(u);
+#pragma unroll
+            for (int yy = 0; yy < 4; yy++) px[((afv_y == 1 ? 0 : 4) + yy) * 8 + l] = u[yy];
+          }
+          break;
+        }
+      }
+    }
+    __syncwarp();
+    if (active) {  // lane l stores pixel row l (2 x 16 B)
+      float* out = P.xyb + (size_t)c * P.plane_stride + ((size_t)vb.aby * 8 + l) * P.row_stride + vb.abx * 8;
+      const float4 a = *reinterpret_cast<const float4*>(px + l * 8);
+      const float4 b = *reinterpret_cast<const float4*>(px + l * 8 + 4);
+      *reinterpret_cast<float4*>(out) = a;
+      *reinterpret_cast<float4*>(out + 4) = b;
+    }
+    __syncwarp();
+  }
+}
+
+constexpr int kSmallWarpsPerCta = 8;
+constexpr int kSmallWarpFloats = 1120;  // >= 32*33 + 2*16 and >= 4*200
+
+__device__ __forceinline__ int small_slots(int s) {
+  const int w = max(covered_x(s), covered_y(s));
+  return w == 1 ? 4 : (w == 2 ? 2 : 1);
+}
+
+template <bool I32>
+__global__ void __launch_bounds__(kSmallWarpsPerCta * 32) idct_small_kernel(const __grid_constant__ FrameDev P) {
+  __shared__ __align__(16) float smem[kSmallWarpsPerCta * kSmallWarpFloats];
+  float* sm = smem + (threadIdx.x >> 5) * kSmallWarpFloats;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  // warp items are numbered class by class; larger transforms first for balance
+  const int order[kFirstLarge] = {5, 10, 11, 8, 9, 4, 6, 7, 0, 1, 2, 3, 12, 13, 14, 15, 16, 17};
+  uint32_t base = 0;
+#pragma unroll 1
+  for (int oi = 0; oi < kFirstLarge; oi++) {
+    const int s = order[oi];
+    const uint32_t count = P.counts[s];
+    const uint32_t slots = small_slots(s);
+    const uint32_t items = (count + slots - 1) / slots;
+    // first item of this class handled by this warp
+    uint32_t it = (warp + nwarps - (base % nwarps)) % nwarps;
+#pragma unroll 1
+    for (; it < items; it += nwarps) {
+      const uint32_t e0 = it * slots;
+      switch (s) {
+        case 0: small_dct_item<8, 8, I32>(P, s, e0, count, sm); break;
+        case 4: small_dct_item<16, 16, I32>(P, s, e0, count, sm); break;
+        case 5: small_dct_item<32, 32, I32>(P, s, e0, count, sm); break;
+        case 6: small_dct_item<16, 8, I32>(P, s, e0, count, sm); break;
+        case 7: small_dct_item<8, 16, I32>(P, s, e0, count, sm); break;
+        case 8: small_dct_item<32, 8, I32>(P, s, e0, count, sm); break;
+        case 9: small_dct_item<8, 32, I32>(P, s, e0, count, sm); break;
+        case 10: small_dct_item<32, 16, I32>(P, s, e0, count, sm); break;
+        case 11: small_dct_item<16, 32, I32>(P, s, e0, count, sm); break;
+        default: special_item<I32>(P, s, e0, count, sm); break;
+      }
+    }
+    base += items;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// large IDCT: one CTA (256 threads) per varblock with a 64/128/256 side.
+// Pass 1 writes the horizontally transformed rows into the varblock's own region of
+// the output plane; pass 2 transforms the columns in place.
+// ---------------------------------------------------------------------------
+// Warp-cooperative N-point IDCT (N = 128, 256) on a vector in shared memory:
+// recursion levels down to 32-point leaves done by all lanes, leaves in registers.
+template <int N>
+__device__ __forceinline__ void idct1d_warp(float* v /*N*/, float* w /*N scratch*/) {
+  const int lane = threadIdx.x & 31;
+  // top-down: even/odd split + BTranspose of the odd half, sizes N, N/2, ..., 64
+  float* src = v;
+  float* dst = w;
+#pragma unroll
+  for (int n = N; n > 32; n >>= 1) {
+    const int h = n >> 1;
+    for (int i = lane; i < N; i += 32) {
+      const int seg = i / n, r = i % n;  // element r of segment seg
+      const float* s = src + seg * n;
+      float val;
+      if (r < h) {
+        val = s[2 * r];
+      } else {
+        const int q = r - h;
+        val = (q == 0) ? s[1] * kSqrt2 : (s[2 * q + 1] + s[2 * q - 1]);
+      }
+      dst[i] = val;
+    }
+    __syncwarp();
+    float* t = src; src = dst; dst = t;
+  }
+  // leaves: N/32 independent 32-point IDCTs
+  if (lane < N / 32) {
+    float r[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) r[i] = src[lane * 32 + i];
+    idct1d<32>(r);
+#pragma unroll
+    for (int i = 0; i < 32; i++) src[lane * 32 + i] = r[i];
+  }
+  __syncwarp();
+  // bottom-up: MultiplyAndAdd, sizes 64, ..., N
+#pragma unroll
+  for (int n = 64; n <= N; n <<= 1) {
+    const int h = n >> 1;
+    for (int i = lane; i < N / 2; i += 32) {
+      const int seg = i / h, r = i % h;
+      const float* s = src + seg * n;
+      const float wv = JXT_WC[h - 2 + r];
+      const float e = s[r], o = s[h + r];
+      dst[seg * n + r] = fmaf(wv, o, e);
+      dst[seg * n + n - 1 - r] = fmaf(-wv, o, e);
+    }
+    __syncwarp();
+    float* t = src; src = dst; dst = t;
+  }
+  if (src != v) {
+    for (int i = lane; i < N; i += 32) v[i] = src[i];
+    __syncwarp();
+  }
+}
+
+template <int N>
+__device__ __forceinline__ constexpr bool in_regs() { return N <= 64; }
+
+template <int R, int C, bool I32>
+__device__ __forceinline__ void large_item(const FrameDev& P, int kind, uint32_t entry, float* sm) {
+  constexpr int CY = R / 8, CX = C / 8;
+  const int tid = threadIdx.x;
+  float* llf = sm;                 // 3 * CY*CX
+  float* llf_tmp = sm + 3 * 1024;  // CY*CX
+  float* coop = sm + 4 * 1024;     // 8 warps * 2 * 256
+  const VarblockCtx vb = make_ctx(P, entry);
+  for (int c = 0; c < 3; c++)
+    llf_from_dc<CY, CX>(P.dc + (size_t)c * P.yb * P.xb + (size_t)vb.aby * P.xb + vb.abx, P.xb, tid,
+                        llf_tmp, llf + c * CY * CX, BlockSync());
+  // ---- pass 1: rows (c, j): IDCT over horizontal frequency ----
+  if constexpr (C <= 64) {
+    for (int r = tid; r < 3 * R; r += blockDim.x) {
+      const int c = r / R, j = r % R;
+      float v[C];
+#pragma unroll
+      for (int k = 0; k < C; k++) {
+        const uint32_t i = (R >= C) ? (uint32_t)(k * R + j) : (uint32_t)(j * C + k);
+        v[k] = dequant<I32>(P, vb, kind, c, i);
+      }
+      if (j < CY) {
+#pragma unroll
+        for (int k = 0; k < CX; k++) v[k] = llf[c * CY * CX + j * CX + k];
+      }
+      idct1d<C>(v);
+      float* out = P.xyb + (size_t)c * P.plane_stride + ((size_t)vb.aby * 8 + j) * P.row_stride + vb.abx * 8;
+#pragma unroll
+      for (int x = 0; x < C; x += 4)
+        *reinterpret_cast<float4*>(out + x) = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
+    }
+  } else {
+    const int warp = tid >> 5, lane = tid & 31;
+    float* buf = coop + warp * 512;
+    for (int r = warp; r < 3 * R; r += blockDim.x >> 5) {
+      const int c = r / R, j = r % R;
+      for (int k = lane; k < C; k += 32) {
+        const uint32_t i = (R >= C) ? (uint32_t)(k * R + j) : (uint32_t)(j * C + k);
+        float val = dequant<I32>(P, vb, kind, c, i);
+        if (j < CY && k < CX) val = llf[c * CY * CX + j * CX + k];
+        buf[k] = val;
+      }
+      __syncwarp();
+      idct1d_warp<C>(buf, buf + 256);
+      float* out = P.xyb + (size_t)c * P.plane_stride + ((size_t)vb.aby * 8 + j) * P.row_stride + vb.abx * 8;
+      for (int x = lane; x < C; x += 32) out[x] = buf[x];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // ---- pass 2: columns (c, x): IDCT over vertical frequency, in place ----
+  if constexpr (R <= 64) {
+    for (int r = tid; r < 3 * C; r += blockDim.x) {
+      const int c = r / C, x = r % C;
+      float* col = P.xyb + (size_t)c * P.plane_stride + (size_t)vb.aby * 8 * P.row_stride + vb.abx * 8 + x;
+      float u[R];
+#pragma unroll
+      for (int j = 0; j < R; j++) u[j] = col[(size_t)j * P.row_stride];
+      idct1d<R>(u);
+#pragma unroll
+      for (int y = 0; y < R; y++) col[(size_t)y * P.row_stride] = u[y];
+    }
+  } else {
+    const int warp = tid >> 5, lane = tid & 31;
+    float* buf = coop + warp * 512;
+    for (int r = warp; r < 3 * C; r += blockDim.x >> 5) {
+      const int c = r / C, x = r % C;
+      float* col = P.xyb + (size_t)c * P.plane_stride + (size_t)vb.aby * 8 * P.row_stride + vb.abx * 8 + x;
+      for (int j = lane; j < R; j += 32) buf[j] = col[(size_t)j * P.row_stride];
+      __syncwarp();
+      idct1d_warp<R>(buf, buf + 256);
+      for (int y = lane; y < R; y += 32) col[(size_t)y * P.row_stride] = buf[y];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+}
+
+constexpr int kLargeSmemFloats = 4 * 1024 + 8 * 512;
+
+template <bool I32>
+__global__ void __launch_bounds__(256) idct_large_kernel(const __grid_constant__ FrameDev P) {
+  __shared__ __align__(16) float sm[kLargeSmemFloats];
+  uint32_t base = 0;
+#pragma unroll 1
+  for (int s = kNumStrategies - 1; s >= kFirstLarge; s--) {
+    const uint32_t count = P.counts[s];
+    uint32_t it = (blockIdx.x + gridDim.x - (base % gridDim.x)) % gridDim.x;
+#pragma unroll 1
+    for (; it < count; it += gridDim.x) {
+      const uint32_t entry = P.list[P.list_base[s] + it];
+      switch (s) {
+        case 18: large_item<64, 64, I32>(P, s, entry, sm); break;
+        case 19: large_item<64, 32, I32>(P, s, entry, sm); break;
+        case 20: large_item<32, 64, I32>(P, s, entry, sm); break;
+        case 21: large_item<128, 128, I32>(P, s, entry, sm); break;
+        case 22: large_item<128, 64, I32>(P, s, entry, sm); break;
+        case 23: large_item<64, 128, I32>(P, s, entry, sm); break;
+        case 24: large_item<256, 256, I32>(P, s, entry, sm); break;
+        case 25: large_item<256, 128, I32>(P, s, entry, sm); break;
+        default: large_item<128, 256, I32>(P, s, entry, sm); break;
+      }
+    }
+    base += count;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fused filter kernel: [Gaborish] -> [EPF0] -> [EPF1] -> [EPF2] -> [XYB->linear RGB]
+// One CTA per TW x TH output tile; every enabled stage is evaluated on a shrinking
+// halo inside two shared-memory ping-pong tiles.  Positions outside the image are
+// never computed: reads are redirected to their mirror image inside the tile
+// (Mirror(), lib/jxl/image_ops.h:184-196 -- every stage's input is mirrored about the
+// true image size, simple_render_pipeline.cc:129-164).
+// ---------------------------------------------------------------------------
+constexpr int kTW = 64, kTH = 32, kMaxHalo = 7;
+constexpr int kSW = kTW + 2 * kMaxHalo;       // 78
+constexpr int kSH = kTH + 2 * kMaxHalo;       // 46
+constexpr int kSP = kSW + 1;                  // row pitch 79 (odd)
+constexpr int kTilePlane = kSH * kSP;
+constexpr int kFilterSmemFloats = 2 * 3 * kTilePlane;
+constexpr int kFilterThreads = 256;
+
+__device__ __forceinline__ int mirror_i(int x, int size) {
+  while (x < 0 || x >= size) x = (x < 0) ? (-x - 1) : (2 * size - 1 - x);
+  return x;
+}
+
+struct TileGeom {
+  int x0, y0;      // image coordinate of tile-buffer position (0,0)
+  int W, H;        // image size
+  bool edge;       // tile buffer reaches outside the image
+  // tile-buffer offset of image pixel (y, x) neighbour, with mirroring when needed
+  __device__ __forceinline__ int at(int ty, int tx) const {
+    if (edge) {
+      ty = mirror_i(y0 + ty, H) - y0;
+      tx = mirror_i(x0 + tx, W) - x0;
+    }
+    return ty * kSP + tx;
+  }
+};
+
+__device__ __forceinline__ float epf_weight(float sad, float inv_sigma) {
+  const float v = fmaf(sad, inv_sigma, 1.0f);
+  return v < 0.0f ? 0.0f : v;
+}
+
+__global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_constant__ FrameDev P,
+                                                               float* __restrict__ out,
+                                                               size_t out_row_stride /*floats*/) {
+  extern __shared__ __align__(16) float fsm[];
+  float* bufA = fsm;
+  float* bufB = fsm + 3 * kTilePlane;
+  const int tid = threadIdx.x;
+  const int W = (int)P.xsize, H = (int)P.ysize;
+  const int tile_x = blockIdx.x * kTW;
+  const int tile_y = (int)P.band_y0 + blockIdx.y * kTH;
+  const uint32_t mask = P.stage_mask;
+  const int halo = ((mask & 1) ? 1 : 0) + ((mask & 2) ? 3 : 0) + ((mask & 4) ? 2 : 0) + ((mask & 8) ? 1 : 0);
+  TileGeom G;
+  G.x0 = tile_x - halo;
+  G.y0 = tile_y - halo;
+  G.W = W;
+  G.H = H;
+  const int SW = kTW + 2 * halo, SH = kTH + 2 * halo;
+  G.edge = (G.x0 < 0) || (G.y0 < 0) || (G.x0 + SW > W) || (G.y0 + SH > H);
+  // ---- load (positions inside the image only) ----
+  for (int c = 0; c < 3; c++) {
+    const float* src = P.xyb + (size_t)c * P.plane_stride;
+    for (int i = tid; i < SH * SW; i += kFilterThreads) {
+      const int ty = i / SW, tx = i % SW;
+      const int y = G.y0 + ty, x = G.x0 + tx;
+      if (y >= 0 && y < H && x >= 0 && x < W) bufA[c * kTilePlane + ty * kSP + tx] = src[(size_t)y * P.row_stride + x];
+    }
+  }
+  __syncthreads();
+  float* cur = bufA;
+  float* nxt = bufB;
+  int m = 0;  // margin already consumed
+  // ---- Gaborish (stage_gaborish.cc:56-100) ----
+  if (mask & 1) {
+    m += 1;
+    const int rw = SW - 2 * m, rh = SH - 2 * m;
+    for (int i = tid; i < rw * rh; i += kFilterThreads) {
+      const int ty = m + i / rw, tx = m + i % rw;
+      const int y = G.y0 + ty, x = G.x0 + tx;
+      if (y < 0 || y >= H || x < 0 || x >= W) continue;
+      const int o_t = G.at(ty - 1, tx), o_b = G.at(ty + 1, tx), o_l = G.at(ty, tx - 1), o_r = G.at(ty, tx + 1);
+      const int o_tl = G.at(ty - 1, tx - 1), o_tr = G.at(ty - 1, tx + 1);
+      const int o_bl = G.at(ty + 1, tx - 1), o_br = G.at(ty + 1, tx + 1);
+      const int o_c = ty * kSP + tx;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float* p = cur + c * kTilePlane;
+        const float sum1 = (p[o_l] + p[o_r]) + (p[o_t] + p[o_b]);
+        const float sum2 = (p[o_tl] + p[o_tr]) + (p[o_bl] + p[o_br]);
+        nxt[c * kTilePlane + o_c] = fmaf(sum2, P.gab_w[3 * c + 2], fmaf(sum1, P.gab_w[3 * c + 1], p[o_c] * P.gab_w[3 * c]));
+      }
+    }
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  // ---- EPF passes (stage_epf.cc) ----
+  const float kMinSigma = -3.90524291751269967465540850526868f;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; pass++) {
+    if (!(mask & (2u << pass))) continue;
+    m += (pass == 0) ? 3 : (pass == 1 ? 2 : 1);
+    const int rw = SW - 2 * m, rh = SH - 2 * m;
+    const float sm_ = P.epf_sm[pass];
+    const float bsm = sm_ * P.epf_border_mul;
+    for (int i = tid; i < rw * rh; i += kFilterThreads) {
+      const int ty = m + i / rw, tx = m + i % rw;
+      const int y = G.y0 + ty, x = G.x0 + tx;
+      if (y < 0 || y >= H || x < 0 || x >= W) continue;
+      const int o_c = ty * kSP + tx;
+      const float s = P.sigma[(size_t)(y >> 3) * P.xb + (x >> 3)];
+      const float* pX = cur;
+      const float* pY = cur + kTilePlane;
+      const float* pB = cur + 2 * kTilePlane;
+      if (s < kMinSigma) {
+        nxt[o_c] = pX[o_c];
+        nxt[kTilePlane + o_c] = pY[o_c];
+        nxt[2 * kTilePlane + o_c] = pB[o_c];
+        continue;
+      }
+      const int iy = y & 7, ix = x & 7;
+      const float vsm = (iy == 0 || iy == 7 || ix == 0 || ix == 7) ? bsm : sm_;
+      const float inv_sigma = s * vsm;
+      float w = 1.0f, X = pX[o_c], Y = pY[o_c], B = pB[o_c];
+      if (pass == 0) {
+        // 12 neighbours, SAD over the 5-pixel plus window (stage_epf.cc:134-166)
+        const int dy12[12] = {-2, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 2};
+        const int dx12[12] = {0, -1, 0, 1, -2, -1, 1, 2, -1, 0, 1, 0};
+        const int py5[5] = {0, -1, 0, 1, 0};
+        const int px5[5] = {0, 0, -1, 0, 1};
+        float sads[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) sads[k] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float* p = cur + c * kTilePlane;
+          const float scale = P.epf_scale[c];
+#pragma unroll
+          for (int k = 0; k < 12; k++) {
+            float sad = 0.0f;
+#pragma unroll
+            for (int o = 0; o < 5; o++) {
+              const float r11 = p[G.at(ty + py5[o], tx + px5[o])];
+              const float c11 = p[G.at(ty + dy12[k] + py5[o], tx + dx12[k] + px5[o])];
+              sad = sad + fabsf(r11 - c11);
+            }
+            sads[k] = fmaf(sad, scale, sads[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+          const float wt = epf_weight(sads[k], inv_sigma);
+          const int o = G.at(ty + dy12[k], tx + dx12[k]);
+          w = w + wt;
+          X = fmaf(wt, pX[o], X);
+          Y = fmaf(wt, pY[o], Y);
+          B = fmaf(wt, pB[o], B);
+        }
+      } else if (pass == 1) {
+        // 4 neighbours, plus-window SADs with shared terms (stage_epf.cc:278-336)
+        const int o20 = G.at(ty - 2, tx), o21 = G.at(ty - 1, tx), o11 = G.at(ty - 1, tx - 1), o31 = G.at(ty - 1, tx + 1);
+        const int o02 = G.at(ty, tx - 2), o12 = G.at(ty, tx - 1), o32 = G.at(ty, tx + 1), o42 = G.at(ty, tx + 2);
+        const int o13 = G.at(ty + 1, tx - 1), o23 = G.at(ty + 1, tx), o33 = G.at(ty + 1, tx + 1), o24 = G.at(ty + 2, tx);
+        float sad0 = 0.0f, sad1 = 0.0f, sad2 = 0.0f, sad3 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float* p = cur + c * kTilePlane;
+          const float p20 = p[o20], p21 = p[o21], p11 = p[o11], p31 = p[o31];
+          const float p02 = p[o02], p12 = p[o12], p22 = p[o_c], p32 = p[o32], p42 = p[o42];
+          const float p13 = p[o13], p23 = p[o23], p33 = p[o33], p24 = p[o24];
+          float t;
+          float sad0c = fabsf(p20 - p21);
+          float sad1c = fabsf(p11 - p21);
+          float sad2c = fabsf(p31 - p21);
+          sad1c = sad1c + fabsf(p02 - p12);
+          sad0c = sad0c + fabsf(p11 - p12);
+          t = fabsf(p12 - p22);
+          sad1c = sad1c + t;
+          sad2c = sad2c + t;
+          t = fabsf(p22 - p21);
+          float sad3c = t;
+          sad0c = sad0c + t;
+          sad0c = sad0c + fabsf(p31 - p32);
+          t = fabsf(p22 - p32);
+          sad1c = sad1c + t;
+          sad2c = sad2c + t;
+          sad2c = sad2c + fabsf(p42 - p32);
+          sad3c = sad3c + fabsf(p13 - p12);
+          t = fabsf(p22 - p23);
+          sad0c = sad0c + t;
+          sad3c = sad3c + t;
+          sad1c = sad1c + fabsf(p13 - p23);
+          sad2c = sad2c + fabsf(p33 - p23);
+          sad3c = sad3c + fabsf(p33 - p32);
+          sad3c = sad3c + fabsf(p24 - p23);
+          const float scale = P.epf_scale[c];
+          sad0 = fmaf(sad0c, scale, sad0);
+          sad1 = fmaf(sad1c, scale, sad1);
+          sad2 = fmaf(sad2c, scale, sad2);
+          sad3 = fmaf(sad3c, scale, sad3);
+        }
+        const float sd[4] = {sad0, sad1, sad2, sad3};
+        const int on[4] = {o21, o12, o32, o23};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float wt = epf_weight(sd[k], inv_sigma);
+          w = w + wt;
+          X = fmaf(wt, pX[on[k]], X);
+          Y = fmaf(wt, pY[on[k]], Y);
+          B = fmaf(wt, pB[on[k]], B);
+        }
+      } else {
+        // 4 neighbours, single-pixel 3-channel SAD (stage_epf.cc:395-413)
+        const float rx = X, ry = Y, rb = B;
+        const int on[4] = {G.at(ty - 1, tx), G.at(ty, tx - 1), G.at(ty, tx + 1), G.at(ty + 1, tx)};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float cx = pX[on[k]], cy = pY[on[k]], cb = pB[on[k]];
+          float sad = fabsf(cx - rx) * P.epf_scale[0];
+          sad = fmaf(fabsf(cy - ry), P.epf_scale[1], sad);
+          sad = fmaf(fabsf(cb - rb), P.epf_scale[2], sad);
+          const float wt = epf_weight(sad, inv_sigma);
+          w = w + wt;
+          X = fmaf(wt, cx, X);
+          Y = fmaf(wt, cy, Y);
+          B = fmaf(wt, cb, B);
+        }
+      }
+      const float inv_w = 1.0f / w;
+      nxt[o_c] = X * inv_w;
+      nxt[kTilePlane + o_c] = Y * inv_w;
+      nxt[2 * kTilePlane + o_c] = B * inv_w;
+    }
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  // ---- XYB -> linear RGB (dec_xyb-inl.h:38-86) + store ----
+  const int band_h = (int)(P.band_y1 - P.band_y0);
+  for (int i = tid; i < kTW * kTH; i += kFilterThreads) {
+    const int ty = halo + i / kTW, tx = halo + i % kTW;
+    const int y = G.y0 + ty, x = G.x0 + tx;
+    if (y >= (int)P.band_y1 || x >= W) continue;
+    const int o_c = ty * kSP + tx;
+    float a = cur[o_c], b = cur[kTilePlane + o_c], c3 = cur[2 * kTilePlane + o_c];
+    if (mask & 16) {
+      float gr = b + a, gg = b - a, gb = c3;
+      gr = gr - P.opsin_cbrt[0];
+      gg = gg - P.opsin_cbrt[1];
+      gb = gb - P.opsin_cbrt[2];
+      const float r2 = gr * gr, g2 = gg * gg, b2 = gb * gb;
+      const float mr = fmaf(r2, gr, P.opsin_bias[0]);
+      const float mg = fmaf(g2, gg, P.opsin_bias[1]);
+      const float mb = fmaf(b2, gb, P.opsin_bias[2]);
+      float lr = P.opsin_m[0] * mr, lg = P.opsin_m[3] * mr, lb = P.opsin_m[6] * mr;
+      lr = fmaf(P.opsin_m[1], mg, lr); lg = fmaf(P.opsin_m[4], mg, lg); lb = fmaf(P.opsin_m[7], mg, lb);
+      lr = fmaf(P.opsin_m[2], mb, lr); lg = fmaf(P.opsin_m[5], mb, lg); lb = fmaf(P.opsin_m[8], mb, lb);
+      a = lr; b = lg; c3 = lb;
+    }
+    const int yo = y - (int)P.band_y0;
+    if (P.out_format == 0) {
+      float* o = out + (size_t)yo * out_row_stride + (size_t)x * 3;
+      o[0] = a; o[1] = b; o[2] = c3;
+    } else {
+      const size_t plane = (size_t)band_h * out_row_stride;
+      out[(size_t)yo * out_row_stride + x] = a;
+      out[plane + (size_t)yo * out_row_stride + x] = b;
+      out[2 * plane + (size_t)yo * out_row_stride + x] = c3;
+    }
+  }
+}
+
+}  // namespace jxlb

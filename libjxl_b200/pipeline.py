@@ -1,0 +1,197 @@
+"""Host-side mirror of the C ABI (include/jxl_b200.h): the object a libjxl-like host drives.
+
+`TransformPipeline` plays the role the render pipeline + DecodeGroup play inside
+FrameDecoder (lib/jxl/dec_frame.cc:573-735): begin a frame with its side information,
+submit entropy-decoded coefficient groups from worker threads, finish the frame.
+
+There is no CPU fallback here: if libjxl_b200.so or a CUDA device is missing the
+constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from . import abi
+
+PKG = Path(__file__).resolve().parent
+SO = PKG / "libjxl_b200.so"
+CSRC = PKG / "csrc"
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared"]
+
+EXPORTS = ["jxlgpu_abi_version", "jxlgpu_error_string", "jxlgpu_last_error", "jxlgpu_create",
+           "jxlgpu_destroy", "jxlgpu_frame_begin", "jxlgpu_submit_group", "jxlgpu_frame_finish",
+           "jxlgpu_set_device_coefficients", "jxlgpu_render_device", "jxlgpu_device_output",
+           "jxlgpu_device_xyb", "jxlgpu_synchronize", "jxlgpu_launch_count", "jxlgpu_alloc_pinned",
+           "jxlgpu_free_pinned", "jxlgpu_set_profiling", "jxlgpu_kernel_times"]
+
+
+class JxlGpuError(RuntimeError):
+    def __init__(self, code: int, where: str, detail: str = ""):
+        self.code = code
+        super().__init__(f"{where}: error {code}" + (f" ({detail})" if detail else ""))
+
+
+def build(force: bool = False) -> Path:
+    """Compile csrc/jxl_b200.cu for sm_100a into libjxl_b200.so (in-tree)."""
+    srcs = [CSRC / "jxl_b200.cu", CSRC / "jxl_kernels.cuh", CSRC / "jxl_tables.h",
+            PKG.parent / "include" / "jxl_b200.h"]
+    if not force and SO.exists() and all(SO.stat().st_mtime >= s.stat().st_mtime for s in srcs):
+        return SO
+    cmd = ["nvcc", *NVCC_FLAGS, str(CSRC / "jxl_b200.cu"), "-o", str(SO)]
+    subprocess.check_call(cmd)
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not SO.exists():
+            raise RuntimeError(f"{SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(str(SO))
+        L.jxlgpu_abi_version.restype = C.c_uint32
+        L.jxlgpu_error_string.restype = C.c_char_p
+        L.jxlgpu_error_string.argtypes = [C.c_int]
+        L.jxlgpu_last_error.restype = C.c_char_p
+        L.jxlgpu_last_error.argtypes = [C.c_void_p]
+        L.jxlgpu_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(abi.JxlGpuConfig)]
+        L.jxlgpu_destroy.argtypes = [C.c_void_p]
+        L.jxlgpu_frame_begin.argtypes = [C.c_void_p, C.POINTER(abi.JxlGpuFrame)]
+        L.jxlgpu_submit_group.argtypes = [C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p * 3, C.c_size_t]
+        L.jxlgpu_frame_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.jxlgpu_set_device_coefficients.argtypes = [C.c_void_p, C.c_void_p]
+        L.jxlgpu_render_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.jxlgpu_device_output.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.jxlgpu_device_xyb.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                        C.POINTER(C.c_size_t)]
+        L.jxlgpu_synchronize.argtypes = [C.c_void_p]
+        L.jxlgpu_launch_count.restype = C.c_uint64
+        L.jxlgpu_launch_count.argtypes = [C.c_void_p]
+        L.jxlgpu_alloc_pinned.restype = C.c_void_p
+        L.jxlgpu_alloc_pinned.argtypes = [C.c_size_t]
+        L.jxlgpu_free_pinned.argtypes = [C.c_void_p]
+        L.jxlgpu_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.jxlgpu_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float * 4)]
+        if L.jxlgpu_abi_version() != abi.ABI_VERSION:
+            raise RuntimeError("libjxl_b200.so ABI version mismatch: rebuild")
+        _lib = L
+    return _lib
+
+
+def pinned_array(shape, dtype) -> np.ndarray:
+    """numpy array over page-locked host memory (freed with the process)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = lib().jxlgpu_alloc_pinned(n)
+    if not p:
+        raise JxlGpuError(abi.ERR_OOM, "jxlgpu_alloc_pinned")
+    buf = (C.c_uint8 * n).from_address(p)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+class TransformPipeline:
+    def __init__(self, device: int = 0, num_host_threads: int = 1):
+        self._h = C.c_void_p()
+        cfg = abi.JxlGpuConfig(abi.ABI_VERSION, device, num_host_threads, 0)
+        rc = lib().jxlgpu_create(C.byref(self._h), C.byref(cfg))
+        if rc:
+            self._h = C.c_void_p()
+            raise JxlGpuError(rc, "jxlgpu_create", lib().jxlgpu_error_string(rc).decode())
+        self.desc: abi.FrameDesc | None = None
+        self._struct = None
+
+    def close(self):
+        if self._h:
+            lib().jxlgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, where: str):
+        if rc:
+            raise JxlGpuError(rc, where, lib().jxlgpu_last_error(self._h).decode() or
+                              lib().jxlgpu_error_string(rc).decode())
+
+    # ---- the three calls a host decoder makes ----
+    def frame_begin(self, desc: abi.FrameDesc):
+        self.desc = desc
+        self._struct = desc.to_struct()
+        self._check(lib().jxlgpu_frame_begin(self._h, C.byref(self._struct)), "jxlgpu_frame_begin")
+
+    def submit_group(self, group_idx: int, coeff_xyb, thread_id: int = 0, ncoeff: int | None = None):
+        """coeff_xyb: three 1-D arrays (X, Y, B) of the frame's ac_type for AC group `group_idx`."""
+        want = np.int16 if self.desc.ac_type == abi.AC_INT16 else np.int32
+        arrs = [np.ascontiguousarray(a, want) if a.dtype != want or not a.flags.c_contiguous else a
+                for a in coeff_xyb]
+        n = ncoeff if ncoeff is not None else self.desc.group_ncoeff(group_idx)
+        ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in arrs])
+        self._check(lib().jxlgpu_submit_group(self._h, group_idx, thread_id, ptrs, n), "jxlgpu_submit_group")
+
+    def frame_finish(self, out: np.ndarray | None = None) -> np.ndarray:
+        d = self.desc
+        _, rows = d.band_rows()
+        shape = (rows, d.xsize, 3) if d.out_format == abi.OUT_RGB_F32 else (3, rows, d.xsize)
+        if out is None:
+            out = np.empty(shape, np.float32)
+        assert out.shape == shape and out.dtype == np.float32 and out.flags.c_contiguous
+        stride = d.xsize * 4 * (3 if d.out_format == abi.OUT_RGB_F32 else 1)
+        self._check(lib().jxlgpu_frame_finish(self._h, out.ctypes.data, stride), "jxlgpu_frame_finish")
+        return out
+
+    # convenience: whole frame from a (3, num_groups, 65536) host array
+    def decode_frame(self, desc: abi.FrameDesc, coeffs: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        self.set_device_coefficients(None)
+        self.frame_begin(desc)
+        for g in range(desc.num_groups):
+            self.submit_group(g, [coeffs[c, g] for c in range(3)])
+        return self.frame_finish(out)
+
+    # ---- device-resident entry points ----
+    def set_device_coefficients(self, ptrs):
+        if ptrs is None:
+            self._check(lib().jxlgpu_set_device_coefficients(self._h, None), "jxlgpu_set_device_coefficients")
+            return
+        arr = (C.c_void_p * 3)(*ptrs)
+        self._keep_ptrs = arr
+        self._check(lib().jxlgpu_set_device_coefficients(self._h, arr), "jxlgpu_set_device_coefficients")
+
+    def render_device(self, dev_out: int = 0, out_stride_bytes: int = 0, stream: int = 0):
+        self._check(lib().jxlgpu_render_device(self._h, dev_out or None, out_stride_bytes, stream or None),
+                    "jxlgpu_render_device")
+
+    def device_output(self) -> tuple[int, int]:
+        p, s = C.c_void_p(), C.c_size_t()
+        self._check(lib().jxlgpu_device_output(self._h, C.byref(p), C.byref(s)), "jxlgpu_device_output")
+        return p.value, s.value
+
+    def device_xyb(self) -> tuple[int, int, int]:
+        p, ps, rs = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self._check(lib().jxlgpu_device_xyb(self._h, C.byref(p), C.byref(ps), C.byref(rs)), "jxlgpu_device_xyb")
+        return p.value, ps.value, rs.value
+
+    def synchronize(self):
+        self._check(lib().jxlgpu_synchronize(self._h), "jxlgpu_synchronize")
+
+    def set_profiling(self, enable: bool):
+        self._check(lib().jxlgpu_set_profiling(self._h, int(enable)), "jxlgpu_set_profiling")
+
+    def kernel_times_ms(self) -> dict[str, float]:
+        ms = (C.c_float * 4)()
+        self._check(lib().jxlgpu_kernel_times(self._h, C.byref(ms)), "jxlgpu_kernel_times")
+        return dict(zip(("plan", "idct_small", "idct_large", "filter"), [float(v) for v in ms]))
+
+    def launch_count(self) -> int:
+        return int(lib().jxlgpu_launch_count(self._h))

@@ -1,0 +1,92 @@
+#!/usr/bin/env python3
+"""Regenerate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref, built by
+oracle/build_ref.py from /root/reference).  Run where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+Fixtures
+  transforms.npz   jxl::TransformToPixels + LowestFrequenciesFromDC for all 27 AcStrategy types
+                   (strict build: -ffp-contract=off, i.e. FMAs exactly where the source says so).
+                   Inputs are NOT stored: tests re-create them from the seeds below.
+  frame_small.npz  a 264x72 VarDCT d1.0 e7 frame (gab on, epf 3 forced): the reference decoder's
+                   coefficient hand-off (quantised coefficients + all side info) and the reference
+                   pixels: full decode (default build, public API) and stage taps of the strict
+                   build rendered with the reference's own DecodeGroupForRoundtrip + stages.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+import jxl_workload as wl  # noqa: E402
+from libjxl_b200 import abi  # noqa: E402
+from oracle import ref  # noqa: E402
+
+HERE = Path(__file__).resolve().parent
+TRANSFORM_SEED = 20260922
+FRAME = dict(w=264, h=72, distance=1.0, effort=7, gaborish=1, epf=3, seed=99, kind="photo")
+TAPS = {"idct": 0, "gab_epf012": 15, "full": 31}
+
+
+def transform_inputs(strategy: int):
+    rng = np.random.default_rng(TRANSFORM_SEED + strategy)
+    r, c = abi.COVERED_Y[strategy] * 8, abi.COVERED_X[strategy] * 8
+    coeffs = rng.laplace(0, 1.0, r * c).astype(np.float32)
+    dc = rng.normal(0, 1, (abi.COVERED_Y[strategy], abi.COVERED_X[strategy])).astype(np.float32)
+    return coeffs, dc
+
+
+def main() -> int:
+    ref.use_variant("strict")
+    out = {}
+    for s in range(27):
+        r, c = abi.COVERED_Y[s] * 8, abi.COVERED_X[s] * 8
+        coeffs, dc = transform_inputs(s)
+        out[f"px_{s}"] = ref.transform_to_pixels(s, coeffs, r, c)
+        llf = ref.llf_from_dc(s, dc, np.zeros(r * c, np.float32))
+        nz = np.flatnonzero(llf)
+        out[f"llf_idx_{s}"] = nz.astype(np.int32)
+        out[f"llf_val_{s}"] = llf[nz]
+    np.savez_compressed(HERE / "transforms.npz", **out)
+
+    img = wl.synth_image(FRAME["w"], FRAME["h"], FRAME["seed"], FRAME["kind"])
+    ref.use_variant("default")
+    data = ref.encode_rgb8(img, FRAME["distance"], FRAME["effort"], FRAME["gaborish"], FRAME["epf"], 1)
+    full_default = ref.decode_linear_f32(data, 1)
+    ref.use_variant("strict")
+    fr = ref.Frame(data, 1)
+    d = fr.dump()
+    i = d.info
+    scal = {name: np.array(getattr(i, name)) for name, _ in type(i)._fields_}
+    # keep only the dequant matrices of strategies this frame uses (the rest zeroed: compresses)
+    used = np.unique(d.ac_strategy[(d.ac_strategy & 1) == 1] >> 1)
+    keep = np.zeros(d.dequant.size, bool)
+    for s_ in used:
+        n = 64 * abi.COVERED_X[s_] * abi.COVERED_Y[s_]
+        for c in range(3):
+            keep[d.dequant_offsets[s_, c]: d.dequant_offsets[s_, c] + n] = True
+    d.dequant[~keep] = 0
+    fx = dict(jxl=np.frombuffer(data, np.uint8), decoded_default=full_default,
+              ac_strategy=d.ac_strategy, raw_quant=np.where(d.ac_strategy & 1, d.raw_quant, 0).astype(np.int32),
+              sharpness=d.sharpness, ytox=d.ytox, ytob=d.ytob, dc=d.dc, dequant=d.dequant,
+              dequant_offsets=d.dequant_offsets, coeffs=d.coeffs,
+              sigma_interior=d.sigma[2:-2, 2:-2])
+    for k, v in scal.items():
+        fx["info_" + k] = v
+    for name, mask in TAPS.items():
+        img_t, _ = fr.render(mask)
+        fx["tap_" + name] = img_t
+    fr.close()
+    np.savez_compressed(HERE / "frame_small.npz", **fx)
+    for f in ("transforms.npz", "frame_small.npz"):
+        print(f, (HERE / f).stat().st_size, "bytes")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,63 @@
+"""The C-ABI library: loads without a GPU, exports every symbol include/jxl_b200.h declares,
+and refuses to run without a CUDA device (no silent CPU fallback)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+from libjxl_b200 import abi, pipeline
+
+ROOT = Path(__file__).resolve().parents[1]
+pytestmark = pytest.mark.usefixtures("built")
+
+
+def declared_symbols():
+    txt = (ROOT / "include" / "jxl_b200.h").read_text()
+    return re.findall(r"JXLGPU_API\s+[\w\s\*]+?\b(jxlgpu_\w+)\s*\(", txt)
+
+
+def test_every_declared_symbol_is_exported():
+    names = declared_symbols()
+    assert len(names) >= 14
+    lib = C.CDLL(str(pipeline.SO))
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(names) == sorted(pipeline.EXPORTS)
+
+
+def test_abi_version_and_error_strings():
+    lib = pipeline.lib()
+    assert lib.jxlgpu_abi_version() == abi.ABI_VERSION
+    assert lib.jxlgpu_error_string(0) == b"ok"
+    assert b"device" in lib.jxlgpu_error_string(abi.ERR_NO_DEVICE)
+
+
+def test_struct_layout_matches_header():
+    """sizeof(jxlgpu_frame) computed by the C compiler == ctypes mirror."""
+    import subprocess
+    import tempfile
+    src = '#include <stdio.h>\n#include "jxl_b200.h"\nint main(){printf("%zu %zu\\n", sizeof(jxlgpu_frame), sizeof(jxlgpu_config));return 0;}\n'
+    with tempfile.TemporaryDirectory() as td:
+        (Path(td) / "t.c").write_text(src)
+        subprocess.check_call(["/usr/bin/gcc", "-I", str(ROOT / "include"), str(Path(td) / "t.c"), "-o", str(Path(td) / "t")])
+        out = subprocess.check_output([str(Path(td) / "t")]).split()
+    assert int(out[0]) == C.sizeof(abi.JxlGpuFrame)
+    assert int(out[1]) == C.sizeof(abi.JxlGpuConfig)
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pipeline.JxlGpuError) as e:
+        pipeline.TransformPipeline(device=0)
+    assert e.value.code in (abi.ERR_NO_DEVICE, abi.ERR_CUDA)
+
+
+def test_product_never_imports_oracle():
+    """The product package must not reference oracle/ (tier rule ③)."""
+    for f in (ROOT / "libjxl_b200").rglob("*"):
+        if f.suffix in (".py", ".cu", ".cuh", ".h"):
+            txt = f.read_text()
+            assert "oracle" not in txt.replace("oracle/jxl_oracle.c (rcp_mode 0)", ""), f

@@ -1,0 +1,150 @@
+"""-m gpu: the CUDA path, called through the C ABI (include/jxl_b200.h), against the oracle and
+the committed reference goldens.  Bar: bit-exact vs oracle/jxl_oracle.c in exact-reciprocal mode
+(float work whose operation order is pinned); vs the reference pixels the stated tolerance
+(the reference's AdjustQuantBias uses a 12-bit rcpps: quantizer-inl.h:62-64)."""
+import numpy as np
+import pytest
+
+import jxl_workload as wl
+from libjxl_b200 import abi, pipeline, sharding
+from tests import support
+
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("built")]
+
+
+@pytest.fixture(scope="module")
+def pipe():
+    p = pipeline.TransformPipeline(device=0, num_host_threads=4)
+    yield p
+    p.close()
+
+
+def oracle(desc, coeffs):
+    from oracle import cpu
+    return cpu.render_frame(desc, coeffs, rcp_mode=0)
+
+
+def assert_same(got, want, what=""):
+    assert got.shape == want.shape
+    if not np.array_equal(got, want):
+        d = np.abs(got - want)
+        idx = np.unravel_index(np.argmax(d), d.shape)
+        raise AssertionError(f"{what}: max|diff| {d.max():.3e} at {idx} ({got[idx]} vs {want[idx]}), "
+                             f"{int((d > 0).sum())} of {d.size} differ, {support.ulp_diff(got, want)} ulp")
+
+
+@pytest.mark.parametrize("w,h,ac_type", [(520, 264, abi.AC_INT16), (2048, 1032, abi.AC_INT16),
+                                          (777, 523, abi.AC_INT32)])
+def test_all_strategies_bit_exact(pipe, w, h, ac_type):
+    desc, coeffs = wl.synthetic_frame(w, h, seed=w + h, ac_type=ac_type)
+    if w >= 2048:
+        assert len(wl.strategy_histogram(desc.ac_strategy)) == 27
+    assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), "full chain")
+
+
+@pytest.mark.parametrize("mask", [0, 1, 2, 4, 8, 16, 1 | 4, 1 | 4 | 8, 1 | 2 | 4 | 8, 31])
+def test_stage_taps_bit_exact(pipe, mask):
+    desc, coeffs = wl.synthetic_frame(600, 300, seed=mask)
+    desc.stage_mask = abi.STAGE_EXPLICIT | mask
+    desc.out_format = abi.OUT_PLANAR_F32
+    assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), f"mask {mask}")
+
+
+@pytest.mark.parametrize("strategy", range(27))
+def test_single_strategy_frames(pipe, strategy):
+    """One strategy at a time (plus 8x8 filler where it does not tile): isolates each transform."""
+    desc, coeffs = wl.synthetic_frame(512, 256, seed=100 + strategy, strategies=f"{strategy},0", gab=0,
+                                      epf_iters=0)
+    desc.stage_mask = abi.STAGE_EXPLICIT | 0
+    desc.out_format = abi.OUT_PLANAR_F32
+    assert wl.strategy_histogram(desc.ac_strategy).get(abi.STRATEGY_NAMES[strategy], 0) > 0
+    assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), abi.STRATEGY_NAMES[strategy])
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (5, 3), (8, 8), (9, 17), (255, 257), (256, 256), (264, 72), (31, 700)])
+def test_ragged_and_tiny_sizes(pipe, w, h):
+    """Mirror padding about the true image size (image_ops.h:184-196), partial blocks/groups."""
+    desc, coeffs = wl.synthetic_frame(w, h, seed=w * 1000 + h)
+    assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), f"{w}x{h}")
+
+
+def test_zero_coefficients_and_extremes(pipe):
+    desc, coeffs = wl.synthetic_frame(300, 200, seed=4)
+    coeffs[:] = 0
+    assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), "all-zero AC")
+    coeffs[:, :, ::97] = 32767
+    coeffs[:, :, 1::89] = -32768
+    assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), "int16 extremes")
+
+
+def test_golden_frame_against_reference_pixels(pipe):
+    """Real bitstream (tests/golden/frame_small.npz): coefficients as the reference's entropy
+    decoder produced them; pixels vs the reference decoder. Tolerances in absolute units."""
+    desc, coeffs, g = support.golden_desc()
+    got = pipe.decode_frame(desc, coeffs)
+    assert_same(got, oracle(desc, coeffs), "golden frame vs oracle")
+    peak = float(np.abs(got - g.decoded_default).max())
+    rmse = float(np.sqrt(np.mean((got - g.decoded_default) ** 2)))
+    assert peak <= 5e-5 and rmse <= 5e-6, (peak, rmse)   # conformance tooling default is 1e-3 / 1e-3
+    for tap, mask in support.TAP_MASKS.items():
+        desc.stage_mask = abi.STAGE_EXPLICIT | mask
+        desc.out_format = abi.OUT_PLANAR_F32
+        got = pipe.decode_frame(desc, coeffs)
+        assert np.abs(got - g.taps[tap]).max() <= 2e-5, tap
+
+
+def test_band_sharded_equals_whole_frame(pipe):
+    """Each band rendered separately (as a rank would, receiving only the groups it needs)
+    concatenates to exactly the whole-frame result: sharding is invisible in the pixels."""
+    desc, coeffs = wl.synthetic_frame(700, 1500, seed=21)     # 3 x 6 groups
+    whole = pipe.decode_frame(desc, coeffs)
+    for world in (2, 4):
+        rows = []
+        for (y0, ny) in sharding.band_partition(desc.ysize_groups, world):
+            if ny == 0:
+                continue
+            desc.band_y0_groups, desc.band_ny_groups = y0, ny
+            pipe.set_device_coefficients(None)
+            pipe.frame_begin(desc)
+            for gidx in sharding.groups_needed(desc, y0, ny):
+                pipe.submit_group(gidx, [coeffs[c, gidx] for c in range(3)])
+            rows.append(pipe.frame_finish())
+        desc.band_y0_groups = desc.band_ny_groups = 0
+        assert_same(np.concatenate(rows, axis=0), whole, f"world={world}")
+
+
+def test_device_resident_entry_points(pipe):
+    import torch
+    desc, coeffs = wl.synthetic_frame(640, 520, seed=9)
+    want = pipe.decode_frame(desc, coeffs)
+    dev = torch.from_numpy(coeffs).cuda()
+    out = torch.empty((desc.ysize, desc.xsize, 3), dtype=torch.float32, device="cuda")
+    pipe.set_device_coefficients([dev[c].data_ptr() for c in range(3)])
+    pipe.frame_begin(desc)
+    before = pipe.launch_count()
+    pipe.render_device(out.data_ptr(), desc.xsize * 12, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert pipe.launch_count() - before == 4
+    assert_same(out.cpu().numpy(), want, "device-resident")
+    pipe.set_device_coefficients(None)
+
+
+def test_full_size_4096_against_oracle(pipe):
+    """BASELINE config 2 size (4096x4096, all IDCT sizes + Gaborish + EPF): full compare, the
+    oracle takes a few seconds with OpenMP."""
+    desc, coeffs = wl.synthetic_frame(4096, 4096, seed=4096)
+    got = pipe.decode_frame(desc, coeffs)
+    assert np.isfinite(got).all()
+    assert_same(got, oracle(desc, coeffs), "4096x4096")
+    # determinism (work lists are filled with atomics; results must not depend on their order)
+    assert_same(pipe.decode_frame(desc, coeffs), got, "second run")
+
+
+def test_submit_errors(pipe):
+    desc, coeffs = wl.synthetic_frame(300, 300, seed=1)
+    pipe.set_device_coefficients(None)
+    pipe.frame_begin(desc)
+    with pytest.raises(pipeline.JxlGpuError):      # group index out of range
+        pipe.submit_group(99, [coeffs[c, 0] for c in range(3)])
+    with pytest.raises(pipeline.JxlGpuError):      # finishing with missing groups
+        pipe.frame_finish()

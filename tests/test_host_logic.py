@@ -1,0 +1,84 @@
+"""Host-side logic: frame description, geometry, synthetic workloads, band sharding."""
+import numpy as np
+import pytest
+
+import jxl_workload as wl
+from libjxl_b200 import abi, sharding
+
+pytestmark = pytest.mark.usefixtures("built")
+
+
+def test_geometry_matches_frame_dimensions():
+    # SURVEY.md §8 size table (FrameDimensions::Set, frame_dimensions.h:34-60)
+    for (w, h), (xb, yb, groups) in {(512, 512): (64, 64, 4), (4096, 4096): (512, 512, 256),
+                                     (7680, 4320): (960, 540, 510), (1920, 1080): (240, 135, 40)}.items():
+        d = abi.FrameDesc(xsize=w, ysize=h, ac_strategy=None, raw_quant=None, dc=None, ytox=None, ytob=None,
+                          dequant=None, dequant_offsets=None, inv_global_scale=1, quant_scale=1)
+        assert (d.xsize_blocks, d.ysize_blocks, d.num_groups) == (xb, yb, groups)
+    d = abi.FrameDesc(xsize=7680, ysize=4320, ac_strategy=None, raw_quant=None, dc=None, ytox=None, ytob=None,
+                      dequant=None, dequant_offsets=None, inv_global_scale=1, quant_scale=1)
+    assert d.group_ncoeff(0) == 65536
+    assert d.group_ncoeff(d.num_groups - 1) == 64 * 32 * 28      # last row: 224 px
+
+
+def test_synthetic_frame_covers_all_strategies_and_is_consistent():
+    desc, coeffs = wl.synthetic_frame(2048, 1032, seed=3)
+    hist = wl.strategy_histogram(desc.ac_strategy)
+    assert len(hist) == 27
+    acs = desc.ac_strategy
+    covered = np.zeros(acs.shape, int)
+    for by, bx in zip(*np.nonzero(acs & 1)):
+        s = acs[by, bx] >> 1
+        cy, cx = abi.COVERED_Y[s], abi.COVERED_X[s]
+        assert by // 32 == (by + cy - 1) // 32 and bx // 32 == (bx + cx - 1) // 32  # never crosses a group
+        assert (acs[by:by + cy, bx:bx + cx] >> 1 == s).all()
+        covered[by:by + cy, bx:bx + cx] += 1
+    assert (covered == 1).all()
+    # coefficients beyond the used part of each group are zero
+    for g in range(desc.num_groups):
+        assert not coeffs[:, g, desc.group_ncoeff(g):].any()
+
+
+def test_struct_roundtrip_keeps_scalars():
+    desc, _ = wl.synthetic_frame(264, 136, seed=1)
+    s = desc.to_struct()
+    assert (s.xsize, s.ysize, s.xsize_blocks, s.ysize_blocks) == (264, 136, 33, 17)
+    assert s.epf_iters == 3 and s.gab == 1
+    assert abs(s.epf_channel_scale[0] - 40.0) < 1e-6
+    assert s.dequant_table_floats == desc.dequant.size
+
+
+def test_default_opsin_matches_reference_values():
+    m, bias, cbrt = abi.default_opsin()
+    # values printed by the reference for an sRGB 255-nit image (oracle/ref_harness.cc dump)
+    want = [11.031566619873047, -9.866944313049316, -0.16462299227714539, -3.2541472911834717,
+            4.4187703132629395, -0.16462299227714539, -3.658851385116577, 2.712923049926758,
+            1.9459282159805298]
+    assert np.allclose(m, want, rtol=0, atol=0)
+    assert abs(bias[0] - -0.0037930733524262905) == 0
+    assert abs(cbrt[0] - -0.15595419704914093) < 1e-8
+
+
+@pytest.mark.parametrize("yg,world", [(17, 8), (16, 8), (2, 8), (5, 2), (1, 1), (64, 8)])
+def test_band_partition(yg, world):
+    bands = sharding.band_partition(yg, world)
+    assert len(bands) == world
+    assert sum(n for _, n in bands) == yg
+    y = 0
+    for y0, n in bands:
+        assert y0 == y
+        y += n
+    sizes = [n for _, n in bands]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_groups_needed_includes_halo_rows():
+    desc, _ = wl.synthetic_frame(600, 1100, seed=2)       # 3 x 5 groups
+    assert sharding.filter_halo(desc) == 7
+    xg = desc.xsize_groups
+    assert sharding.groups_needed(desc, 0, 5) == list(range(15))
+    assert sharding.groups_needed(desc, 2, 1) == list(range(1 * xg, 4 * xg))
+    assert sharding.groups_needed(desc, 0, 1) == list(range(0, 2 * xg))
+    desc.gab, desc.epf_iters = 0, 0
+    assert sharding.filter_halo(desc) == 0
+    assert sharding.groups_needed(desc, 2, 1) == list(range(2 * xg, 3 * xg))

@@ -1,0 +1,91 @@
+"""Pins oracle/jxl_oracle.c against the UNMODIFIED reference compiled here by
+oracle/build_ref.py (skipped where oracle/_ref is absent, e.g. a box without /root/reference
+and without the prebuilt .so).  strict build = -ffp-contract=off => bit-exact expected."""
+import numpy as np
+import pytest
+
+import jxl_workload as wl
+from libjxl_b200 import abi
+
+pytestmark = pytest.mark.usefixtures("built")
+
+
+@pytest.fixture(scope="module")
+def refmod(ref_available):
+    if not ref_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref
+    ref.use_variant("strict")
+    yield ref
+    ref.use_variant("default")
+
+
+@pytest.mark.parametrize("strategy", range(27))
+def test_all_strategies_bit_exact(strategy, refmod):
+    from oracle import cpu
+    rng = np.random.default_rng(1000 + strategy)
+    r, c = abi.COVERED_Y[strategy] * 8, abi.COVERED_X[strategy] * 8
+    for trial in range(2):
+        co = (rng.laplace(0, 1.0, r * c) * (rng.random(r * c) < 0.3)).astype(np.float32)
+        assert np.array_equal(refmod.transform_to_pixels(strategy, co, r, c), cpu.transform_to_pixels(strategy, co))
+    dc = rng.normal(0, 1, (abi.COVERED_Y[strategy], abi.COVERED_X[strategy])).astype(np.float32)
+    z = np.zeros(r * c, np.float32)
+    assert np.array_equal(refmod.llf_from_dc(strategy, dc, z), cpu.llf_from_dc(strategy, dc, z))
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(w=517, h=331, distance=1.0, gaborish=1, epf=3),      # odd size, full chain
+    dict(w=512, h=512, distance=1.0, gaborish=-1, epf=-1),    # BASELINE config 1 (defaults: gab, epf 1)
+    dict(w=300, h=520, distance=0.5, gaborish=0, epf=0),      # no filters: dequant+IDCT+XYB only
+    dict(w=640, h=264, distance=3.0, gaborish=1, epf=2, kind="smooth"),  # large transforms
+])
+def test_frames_stage_by_stage(cfg, refmod):
+    """Every stage prefix, hot path only, same coefficients: the reference's own
+    DecodeGroupForRoundtrip + stages vs the C restatement. rcp_mode 1 (host rcpss, what the
+    reference's AVX2 path executes on this machine) must be bit-exact; rcp_mode 0 (exact
+    reciprocal = what the CUDA path computes) within 2e-5 absolute."""
+    from oracle import cpu
+    kind = cfg.pop("kind", "photo")
+    img = wl.synth_image(cfg["w"], cfg["h"], 77, kind)
+    data = refmod.encode_rgb8(img, cfg["distance"], 7, cfg["gaborish"], cfg["epf"], 2)
+    fr = refmod.Frame(data, 2)
+    d = fr.dump()
+    desc = cpu.desc_from_dump(d, out_format=abi.OUT_PLANAR_F32)
+    frame_mask = (1 if d.info.gab else 0) | (2 if d.info.epf_iters >= 3 else 0) | \
+        (4 if d.info.epf_iters >= 1 else 0) | (8 if d.info.epf_iters >= 2 else 0)
+    masks = [0, 16, frame_mask, frame_mask | 16]
+    if d.info.epf_iters > 0:
+        masks += [1, 1 | 4, 2 | 4 | 8]
+    for mask in sorted(set(masks)):
+        want, _ = fr.render(mask)
+        desc.stage_mask = abi.STAGE_EXPLICIT | mask
+        got1 = cpu.render_frame(desc, d.coeffs, rcp_mode=1)
+        assert np.array_equal(got1, want), (mask, float(np.abs(got1 - want).max()))
+        got0 = cpu.render_frame(desc, d.coeffs, rcp_mode=0)
+        assert np.abs(got0 - want).max() <= 2e-5, mask
+    # and the full public-API decode of the default-flag build (compiler-made FMAs differ)
+    refmod.use_variant("default")
+    full = refmod.decode_linear_f32(data, 1)
+    refmod.use_variant("strict")
+    desc.stage_mask = 0
+    desc.out_format = abi.OUT_RGB_F32
+    got = cpu.render_frame(desc, d.coeffs, rcp_mode=0)
+    assert np.abs(got - full).max() <= 5e-5
+    fr.close()
+
+
+def test_hot_path_render_equals_public_decode(refmod):
+    """The transform-only CPU baseline (ref_frame_render) is the same computation the public
+    decoder does after entropy decoding: identical pixels."""
+    refmod.use_variant("default")
+    try:
+        img = wl.synth_image(520, 300, 5)
+        data = refmod.encode_rgb8(img, 1.0, 7, -1, -1, 2)
+        full = refmod.decode_linear_f32(data, 2)
+        fr = refmod.Frame(data, 2)
+        planar, secs = fr.render(-1, reps=2)
+        assert np.array_equal(planar.transpose(1, 2, 0), full)
+        assert len(secs) == 2 and all(s > 0 for s in secs)
+        fr.close()
+    finally:
+        refmod.use_variant("strict")
