@@ -1,0 +1,412 @@
+#!/usr/bin/env python3
+"""bench.py -- decode Mpixels/s of the VarDCT transform pipeline on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One "step" = one pass of the hot path (dequant+CfL+LLF+IDCT -> Gaborish -> EPF -> XYB->linear RGB)
+over one frame of synthetic content.
+
+  value     whole-job Mpixels/s with the coefficient groups + side info already resident in HBM
+            (CUDA events on the launch stream, K steps, max over ranks).
+  e2e       the same metric through the C ABI with HOST buffers: every step does frame_begin
+            (side-info H2D) + submit_group per AC group (pinned H2D) + frame_finish (kernels + D2H of
+            the pixels into pinned host memory).
+  roofline  dominant kernel: algorithmic bytes per launch / its CUDA-event time, vs measured HBM peak.
+  cpu_baseline  the reference's own CPU code for the same hot path (DecodeGroupForRoundtrip + its
+            render-pipeline stages, oracle/_ref built from /root/reference) on all host cores.
+
+N > 1 (launched by torchrun, one rank per GPU): the frame is sharded into bands of AC-group rows;
+every rank inverse-transforms and filters its band (plus the varblocks touching its 7-row halo) and the
+bands are all-gathered over NCCL so that every GPU holds the full frame ("scaling": "strong").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (w, h, distance, effort, gaborish, epf, kind)  -- -1 = encoder default for the distance
+    "8k-d1": (7680, 4320, 1.0, 7, -1, -1, "photo"),          # metric: 8K VarDCT d1.0 (gab on, epf 1)
+    "8k-d0.5-full": (7680, 4320, 0.5, 7, 1, 3, "photo"),     # BASELINE config 3
+    "4k-d1": (4096, 4096, 1.0, 7, -1, -1, "photo"),          # BASELINE config 2
+    "1080p-d1": (1920, 1080, 1.0, 7, -1, -1, "photo"),
+    "512-d1": (512, 512, 1.0, 7, -1, -1, "photo"),
+}
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # samples under load = upper half of the SM clock samples
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def prepare_frame(name: str, rank: int, world: int, barrier):
+    """Workload preparation (untimed): the reference (oracle/_ref) plays the host libjxl --
+    synthetic image -> bitstream -> entropy-decoded coefficient groups + side info. Rank 0
+    builds the cache file, the other ranks load it."""
+    import jxl_workload as wl
+    from oracle import ref
+    w, h, dist, effort, gab, epf, kind = WORKLOADS[name]
+    source = "reference-encoded"
+    if not ref.available():
+        log("oracle/_ref missing: falling back to a synthetic all-strategy frame")
+        desc, coeffs = wl.synthetic_frame(w, h, seed=1234)
+        return dict(desc=desc, coeffs=coeffs, jxl=None, hist=wl.strategy_histogram(desc.ac_strategy), bpp=None,
+                    decoded=None), "synthetic-coefficients"
+    if rank == 0:
+        t = time.time()
+        fr = wl.reference_frame(w, h, dist, effort, gab, epf, seed=1234, kind=kind, cache=True)
+        log(f"frame ready in {time.time() - t:.1f}s: {w}x{h} d{dist} e{effort} gab={fr['desc'].gab} "
+            f"epf={fr['desc'].epf_iters} bpp={fr['bpp']:.2f} ac_type={'int16' if fr['desc'].ac_type == 0 else 'int32'}")
+    barrier()
+    if rank != 0:
+        fr = wl.reference_frame(w, h, dist, effort, gab, epf, seed=1234, kind=kind, cache=True)
+    return fr, source
+
+
+def algorithmic_bytes(desc, rows: int) -> dict:
+    """bytes one launch must move, per kernel, for `rows` pixel rows."""
+    px = desc.xsize * rows
+    es = 2 if desc.ac_type == 0 else 4
+    side = 21.0 / 64.0  # acs 1 + quant 4 + sigma 4 + dc 12 bytes per 8x8 block
+    return {"idct": px * (3 * es + side + 12), "filter": px * (12 + 12 + 4.0 / 64),
+            "fused_path": px * (3 * es + side + 12)}
+
+
+def run_reference(args, rank: int) -> int:
+    """--impl reference: the reference's own CPU implementation of the hot path (not the whole
+    decoder: entropy decoding is outside the path), all host threads, same frame."""
+    if rank != 0:
+        return 0
+    import jxl_workload as wl
+    from oracle import ref
+    name = args.workload
+    w, h, dist, effort, gab, epf, kind = WORKLOADS[name]
+    cores = os.cpu_count() or 1
+    fr = wl.reference_frame(w, h, dist, effort, gab, epf, seed=1234, kind=kind, cache=True)
+    frame = ref.Frame(fr["jxl"], cores)
+    _, _ = frame.render(-1, reps=max(1, args.warmup), want_output=False)
+    _, secs = frame.render(-1, reps=args.steps, want_output=False)
+    frame.close()
+    total = float(np.sum(secs))
+    mps = w * h * args.steps / total / 1e6
+    # whole decoder (entropy decode included) for context
+    runner = ref.Runner(cores)
+    out = np.empty((h, w, 3), np.float32)
+    ref.decode_linear_f32(fr["jxl"], cores, out, runner)
+    t0 = time.perf_counter()
+    reps = max(2, min(5, args.steps))
+    for _ in range(reps):
+        ref.decode_linear_f32(fr["jxl"], cores, out, runner)
+    full = w * h * reps / (time.perf_counter() - t0) / 1e6
+    runner.close()
+    line = {
+        "impl": "reference", "metric": "decode_mpixels_per_s", "value": mps, "unit": "Mpixel/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name}: {w}x{h} VarDCT d{dist} e{effort}, hot path only "
+                               "(DecodeGroupForRoundtrip + reference Gaborish/EPF/XYB stages) on host CPU"},
+        "cpu_baseline": {"value": mps, "unit": "Mpixel/s", "cores": cores, "kind": "reference",
+                         "sample": f"{args.steps} passes over the full {w}x{h} frame",
+                         "full_decode_mpixels_per_s": full},
+        "e2e": {"value": mps, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="8k-d1", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+
+    import jxl_workload as wl  # noqa: F401
+    from libjxl_b200 import abi, pipeline, sharding
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the product path has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    fr, source = prepare_frame(args.workload, rank, world, barrier)
+    desc, coeffs = fr["desc"], fr["coeffs"]
+    W, H = desc.xsize, desc.ysize
+    es = 2 if desc.ac_type == abi.AC_INT16 else 4
+    bands = sharding.band_partition(desc.ysize_groups, world)
+    y0g, nyg = bands[rank]
+    if world > 1:
+        desc.band_y0_groups, desc.band_ny_groups = y0g, nyg
+    band_y0, band_rows = sharding.band_pixel_rows(desc, y0g, nyg) if world > 1 else (0, H)
+    need = sharding.groups_needed(desc, y0g, nyg) if world > 1 else list(range(desc.num_groups))
+    max_rows = max(sharding.band_pixel_rows(desc, a, b)[1] for a, b in bands) if world > 1 else H
+
+    pipe = pipeline.TransformPipeline(device=local_rank, num_host_threads=1)
+    stream = torch.cuda.current_stream()
+
+    # ---------------- device-resident arm ----------------
+    dev_coeff = torch.zeros((3, desc.num_groups, abi.GROUP_COEFFS), dtype=torch.int16 if es == 2 else torch.int32,
+                            device="cuda") if world == 1 else None
+    if world == 1:
+        dev_coeff.copy_(torch.from_numpy(coeffs))
+        ptrs = [dev_coeff[c].data_ptr() for c in range(3)]
+    else:
+        # only the groups this rank needs live on its GPU; the planes keep frame-wide indexing
+        g0, g1 = min(need), max(need) + 1
+        dev_part = torch.from_numpy(np.ascontiguousarray(coeffs[:, g0:g1])).cuda()
+        ptrs = [dev_part[c].data_ptr() - g0 * abi.GROUP_COEFFS * es for c in range(3)]
+    pipe.set_device_coefficients(ptrs)
+    pipe.frame_begin(desc)
+    if world == 1:
+        gathered = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+        my_out = gathered
+    else:
+        gathered = torch.empty((world, max_rows, W, 3), dtype=torch.float32, device="cuda")
+        my_out = gathered[rank]
+
+    def step():
+        pipe.render_device(my_out.data_ptr(), W * 12, stream.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), my_out.reshape(-1))
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = pipe.launch_count()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = pipe.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = W * H / (ms_step * 1e-3) / 1e6
+
+    # per-kernel times (separate pass, CUDA events inside the library on the same stream)
+    pipe.set_profiling(True)
+    ktimes = {"plan": [], "idct_small": [], "idct_large": [], "filter": []}
+    for _ in range(max(5, min(args.steps, 20))):
+        pipe.render_device(my_out.data_ptr(), W * 12, stream.cuda_stream)
+        for k, v in pipe.kernel_times_ms().items():
+            ktimes[k].append(v)
+    pipe.set_profiling(False)
+    kavg = {k: float(np.mean(v)) for k, v in ktimes.items()}
+
+    # correctness spot check of the timed output against the reference decoder's pixels
+    parity = None
+    if fr.get("decoded") is not None and rank == 0:
+        got = (gathered if world == 1 else gathered[0, :sharding.band_pixel_rows(desc, *bands[0])[1]]).cpu().numpy()
+        want = fr["decoded"][:got.shape[0]]
+        d = np.abs(got - want)
+        parity = {"peak_abs_err_vs_reference": float(d.max()), "rmse_vs_reference": float(np.sqrt(np.mean(d * d)))}
+
+    # ---------------- end-to-end arm: host buffers through the C ABI ----------------
+    pipe.set_device_coefficients(None)
+    host_groups = {}
+    h2d = 0
+    for g in need:
+        n = desc.group_ncoeff(g)
+        bufs = []
+        for c in range(3):
+            a = pipeline.pinned_array((n,), coeffs.dtype)
+            a[:] = coeffs[c, g, :n]
+            bufs.append(a)
+            h2d += a.nbytes
+        host_groups[g] = bufs
+    yb, xb = desc.ysize_blocks, desc.xsize_blocks
+    h2d += yb * xb * (1 + 4 + 1 + 12) + desc.dequant.nbytes + 2 * desc.ytox.size
+    host_out = pipeline.pinned_array((band_rows, W, 3), np.float32)
+    d2h = host_out.nbytes
+
+    def e2e_step():
+        pipe.frame_begin(desc)
+        for g in need:
+            pipe.submit_group(g, host_groups[g], 0, host_groups[g][0].size)
+        pipe.frame_finish(host_out)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    n_e2e = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    te = torch.tensor([e2e_s], device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = W * H / float(te.item()) / 1e6
+    h2d_t = torch.tensor([float(h2d), float(d2h)], device="cuda")
+    if world > 1:
+        dist.all_reduce(h2d_t)
+    pipe.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline + CPU baseline (rank 0) ----------------
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak = float(json.loads(peaks_path.read_text())["hbm_gbs"])
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    ab = algorithmic_bytes(desc, band_rows)
+    k_idct = kavg["idct_small"] + kavg["idct_large"]
+    dominant = "filter" if kavg["filter"] >= k_idct else "idct"
+    dom_ms = kavg["filter"] if dominant == "filter" else k_idct
+    achieved = ab[dominant] / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "filter_kernel" if dominant == "filter" else "idct_small_kernel+idct_large_kernel",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": ab[dominant],
+                "kernel_ms": kavg,
+                "pipeline": {"algorithmic_bytes": ab["fused_path"],
+                             "achieved_gbs": ab["fused_path"] / (sum(kavg.values()) * 1e-3) / 1e9,
+                             "frac": ab["fused_path"] / (sum(kavg.values()) * 1e-3) / 1e9 / peak}}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1 and fr.get("jxl") is not None:
+        from oracle import ref
+        cores = os.cpu_count() or 1
+        frame = ref.Frame(fr["jxl"], cores)
+        frame.render(-1, reps=1, want_output=False)
+        reps = 8
+        _, secs = frame.render(-1, reps=reps, want_output=False)
+        frame.close()
+        hot = W * H * reps / float(np.sum(secs)) / 1e6
+        runner = ref.Runner(cores)
+        out = np.empty((H, W, 3), np.float32)
+        ref.decode_linear_f32(fr["jxl"], cores, out, runner)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ref.decode_linear_f32(fr["jxl"], cores, out, runner)
+        full = W * H * 3 / (time.perf_counter() - t0) / 1e6
+        runner.close()
+        cpu_baseline = {"value": hot, "unit": "Mpixel/s", "cores": cores, "kind": "reference",
+                        "sample": f"{reps} passes of the reference's own hot-path code over the same {W}x{H} frame "
+                                  "(coefficients pre-decoded); full_decode = whole libjxl decoder incl. entropy decode, 3 passes",
+                        "full_decode_mpixels_per_s": full}
+
+    w_, h_, dist_, effort_, _, _, _ = WORKLOADS[args.workload]
+    line = {
+        "metric": "decode_mpixels_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {W}x{H} VarDCT d{dist_} e{effort_}, gab={desc.gab} epf_iters={desc.epf_iters}, "
+                               f"{source}, coefficients {'int16' if es == 2 else 'int32'} as the reference decoder chose, "
+                               "output interleaved linear RGB f32",
+                   "groups": desc.num_groups, "parallelism": f"band-sharded x{world} + NCCL all-gather" if world > 1 else "1 GPU",
+                   "strategy_histogram": fr["hist"], "bpp": fr["bpp"],
+                   "l2": "inputs larger than L2 (coefficients + XYB planes + output >> 126 MB per step)"},
+        "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d_t[0].item()),
+                "d2h_bytes_per_step": int(h2d_t[1].item()), "steps": n_e2e,
+                "how": "frame_begin + submit_group per AC group (pinned host) + frame_finish into pinned host memory"},
+        "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "parity": parity,
+    }
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
