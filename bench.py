@@ -224,7 +224,10 @@ def main() -> int:
     max_rows = max(sharding.band_pixel_rows(desc, a, b)[1] for a, b in bands) if world > 1 else H
 
     pipe = pipeline.TransformPipeline(device=local_rank, num_host_threads=1)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library launches on exactly this stream, so the
+    # torch.cuda.Event pair below brackets its kernels (and NCCL's, which torch enqueues on it)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
 
     # ---------------- device-resident arm ----------------
     dev_coeff = torch.zeros((3, desc.num_groups, abi.GROUP_COEFFS), dtype=torch.int16 if es == 2 else torch.int32,
