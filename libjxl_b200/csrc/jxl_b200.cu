@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -57,6 +58,7 @@ struct jxlgpu_ctx {
   DevBuf acs, quant, sharp, ytox, ytob, dc, dq, coeff[3], coeff_off, sigma, list, counts, xyb, out;
   size_t out_stride_floats = 0;
   std::atomic<uint64_t> launches{0};
+  bool force_generic_filter = false;  // JXLGPU_FORCE_GENERIC_FILTER=1: tile kernel for every chain
   bool profile = false;          // record CUDA events around every kernel (bench roofline)
   cudaEvent_t prof_ev[5] = {};
   std::string last_error;
@@ -97,6 +99,43 @@ uint32_t effective_mask(const jxlgpu_frame& f) {
   return m;
 }
 
+template <uint32_t MASK>
+void launch_strip_mask(jxlgpu_ctx* ctx, float* dev_out, size_t out_stride_floats, cudaStream_t s) {
+  using C = StripCfg<MASK>;
+  const FrameDev& P = ctx->P;
+  const int band_h = (int)(P.band_y1 - P.band_y0);
+  const int strips = ((int)P.xsize + C::kOutCols - 1) / C::kOutCols;
+  // enough CTAs for ~4 per SM, but segments long enough to amortise the pipeline fill
+  int segs = (ctx->num_sms * 4 + strips - 1) / strips;
+  int seg_rows = (band_h + segs - 1) / segs;
+  if (seg_rows < 64) seg_rows = 64;
+  seg_rows = (seg_rows + 7) & ~7;
+  segs = (band_h + seg_rows - 1) / seg_rows;
+  filter_strip_kernel<MASK><<<dim3(strips, segs), kStripThreads, C::kSmemBytes, s>>>(P, dev_out, out_stride_floats, seg_rows);
+}
+
+// the stage chains PreparePipeline can build for a VarDCT XYB frame (dec_cache.cc:151-170)
+bool launch_strip(jxlgpu_ctx* ctx, float* dev_out, size_t out_stride_floats, cudaStream_t s) {
+  if (ctx->force_generic_filter) return false;
+  switch (ctx->P.stage_mask) {
+    case 16: launch_strip_mask<16>(ctx, dev_out, out_stride_floats, s); return true;
+    case 17: launch_strip_mask<17>(ctx, dev_out, out_stride_floats, s); return true;
+    case 20: launch_strip_mask<20>(ctx, dev_out, out_stride_floats, s); return true;
+    case 21: launch_strip_mask<21>(ctx, dev_out, out_stride_floats, s); return true;
+    case 28: launch_strip_mask<28>(ctx, dev_out, out_stride_floats, s); return true;
+    case 29: launch_strip_mask<29>(ctx, dev_out, out_stride_floats, s); return true;
+    case 30: launch_strip_mask<30>(ctx, dev_out, out_stride_floats, s); return true;
+    case 31: launch_strip_mask<31>(ctx, dev_out, out_stride_floats, s); return true;
+    default: return false;
+  }
+}
+
+template <uint32_t MASK>
+cudaError_t strip_attr() {
+  return cudaFuncSetAttribute(filter_strip_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)StripCfg<MASK>::kSmemBytes);
+}
+
 int launch_all(jxlgpu_ctx* ctx, float* dev_out, size_t out_stride_floats, cudaStream_t s) {
   FrameDev& P = ctx->P;
   CU(cudaMemsetAsync(ctx->counts.p, 0, kNumStrategies * sizeof(uint32_t), s));
@@ -114,8 +153,11 @@ int launch_all(jxlgpu_ctx* ctx, float* dev_out, size_t out_stride_floats, cudaSt
   else idct_large_kernel<false><<<large_grid, 256, 0, s>>>(P);
   if (prof) CU(cudaEventRecord(ctx->prof_ev[3], s));
   const uint32_t band_h = P.band_y1 - P.band_y0;
-  dim3 grid((P.xsize + kTW - 1) / kTW, (band_h + kTH - 1) / kTH);
-  filter_kernel<<<grid, kFilterThreads, kFilterSmemFloats * sizeof(float), s>>>(P, dev_out, out_stride_floats);
+  if (!launch_strip(ctx, dev_out, out_stride_floats, s)) {
+    // stage chains outside the production set (test taps): generic tile kernel
+    dim3 grid((P.xsize + kTW - 1) / kTW, (band_h + kTH - 1) / kTH);
+    filter_kernel<<<grid, kFilterThreads, kFilterSmemFloats * sizeof(float), s>>>(P, dev_out, out_stride_floats);
+  }
   if (prof) CU(cudaEventRecord(ctx->prof_ev[4], s));
   ctx->launches += 4;
   CU(cudaGetLastError());
@@ -171,6 +213,13 @@ int jxlgpu_create(jxlgpu_ctx** out, const jxlgpu_config* cfg) {
   if ((e = cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(kFilterSmemFloats * sizeof(float)))) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(filter_kernel)");
+  for (cudaError_t ea : {strip_attr<16>(), strip_attr<17>(), strip_attr<20>(), strip_attr<21>(), strip_attr<28>(),
+                         strip_attr<29>(), strip_attr<30>(), strip_attr<31>()})
+    if (ea != cudaSuccess) return bail(ea, "cudaFuncSetAttribute(filter_strip_kernel)");
+  {
+    const char* env = getenv("JXLGPU_FORCE_GENERIC_FILTER");
+    ctx->force_generic_filter = env && env[0] == '1';
+  }
   if ((e = ctx->counts.ensure(kNumStrategies * sizeof(uint32_t))) != cudaSuccess) return bail(e, "alloc");
   for (auto& ev : ctx->prof_ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "event");

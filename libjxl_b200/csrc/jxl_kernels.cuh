@@ -28,6 +28,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #define JXT_CONST __device__ __constant__ const
 #include "jxl_tables.h"
 
@@ -1104,6 +1106,351 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_con
       out[2 * plane + (size_t)yo * out_row_stride + x] = c3;
     }
   }
+}
+
+}  // namespace jxlb
+
+// ===========================================================================
+// filter v2: row-streaming strip kernel (the fast path for the stage chains real
+// frames use).  One CTA owns a vertical strip of kStripThreads columns (output
+// columns + the chain's halo on both sides) and marches down the rows of its
+// segment.  Every enabled stage keeps a small ring of its INPUT rows in shared
+// memory and produces exactly one row per step; stage k works on the row that
+// became computable after the previous step, so one __syncthreads() per step
+// orders everything.  No vertical halo is recomputed inside a segment, the
+// horizontal halo costs 2*H of 256 lanes, and nothing but the final RGB row is
+// written to global memory.  Arithmetic (operation order, FMAs) is identical to
+// filter_kernel above and to the reference stages it cites.
+// ===========================================================================
+namespace jxlb {
+
+constexpr int kStripThreads = 256;
+
+template <uint32_t MASK>
+struct StripCfg {
+  static constexpr bool G = (MASK & 1) != 0, E0 = (MASK & 2) != 0, E1 = (MASK & 4) != 0, E2 = (MASK & 8) != 0;
+  static constexpr bool XYB = (MASK & 16) != 0;
+  static constexpr int H = (G ? 1 : 0) + (E0 ? 3 : 0) + (E1 ? 2 : 0) + (E2 ? 1 : 0);
+  // ring sizes (rows, power of two >= 2*border+2) of each stage's input; 0 when absent
+  static constexpr int NG = G ? 4 : 0, N0 = E0 ? 8 : 0, N1 = E1 ? 8 : 0, N2 = E2 ? 4 : 0;
+  static constexpr int kRows = NG + N0 + N1 + N2;
+  static constexpr size_t kSmemBytes = (size_t)(kRows ? kRows : 1) * 3 * kStripThreads * sizeof(float);
+  static constexpr int kOutCols = kStripThreads - 2 * H;
+};
+
+__device__ __forceinline__ float* ring_row(float* ring, int n, int r, int c) {
+  return ring + ((r & (n - 1)) * 3 + c) * kStripThreads;
+}
+
+template <uint32_t MASK, bool EDGE>
+__device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __restrict__ out,
+                                                  size_t out_row_stride, int x0, int y_begin, int y_end,
+                                                  float* smem) {
+  using C = StripCfg<MASK>;
+  constexpr int H = C::H;
+  const int t = threadIdx.x;
+  const int W = (int)P.xsize, HI = (int)P.ysize;
+  const int x = x0 - H + t;  // image column of this thread
+  const bool xin = x >= 0 && x < W;
+  // strip-relative indices of the horizontal neighbours x-3 .. x+3 (mirrored at the image edge)
+  int cn[7];
+#pragma unroll
+  for (int d = -3; d <= 3; d++) cn[d + 3] = EDGE ? (mirror_i(x + d, W) - (x0 - H)) : (t + d);
+  auto mrow = [&](int r) { return r < 0 ? -r - 1 : (r >= HI ? 2 * HI - 1 - r : r); };
+
+  float* ringG = smem;
+  float* ring0 = ringG + C::NG * 3 * kStripThreads;
+  float* ring1 = ring0 + C::N0 * 3 * kStripThreads;
+  float* ring2 = ring1 + C::N1 * 3 * kStripThreads;
+
+  // halo consumed after each stage: that stage computes lanes [h, 256 - h)
+  constexpr int hG = C::G ? 1 : 0;
+  constexpr int h0 = hG + (C::E0 ? 3 : 0);
+  constexpr int h1 = h0 + (C::E1 ? 2 : 0);
+  constexpr int h2 = h1 + (C::E2 ? 1 : 0);
+  static_assert(h2 == H, "halo bookkeeping");
+  // a stage whose output still feeds `rem` rows of halo produces rows [y_begin-rem, y_end+rem) ∩ image
+  auto lo = [&](int rem) { return max(0, y_begin - rem); };
+  auto hi = [&](int rem) { return min(HI, y_end + rem); };
+
+  const float kMinSigma = -3.90524291751269967465540850526868f;
+  const bool xborder = ((x & 7) == 0 || (x & 7) == 7);
+  const int band_h = (int)(P.band_y1 - P.band_y0);
+
+  // Final step of the chain: XYB -> linear RGB (dec_xyb-inl.h:38-86) and the global store.
+  auto emit = [&](int r, float a, float b, float c3) {
+    if constexpr (C::XYB) {
+      float gr = b + a, gg = b - a, gb = c3;
+      gr = gr - P.opsin_cbrt[0];
+      gg = gg - P.opsin_cbrt[1];
+      gb = gb - P.opsin_cbrt[2];
+      const float r2 = gr * gr, g2 = gg * gg, b2 = gb * gb;
+      const float mr = fmaf(r2, gr, P.opsin_bias[0]);
+      const float mg = fmaf(g2, gg, P.opsin_bias[1]);
+      const float mb = fmaf(b2, gb, P.opsin_bias[2]);
+      float lr = P.opsin_m[0] * mr, lg = P.opsin_m[3] * mr, lb = P.opsin_m[6] * mr;
+      lr = fmaf(P.opsin_m[1], mg, lr); lg = fmaf(P.opsin_m[4], mg, lg); lb = fmaf(P.opsin_m[7], mg, lb);
+      lr = fmaf(P.opsin_m[2], mb, lr); lg = fmaf(P.opsin_m[5], mb, lg); lb = fmaf(P.opsin_m[8], mb, lb);
+      a = lr; b = lg; c3 = lb;
+    }
+    const int yo = r - (int)P.band_y0;
+    if (P.out_format == 0) {
+      float* o = out + (size_t)yo * out_row_stride + (size_t)x * 3;
+      o[0] = a; o[1] = b; o[2] = c3;
+    } else {
+      const size_t plane = (size_t)band_h * out_row_stride;
+      out[(size_t)yo * out_row_stride + x] = a;
+      out[plane + (size_t)yo * out_row_stride + x] = b;
+      out[2 * plane + (size_t)yo * out_row_stride + x] = c3;
+    }
+  };
+  // Hand a stage's result to the next stage's ring, or emit it when it was the last stage.
+  // `which`: 0 = output of the loader, 1 = Gaborish, 2 = EPF0, 3 = EPF1, 4 = EPF2.
+  auto deliver = [&](auto which_tag, int r, float X, float Y, float B) {
+    constexpr int which = decltype(which_tag)::value;
+    constexpr bool toG = which < 1 && C::G;
+    constexpr bool to0 = !toG && which < 2 && C::E0;
+    constexpr bool to1 = !toG && !to0 && which < 3 && C::E1;
+    constexpr bool to2 = !toG && !to0 && !to1 && which < 4 && C::E2;
+    if constexpr (toG) {
+      ring_row(ringG, C::NG, r, 0)[t] = X; ring_row(ringG, C::NG, r, 1)[t] = Y; ring_row(ringG, C::NG, r, 2)[t] = B;
+    } else if constexpr (to0) {
+      ring_row(ring0, C::N0, r, 0)[t] = X; ring_row(ring0, C::N0, r, 1)[t] = Y; ring_row(ring0, C::N0, r, 2)[t] = B;
+    } else if constexpr (to1) {
+      ring_row(ring1, C::N1, r, 0)[t] = X; ring_row(ring1, C::N1, r, 1)[t] = Y; ring_row(ring1, C::N1, r, 2)[t] = B;
+    } else if constexpr (to2) {
+      ring_row(ring2, C::N2, r, 0)[t] = X; ring_row(ring2, C::N2, r, 1)[t] = Y; ring_row(ring2, C::N2, r, 2)[t] = B;
+    } else {
+      emit(r, X, Y, B);
+    }
+  };
+  using T0 = std::integral_constant<int, 0>;
+  using T1 = std::integral_constant<int, 1>;
+  using T2 = std::integral_constant<int, 2>;
+  using T3 = std::integral_constant<int, 3>;
+  using T4 = std::integral_constant<int, 4>;
+
+  // steps between loading a row and the last stage producing that row
+  constexpr int kDelay = (C::G ? 2 : 0) + (C::E0 ? 4 : 0) + (C::E1 ? 3 : 0) + (C::E2 ? 2 : 0);
+  const int r_in_lo = lo(H), r_in_hi = hi(H);
+  const int r_end = hi(0) + kDelay;  // after this many input-row steps the last output row is out
+
+  for (int rin = r_in_lo; rin < r_end; rin++) {
+    // ---- loader: XYB row rin ----
+    if (rin < r_in_hi && xin) {
+      const size_t off = (size_t)rin * P.row_stride + x;
+      const float a = __ldg(P.xyb + off);
+      const float b = __ldg(P.xyb + P.plane_stride + off);
+      const float c3 = __ldg(P.xyb + 2 * P.plane_stride + off);
+      deliver(T0(), rin, a, b, c3);
+    }
+    int r = rin;
+    // ---- Gaborish (stage_gaborish.cc:56-100) ----
+    if constexpr (C::G) {
+      r -= 2;
+      if (r >= lo(H - hG) && r < hi(H - hG) && xin && t >= hG && t < kStripThreads - hG) {
+        const int rt = mrow(r - 1), rb = mrow(r + 1);
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float* pT = ring_row(ringG, C::NG, rt, c);
+          const float* pM = ring_row(ringG, C::NG, r, c);
+          const float* pB = ring_row(ringG, C::NG, rb, c);
+          const float sum1 = (pM[cn[2]] + pM[cn[4]]) + (pT[t] + pB[t]);
+          const float sum2 = (pT[cn[2]] + pT[cn[4]]) + (pB[cn[2]] + pB[cn[4]]);
+          v[c] = fmaf(sum2, P.gab_w[3 * c + 2], fmaf(sum1, P.gab_w[3 * c + 1], pM[t] * P.gab_w[3 * c]));
+        }
+        deliver(T1(), r, v[0], v[1], v[2]);
+      }
+    }
+    // ---- EPF0 (stage_epf.cc:54-193) ----
+    if constexpr (C::E0) {
+      r -= 4;
+      if (r >= lo(H - h0) && r < hi(H - h0) && xin && t >= h0 && t < kStripThreads - h0) {
+        const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + (x >> 3));
+        float X = ring_row(ring0, C::N0, r, 0)[t];
+        float Y = ring_row(ring0, C::N0, r, 1)[t];
+        float B = ring_row(ring0, C::N0, r, 2)[t];
+        if (!(s < kMinSigma)) {
+          const int iy = r & 7;
+          const float sm_ = P.epf_sm[0];
+          const float vsm = (iy == 0 || iy == 7 || xborder) ? sm_ * P.epf_border_mul : sm_;
+          const float inv_sigma = s * vsm;
+          int rr[7];
+#pragma unroll
+          for (int k = 0; k < 7; k++) rr[k] = mrow(r + k - 3);
+          const int dy12[12] = {-2, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 2};
+          const int dx12[12] = {0, -1, 0, 1, -2, -1, 1, 2, -1, 0, 1, 0};
+          const int py5[5] = {0, -1, 0, 1, 0};
+          const int px5[5] = {0, 0, -1, 0, 1};
+          float sads[12];
+#pragma unroll
+          for (int k = 0; k < 12; k++) sads[k] = 0.0f;
+          float nbv[3][12];
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            // the 25 pixels of the radius-3 diamond, in registers
+            float v[7][7];
+#pragma unroll
+            for (int a = 0; a < 7; a++)
+#pragma unroll
+              for (int b = 0; b < 7; b++)
+                if ((a > 3 ? a - 3 : 3 - a) + (b > 3 ? b - 3 : 3 - b) <= 3)
+                  v[a][b] = ring_row(ring0, C::N0, rr[a], c)[cn[b]];
+            const float scale = P.epf_scale[c];
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+              float sad = 0.0f;
+#pragma unroll
+              for (int o = 0; o < 5; o++)
+                sad = sad + fabsf(v[3 + py5[o]][3 + px5[o]] - v[3 + dy12[k] + py5[o]][3 + dx12[k] + px5[o]]);
+              sads[k] = fmaf(sad, scale, sads[k]);
+              nbv[c][k] = v[3 + dy12[k]][3 + dx12[k]];
+            }
+          }
+          float w = 1.0f;
+#pragma unroll
+          for (int k = 0; k < 12; k++) {
+            const float wt = epf_weight(sads[k], inv_sigma);
+            w = w + wt;
+            X = fmaf(wt, nbv[0][k], X);
+            Y = fmaf(wt, nbv[1][k], Y);
+            B = fmaf(wt, nbv[2][k], B);
+          }
+          const float inv_w = 1.0f / w;
+          X = X * inv_w; Y = Y * inv_w; B = B * inv_w;
+        }
+        deliver(T2(), r, X, Y, B);
+      }
+    }
+    // ---- EPF1 (stage_epf.cc:197-379) ----
+    if constexpr (C::E1) {
+      r -= 3;
+      if (r >= lo(H - h1) && r < hi(H - h1) && xin && t >= h1 && t < kStripThreads - h1) {
+        const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + (x >> 3));
+        float X = ring_row(ring1, C::N1, r, 0)[t];
+        float Y = ring_row(ring1, C::N1, r, 1)[t];
+        float B = ring_row(ring1, C::N1, r, 2)[t];
+        if (!(s < kMinSigma)) {
+          const int iy = r & 7;
+          const float sm_ = P.epf_sm[1];
+          const float vsm = (iy == 0 || iy == 7 || xborder) ? sm_ * P.epf_border_mul : sm_;
+          const float inv_sigma = s * vsm;
+          const int r0 = mrow(r - 2), r1 = mrow(r - 1), r3 = mrow(r + 1), r4 = mrow(r + 2);
+          float sad0 = 0.0f, sad1 = 0.0f, sad2 = 0.0f, sad3 = 0.0f;
+          float nb[3][4];  // neighbour pixels N, W, E, S per channel
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const float* q0 = ring_row(ring1, C::N1, r0, c);
+            const float* q1 = ring_row(ring1, C::N1, r1, c);
+            const float* q2 = ring_row(ring1, C::N1, r, c);
+            const float* q3 = ring_row(ring1, C::N1, r3, c);
+            const float* q4 = ring_row(ring1, C::N1, r4, c);
+            const float p20 = q0[t], p11 = q1[cn[2]], p21 = q1[t], p31 = q1[cn[4]];
+            const float p02 = q2[cn[1]], p12 = q2[cn[2]], p22 = q2[t], p32 = q2[cn[4]], p42 = q2[cn[5]];
+            const float p13 = q3[cn[2]], p23 = q3[t], p33 = q3[cn[4]], p24 = q4[t];
+            nb[c][0] = p21; nb[c][1] = p12; nb[c][2] = p32; nb[c][3] = p23;
+            float tt;
+            float sad0c = fabsf(p20 - p21);
+            float sad1c = fabsf(p11 - p21);
+            float sad2c = fabsf(p31 - p21);
+            sad1c = sad1c + fabsf(p02 - p12);
+            sad0c = sad0c + fabsf(p11 - p12);
+            tt = fabsf(p12 - p22);
+            sad1c = sad1c + tt;
+            sad2c = sad2c + tt;
+            tt = fabsf(p22 - p21);
+            float sad3c = tt;
+            sad0c = sad0c + tt;
+            sad0c = sad0c + fabsf(p31 - p32);
+            tt = fabsf(p22 - p32);
+            sad1c = sad1c + tt;
+            sad2c = sad2c + tt;
+            sad2c = sad2c + fabsf(p42 - p32);
+            sad3c = sad3c + fabsf(p13 - p12);
+            tt = fabsf(p22 - p23);
+            sad0c = sad0c + tt;
+            sad3c = sad3c + tt;
+            sad1c = sad1c + fabsf(p13 - p23);
+            sad2c = sad2c + fabsf(p33 - p23);
+            sad3c = sad3c + fabsf(p33 - p32);
+            sad3c = sad3c + fabsf(p24 - p23);
+            const float scale = P.epf_scale[c];
+            sad0 = fmaf(sad0c, scale, sad0);
+            sad1 = fmaf(sad1c, scale, sad1);
+            sad2 = fmaf(sad2c, scale, sad2);
+            sad3 = fmaf(sad3c, scale, sad3);
+          }
+          const float sd[4] = {sad0, sad1, sad2, sad3};
+          float w = 1.0f;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float wt = epf_weight(sd[k], inv_sigma);
+            w = w + wt;
+            X = fmaf(wt, nb[0][k], X);
+            Y = fmaf(wt, nb[1][k], Y);
+            B = fmaf(wt, nb[2][k], B);
+          }
+          const float inv_w = 1.0f / w;
+          X = X * inv_w; Y = Y * inv_w; B = B * inv_w;
+        }
+        deliver(T3(), r, X, Y, B);
+      }
+    }
+    // ---- EPF2 (stage_epf.cc:383-506) ----
+    if constexpr (C::E2) {
+      r -= 2;
+      if (r >= lo(0) && r < hi(0) && xin && t >= h2 && t < kStripThreads - h2) {
+        const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + (x >> 3));
+        float X = ring_row(ring2, C::N2, r, 0)[t];
+        float Y = ring_row(ring2, C::N2, r, 1)[t];
+        float B = ring_row(ring2, C::N2, r, 2)[t];
+        if (!(s < kMinSigma)) {
+          const int iy = r & 7;
+          const float sm_ = P.epf_sm[2];
+          const float vsm = (iy == 0 || iy == 7 || xborder) ? sm_ * P.epf_border_mul : sm_;
+          const float inv_sigma = s * vsm;
+          const int nr[4] = {mrow(r - 1), r, r, mrow(r + 1)};
+          const int nc[4] = {t, cn[2], cn[4], t};
+          const float rx = X, ry = Y, rb = B;
+          float w = 1.0f;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float cx = ring_row(ring2, C::N2, nr[k], 0)[nc[k]];
+            const float cy = ring_row(ring2, C::N2, nr[k], 1)[nc[k]];
+            const float cb = ring_row(ring2, C::N2, nr[k], 2)[nc[k]];
+            float sad = fabsf(cx - rx) * P.epf_scale[0];
+            sad = fmaf(fabsf(cy - ry), P.epf_scale[1], sad);
+            sad = fmaf(fabsf(cb - rb), P.epf_scale[2], sad);
+            const float wt = epf_weight(sad, inv_sigma);
+            w = w + wt;
+            X = fmaf(wt, cx, X);
+            Y = fmaf(wt, cy, Y);
+            B = fmaf(wt, cb, B);
+          }
+          const float inv_w = 1.0f / w;
+          X = X * inv_w; Y = Y * inv_w; B = B * inv_w;
+        }
+        deliver(T4(), r, X, Y, B);
+      }
+    }
+    if constexpr (H > 0) __syncthreads();
+  }
+}
+
+template <uint32_t MASK>
+__global__ void __launch_bounds__(kStripThreads) filter_strip_kernel(const __grid_constant__ FrameDev P,
+                                                                    float* __restrict__ out,
+                                                                    size_t out_row_stride, int seg_rows) {
+  extern __shared__ __align__(16) float fsm[];
+  using C = StripCfg<MASK>;
+  const int x0 = blockIdx.x * C::kOutCols;
+  const int y_begin = (int)P.band_y0 + blockIdx.y * seg_rows;
+  const int y_end = min((int)P.band_y1, y_begin + seg_rows);
+  if (y_begin >= y_end) return;
+  const bool edge = (x0 - C::H < 0) || (x0 - C::H + kStripThreads > (int)P.xsize);
+  if (edge) filter_strip_body<MASK, true>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
+  else filter_strip_body<MASK, false>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
 }
 
 }  // namespace jxlb

@@ -50,6 +50,17 @@ def test_stage_taps_bit_exact(pipe, mask):
     assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), f"mask {mask}")
 
 
+@pytest.mark.parametrize("gab", [0, 1])
+@pytest.mark.parametrize("epf_iters", [0, 1, 2, 3])
+@pytest.mark.parametrize("w,h", [(1000, 700), (261, 1031)])
+def test_production_stage_chains(pipe, gab, epf_iters, w, h):
+    """The eight stage chains PreparePipeline can build (dec_cache.cc:151-170) run through the
+    row-streaming strip kernel; sizes chosen so that strips have left/right edge handling, several
+    strips and several vertical segments."""
+    desc, coeffs = wl.synthetic_frame(w, h, seed=gab * 10 + epf_iters, gab=gab, epf_iters=epf_iters)
+    assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), f"gab={gab} epf={epf_iters}")
+
+
 @pytest.mark.parametrize("strategy", range(27))
 def test_single_strategy_frames(pipe, strategy):
     """One strategy at a time (plus 8x8 filler where it does not tile): isolates each transform."""
