@@ -281,7 +281,7 @@ def main() -> int:
 
     # per-kernel times (separate pass, CUDA events inside the library on the same stream)
     pipe.set_profiling(True)
-    ktimes = {"plan": [], "idct_small": [], "idct_large": [], "filter": []}
+    ktimes = {"plan": [], "idct8": [], "idct_mid": [], "idct_large": [], "filter": []}
     for _ in range(max(5, min(args.steps, 20))):
         pipe.render_device(my_out.data_ptr(), W * 12, stream.cuda_stream)
         for k, v in pipe.kernel_times_ms().items():
@@ -352,11 +352,11 @@ def main() -> int:
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     ab = algorithmic_bytes(desc, band_rows)
-    k_idct = kavg["idct_small"] + kavg["idct_large"]
+    k_idct = kavg["idct8"] + kavg["idct_mid"] + kavg["idct_large"]
     dominant = "filter" if kavg["filter"] >= k_idct else "idct"
     dom_ms = kavg["filter"] if dominant == "filter" else k_idct
     achieved = ab[dominant] / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "filter_kernel" if dominant == "filter" else "idct_small_kernel+idct_large_kernel",
+    roofline = {"bound": "hbm", "kernel": "filter_strip_kernel" if dominant == "filter" else "idct8_kernel+idct_mid_kernel+idct_large_kernel",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ab[dominant],
                 "kernel_ms": kavg,

@@ -111,7 +111,7 @@ typedef struct jxlgpu_frame {
   const float* dc[3];           size_t dc_stride;
 
   /* DequantMatrices table (quant_weights.h:364-367): matrix of strategy k, channel c starts
-   * at dequant_table[dequant_offsets[3*k+c]] and has 64*covered_blocks entries. */
+   * at dequant_table[dequant_offsets[3*k+c]] (a multiple of 4) and has 64*covered_blocks entries. */
   const float* dequant_table;   size_t dequant_table_floats;
   uint32_t dequant_offsets[3 * JXLGPU_NUM_STRATEGIES];
 
@@ -185,10 +185,11 @@ JXLGPU_API int jxlgpu_device_xyb(jxlgpu_ctx* ctx, float** dev_ptr, size_t* plane
 JXLGPU_API int jxlgpu_synchronize(jxlgpu_ctx* ctx);
 /* Number of kernel launches issued by this context since creation (bench "gpu_launches"). */
 JXLGPU_API uint64_t jxlgpu_launch_count(const jxlgpu_ctx* ctx);
-/* Per-kernel device times of the LAST render (ms): plan, small IDCT, large IDCT, filter.
+/* Per-kernel device times of the LAST render (ms): plan, 8x8-class IDCT, mid IDCT (16/32),
+ * large IDCT (64+), filter.
  * Measured with CUDA events recorded on the launch stream; enable before rendering. */
 JXLGPU_API int jxlgpu_set_profiling(jxlgpu_ctx* ctx, int enable);
-JXLGPU_API int jxlgpu_kernel_times(jxlgpu_ctx* ctx, float ms[4]);
+JXLGPU_API int jxlgpu_kernel_times(jxlgpu_ctx* ctx, float ms[5]);
 /* Page-locked host memory for coefficient / output staging (truly asynchronous copies). */
 JXLGPU_API void* jxlgpu_alloc_pinned(size_t bytes);
 JXLGPU_API void jxlgpu_free_pinned(void* p);

@@ -21,7 +21,7 @@ import numpy as np
 from libjxl_b200 import abi
 
 ROOT = Path(__file__).resolve().parent
-CACHE = Path(os.environ.get("JXL_B200_CACHE", ROOT / "bench_cache"))
+CACHE = Path(os.environ.get("JXL_B200_CACHE", "/tmp/jxl_b200_cache"))
 
 
 def synth_image(w: int, h: int, seed: int = 1234, kind: str = "photo") -> np.ndarray:

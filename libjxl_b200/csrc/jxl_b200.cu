@@ -60,7 +60,7 @@ struct jxlgpu_ctx {
   std::atomic<uint64_t> launches{0};
   bool force_generic_filter = false;  // JXLGPU_FORCE_GENERIC_FILTER=1: tile kernel for every chain
   bool profile = false;          // record CUDA events around every kernel (bench roofline)
-  cudaEvent_t prof_ev[5] = {};
+  cudaEvent_t prof_ev[6] = {};
   std::string last_error;
   std::mutex mu;
 };
@@ -105,8 +105,17 @@ void launch_strip_mask(jxlgpu_ctx* ctx, float* dev_out, size_t out_stride_floats
   const FrameDev& P = ctx->P;
   const int band_h = (int)(P.band_y1 - P.band_y0);
   const int strips = ((int)P.xsize + C::kOutCols - 1) / C::kOutCols;
-  // enough CTAs for ~4 per SM, but segments long enough to amortise the pipeline fill
-  int segs = (ctx->num_sms * 4 + strips - 1) / strips;
+  // Exactly one wave: as many CTAs as fit on the chip at this kernel's occupancy (a 5% second
+  // wave would double the kernel time), segments long enough to amortise the pipeline fill.
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, filter_strip_kernel<MASK>, kStripThreads,
+                                                  C::kSmemBytes);
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  const int slots = ctx->num_sms * blocks_per_sm;
+  int segs = slots / strips;
+  if (segs < 1) segs = 1;
   int seg_rows = (band_h + segs - 1) / segs;
   if (seg_rows < 64) seg_rows = 64;
   seg_rows = (seg_rows + 7) & ~7;
@@ -144,22 +153,26 @@ int launch_all(jxlgpu_ctx* ctx, float* dev_out, size_t out_stride_floats, cudaSt
   if (prof) CU(cudaEventRecord(ctx->prof_ev[0], s));
   plan_kernel<<<ctx->plan_groups, 1024, 0, s>>>(P, want_sigma);
   if (prof) CU(cudaEventRecord(ctx->prof_ev[1], s));
-  const int small_grid = ctx->num_sms * 4;
+  const int grid8 = ctx->num_sms * 3;   // idct8_kernel: __launch_bounds__(256, 3)
+  const int grid_mid = ctx->num_sms * 2;
   const int large_grid = ctx->num_sms * 2;
-  if (P.ac_is32) idct_small_kernel<true><<<small_grid, kSmallWarpsPerCta * 32, 0, s>>>(P);
-  else idct_small_kernel<false><<<small_grid, kSmallWarpsPerCta * 32, 0, s>>>(P);
+  if (P.ac_is32) idct8_kernel<true><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
+  else idct8_kernel<false><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
   if (prof) CU(cudaEventRecord(ctx->prof_ev[2], s));
+  if (P.ac_is32) idct_mid_kernel<true><<<grid_mid, kSmallWarpsPerCta * 32, 0, s>>>(P);
+  else idct_mid_kernel<false><<<grid_mid, kSmallWarpsPerCta * 32, 0, s>>>(P);
+  if (prof) CU(cudaEventRecord(ctx->prof_ev[3], s));
   if (P.ac_is32) idct_large_kernel<true><<<large_grid, 256, 0, s>>>(P);
   else idct_large_kernel<false><<<large_grid, 256, 0, s>>>(P);
-  if (prof) CU(cudaEventRecord(ctx->prof_ev[3], s));
+  if (prof) CU(cudaEventRecord(ctx->prof_ev[4], s));
   const uint32_t band_h = P.band_y1 - P.band_y0;
   if (!launch_strip(ctx, dev_out, out_stride_floats, s)) {
     // stage chains outside the production set (test taps): generic tile kernel
     dim3 grid((P.xsize + kTW - 1) / kTW, (band_h + kTH - 1) / kTH);
     filter_kernel<<<grid, kFilterThreads, kFilterSmemFloats * sizeof(float), s>>>(P, dev_out, out_stride_floats);
   }
-  if (prof) CU(cudaEventRecord(ctx->prof_ev[4], s));
-  ctx->launches += 4;
+  if (prof) CU(cudaEventRecord(ctx->prof_ev[5], s));
+  ctx->launches += 5;
   CU(cudaGetLastError());
   return JXLGPU_OK;
 }
@@ -257,6 +270,7 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   for (int i = 0; i < 3 * kNumStrategies; i++) {
     const size_t n = (size_t)64 * covered_x(i / 3) * covered_y(i / 3);
     if (f->dequant_offsets[i] + n > f->dequant_table_floats) return JXLGPU_ERR_INVALID_ARGUMENT;
+    if (f->dequant_offsets[i] % 4) return JXLGPU_ERR_INVALID_ARGUMENT;  // 16-byte vector loads
   }
   FrameDev& P = ctx->P;
   const size_t xb = f->xsize_blocks, yb = f->ysize_blocks, nblocks = xb * yb;
@@ -473,12 +487,12 @@ int jxlgpu_set_profiling(jxlgpu_ctx* ctx, int enable) {
   return JXLGPU_OK;
 }
 
-int jxlgpu_kernel_times(jxlgpu_ctx* ctx, float ms[4]) {
+int jxlgpu_kernel_times(jxlgpu_ctx* ctx, float ms[5]) {
   if (!ctx || !ms) return JXLGPU_ERR_INVALID_ARGUMENT;
   if (!ctx->profile) return JXLGPU_ERR_STATE;
   CU(cudaSetDevice(ctx->device));
-  CU(cudaEventSynchronize(ctx->prof_ev[4]));
-  for (int i = 0; i < 4; i++) CU(cudaEventElapsedTime(&ms[i], ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+  CU(cudaEventSynchronize(ctx->prof_ev[5]));
+  for (int i = 0; i < 5; i++) CU(cudaEventElapsedTime(&ms[i], ctx->prof_ev[i], ctx->prof_ev[i + 1]));
   return JXLGPU_OK;
 }
 

@@ -379,33 +379,108 @@ __device__ __forceinline__ void hadamard4(float b00, float b01, float b10, float
   dcs[3] = b00 - b01 - b10 + b11;
 }
 
+// One row (8 consecutive coefficients) of a channel plane as integers.
 template <bool I32>
-__device__ __forceinline__ void special_item(const FrameDev& P, int kind, uint32_t first_entry_idx,
-                                             uint32_t count, float* sm) {
+__device__ __forceinline__ void load_row8(const void* plane, size_t elem, int* q) {
+  if constexpr (I32) {
+    const int4* p = reinterpret_cast<const int4*>(reinterpret_cast<const int32_t*>(plane) + elem);
+    const int4 a = __ldg(p), b = __ldg(p + 1);
+    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+  } else {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const int16_t*>(plane) + elem));
+    const int w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      q[2 * i] = (int)(short)(w[i] & 0xffff);
+      q[2 * i + 1] = w[i] >> 16;
+    }
+  }
+}
+
+__device__ __forceinline__ void load_row8f(const float* p, float* m) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+}
+
+// 8x8-class varblocks (DCT and the specials): 8 lanes per block, 4 blocks per warp.
+// Phase A: lane l loads row l (8 coefficients, 16/32 contiguous bytes) of all three channels with
+// vector loads and dequantises them in registers (CfL needs Y next to X and B anyway).
+// Phase B, per channel: rows go to shared memory, the strategy's transform runs on them.
+template <bool I32>
+__device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint32_t first_entry_idx,
+                                            uint32_t count, float* sm) {
   const int lane = threadIdx.x & 31;
   const int slot = lane >> 3, l = lane & 7;
   const uint32_t eidx = first_entry_idx + slot;
   const bool active = eidx < count;
   // Inactive slots (tail of a list) run the same instruction stream on scratch data so that
   // every __syncwarp() is reached by all 32 lanes; only their loads and stores are masked.
-  float* co = sm + slot * 200;   // 200 = 3*64 + 8 pad: slot bases fall on different banks
-  float* tmp = co + 64;
-  float* px = co + 128;
+  float* co = sm + slot * 264;   // 264 = 96 + 96 + 64 + 8: slot bases 8 banks apart
+  float* tmp = co + 96;
+  float* px = co + 192;
   VarblockCtx vb;
-  if (active) vb = make_ctx(P, P.list[P.list_base[kind] + eidx]);
-  else vb = VarblockCtx{};
-#pragma unroll 1
-  for (int c = 0; c < 3; c++) {
-    if (active) {
+  float val[3][8];
+  if (active) {
+    vb = make_ctx(P, P.list[P.list_base[kind] + eidx]);
+    int qx[8], qy[8], qb[8];
+    float mx[8], my[8], mb[8];
+    const size_t e0 = vb.cbase + (size_t)l * 8;
+    load_row8<I32>(P.coeff[1], e0, qy);
+    load_row8<I32>(P.coeff[0], e0, qx);
+    load_row8<I32>(P.coeff[2], e0, qb);
+    load_row8f(P.dq + P.dq_off[3 * kind + 1] + l * 8, my);
+    load_row8f(P.dq + P.dq_off[3 * kind + 0] + l * 8, mx);
+    load_row8f(P.dq + P.dq_off[3 * kind + 2] + l * 8, mb);
 #pragma unroll
-      for (int t = 0; t < 8; t++) {
-        const uint32_t i = (uint32_t)(t * 8 + l);
-        co[i] = dequant<I32>(P, vb, kind, c, i);
-      }
+    for (int e = 0; e < 8; e++) {
+      const float dy = adjust_quant_bias(qy[e], P.qbias[1], P.qbias[3]) * (my[e] * vb.sy);
+      const float dx = adjust_quant_bias(qx[e], P.qbias[0], P.qbias[3]) * (mx[e] * vb.sx);
+      const float db = adjust_quant_bias(qb[e], P.qbias[2], P.qbias[3]) * (mb[e] * vb.sb);
+      val[1][e] = dy;
+      val[0][e] = fmaf(vb.x_cc, dy, dx);
+      val[2][e] = fmaf(vb.b_cc, dy, db);
     }
-    __syncwarp();
-    if (active && l == 0)  // LowestFrequenciesFromDC: llf[0] = dc[0]
-      co[0] = __ldg(P.dc + (size_t)c * P.yb * P.xb + (size_t)vb.aby * P.xb + vb.abx);
+    if (l == 0) {  // LowestFrequenciesFromDC for the 8x8 class: llf[0] = dc[0]
+      const size_t bi = (size_t)vb.aby * P.xb + vb.abx;
+#pragma unroll
+      for (int c = 0; c < 3; c++) val[c][0] = __ldg(P.dc + (size_t)c * P.yb * P.xb + bi);
+    }
+  } else {
+    vb = VarblockCtx{};
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int e = 0; e < 8; e++) val[c][e] = 0.0f;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    if (kind == 0) {
+      // ---- DCT 8x8: ComputeScaledIDCT<8,8> (dct-inl.h:376-397); rows at pitch 12 ----
+      *reinterpret_cast<float4*>(co + l * 12) = make_float4(val[c][0], val[c][1], val[c][2], val[c][3]);
+      *reinterpret_cast<float4*>(co + l * 12 + 4) = make_float4(val[c][4], val[c][5], val[c][6], val[c][7]);
+      __syncwarp();
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = co[k * 12 + l];  // lane l = vertical frequency j
+      idct1d<8>(v);
+      *reinterpret_cast<float4*>(tmp + l * 12) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(tmp + l * 12 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      __syncwarp();
+      float u[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) u[j] = tmp[j * 12 + l];  // lane l = pixel column x
+      idct1d<8>(u);
+      if (active) {
+        float* out = P.xyb + (size_t)c * P.plane_stride + (size_t)vb.aby * 8 * P.row_stride + vb.abx * 8 + l;
+#pragma unroll
+        for (int y = 0; y < 8; y++) out[(size_t)y * P.row_stride] = u[y];
+      }
+      __syncwarp();
+      continue;
+    }
+    *reinterpret_cast<float4*>(co + l * 8) = make_float4(val[c][0], val[c][1], val[c][2], val[c][3]);
+    *reinterpret_cast<float4*>(co + l * 8 + 4) = make_float4(val[c][4], val[c][5], val[c][6], val[c][7]);
     __syncwarp();
     {
       switch (kind) {
@@ -622,35 +697,55 @@ __device__ __forceinline__ void special_item(const FrameDev& P, int kind, uint32
 }
 
 constexpr int kSmallWarpsPerCta = 8;
-constexpr int kSmallWarpFloats = 1120;  // >= 32*33 + 2*16 and >= 4*200
+constexpr int kSmallWarpFloats = 1120;  // >= 32*33 + 2*16 and >= 4*264
 
 __device__ __forceinline__ int small_slots(int s) {
   const int w = max(covered_x(s), covered_y(s));
   return w == 1 ? 4 : (w == 2 ? 2 : 1);
 }
 
+// 8x8-class strategies (DCT, IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4, AFV0-3).
 template <bool I32>
-__global__ void __launch_bounds__(kSmallWarpsPerCta * 32) idct_small_kernel(const __grid_constant__ FrameDev P) {
+__global__ void __launch_bounds__(kSmallWarpsPerCta * 32, 3) idct8_kernel(const __grid_constant__ FrameDev P) {
+  __shared__ __align__(16) float smem[kSmallWarpsPerCta * 1056];
+  float* sm = smem + (threadIdx.x >> 5) * 1056;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int order[10] = {0, 2, 12, 13, 1, 3, 14, 15, 16, 17};
+  uint32_t base = 0;
+#pragma unroll 1
+  for (int oi = 0; oi < 10; oi++) {
+    const int s = order[oi];
+    const uint32_t count = P.counts[s];
+    const uint32_t items = (count + 3) / 4;
+    uint32_t it = (warp + nwarps - (base % nwarps)) % nwarps;
+#pragma unroll 1
+    for (; it < items; it += nwarps) block8_item<I32>(P, s, it * 4, count, sm);
+    base += items;
+  }
+}
+
+// multi-block DCTs with sides <= 32 (DCT16X16 .. DCT16X32).
+template <bool I32>
+__global__ void __launch_bounds__(kSmallWarpsPerCta * 32) idct_mid_kernel(const __grid_constant__ FrameDev P) {
   __shared__ __align__(16) float smem[kSmallWarpsPerCta * kSmallWarpFloats];
   float* sm = smem + (threadIdx.x >> 5) * kSmallWarpFloats;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   // warp items are numbered class by class; larger transforms first for balance
-  const int order[kFirstLarge] = {5, 10, 11, 8, 9, 4, 6, 7, 0, 1, 2, 3, 12, 13, 14, 15, 16, 17};
+  const int order[8] = {5, 10, 11, 8, 9, 4, 6, 7};
   uint32_t base = 0;
 #pragma unroll 1
-  for (int oi = 0; oi < kFirstLarge; oi++) {
+  for (int oi = 0; oi < 8; oi++) {
     const int s = order[oi];
     const uint32_t count = P.counts[s];
     const uint32_t slots = small_slots(s);
     const uint32_t items = (count + slots - 1) / slots;
-    // first item of this class handled by this warp
     uint32_t it = (warp + nwarps - (base % nwarps)) % nwarps;
 #pragma unroll 1
     for (; it < items; it += nwarps) {
       const uint32_t e0 = it * slots;
       switch (s) {
-        case 0: small_dct_item<8, 8, I32>(P, s, e0, count, sm); break;
         case 4: small_dct_item<16, 16, I32>(P, s, e0, count, sm); break;
         case 5: small_dct_item<32, 32, I32>(P, s, e0, count, sm); break;
         case 6: small_dct_item<16, 8, I32>(P, s, e0, count, sm); break;
@@ -658,8 +753,7 @@ __global__ void __launch_bounds__(kSmallWarpsPerCta * 32) idct_small_kernel(cons
         case 8: small_dct_item<32, 8, I32>(P, s, e0, count, sm); break;
         case 9: small_dct_item<8, 32, I32>(P, s, e0, count, sm); break;
         case 10: small_dct_item<32, 16, I32>(P, s, e0, count, sm); break;
-        case 11: small_dct_item<16, 32, I32>(P, s, e0, count, sm); break;
-        default: special_item<I32>(P, s, e0, count, sm); break;
+        default: small_dct_item<16, 32, I32>(P, s, e0, count, sm); break;
       }
     }
     base += items;

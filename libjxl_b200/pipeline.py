@@ -80,7 +80,7 @@ def lib():
         L.jxlgpu_alloc_pinned.argtypes = [C.c_size_t]
         L.jxlgpu_free_pinned.argtypes = [C.c_void_p]
         L.jxlgpu_set_profiling.argtypes = [C.c_void_p, C.c_int]
-        L.jxlgpu_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float * 4)]
+        L.jxlgpu_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float * 5)]
         if L.jxlgpu_abi_version() != abi.ABI_VERSION:
             raise RuntimeError("libjxl_b200.so ABI version mismatch: rebuild")
         _lib = L
@@ -189,9 +189,9 @@ class TransformPipeline:
         self._check(lib().jxlgpu_set_profiling(self._h, int(enable)), "jxlgpu_set_profiling")
 
     def kernel_times_ms(self) -> dict[str, float]:
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 5)()
         self._check(lib().jxlgpu_kernel_times(self._h, C.byref(ms)), "jxlgpu_kernel_times")
-        return dict(zip(("plan", "idct_small", "idct_large", "filter"), [float(v) for v in ms]))
+        return dict(zip(("plan", "idct8", "idct_mid", "idct_large", "filter"), [float(v) for v in ms]))
 
     def launch_count(self) -> int:
         return int(lib().jxlgpu_launch_count(self._h))
