@@ -152,12 +152,19 @@ JXLGPU_API void jxlgpu_destroy(jxlgpu_ctx* ctx);
  * Replaces the per-frame setup in DecodeGroupImpl (dec_group.cc:183-228). */
 JXLGPU_API int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* frame);
 
+/* Optional, right after frame_begin: announce the host output buffer (what libjxl knows since
+ * JxlDecoderSetImageOutBuffer, decode.h:1021).  Finished AC-group rows are then copied back
+ * while later groups are still being submitted; frame_finish(out) with the same pointer only
+ * waits.  Layout as in frame_finish. */
+JXLGPU_API int jxlgpu_frame_set_output(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes);
+
 /* One entropy-decoded AC group: coeff[c] points at `ncoeff` quantised coefficients of
  * channel c (X, Y, B) in libjxl's ACImage order -- varblocks in raster order of their
  * first block, each 64*covered_blocks long (dec_group.cc:335-359).  Asynchronous H2D on
- * the stream of `thread_id`; the host buffers may be reused as soon as the call returns
- * only if they are NOT pinned (they are staged); pinned buffers must stay valid until
- * frame_finish.  Replaces dec_group.cc:431-450 + RenderPipelineInput::Done(). */
+ * the stream of `thread_id`: pinned buffers must stay valid until frame_finish, pageable ones
+ * are staged by the driver before the call returns.  When the last group of an AC-group row
+ * arrives, that row's kernels are enqueued right away (see jxl_b200.cu).
+ * Replaces dec_group.cc:431-450 + RenderPipelineInput::Done(). */
 JXLGPU_API int jxlgpu_submit_group(jxlgpu_ctx* ctx, uint32_t group_idx, size_t thread_id,
                                    const void* const coeff[3], size_t ncoeff);
 

@@ -1,6 +1,16 @@
 // jxl_b200.cu -- context management and the C ABI of include/jxl_b200.h.
 // The product path: there is NO CPU fallback in this library; without a CUDA device every
 // entry point fails with JXLGPU_ERR_NO_DEVICE / JXLGPU_ERR_CUDA.
+//
+// Two ways to run a frame:
+//   * device-resident (jxlgpu_set_device_coefficients + jxlgpu_render_device): the whole band in
+//     one go on the caller's stream: plan -> IDCT kernels -> filter.
+//   * host-fed (jxlgpu_frame_begin / jxlgpu_submit_group / jxlgpu_frame_finish): coefficient
+//     groups arrive from the host's worker threads in any order.  As soon as every group of an
+//     AC-group row has been submitted, that row's plan+IDCT is enqueued; as soon as rows g-1, g,
+//     g+1 are transformed, row g is filtered and -- when the output buffer was announced with
+//     jxlgpu_frame_set_output -- copied back.  H2D of later rows, kernels and D2H of earlier rows
+//     overlap (three engines: copy-in, SMs, copy-out).
 #include "../../include/jxl_b200.h"
 
 #include <cuda_runtime.h>
@@ -43,23 +53,32 @@ struct DevBuf {
 struct jxlgpu_ctx {
   int device = 0;
   uint32_t num_threads = 1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;                 // compute (and side-info upload) stream
+  cudaStream_t s_mid = nullptr, s_large = nullptr, s_down = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_mid = nullptr, ev_large = nullptr, ev_filter = nullptr, ev_ext = nullptr;
   std::vector<cudaStream_t> up_streams;
   std::vector<cudaEvent_t> up_events;
   int num_sms = 148;
   bool in_frame = false;
   bool coeff_external = false;
   FrameDev P{};
+  uint32_t halo = 0;
   uint32_t num_groups = 0;
-  uint32_t plan_groups = 0;      // groups the plan kernel visits (band +- halo)
-  uint32_t need_g0 = 0, need_g1 = 0;
+  uint32_t need_row0 = 0, need_row1 = 0;         // AC-group rows this band needs (band +- halo)
+  uint32_t band_row0 = 0, band_row1 = 0;         // AC-group rows this band renders
   size_t elem_size = 2;
+  // streaming state (guarded by mu)
   std::vector<uint8_t> submitted;
+  std::vector<uint32_t> row_count;               // groups submitted per group row
+  std::vector<uint8_t> row_idct, row_filtered;
+  void* host_out = nullptr;
+  size_t host_out_stride = 0;
+  int stream_error = 0;
   DevBuf acs, quant, sharp, ytox, ytob, dc, dq, coeff[3], coeff_off, sigma, list, counts, xyb, out;
   size_t out_stride_floats = 0;
   std::atomic<uint64_t> launches{0};
   bool force_generic_filter = false;  // JXLGPU_FORCE_GENERIC_FILTER=1: tile kernel for every chain
-  bool profile = false;          // record CUDA events around every kernel (bench roofline)
+  bool profile = false;               // record CUDA events around every kernel (bench roofline)
   cudaEvent_t prof_ev[6] = {};
   std::string last_error;
   std::mutex mu;
@@ -100,9 +119,9 @@ uint32_t effective_mask(const jxlgpu_frame& f) {
 }
 
 template <uint32_t MASK>
-void launch_strip_mask(jxlgpu_ctx* ctx, float* dev_out, size_t out_stride_floats, cudaStream_t s) {
+void launch_strip_mask(jxlgpu_ctx* ctx, const FrameDev& P, float* dev_out, size_t out_stride_floats,
+                       cudaStream_t s) {
   using C = StripCfg<MASK>;
-  const FrameDev& P = ctx->P;
   const int band_h = (int)(P.band_y1 - P.band_y0);
   const int strips = ((int)P.xsize + C::kOutCols - 1) / C::kOutCols;
   // Exactly one wave: as many CTAs as fit on the chip at this kernel's occupancy (a 5% second
@@ -124,17 +143,17 @@ void launch_strip_mask(jxlgpu_ctx* ctx, float* dev_out, size_t out_stride_floats
 }
 
 // the stage chains PreparePipeline can build for a VarDCT XYB frame (dec_cache.cc:151-170)
-bool launch_strip(jxlgpu_ctx* ctx, float* dev_out, size_t out_stride_floats, cudaStream_t s) {
+bool launch_strip(jxlgpu_ctx* ctx, const FrameDev& P, float* dev_out, size_t out_stride_floats, cudaStream_t s) {
   if (ctx->force_generic_filter) return false;
-  switch (ctx->P.stage_mask) {
-    case 16: launch_strip_mask<16>(ctx, dev_out, out_stride_floats, s); return true;
-    case 17: launch_strip_mask<17>(ctx, dev_out, out_stride_floats, s); return true;
-    case 20: launch_strip_mask<20>(ctx, dev_out, out_stride_floats, s); return true;
-    case 21: launch_strip_mask<21>(ctx, dev_out, out_stride_floats, s); return true;
-    case 28: launch_strip_mask<28>(ctx, dev_out, out_stride_floats, s); return true;
-    case 29: launch_strip_mask<29>(ctx, dev_out, out_stride_floats, s); return true;
-    case 30: launch_strip_mask<30>(ctx, dev_out, out_stride_floats, s); return true;
-    case 31: launch_strip_mask<31>(ctx, dev_out, out_stride_floats, s); return true;
+  switch (P.stage_mask) {
+    case 16: launch_strip_mask<16>(ctx, P, dev_out, out_stride_floats, s); return true;
+    case 17: launch_strip_mask<17>(ctx, P, dev_out, out_stride_floats, s); return true;
+    case 20: launch_strip_mask<20>(ctx, P, dev_out, out_stride_floats, s); return true;
+    case 21: launch_strip_mask<21>(ctx, P, dev_out, out_stride_floats, s); return true;
+    case 28: launch_strip_mask<28>(ctx, P, dev_out, out_stride_floats, s); return true;
+    case 29: launch_strip_mask<29>(ctx, P, dev_out, out_stride_floats, s); return true;
+    case 30: launch_strip_mask<30>(ctx, P, dev_out, out_stride_floats, s); return true;
+    case 31: launch_strip_mask<31>(ctx, P, dev_out, out_stride_floats, s); return true;
     default: return false;
   }
 }
@@ -145,35 +164,131 @@ cudaError_t strip_attr() {
                               (int)StripCfg<MASK>::kSmemBytes);
 }
 
-int launch_all(jxlgpu_ctx* ctx, float* dev_out, size_t out_stride_floats, cudaStream_t s) {
-  FrameDev& P = ctx->P;
+// plan + inverse transforms of AC-group rows [row0, row1), restricted to the varblocks that
+// intersect pixel rows [need_y0, need_y1).
+int launch_idct(jxlgpu_ctx* ctx, uint32_t row0, uint32_t row1, uint32_t need_y0, uint32_t need_y1, cudaStream_t s) {
+  FrameDev P = ctx->P;
+  P.plan_g0 = row0 * P.xg;
+  P.need_y0 = need_y0;
+  P.need_y1 = need_y1;
+  const uint32_t plan_groups = (row1 - row0) * P.xg;
+  if (!plan_groups) return JXLGPU_OK;
+  const bool prof = ctx->profile;
   CU(cudaMemsetAsync(ctx->counts.p, 0, kNumStrategies * sizeof(uint32_t), s));
   const int want_sigma = (P.stage_mask & 14u) ? 1 : 0;
-  const bool prof = ctx->profile;
   if (prof) CU(cudaEventRecord(ctx->prof_ev[0], s));
-  plan_kernel<<<ctx->plan_groups, 1024, 0, s>>>(P, want_sigma);
+  plan_kernel<<<plan_groups, 1024, 0, s>>>(P, want_sigma);
   if (prof) CU(cudaEventRecord(ctx->prof_ev[1], s));
-  const int grid8 = ctx->num_sms * 3;   // idct8_kernel: __launch_bounds__(256, 3)
-  const int grid_mid = ctx->num_sms * 2;
-  const int large_grid = ctx->num_sms * 2;
+  // grids: persistent, never larger than the work (one CTA round = 32 8x8 blocks)
+  const uint32_t px_blocks = plan_groups * 1024u;
+  int grid8 = ctx->num_sms * 3;  // idct8_kernel: __launch_bounds__(256, 3)
+  if ((uint32_t)grid8 > px_blocks / 32u + 1u) grid8 = (int)(px_blocks / 32u + 1u);
+  int grid_mid = ctx->num_sms * 2, grid_large = ctx->num_sms * 2;
+  if ((uint32_t)grid_mid > px_blocks / 32u + 1u) grid_mid = (int)(px_blocks / 32u + 1u);
+  if ((uint32_t)grid_large > px_blocks / 64u + 1u) grid_large = (int)(px_blocks / 64u + 1u);
+  // The mid/large kernels usually have little work: run them beside the 8x8 kernel (fork/join)
+  // unless per-kernel times are being measured.
+  cudaStream_t sm = prof ? s : ctx->s_mid, sl = prof ? s : ctx->s_large;
+  if (!prof) {
+    CU(cudaEventRecord(ctx->ev_fork, s));
+    CU(cudaStreamWaitEvent(sm, ctx->ev_fork, 0));
+    CU(cudaStreamWaitEvent(sl, ctx->ev_fork, 0));
+  }
   if (P.ac_is32) idct8_kernel<true><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
   else idct8_kernel<false><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
   if (prof) CU(cudaEventRecord(ctx->prof_ev[2], s));
-  if (P.ac_is32) idct_mid_kernel<true><<<grid_mid, kSmallWarpsPerCta * 32, 0, s>>>(P);
-  else idct_mid_kernel<false><<<grid_mid, kSmallWarpsPerCta * 32, 0, s>>>(P);
+  if (P.ac_is32) idct_mid_kernel<true><<<grid_mid, kSmallWarpsPerCta * 32, 0, sm>>>(P);
+  else idct_mid_kernel<false><<<grid_mid, kSmallWarpsPerCta * 32, 0, sm>>>(P);
   if (prof) CU(cudaEventRecord(ctx->prof_ev[3], s));
-  if (P.ac_is32) idct_large_kernel<true><<<large_grid, 256, 0, s>>>(P);
-  else idct_large_kernel<false><<<large_grid, 256, 0, s>>>(P);
+  if (P.ac_is32) idct_large_kernel<true><<<grid_large, 256, 0, sl>>>(P);
+  else idct_large_kernel<false><<<grid_large, 256, 0, sl>>>(P);
   if (prof) CU(cudaEventRecord(ctx->prof_ev[4], s));
-  const uint32_t band_h = P.band_y1 - P.band_y0;
-  if (!launch_strip(ctx, dev_out, out_stride_floats, s)) {
+  if (!prof) {
+    CU(cudaEventRecord(ctx->ev_mid, sm));
+    CU(cudaEventRecord(ctx->ev_large, sl));
+    CU(cudaStreamWaitEvent(s, ctx->ev_mid, 0));
+    CU(cudaStreamWaitEvent(s, ctx->ev_large, 0));
+  }
+  ctx->launches += 4;
+  CU(cudaGetLastError());
+  return JXLGPU_OK;
+}
+
+// filters pixel rows [y0, y1) into dev_out, whose row 0 is image row out_y0.
+int launch_filter(jxlgpu_ctx* ctx, uint32_t y0, uint32_t y1, uint32_t out_y0, uint32_t out_h, float* dev_out,
+                  size_t out_stride_floats, cudaStream_t s) {
+  if (y1 <= y0) return JXLGPU_OK;
+  FrameDev P = ctx->P;
+  P.band_y0 = y0;
+  P.band_y1 = y1;
+  P.out_y0 = out_y0;
+  P.out_h = out_h;
+  if (!launch_strip(ctx, P, dev_out, out_stride_floats, s)) {
     // stage chains outside the production set (test taps): generic tile kernel
-    dim3 grid((P.xsize + kTW - 1) / kTW, (band_h + kTH - 1) / kTH);
+    dim3 grid((P.xsize + kTW - 1) / kTW, (y1 - y0 + kTH - 1) / kTH);
     filter_kernel<<<grid, kFilterThreads, kFilterSmemFloats * sizeof(float), s>>>(P, dev_out, out_stride_floats);
   }
-  if (prof) CU(cudaEventRecord(ctx->prof_ev[5], s));
-  ctx->launches += 5;
+  if (ctx->profile) CU(cudaEventRecord(ctx->prof_ev[5], s));
+  ctx->launches += 1;
   CU(cudaGetLastError());
+  return JXLGPU_OK;
+}
+
+int ensure_out(jxlgpu_ctx* ctx) {
+  const uint32_t band_h = ctx->P.band_y1 - ctx->P.band_y0;
+  const size_t planes = ctx->P.out_format == JXLGPU_OUT_RGB_F32 ? 1 : 3;
+  CU(ctx->out.ensure(planes * band_h * ctx->out_stride_floats * 4));
+  return JXLGPU_OK;
+}
+
+// Streaming scheduler, called with ctx->mu held: enqueue whatever became runnable.
+int pump(jxlgpu_ctx* ctx) {
+  const FrameDev& P = ctx->P;
+  cudaStream_t s = ctx->stream;
+  for (uint32_t g = ctx->need_row0; g < ctx->need_row1; g++) {
+    if (ctx->row_idct[g] || ctx->row_count[g] < P.xg) continue;
+    // the row's coefficients are in flight on the upload streams
+    if (!ctx->coeff_external)
+      for (uint32_t i = 0; i < ctx->num_threads; i++) {
+        CU(cudaEventRecord(ctx->up_events[i], ctx->up_streams[i]));
+        CU(cudaStreamWaitEvent(s, ctx->up_events[i], 0));
+      }
+    uint32_t ny0 = g * 256u, ny1 = (g + 1) * 256u;
+    if (ny0 < P.need_y0) ny0 = P.need_y0;
+    if (ny1 > P.need_y1 || g + 1 == ctx->need_row1) ny1 = P.need_y1;
+    int rc = launch_idct(ctx, g, g + 1, ny0, ny1, s);
+    if (rc) return rc;
+    ctx->row_idct[g] = 1;
+  }
+  const uint32_t band_h = P.band_y1 - P.band_y0;
+  for (uint32_t g = ctx->band_row0; g < ctx->band_row1; g++) {
+    if (ctx->row_filtered[g]) continue;
+    const uint32_t lo = g > ctx->need_row0 ? g - 1 : g;
+    const uint32_t hi = g + 1 < ctx->need_row1 ? g + 1 : g;
+    bool ready = true;
+    for (uint32_t r = lo; r <= hi; r++) ready = ready && ctx->row_idct[r];
+    if (!ready) continue;
+    uint32_t y0 = g * 256u, y1 = (g + 1) * 256u;
+    if (y0 < P.band_y0) y0 = P.band_y0;
+    if (y1 > P.band_y1) y1 = P.band_y1;
+    int rc = ensure_out(ctx);
+    if (rc) return rc;
+    rc = launch_filter(ctx, y0, y1, P.band_y0, band_h, (float*)ctx->out.p, ctx->out_stride_floats, s);
+    if (rc) return rc;
+    ctx->row_filtered[g] = 1;
+    if (ctx->host_out && y1 > y0) {  // copy the finished rows back while later rows still arrive
+      CU(cudaEventRecord(ctx->ev_filter, s));
+      CU(cudaStreamWaitEvent(ctx->s_down, ctx->ev_filter, 0));
+      const size_t row_bytes = ctx->out_stride_floats * 4;
+      const size_t planes = P.out_format == JXLGPU_OUT_RGB_F32 ? 1 : 3;
+      for (size_t pl = 0; pl < planes; pl++) {
+        const size_t row = pl * band_h + (y0 - P.band_y0);
+        CU(cudaMemcpy2DAsync((uint8_t*)ctx->host_out + row * ctx->host_out_stride, ctx->host_out_stride,
+                             (uint8_t*)ctx->out.p + row * row_bytes, row_bytes, row_bytes, y1 - y0,
+                             cudaMemcpyDeviceToHost, ctx->s_down));
+      }
+    }
+  }
   return JXLGPU_OK;
 }
 
@@ -216,7 +331,10 @@ int jxlgpu_create(jxlgpu_ctx** out, const jxlgpu_config* cfg) {
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) return bail(e, "props");
   ctx->num_sms = prop.multiProcessorCount;
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+  for (cudaStream_t* sp : {&ctx->stream, &ctx->s_mid, &ctx->s_large, &ctx->s_down})
+    if ((e = cudaStreamCreateWithFlags(sp, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+  for (cudaEvent_t* ep : {&ctx->ev_fork, &ctx->ev_mid, &ctx->ev_large, &ctx->ev_filter, &ctx->ev_ext})
+    if ((e = cudaEventCreateWithFlags(ep, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
   ctx->up_streams.resize(ctx->num_threads);
   ctx->up_events.resize(ctx->num_threads);
   for (uint32_t i = 0; i < ctx->num_threads; i++) {
@@ -250,8 +368,12 @@ void jxlgpu_destroy(jxlgpu_ctx* ctx) {
     b->release();
   for (auto s : ctx->up_streams) cudaStreamDestroy(s);
   for (auto ev : ctx->up_events) cudaEventDestroy(ev);
-  for (auto ev : ctx->prof_ev) if (ev) cudaEventDestroy(ev);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  for (auto ev : ctx->prof_ev)
+    if (ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : {ctx->ev_fork, ctx->ev_mid, ctx->ev_large, ctx->ev_filter, ctx->ev_ext})
+    if (ev) cudaEventDestroy(ev);
+  for (cudaStream_t s : {ctx->stream, ctx->s_mid, ctx->s_large, ctx->s_down})
+    if (s) cudaStreamDestroy(s);
   delete ctx;
 }
 
@@ -272,6 +394,7 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
     if (f->dequant_offsets[i] + n > f->dequant_table_floats) return JXLGPU_ERR_INVALID_ARGUMENT;
     if (f->dequant_offsets[i] % 4) return JXLGPU_ERR_INVALID_ARGUMENT;  // 16-byte vector loads
   }
+  std::lock_guard<std::mutex> lk(ctx->mu);
   FrameDev& P = ctx->P;
   const size_t xb = f->xsize_blocks, yb = f->ysize_blocks, nblocks = xb * yb;
   P.xsize = f->xsize; P.ysize = f->ysize; P.xb = xb; P.yb = yb;
@@ -283,22 +406,26 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   P.out_format = f->out_format;
   if (f->band_ny_groups == 0) {
     P.band_y0 = 0; P.band_y1 = f->ysize;
+    ctx->band_row0 = 0; ctx->band_row1 = P.yg;
   } else {
     if (f->band_y0_groups + f->band_ny_groups > P.yg) return JXLGPU_ERR_INVALID_ARGUMENT;
     P.band_y0 = f->band_y0_groups * 256u;
     const uint32_t y1 = (f->band_y0_groups + f->band_ny_groups) * 256u;
     P.band_y1 = y1 < f->ysize ? y1 : f->ysize;
+    ctx->band_row0 = f->band_y0_groups; ctx->band_row1 = f->band_y0_groups + f->band_ny_groups;
   }
+  P.out_y0 = P.band_y0;
+  P.out_h = P.band_y1 - P.band_y0;
   {
     const uint32_t halo = ((mask & 1) ? 1 : 0) + ((mask & 2) ? 3 : 0) + ((mask & 4) ? 2 : 0) + ((mask & 8) ? 1 : 0);
+    ctx->halo = halo;
     P.need_y0 = P.band_y0 > halo ? P.band_y0 - halo : 0;
     P.need_y1 = P.band_y1 + halo < f->ysize ? P.band_y1 + halo : f->ysize;
     if (P.band_y1 >= f->ysize) P.need_y1 = (uint32_t)yb * 8;  // bottom band also owns the padded block rows
-    const uint32_t gy0 = P.need_y0 / 256, gy1 = (P.need_y1 + 255) / 256;
-    ctx->need_g0 = gy0 * P.xg;
-    ctx->need_g1 = (gy1 < P.yg ? gy1 : P.yg) * P.xg;
-    P.plan_g0 = ctx->need_g0;
-    ctx->plan_groups = ctx->need_g1 - ctx->need_g0;
+    ctx->need_row0 = P.need_y0 / 256;
+    const uint32_t gy1 = (P.need_y1 + 255) / 256;
+    ctx->need_row1 = gy1 < P.yg ? gy1 : P.yg;
+    P.plan_g0 = ctx->need_row0 * P.xg;
   }
   const size_t cmw = (xb + 7) / 8, cmh = (yb + 7) / 8;
   CU(ctx->acs.ensure(nblocks));
@@ -371,7 +498,23 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   memcpy(P.opsin_cbrt, f->opsin_biases_cbrt, sizeof(P.opsin_cbrt));
   ctx->out_stride_floats = out_floats_per_row(*f);
   ctx->submitted.assign(ctx->num_groups, ctx->coeff_external ? 1 : 0);
+  ctx->row_count.assign(P.yg, ctx->coeff_external ? P.xg : 0);
+  ctx->row_idct.assign(P.yg, 0);
+  ctx->row_filtered.assign(P.yg, 0);
+  ctx->host_out = nullptr;
+  ctx->host_out_stride = 0;
+  ctx->stream_error = 0;
   ctx->in_frame = true;
+  return JXLGPU_OK;
+}
+
+int jxlgpu_frame_set_output(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes) {
+  if (!ctx) return JXLGPU_ERR_INVALID_ARGUMENT;
+  if (!ctx->in_frame) return JXLGPU_ERR_STATE;
+  if (out && out_stride_bytes < ctx->out_stride_floats * 4) return JXLGPU_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->host_out = out;
+  ctx->host_out_stride = out_stride_bytes;
   return JXLGPU_OK;
 }
 
@@ -392,7 +535,17 @@ int jxlgpu_submit_group(jxlgpu_ctx* ctx, uint32_t g, size_t thread_id, const voi
       return fail_cuda(ctx, e, "cudaMemcpyAsync(coefficients)");
     }
   }
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ctx->submitted[g]) return JXLGPU_OK;  // a re-submission is not streamed again
   ctx->submitted[g] = 1;
+  const uint32_t row = g / ctx->P.xg;
+  if (++ctx->row_count[row] == ctx->P.xg && row >= ctx->need_row0 && row < ctx->need_row1) {
+    int rc = pump(ctx);
+    if (rc) {
+      ctx->stream_error = rc;
+      return rc;
+    }
+  }
   return JXLGPU_OK;
 }
 
@@ -404,7 +557,10 @@ int jxlgpu_set_device_coefficients(jxlgpu_ctx* ctx, const void* const dev_coeff[
   }
   ctx->coeff_external = true;
   for (int c = 0; c < 3; c++) ctx->P.coeff[c] = dev_coeff[c];
-  if (ctx->in_frame) ctx->submitted.assign(ctx->num_groups, 1);
+  if (ctx->in_frame) {
+    ctx->submitted.assign(ctx->num_groups, 1);
+    ctx->row_count.assign(ctx->P.yg, ctx->P.xg);
+  }
   return JXLGPU_OK;
 }
 
@@ -412,39 +568,51 @@ int jxlgpu_render_device(jxlgpu_ctx* ctx, void* dev_out, size_t out_stride_bytes
   if (!ctx) return JXLGPU_ERR_INVALID_ARGUMENT;
   if (!ctx->in_frame) return JXLGPU_ERR_STATE;
   CU(cudaSetDevice(ctx->device));
+  std::lock_guard<std::mutex> lk(ctx->mu);
   cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
   if (cuda_stream) {  // side info was uploaded on the context stream
-    CU(cudaEventRecord(ctx->up_events[0], ctx->stream));
-    CU(cudaStreamWaitEvent(s, ctx->up_events[0], 0));
+    CU(cudaEventRecord(ctx->ev_ext, ctx->stream));
+    CU(cudaStreamWaitEvent(s, ctx->ev_ext, 0));
   }
-  const uint32_t band_h = ctx->P.band_y1 - ctx->P.band_y0;
+  const FrameDev& P = ctx->P;
+  const uint32_t band_h = P.band_y1 - P.band_y0;
   float* o = (float*)dev_out;
   size_t stride = out_stride_bytes / 4;
   if (!o) {
-    const size_t planes = ctx->P.out_format == JXLGPU_OUT_RGB_F32 ? 1 : 3;
-    CU(ctx->out.ensure(planes * band_h * ctx->out_stride_floats * 4));
+    int rc = ensure_out(ctx);
+    if (rc) return rc;
     o = (float*)ctx->out.p;
     stride = ctx->out_stride_floats;
   } else if (out_stride_bytes % 4 || stride < ctx->out_stride_floats) {
     return JXLGPU_ERR_INVALID_ARGUMENT;
   }
-  return launch_all(ctx, o, stride, s);
+  int rc = launch_idct(ctx, ctx->need_row0, ctx->need_row1, P.need_y0, P.need_y1, s);
+  if (rc) return rc;
+  return launch_filter(ctx, P.band_y0, P.band_y1, P.band_y0, band_h, o, stride, s);
 }
 
 int jxlgpu_frame_finish(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes) {
   if (!ctx) return JXLGPU_ERR_INVALID_ARGUMENT;
   if (!ctx->in_frame) return JXLGPU_ERR_STATE;
   CU(cudaSetDevice(ctx->device));
-  // every group of the band (+ halo rows) must have arrived
-  for (uint32_t g = ctx->need_g0; g < ctx->need_g1; g++)
-    if (!ctx->submitted[g]) { ctx->last_error = "missing group"; return JXLGPU_ERR_STATE; }
-  for (uint32_t i = 0; i < ctx->num_threads; i++) {
-    CU(cudaEventRecord(ctx->up_events[i], ctx->up_streams[i]));
-    CU(cudaStreamWaitEvent(ctx->stream, ctx->up_events[i], 0));
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->stream_error) return ctx->stream_error;
+    // every group of the band (+ halo rows) must have arrived
+    for (uint32_t g = ctx->need_row0 * ctx->P.xg; g < ctx->need_row1 * ctx->P.xg; g++)
+      if (!ctx->submitted[g]) {
+        ctx->last_error = "missing group";
+        return JXLGPU_ERR_STATE;
+      }
+    int rc = pump(ctx);  // device-resident coefficients: nothing was streamed yet
+    if (rc) return rc;
+    for (uint32_t g = ctx->band_row0; g < ctx->band_row1; g++)
+      if (!ctx->row_filtered[g]) {
+        ctx->last_error = "scheduler left a row unrendered";
+        return JXLGPU_ERR_STATE;
+      }
   }
-  int rc = jxlgpu_render_device(ctx, nullptr, 0, nullptr);
-  if (rc) return rc;
-  if (out) {
+  if (out && out != ctx->host_out) {
     const uint32_t band_h = ctx->P.band_y1 - ctx->P.band_y0;
     const size_t row_bytes = ctx->out_stride_floats * 4;
     if (out_stride_bytes < row_bytes) return JXLGPU_ERR_INVALID_ARGUMENT;
@@ -453,6 +621,7 @@ int jxlgpu_frame_finish(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes) {
                          cudaMemcpyDeviceToHost, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->s_down));
   ctx->in_frame = false;
   return JXLGPU_OK;
 }
@@ -476,6 +645,7 @@ int jxlgpu_synchronize(jxlgpu_ctx* ctx) {
   if (!ctx) return JXLGPU_ERR_INVALID_ARGUMENT;
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->s_down));
   return JXLGPU_OK;
 }
 

@@ -55,6 +55,7 @@ struct FrameDev {
   uint32_t stage_mask;       // JXLGPU_STAGE_* bits actually run
   uint32_t out_format;
   uint32_t band_y0, band_y1; // pixel rows [band_y0, band_y1) rendered by the filter kernel
+  uint32_t out_y0, out_h;    // output addressing: image row stored at output row 0, rows per plane
   uint32_t need_y0, need_y1; // pixel rows of post-IDCT data the band's filters read (band +- halo)
   uint32_t plan_g0;          // first AC group handled by the plan kernel (band sharding)
   // side info (device)
@@ -1168,7 +1169,7 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_con
     float* t = cur; cur = nxt; nxt = t;
   }
   // ---- XYB -> linear RGB (dec_xyb-inl.h:38-86) + store ----
-  const int band_h = (int)(P.band_y1 - P.band_y0);
+  const int band_h = (int)P.out_h;
   for (int i = tid; i < kTW * kTH; i += kFilterThreads) {
     const int ty = halo + i / kTW, tx = halo + i % kTW;
     const int y = G.y0 + ty, x = G.x0 + tx;
@@ -1189,7 +1190,7 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_con
       lr = fmaf(P.opsin_m[2], mb, lr); lg = fmaf(P.opsin_m[5], mb, lg); lb = fmaf(P.opsin_m[8], mb, lb);
       a = lr; b = lg; c3 = lb;
     }
-    const int yo = y - (int)P.band_y0;
+    const int yo = y - (int)P.out_y0;
     if (P.out_format == 0) {
       float* o = out + (size_t)yo * out_row_stride + (size_t)x * 3;
       o[0] = a; o[1] = b; o[2] = c3;
@@ -1269,7 +1270,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
 
   const float kMinSigma = -3.90524291751269967465540850526868f;
   const bool xborder = ((x & 7) == 0 || (x & 7) == 7);
-  const int band_h = (int)(P.band_y1 - P.band_y0);
+  const int band_h = (int)P.out_h;
 
   // Final step of the chain: XYB -> linear RGB (dec_xyb-inl.h:38-86) and the global store.
   auto emit = [&](int r, float a, float b, float c3) {
@@ -1287,7 +1288,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
       lr = fmaf(P.opsin_m[2], mb, lr); lg = fmaf(P.opsin_m[5], mb, lg); lb = fmaf(P.opsin_m[8], mb, lb);
       a = lr; b = lg; c3 = lb;
     }
-    const int yo = r - (int)P.band_y0;
+    const int yo = r - (int)P.out_y0;
     if (P.out_format == 0) {
       float* o = out + (size_t)yo * out_row_stride + (size_t)x * 3;
       o[0] = a; o[1] = b; o[2] = c3;

@@ -25,7 +25,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared"]
 
 EXPORTS = ["jxlgpu_abi_version", "jxlgpu_error_string", "jxlgpu_last_error", "jxlgpu_create",
-           "jxlgpu_destroy", "jxlgpu_frame_begin", "jxlgpu_submit_group", "jxlgpu_frame_finish",
+           "jxlgpu_destroy", "jxlgpu_frame_begin", "jxlgpu_frame_set_output", "jxlgpu_submit_group",
+           "jxlgpu_frame_finish",
            "jxlgpu_set_device_coefficients", "jxlgpu_render_device", "jxlgpu_device_output",
            "jxlgpu_device_xyb", "jxlgpu_synchronize", "jxlgpu_launch_count", "jxlgpu_alloc_pinned",
            "jxlgpu_free_pinned", "jxlgpu_set_profiling", "jxlgpu_kernel_times"]
@@ -66,6 +67,7 @@ def lib():
         L.jxlgpu_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(abi.JxlGpuConfig)]
         L.jxlgpu_destroy.argtypes = [C.c_void_p]
         L.jxlgpu_frame_begin.argtypes = [C.c_void_p, C.POINTER(abi.JxlGpuFrame)]
+        L.jxlgpu_frame_set_output.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.jxlgpu_submit_group.argtypes = [C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p * 3, C.c_size_t]
         L.jxlgpu_frame_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.jxlgpu_set_device_coefficients.argtypes = [C.c_void_p, C.c_void_p]
@@ -131,6 +133,15 @@ class TransformPipeline:
         self._struct = desc.to_struct()
         self._check(lib().jxlgpu_frame_begin(self._h, C.byref(self._struct)), "jxlgpu_frame_begin")
 
+    def frame_set_output(self, out: np.ndarray):
+        """Announce the (ideally pinned) host output array: rows stream back as they finish."""
+        d = self.desc
+        _, rows = d.band_rows()
+        shape = (rows, d.xsize, 3) if d.out_format == abi.OUT_RGB_F32 else (3, rows, d.xsize)
+        assert out.shape == shape and out.dtype == np.float32 and out.flags.c_contiguous
+        stride = d.xsize * 4 * (3 if d.out_format == abi.OUT_RGB_F32 else 1)
+        self._check(lib().jxlgpu_frame_set_output(self._h, out.ctypes.data, stride), "jxlgpu_frame_set_output")
+
     def submit_group(self, group_idx: int, coeff_xyb, thread_id: int = 0, ncoeff: int | None = None):
         """coeff_xyb: three 1-D arrays (X, Y, B) of the frame's ac_type for AC group `group_idx`."""
         want = np.int16 if self.desc.ac_type == abi.AC_INT16 else np.int32
@@ -152,10 +163,18 @@ class TransformPipeline:
         return out
 
     # convenience: whole frame from a (3, num_groups, 65536) host array
-    def decode_frame(self, desc: abi.FrameDesc, coeffs: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+    def decode_frame(self, desc: abi.FrameDesc, coeffs: np.ndarray, out: np.ndarray | None = None,
+                     order=None, stream_output: bool = False) -> np.ndarray:
+        """frame_begin + submit_group for every group (`order`: submission order) + frame_finish."""
         self.set_device_coefficients(None)
         self.frame_begin(desc)
-        for g in range(desc.num_groups):
+        if stream_output:
+            if out is None:
+                _, rows = desc.band_rows()
+                shape = (rows, desc.xsize, 3) if desc.out_format == abi.OUT_RGB_F32 else (3, rows, desc.xsize)
+                out = np.empty(shape, np.float32)
+            self.frame_set_output(out)
+        for g in (order if order is not None else range(desc.num_groups)):
             self.submit_group(g, [coeffs[c, g] for c in range(3)])
         return self.frame_finish(out)
 

@@ -151,6 +151,24 @@ def test_full_size_4096_against_oracle(pipe):
     assert_same(pipe.decode_frame(desc, coeffs), got, "second run")
 
 
+def test_streaming_any_submission_order(pipe):
+    """Groups may arrive in any order from the host's worker threads (FakeParallelRunner-style
+    shuffle, render_pipeline_test.cc:254-255); rows are transformed / filtered / copied back as
+    they complete. Result identical to the in-order run."""
+    desc, coeffs = wl.synthetic_frame(900, 1300, seed=33)     # 4 x 6 groups
+    want = pipe.decode_frame(desc, coeffs)
+    rng = np.random.default_rng(123)
+    for trial in range(3):
+        order = rng.permutation(desc.num_groups)
+        assert_same(pipe.decode_frame(desc, coeffs, order=order, stream_output=bool(trial % 2)), want,
+                    f"shuffle {trial}")
+    out = pipeline.pinned_array((desc.ysize, desc.xsize, 3), np.float32)
+    out[:] = -1
+    got = pipe.decode_frame(desc, coeffs, out=out, order=rng.permutation(desc.num_groups), stream_output=True)
+    assert got is out
+    assert_same(got, want, "pinned streamed output")
+
+
 def test_submit_errors(pipe):
     desc, coeffs = wl.synthetic_frame(300, 300, seed=1)
     pipe.set_device_coefficients(None)
