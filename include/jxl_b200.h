@@ -168,6 +168,10 @@ JXLGPU_API int jxlgpu_frame_set_output(jxlgpu_ctx* ctx, void* out, size_t out_st
 JXLGPU_API int jxlgpu_submit_group(jxlgpu_ctx* ctx, uint32_t group_idx, size_t thread_id,
                                    const void* const coeff[3], size_t ncoeff);
 
+/* Same, for `n` groups in one call: coeff[3*i + c] is channel c of group group_idx[i]. */
+JXLGPU_API int jxlgpu_submit_groups(jxlgpu_ctx* ctx, size_t n, const uint32_t* group_idx, size_t thread_id,
+                                    const void* const* coeff, const size_t* ncoeff);
+
 /* Runs the kernels for every submitted group of the band and copies the band's pixels to
  * `out` (host; row stride in bytes).  out == NULL keeps the result on the device
  * (jxlgpu_device_output).  Replaces LowMemoryRenderPipeline::ProcessBuffers + the write

@@ -194,15 +194,21 @@ int launch_idct(jxlgpu_ctx* ctx, uint32_t row0, uint32_t row1, uint32_t need_y0,
     CU(cudaStreamWaitEvent(sm, ctx->ev_fork, 0));
     CU(cudaStreamWaitEvent(sl, ctx->ev_fork, 0));
   }
-  if (P.ac_is32) idct8_kernel<true><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
-  else idct8_kernel<false><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
-  if (prof) CU(cudaEventRecord(ctx->prof_ev[2], s));
+  auto run8 = [&]() {
+    if (P.ac_is32) idct8_kernel<true><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
+    else idct8_kernel<false><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
+  };
+  if (prof) {
+    run8();
+    CU(cudaEventRecord(ctx->prof_ev[2], s));
+  }
   if (P.ac_is32) idct_mid_kernel<true><<<grid_mid, kSmallWarpsPerCta * 32, 0, sm>>>(P);
   else idct_mid_kernel<false><<<grid_mid, kSmallWarpsPerCta * 32, 0, sm>>>(P);
   if (prof) CU(cudaEventRecord(ctx->prof_ev[3], s));
   if (P.ac_is32) idct_large_kernel<true><<<grid_large, 256, 0, sl>>>(P);
   else idct_large_kernel<false><<<grid_large, 256, 0, sl>>>(P);
   if (prof) CU(cudaEventRecord(ctx->prof_ev[4], s));
+  if (!prof) run8();  // after the (usually tiny) side kernels grabbed their few SM slots
   if (!prof) {
     CU(cudaEventRecord(ctx->ev_mid, sm));
     CU(cudaEventRecord(ctx->ev_large, sl));
@@ -545,6 +551,16 @@ int jxlgpu_submit_group(jxlgpu_ctx* ctx, uint32_t g, size_t thread_id, const voi
       ctx->stream_error = rc;
       return rc;
     }
+  }
+  return JXLGPU_OK;
+}
+
+int jxlgpu_submit_groups(jxlgpu_ctx* ctx, size_t n, const uint32_t* group_idx, size_t thread_id,
+                         const void* const* coeff, const size_t* ncoeff) {
+  if (!ctx || !group_idx || !coeff || !ncoeff) return JXLGPU_ERR_INVALID_ARGUMENT;
+  for (size_t i = 0; i < n; i++) {
+    int rc = jxlgpu_submit_group(ctx, group_idx[i], thread_id, coeff + 3 * i, ncoeff[i]);
+    if (rc) return rc;
   }
   return JXLGPU_OK;
 }

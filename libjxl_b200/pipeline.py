@@ -26,7 +26,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 EXPORTS = ["jxlgpu_abi_version", "jxlgpu_error_string", "jxlgpu_last_error", "jxlgpu_create",
            "jxlgpu_destroy", "jxlgpu_frame_begin", "jxlgpu_frame_set_output", "jxlgpu_submit_group",
-           "jxlgpu_frame_finish",
+           "jxlgpu_submit_groups", "jxlgpu_frame_finish",
            "jxlgpu_set_device_coefficients", "jxlgpu_render_device", "jxlgpu_device_output",
            "jxlgpu_device_xyb", "jxlgpu_synchronize", "jxlgpu_launch_count", "jxlgpu_alloc_pinned",
            "jxlgpu_free_pinned", "jxlgpu_set_profiling", "jxlgpu_kernel_times"]
@@ -69,6 +69,7 @@ def lib():
         L.jxlgpu_frame_begin.argtypes = [C.c_void_p, C.POINTER(abi.JxlGpuFrame)]
         L.jxlgpu_frame_set_output.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.jxlgpu_submit_group.argtypes = [C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p * 3, C.c_size_t]
+        L.jxlgpu_submit_groups.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.jxlgpu_frame_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.jxlgpu_set_device_coefficients.argtypes = [C.c_void_p, C.c_void_p]
         L.jxlgpu_render_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -150,6 +151,19 @@ class TransformPipeline:
         n = ncoeff if ncoeff is not None else self.desc.group_ncoeff(group_idx)
         ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in arrs])
         self._check(lib().jxlgpu_submit_group(self._h, group_idx, thread_id, ptrs, n), "jxlgpu_submit_group")
+
+    @staticmethod
+    def make_batch(groups, host_groups):
+        """Pre-marshalled arguments for submit_batch: (n, idx array, ptr array, ncoeff array)."""
+        n = len(groups)
+        idx = (C.c_uint32 * n)(*groups)
+        ptrs = (C.c_void_p * (3 * n))(*[host_groups[g][c].ctypes.data for g in groups for c in range(3)])
+        nco = (C.c_size_t * n)(*[host_groups[g][0].size for g in groups])
+        return n, idx, ptrs, nco
+
+    def submit_batch(self, batch, thread_id: int = 0):
+        n, idx, ptrs, nco = batch
+        self._check(lib().jxlgpu_submit_groups(self._h, n, idx, thread_id, ptrs, nco), "jxlgpu_submit_groups")
 
     def frame_finish(self, out: np.ndarray | None = None) -> np.ndarray:
         d = self.desc
