@@ -300,17 +300,16 @@ def main() -> int:
 
     # ---------------- end-to-end arm: host buffers through the C ABI ----------------
     pipe.set_device_coefficients(None)
+    # Host layout: one pinned [3][65536] block per AC group (what a pinned ACImage subclass gives
+    # libjxl's entropy decoder to write into) -> each group is one DMA.
+    host_all = pipeline.pinned_array((len(need), 3, abi.GROUP_COEFFS), coeffs.dtype)
     host_groups = {}
     h2d = 0
-    for g in need:
+    for i, g in enumerate(need):
         n = desc.group_ncoeff(g)
-        bufs = []
-        for c in range(3):
-            a = pipeline.pinned_array((n,), coeffs.dtype)
-            a[:] = coeffs[c, g, :n]
-            bufs.append(a)
-            h2d += a.nbytes
-        host_groups[g] = bufs
+        host_all[i] = coeffs[:, g]
+        host_groups[g] = [host_all[i, c, :n] for c in range(3)]
+        h2d += (2 * abi.GROUP_COEFFS + n) * coeffs.dtype.itemsize
     yb, xb = desc.ysize_blocks, desc.xsize_blocks
     h2d += yb * xb * (1 + 4 + 1 + 12) + desc.dequant.nbytes + 2 * desc.ytox.size
     host_out = pipeline.pinned_array((band_rows, W, 3), np.float32)

@@ -162,7 +162,9 @@ JXLGPU_API int jxlgpu_frame_set_output(jxlgpu_ctx* ctx, void* out, size_t out_st
  * channel c (X, Y, B) in libjxl's ACImage order -- varblocks in raster order of their
  * first block, each 64*covered_blocks long (dec_group.cc:335-359).  Asynchronous H2D on
  * the stream of `thread_id`: pinned buffers must stay valid until frame_finish, pageable ones
- * are staged by the driver before the call returns.  When the last group of an AC-group row
+ * are staged by the driver before the call returns.  If the three channel buffers are one
+ * contiguous [3][65536] block (coeff[c] == coeff[0] + c*65536 elements -- e.g. an ACImage subclass
+ * over pinned memory, lib/jxl/dct_util.h:43-91) the group travels as a single DMA.  When the last group of an AC-group row
  * arrives, that row's kernels are enqueued right away (see jxl_b200.cu).
  * Replaces dec_group.cc:431-450 + RenderPipelineInput::Done(). */
 JXLGPU_API int jxlgpu_submit_group(jxlgpu_ctx* ctx, uint32_t group_idx, size_t thread_id,

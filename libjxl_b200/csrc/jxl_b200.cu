@@ -74,7 +74,7 @@ struct jxlgpu_ctx {
   void* host_out = nullptr;
   size_t host_out_stride = 0;
   int stream_error = 0;
-  DevBuf acs, quant, sharp, ytox, ytob, dc, dq, coeff[3], coeff_off, sigma, list, counts, xyb, out;
+  DevBuf acs, quant, sharp, ytox, ytob, dc, dq, coeff, coeff_off, sigma, list, counts, xyb, out;
   size_t out_stride_floats = 0;
   std::atomic<uint64_t> launches{0};
   bool force_generic_filter = false;  // JXLGPU_FORCE_GENERIC_FILTER=1: tile kernel for every chain
@@ -369,7 +369,7 @@ void jxlgpu_destroy(jxlgpu_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (DevBuf* b : {&ctx->acs, &ctx->quant, &ctx->sharp, &ctx->ytox, &ctx->ytob, &ctx->dc, &ctx->dq,
-                    &ctx->coeff[0], &ctx->coeff[1], &ctx->coeff[2], &ctx->coeff_off, &ctx->sigma,
+                    &ctx->coeff, &ctx->coeff_off, &ctx->sigma,
                     &ctx->list, &ctx->counts, &ctx->xyb, &ctx->out})
     b->release();
   for (auto s : ctx->up_streams) cudaStreamDestroy(s);
@@ -453,8 +453,8 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   P.row_stride = xb * 8;
   P.plane_stride = P.row_stride * yb * 8;
   CU(ctx->xyb.ensure(3 * P.plane_stride * 4));
-  if (!ctx->coeff_external)
-    for (int c = 0; c < 3; c++) CU(ctx->coeff[c].ensure((size_t)ctx->num_groups * 65536 * ctx->elem_size));
+  // host-fed coefficients live group-major on the device: [group][channel][65536]
+  if (!ctx->coeff_external) CU(ctx->coeff.ensure((size_t)ctx->num_groups * 3 * 65536 * ctx->elem_size));
   cudaStream_t s = ctx->stream;
   CU(upload_plane<uint8_t>(ctx->acs.p, f->ac_strategy, f->ac_strategy_stride, xb, yb, s));
   CU(upload_plane<int32_t>(ctx->quant.p, f->raw_quant, f->raw_quant_stride, xb, yb, s));
@@ -473,8 +473,10 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   P.dc = (const float*)ctx->dc.p;
   P.dq = (const float*)ctx->dq.p;
   memcpy(P.dq_off, f->dequant_offsets, sizeof(P.dq_off));
-  if (!ctx->coeff_external)
-    for (int c = 0; c < 3; c++) P.coeff[c] = ctx->coeff[c].p;
+  if (!ctx->coeff_external) {
+    for (int c = 0; c < 3; c++) P.coeff[c] = (uint8_t*)ctx->coeff.p + (size_t)c * 65536 * ctx->elem_size;
+    P.coeff_gstride = 3 * 65536;
+  }
   P.coeff_off = (uint16_t*)ctx->coeff_off.p;
   P.sigma = (float*)ctx->sigma.p;
   P.list = (uint32_t*)ctx->list.p;
@@ -532,13 +534,25 @@ int jxlgpu_submit_group(jxlgpu_ctx* ctx, uint32_t g, size_t thread_id, const voi
   cudaError_t e = cudaSetDevice(ctx->device);
   if (e != cudaSuccess) return JXLGPU_ERR_CUDA;
   cudaStream_t s = ctx->up_streams[thread_id];
-  for (int c = 0; c < 3; c++) {
+  for (int c = 0; c < 3; c++)
     if (!coeff[c]) return JXLGPU_ERR_INVALID_ARGUMENT;
-    e = cudaMemcpyAsync((uint8_t*)ctx->coeff[c].p + (size_t)g * 65536 * ctx->elem_size, coeff[c],
-                        ncoeff * ctx->elem_size, cudaMemcpyHostToDevice, s);
+  const size_t es = ctx->elem_size;
+  uint8_t* dst = (uint8_t*)ctx->coeff.p + (size_t)g * 3 * 65536 * es;
+  const uint8_t* c0 = (const uint8_t*)coeff[0];
+  if ((const uint8_t*)coeff[1] == c0 + 65536 * es && (const uint8_t*)coeff[2] == c0 + 2 * 65536 * es) {
+    // the host keeps the group as one [3][65536] block (e.g. a pinned ACImage): one DMA
+    e = cudaMemcpyAsync(dst, c0, (2 * 65536 + ncoeff) * es, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) {
       std::lock_guard<std::mutex> lk(ctx->mu);
-      return fail_cuda(ctx, e, "cudaMemcpyAsync(coefficients)");
+      return fail_cuda(ctx, e, "cudaMemcpyAsync(coefficient group)");
+    }
+  } else {
+    for (int c = 0; c < 3; c++) {
+      e = cudaMemcpyAsync(dst + (size_t)c * 65536 * es, coeff[c], ncoeff * es, cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        return fail_cuda(ctx, e, "cudaMemcpyAsync(coefficients)");
+      }
     }
   }
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -573,6 +587,7 @@ int jxlgpu_set_device_coefficients(jxlgpu_ctx* ctx, const void* const dev_coeff[
   }
   ctx->coeff_external = true;
   for (int c = 0; c < 3; c++) ctx->P.coeff[c] = dev_coeff[c];
+  ctx->P.coeff_gstride = 65536;
   if (ctx->in_frame) {
     ctx->submitted.assign(ctx->num_groups, 1);
     ctx->row_count.assign(ctx->P.yg, ctx->P.xg);

@@ -68,7 +68,8 @@ struct FrameDev {
   const float* dc;           // 3 planes [yb][xb]
   const float* dq;           // dequant table
   uint32_t dq_off[3 * kNumStrategies];
-  const void* coeff[3];      // [num_groups][65536]
+  const void* coeff[3];      // channel c of group g starts at coeff[c] + g * coeff_gstride elements
+  size_t coeff_gstride;      // 65536 (three planes) or 3*65536 (group-major [g][c][65536])
   // produced by the plan kernel
   uint16_t* coeff_off;       // [yb][xb] offset/64 of the varblock inside its group (first blocks)
   float* sigma;              // [yb][xb] inverse sigma
@@ -175,7 +176,7 @@ __device__ __forceinline__ VarblockCtx make_ctx(const FrameDev& P, uint32_t entr
   v.aby = entry >> 16;
   const size_t bi = (size_t)v.aby * P.xb + v.abx;
   const uint32_t g = (v.aby >> 5) * P.xg + (v.abx >> 5);
-  v.cbase = (size_t)g * 65536u + (size_t)P.coeff_off[bi] * 64u;
+  v.cbase = (size_t)g * P.coeff_gstride + (size_t)P.coeff_off[bi] * 64u;
   const float s = P.inv_global_scale / (float)P.quant[bi];
   v.sx = s * P.x_dm;
   v.sy = s;
@@ -1214,12 +1215,22 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_con
 // became computable after the previous step, so one __syncthreads() per step
 // orders everything.  No vertical halo is recomputed inside a segment, the
 // horizontal halo costs 2*H of 256 lanes, and nothing but the final RGB row is
-// written to global memory.  Arithmetic (operation order, FMAs) is identical to
-// filter_kernel above and to the reference stages it cites.
+// written to global memory.
+//
+// The row loop has two bodies generated from the same source: the generic one
+// (row-range predicates, row mirroring, lane-range predicates) runs the few
+// steps of pipeline fill / drain and everything near the top or bottom image
+// edge; the STEADY one assumes every stage has a valid, unmirrored row this
+// step and lets out-of-range lanes compute garbage that nobody reads (the
+// shared-memory rings are padded so their neighbour reads stay in bounds).
+//
+// Arithmetic (operation order, FMAs) is identical to filter_kernel above and to
+// the reference stages it cites.
 // ===========================================================================
 namespace jxlb {
 
 constexpr int kStripThreads = 256;
+constexpr int kStripPad = 4;  // floats of padding before/after the rings
 
 template <uint32_t MASK>
 struct StripCfg {
@@ -1229,7 +1240,7 @@ struct StripCfg {
   // ring sizes (rows, power of two >= 2*border+2) of each stage's input; 0 when absent
   static constexpr int NG = G ? 4 : 0, N0 = E0 ? 8 : 0, N1 = E1 ? 8 : 0, N2 = E2 ? 4 : 0;
   static constexpr int kRows = NG + N0 + N1 + N2;
-  static constexpr size_t kSmemBytes = (size_t)(kRows ? kRows : 1) * 3 * kStripThreads * sizeof(float);
+  static constexpr size_t kSmemBytes = ((size_t)(kRows ? kRows : 1) * 3 * kStripThreads + 2 * kStripPad) * sizeof(float);
   static constexpr int kOutCols = kStripThreads - 2 * H;
 };
 
@@ -1247,13 +1258,14 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
   const int W = (int)P.xsize, HI = (int)P.ysize;
   const int x = x0 - H + t;  // image column of this thread
   const bool xin = x >= 0 && x < W;
+  const int xs = min(max(x, 0), W - 1) >> 3;  // sigma column (clamped: garbage lanes stay in bounds)
   // strip-relative indices of the horizontal neighbours x-3 .. x+3 (mirrored at the image edge)
   int cn[7];
 #pragma unroll
   for (int d = -3; d <= 3; d++) cn[d + 3] = EDGE ? (mirror_i(x + d, W) - (x0 - H)) : (t + d);
   auto mrow = [&](int r) { return r < 0 ? -r - 1 : (r >= HI ? 2 * HI - 1 - r : r); };
 
-  float* ringG = smem;
+  float* ringG = smem + kStripPad;
   float* ring0 = ringG + C::NG * 3 * kStripThreads;
   float* ring1 = ring0 + C::N0 * 3 * kStripThreads;
   float* ring2 = ring1 + C::N1 * 3 * kStripThreads;
@@ -1271,9 +1283,11 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
   const float kMinSigma = -3.90524291751269967465540850526868f;
   const bool xborder = ((x & 7) == 0 || (x & 7) == 7);
   const int band_h = (int)P.out_h;
+  const bool emit_lane = xin && t >= H && t < kStripThreads - H;
 
   // Final step of the chain: XYB -> linear RGB (dec_xyb-inl.h:38-86) and the global store.
   auto emit = [&](int r, float a, float b, float c3) {
+    if (!emit_lane) return;
     if constexpr (C::XYB) {
       float gr = b + a, gg = b - a, gb = c3;
       gr = gr - P.opsin_cbrt[0];
@@ -1325,26 +1339,33 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
   using T3 = std::integral_constant<int, 3>;
   using T4 = std::integral_constant<int, 4>;
 
-  // steps between loading a row and the last stage producing that row
-  constexpr int kDelay = (C::G ? 2 : 0) + (C::E0 ? 4 : 0) + (C::E1 ? 3 : 0) + (C::E2 ? 2 : 0);
+  // cumulative delays (steps between loading row r and the stage producing row r)
+  constexpr int dG = C::G ? 2 : 0;
+  constexpr int d0 = dG + (C::E0 ? 4 : 0);
+  constexpr int d1 = d0 + (C::E1 ? 3 : 0);
+  constexpr int d2 = d1 + (C::E2 ? 2 : 0);
   const int r_in_lo = lo(H), r_in_hi = hi(H);
-  const int r_end = hi(0) + kDelay;  // after this many input-row steps the last output row is out
+  const int r_end = hi(0) + d2;  // after this many input-row steps the last output row is out
 
-  for (int rin = r_in_lo; rin < r_end; rin++) {
+  // One pipeline step. ST (steady): every stage has an in-range, unmirrored row; lanes are not
+  // range-checked (only `xin` in edge strips, where garbage lanes would read global memory).
+  auto step = [&](auto steady_tag, int rin) {
+    constexpr bool ST = decltype(steady_tag)::value;
+    auto mr = [&](int r) { return ST ? r : mrow(r); };
+    const bool lane_ok = (ST && !EDGE) ? true : xin;
     // ---- loader: XYB row rin ----
-    if (rin < r_in_hi && xin) {
+    if ((ST || rin < r_in_hi) && xin) {
       const size_t off = (size_t)rin * P.row_stride + x;
       const float a = __ldg(P.xyb + off);
       const float b = __ldg(P.xyb + P.plane_stride + off);
       const float c3 = __ldg(P.xyb + 2 * P.plane_stride + off);
       deliver(T0(), rin, a, b, c3);
     }
-    int r = rin;
     // ---- Gaborish (stage_gaborish.cc:56-100) ----
     if constexpr (C::G) {
-      r -= 2;
-      if (r >= lo(H - hG) && r < hi(H - hG) && xin && t >= hG && t < kStripThreads - hG) {
-        const int rt = mrow(r - 1), rb = mrow(r + 1);
+      const int r = rin - dG;
+      if ((ST || (r >= lo(H - hG) && r < hi(H - hG) && t >= hG && t < kStripThreads - hG)) && lane_ok) {
+        const int rt = mr(r - 1), rb = mr(r + 1);
         float v[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
@@ -1360,9 +1381,9 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
     }
     // ---- EPF0 (stage_epf.cc:54-193) ----
     if constexpr (C::E0) {
-      r -= 4;
-      if (r >= lo(H - h0) && r < hi(H - h0) && xin && t >= h0 && t < kStripThreads - h0) {
-        const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + (x >> 3));
+      const int r = rin - d0;
+      if ((ST || (r >= lo(H - h0) && r < hi(H - h0) && t >= h0 && t < kStripThreads - h0)) && lane_ok) {
+        const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + xs);
         float X = ring_row(ring0, C::N0, r, 0)[t];
         float Y = ring_row(ring0, C::N0, r, 1)[t];
         float B = ring_row(ring0, C::N0, r, 2)[t];
@@ -1373,7 +1394,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
           const float inv_sigma = s * vsm;
           int rr[7];
 #pragma unroll
-          for (int k = 0; k < 7; k++) rr[k] = mrow(r + k - 3);
+          for (int k = 0; k < 7; k++) rr[k] = mr(r + k - 3);
           const int dy12[12] = {-2, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 2};
           const int dx12[12] = {0, -1, 0, 1, -2, -1, 1, 2, -1, 0, 1, 0};
           const int py5[5] = {0, -1, 0, 1, 0};
@@ -1420,27 +1441,31 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
     }
     // ---- EPF1 (stage_epf.cc:197-379) ----
     if constexpr (C::E1) {
-      r -= 3;
-      if (r >= lo(H - h1) && r < hi(H - h1) && xin && t >= h1 && t < kStripThreads - h1) {
-        const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + (x >> 3));
-        float X = ring_row(ring1, C::N1, r, 0)[t];
-        float Y = ring_row(ring1, C::N1, r, 1)[t];
-        float B = ring_row(ring1, C::N1, r, 2)[t];
+      const int r = rin - d1;
+      if ((ST || (r >= lo(H - h1) && r < hi(H - h1) && t >= h1 && t < kStripThreads - h1)) && lane_ok) {
+        const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + xs);
+        const float* q2x = ring_row(ring1, C::N1, r, 0);
+        float X = q2x[t];
+        float Y = q2x[kStripThreads + t];
+        float B = q2x[2 * kStripThreads + t];
         if (!(s < kMinSigma)) {
           const int iy = r & 7;
           const float sm_ = P.epf_sm[1];
           const float vsm = (iy == 0 || iy == 7 || xborder) ? sm_ * P.epf_border_mul : sm_;
           const float inv_sigma = s * vsm;
-          const int r0 = mrow(r - 2), r1 = mrow(r - 1), r3 = mrow(r + 1), r4 = mrow(r + 2);
+          const float* q0x = ring_row(ring1, C::N1, mr(r - 2), 0);
+          const float* q1x = ring_row(ring1, C::N1, mr(r - 1), 0);
+          const float* q3x = ring_row(ring1, C::N1, mr(r + 1), 0);
+          const float* q4x = ring_row(ring1, C::N1, mr(r + 2), 0);
           float sad0 = 0.0f, sad1 = 0.0f, sad2 = 0.0f, sad3 = 0.0f;
           float nb[3][4];  // neighbour pixels N, W, E, S per channel
 #pragma unroll
           for (int c = 0; c < 3; c++) {
-            const float* q0 = ring_row(ring1, C::N1, r0, c);
-            const float* q1 = ring_row(ring1, C::N1, r1, c);
-            const float* q2 = ring_row(ring1, C::N1, r, c);
-            const float* q3 = ring_row(ring1, C::N1, r3, c);
-            const float* q4 = ring_row(ring1, C::N1, r4, c);
+            const float* q0 = q0x + c * kStripThreads;
+            const float* q1 = q1x + c * kStripThreads;
+            const float* q2 = q2x + c * kStripThreads;
+            const float* q3 = q3x + c * kStripThreads;
+            const float* q4 = q4x + c * kStripThreads;
             const float p20 = q0[t], p11 = q1[cn[2]], p21 = q1[t], p31 = q1[cn[4]];
             const float p02 = q2[cn[1]], p12 = q2[cn[2]], p22 = q2[t], p32 = q2[cn[4]], p42 = q2[cn[5]];
             const float p13 = q3[cn[2]], p23 = q3[t], p33 = q3[cn[4]], p24 = q4[t];
@@ -1494,9 +1519,9 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
     }
     // ---- EPF2 (stage_epf.cc:383-506) ----
     if constexpr (C::E2) {
-      r -= 2;
-      if (r >= lo(0) && r < hi(0) && xin && t >= h2 && t < kStripThreads - h2) {
-        const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + (x >> 3));
+      const int r = rin - d2;
+      if ((ST || (r >= lo(0) && r < hi(0) && t >= h2 && t < kStripThreads - h2)) && lane_ok) {
+        const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + xs);
         float X = ring_row(ring2, C::N2, r, 0)[t];
         float Y = ring_row(ring2, C::N2, r, 1)[t];
         float B = ring_row(ring2, C::N2, r, 2)[t];
@@ -1505,7 +1530,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
           const float sm_ = P.epf_sm[2];
           const float vsm = (iy == 0 || iy == 7 || xborder) ? sm_ * P.epf_border_mul : sm_;
           const float inv_sigma = s * vsm;
-          const int nr[4] = {mrow(r - 1), r, r, mrow(r + 1)};
+          const int nr[4] = {mr(r - 1), r, r, mr(r + 1)};
           const int nc[4] = {t, cn[2], cn[4], t};
           const float rx = X, ry = Y, rb = B;
           float w = 1.0f;
@@ -1530,7 +1555,24 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
       }
     }
     if constexpr (H > 0) __syncthreads();
-  }
+  };
+
+  // Steady interval of rin: every stage's row r = rin - d is produced this step (inside its row
+  // range) and its whole input window r-b .. r+b lies inside the image (no mirroring).
+  int s_lo = r_in_lo, s_hi = r_in_hi;
+  auto constrain = [&](int d, int b, int rem) {
+    s_lo = max(s_lo, max(lo(rem), b) + d);
+    s_hi = min(s_hi, min(hi(rem), HI - b) + d);
+  };
+  if (C::G) constrain(dG, 1, H - hG);
+  if (C::E0) constrain(d0, 3, H - h0);
+  if (C::E1) constrain(d1, 2, H - h1);
+  if (C::E2) constrain(d2, 1, 0);
+  if (s_hi < s_lo) s_hi = s_lo;
+  int rin = r_in_lo;
+  for (; rin < min(s_lo, r_end); rin++) step(std::false_type(), rin);
+  for (; rin < min(s_hi, r_end); rin++) step(std::true_type(), rin);
+  for (; rin < r_end; rin++) step(std::false_type(), rin);
 }
 
 template <uint32_t MASK>
