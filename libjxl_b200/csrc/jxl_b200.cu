@@ -58,6 +58,11 @@ struct jxlgpu_ctx {
   cudaEvent_t ev_fork = nullptr, ev_mid = nullptr, ev_large = nullptr, ev_filter = nullptr, ev_ext = nullptr;
   std::vector<cudaStream_t> up_streams;
   std::vector<cudaEvent_t> up_events;
+  // row_events[r]: recorded on the upload stream after the latest copy of AC-group row r, so that
+  // a row's kernels wait for exactly that row's DMAs and nothing enqueued later
+  std::vector<cudaEvent_t> row_events;
+  std::vector<uint8_t> row_event_used;
+  uint32_t row_cap = 0;
   int num_sms = 148;
   bool in_frame = false;
   bool coeff_external = false;
@@ -101,11 +106,19 @@ size_t out_floats_per_row(const jxlgpu_frame& f) {
   return f.out_format == JXLGPU_OUT_RGB_F32 ? (size_t)f.xsize * 3 : (size_t)f.xsize;
 }
 
-// copies a strided host plane into a dense device plane
+// copies a strided host plane into a dense device plane (one linear DMA when it is dense)
 template <typename T>
 cudaError_t upload_plane(void* dst, const T* src, size_t stride, size_t w, size_t h, cudaStream_t s) {
+  if (stride == w) return cudaMemcpyAsync(dst, src, w * h * sizeof(T), cudaMemcpyHostToDevice, s);
   return cudaMemcpy2DAsync(dst, w * sizeof(T), src, stride * sizeof(T), w * sizeof(T), h,
                            cudaMemcpyHostToDevice, s);
+}
+
+// rows of the output buffer -> host (linear DMA when the host rows are dense)
+cudaError_t download_rows(void* dst, size_t dst_stride, const void* src, size_t row_bytes, size_t rows,
+                          cudaStream_t s) {
+  if (dst_stride == row_bytes) return cudaMemcpyAsync(dst, src, row_bytes * rows, cudaMemcpyDeviceToHost, s);
+  return cudaMemcpy2DAsync(dst, dst_stride, src, row_bytes, row_bytes, rows, cudaMemcpyDeviceToHost, s);
 }
 
 uint32_t effective_mask(const jxlgpu_frame& f) {
@@ -255,10 +268,7 @@ int pump(jxlgpu_ctx* ctx) {
     if (ctx->row_idct[g] || ctx->row_count[g] < P.xg) continue;
     // the row's coefficients are in flight on the upload streams
     if (!ctx->coeff_external)
-      for (uint32_t i = 0; i < ctx->num_threads; i++) {
-        CU(cudaEventRecord(ctx->up_events[i], ctx->up_streams[i]));
-        CU(cudaStreamWaitEvent(s, ctx->up_events[i], 0));
-      }
+      if (ctx->row_event_used[g]) CU(cudaStreamWaitEvent(s, ctx->row_events[g], 0));
     uint32_t ny0 = g * 256u, ny1 = (g + 1) * 256u;
     if (ny0 < P.need_y0) ny0 = P.need_y0;
     if (ny1 > P.need_y1 || g + 1 == ctx->need_row1) ny1 = P.need_y1;
@@ -289,9 +299,8 @@ int pump(jxlgpu_ctx* ctx) {
       const size_t planes = P.out_format == JXLGPU_OUT_RGB_F32 ? 1 : 3;
       for (size_t pl = 0; pl < planes; pl++) {
         const size_t row = pl * band_h + (y0 - P.band_y0);
-        CU(cudaMemcpy2DAsync((uint8_t*)ctx->host_out + row * ctx->host_out_stride, ctx->host_out_stride,
-                             (uint8_t*)ctx->out.p + row * row_bytes, row_bytes, row_bytes, y1 - y0,
-                             cudaMemcpyDeviceToHost, ctx->s_down));
+        CU(download_rows((uint8_t*)ctx->host_out + row * ctx->host_out_stride, ctx->host_out_stride,
+                         (uint8_t*)ctx->out.p + row * row_bytes, row_bytes, y1 - y0, ctx->s_down));
       }
     }
   }
@@ -374,6 +383,8 @@ void jxlgpu_destroy(jxlgpu_ctx* ctx) {
     b->release();
   for (auto s : ctx->up_streams) cudaStreamDestroy(s);
   for (auto ev : ctx->up_events) cudaEventDestroy(ev);
+  for (auto ev : ctx->row_events)
+    if (ev) cudaEventDestroy(ev);
   for (auto ev : ctx->prof_ev)
     if (ev) cudaEventDestroy(ev);
   for (cudaEvent_t ev : {ctx->ev_fork, ctx->ev_mid, ctx->ev_large, ctx->ev_filter, ctx->ev_ext})
@@ -509,6 +520,13 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   ctx->row_count.assign(P.yg, ctx->coeff_external ? P.xg : 0);
   ctx->row_idct.assign(P.yg, 0);
   ctx->row_filtered.assign(P.yg, 0);
+  if (P.yg > ctx->row_cap) {
+    for (auto ev : ctx->row_events) cudaEventDestroy(ev);
+    ctx->row_cap = P.yg;
+    ctx->row_events.assign(ctx->row_cap, nullptr);
+    for (auto& ev : ctx->row_events) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  ctx->row_event_used.assign(ctx->row_cap, 0);
   ctx->host_out = nullptr;
   ctx->host_out_stride = 0;
   ctx->stream_error = 0;
@@ -526,39 +544,14 @@ int jxlgpu_frame_set_output(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes)
   return JXLGPU_OK;
 }
 
-int jxlgpu_submit_group(jxlgpu_ctx* ctx, uint32_t g, size_t thread_id, const void* const coeff[3], size_t ncoeff) {
-  if (!ctx || !coeff) return JXLGPU_ERR_INVALID_ARGUMENT;
-  if (!ctx->in_frame || ctx->coeff_external) return JXLGPU_ERR_STATE;
-  if (g >= ctx->num_groups || thread_id >= ctx->num_threads || ncoeff > 65536) return JXLGPU_ERR_INVALID_ARGUMENT;
-  // NB: cudaSetDevice is per host thread
-  cudaError_t e = cudaSetDevice(ctx->device);
-  if (e != cudaSuccess) return JXLGPU_ERR_CUDA;
-  cudaStream_t s = ctx->up_streams[thread_id];
-  for (int c = 0; c < 3; c++)
-    if (!coeff[c]) return JXLGPU_ERR_INVALID_ARGUMENT;
-  const size_t es = ctx->elem_size;
-  uint8_t* dst = (uint8_t*)ctx->coeff.p + (size_t)g * 3 * 65536 * es;
-  const uint8_t* c0 = (const uint8_t*)coeff[0];
-  if ((const uint8_t*)coeff[1] == c0 + 65536 * es && (const uint8_t*)coeff[2] == c0 + 2 * 65536 * es) {
-    // the host keeps the group as one [3][65536] block (e.g. a pinned ACImage): one DMA
-    e = cudaMemcpyAsync(dst, c0, (2 * 65536 + ncoeff) * es, cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) {
-      std::lock_guard<std::mutex> lk(ctx->mu);
-      return fail_cuda(ctx, e, "cudaMemcpyAsync(coefficient group)");
-    }
-  } else {
-    for (int c = 0; c < 3; c++) {
-      e = cudaMemcpyAsync(dst + (size_t)c * 65536 * es, coeff[c], ncoeff * es, cudaMemcpyHostToDevice, s);
-      if (e != cudaSuccess) {
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        return fail_cuda(ctx, e, "cudaMemcpyAsync(coefficients)");
-      }
-    }
-  }
-  std::lock_guard<std::mutex> lk(ctx->mu);
+// bookkeeping after the DMA(s) of group g were enqueued on the upload stream; ctx->mu is held
+static int mark_submitted(jxlgpu_ctx* ctx, uint32_t g) {
+  const uint32_t row = g / ctx->P.xg;
+  cudaError_t e = cudaEventRecord(ctx->row_events[row], ctx->up_streams[0]);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaEventRecord(row)");
+  ctx->row_event_used[row] = 1;
   if (ctx->submitted[g]) return JXLGPU_OK;  // a re-submission is not streamed again
   ctx->submitted[g] = 1;
-  const uint32_t row = g / ctx->P.xg;
   if (++ctx->row_count[row] == ctx->P.xg && row >= ctx->need_row0 && row < ctx->need_row1) {
     int rc = pump(ctx);
     if (rc) {
@@ -569,14 +562,62 @@ int jxlgpu_submit_group(jxlgpu_ctx* ctx, uint32_t g, size_t thread_id, const voi
   return JXLGPU_OK;
 }
 
+static bool group_is_one_block(const void* const coeff[3], size_t es) {
+  const uint8_t* c0 = (const uint8_t*)coeff[0];
+  return (const uint8_t*)coeff[1] == c0 + 65536 * es && (const uint8_t*)coeff[2] == c0 + 2 * 65536 * es;
+}
+
 int jxlgpu_submit_groups(jxlgpu_ctx* ctx, size_t n, const uint32_t* group_idx, size_t thread_id,
                          const void* const* coeff, const size_t* ncoeff) {
   if (!ctx || !group_idx || !coeff || !ncoeff) return JXLGPU_ERR_INVALID_ARGUMENT;
+  if (!ctx->in_frame || ctx->coeff_external) return JXLGPU_ERR_STATE;
+  if (thread_id >= ctx->num_threads) return JXLGPU_ERR_INVALID_ARGUMENT;
   for (size_t i = 0; i < n; i++) {
-    int rc = jxlgpu_submit_group(ctx, group_idx[i], thread_id, coeff + 3 * i, ncoeff[i]);
-    if (rc) return rc;
+    if (group_idx[i] >= ctx->num_groups || ncoeff[i] > 65536) return JXLGPU_ERR_INVALID_ARGUMENT;
+    for (int c = 0; c < 3; c++)
+      if (!coeff[3 * i + c]) return JXLGPU_ERR_INVALID_ARGUMENT;
+  }
+  // NB: cudaSetDevice is per host thread
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return JXLGPU_ERR_CUDA;
+  // One FIFO upload stream for all host threads: DMAs complete in submission order, so the first
+  // AC-group rows are on the device (and their kernels / D2H running) while later rows still
+  // travel.  (Concurrent upload streams time-slice the copy engine and every row finishes late.)
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaStream_t s = ctx->up_streams[0];
+  const size_t es = ctx->elem_size, gbytes = 3 * 65536 * es;
+  size_t i = 0;
+  while (i < n) {
+    const uint32_t g = group_idx[i];
+    uint8_t* dst = (uint8_t*)ctx->coeff.p + (size_t)g * gbytes;
+    size_t j = i;
+    if (group_is_one_block(coeff + 3 * i, es)) {
+      // Extend over consecutive groups whose [3][65536] host blocks are adjacent: one DMA for the
+      // whole run (a row of AC groups = tens of MB: full-duplex PCIe needs few, large copies).
+      while (j + 1 < n && group_idx[j + 1] == group_idx[j] + 1 && group_is_one_block(coeff + 3 * (j + 1), es) &&
+             (const uint8_t*)coeff[3 * (j + 1)] == (const uint8_t*)coeff[3 * j] + gbytes)
+        j++;
+      e = cudaMemcpyAsync(dst, coeff[3 * i], (j - i) * gbytes + (2 * 65536 + ncoeff[j]) * es,
+                          cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaMemcpyAsync(coefficient groups)");
+    } else {
+      for (int c = 0; c < 3; c++) {
+        e = cudaMemcpyAsync(dst + (size_t)c * 65536 * es, coeff[3 * i + c], ncoeff[i] * es, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaMemcpyAsync(coefficients)");
+      }
+    }
+    for (size_t k = i; k <= j; k++) {
+      int rc = mark_submitted(ctx, group_idx[k]);
+      if (rc) return rc;
+    }
+    i = j + 1;
   }
   return JXLGPU_OK;
+}
+
+int jxlgpu_submit_group(jxlgpu_ctx* ctx, uint32_t g, size_t thread_id, const void* const coeff[3], size_t ncoeff) {
+  if (!coeff) return JXLGPU_ERR_INVALID_ARGUMENT;
+  return jxlgpu_submit_groups(ctx, 1, &g, thread_id, coeff, &ncoeff);
 }
 
 int jxlgpu_set_device_coefficients(jxlgpu_ctx* ctx, const void* const dev_coeff[3]) {
@@ -648,8 +689,7 @@ int jxlgpu_frame_finish(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes) {
     const size_t row_bytes = ctx->out_stride_floats * 4;
     if (out_stride_bytes < row_bytes) return JXLGPU_ERR_INVALID_ARGUMENT;
     const size_t planes = ctx->P.out_format == JXLGPU_OUT_RGB_F32 ? 1 : 3;
-    CU(cudaMemcpy2DAsync(out, out_stride_bytes, ctx->out.p, row_bytes, row_bytes, planes * band_h,
-                         cudaMemcpyDeviceToHost, ctx->stream));
+    CU(download_rows(out, out_stride_bytes, ctx->out.p, row_bytes, planes * band_h, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaStreamSynchronize(ctx->s_down));
