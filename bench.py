@@ -178,6 +178,7 @@ def run_reference(args, rank: int) -> int:
 
 
 def main() -> int:
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (no NCCL version banner)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
