@@ -150,11 +150,38 @@ __device__ __forceinline__ void dct1d(float* v) {
 // ---------------------------------------------------------------------------
 // dequantisation (dec_group.cc:115-181, quantizer-inl.h:35-67)
 // ---------------------------------------------------------------------------
+// Correctly rounded 1/x for the integer-valued x the dequantiser sees: MUFU.RCP + one FMA Newton
+// step equals __frcp_rn(x) for every integer 2 <= |x| <= 2^24 (exhaustively checked on B200 by
+// tools/probe/rcp_probe.cu) and has no special-case branch.  Larger magnitudes (int32 only, never
+// seen in practice) take the library routine.
+__device__ __forceinline__ float rcp_int(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  const float e = fmaf(-x, r, 1.0f);
+  r = fmaf(r, e, r);
+  if (fabsf(x) > 16777216.0f) r = __frcp_rn(x);
+  return r;
+}
+
+// AdjustQuantBias (quantizer-inl.h:35-67), branch-free: q in {-1,0,1} -> q*biases[c] (exact),
+// otherwise q - biases[3] * (1/q) as one FMA.
 __device__ __forceinline__ float adjust_quant_bias(int q, float bias_c, float bias3) {
   const float fq = (float)q;
-  const float a = fabsf(fq);
-  if (a < 1.125f) return a > 0.0f ? copysignf(bias_c, fq) : 0.0f;
-  return fmaf(-bias3, __frcp_rn(fq), fq);
+  const float small = bias_c * fq;
+  const float big = fmaf(-bias3, rcp_int(fq), fq);
+  return fabsf(fq) < 1.125f ? small : big;
+}
+
+// Same without the |q| > 2^24 guard: the caller checks that once per row (never true in practice).
+__device__ __forceinline__ float adjust_quant_bias_nr(int q, float bias_c, float bias3) {
+  const float fq = (float)q;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fq));
+  const float e = fmaf(-fq, r, 1.0f);
+  r = fmaf(r, e, r);
+  const float small = bias_c * fq;
+  const float big = fmaf(-bias3, r, fq);
+  return fabsf(fq) < 1.125f ? small : big;
 }
 
 template <bool I32>
@@ -434,14 +461,32 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint32_
     load_row8f(P.dq + P.dq_off[3 * kind + 1] + l * 8, my);
     load_row8f(P.dq + P.dq_off[3 * kind + 0] + l * 8, mx);
     load_row8f(P.dq + P.dq_off[3 * kind + 2] + l * 8, mb);
+    bool huge = false;  // |q| > 2^24: outside the range rcp_nr was validated on (int32 only)
+    if constexpr (I32) {
+      unsigned m = 0;
+#pragma unroll
+      for (int e = 0; e < 8; e++) m |= (unsigned)abs(qy[e]) | (unsigned)abs(qx[e]) | (unsigned)abs(qb[e]);
+      huge = m > (1u << 24);
+    }
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-      const float dy = adjust_quant_bias(qy[e], P.qbias[1], P.qbias[3]) * (my[e] * vb.sy);
-      const float dx = adjust_quant_bias(qx[e], P.qbias[0], P.qbias[3]) * (mx[e] * vb.sx);
-      const float db = adjust_quant_bias(qb[e], P.qbias[2], P.qbias[3]) * (mb[e] * vb.sb);
+      const float dy = adjust_quant_bias_nr(qy[e], P.qbias[1], P.qbias[3]) * (my[e] * vb.sy);
+      const float dx = adjust_quant_bias_nr(qx[e], P.qbias[0], P.qbias[3]) * (mx[e] * vb.sx);
+      const float db = adjust_quant_bias_nr(qb[e], P.qbias[2], P.qbias[3]) * (mb[e] * vb.sb);
       val[1][e] = dy;
       val[0][e] = fmaf(vb.x_cc, dy, dx);
       val[2][e] = fmaf(vb.b_cc, dy, db);
+    }
+    if (huge) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const float dy = adjust_quant_bias(qy[e], P.qbias[1], P.qbias[3]) * (my[e] * vb.sy);
+        const float dx = adjust_quant_bias(qx[e], P.qbias[0], P.qbias[3]) * (mx[e] * vb.sx);
+        const float db = adjust_quant_bias(qb[e], P.qbias[2], P.qbias[3]) * (mb[e] * vb.sb);
+        val[1][e] = dy;
+        val[0][e] = fmaf(vb.x_cc, dy, dx);
+        val[2][e] = fmaf(vb.b_cc, dy, db);
+      }
     }
     if (l == 0) {  // LowestFrequenciesFromDC for the 8x8 class: llf[0] = dc[0]
       const size_t bi = (size_t)vb.aby * P.xb + vb.abx;
