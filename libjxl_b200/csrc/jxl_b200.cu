@@ -194,7 +194,7 @@ int launch_idct(jxlgpu_ctx* ctx, uint32_t row0, uint32_t row1, uint32_t need_y0,
   if (prof) CU(cudaEventRecord(ctx->prof_ev[1], s));
   // grids: persistent, never larger than the work (one CTA round = 32 8x8 blocks)
   const uint32_t px_blocks = plan_groups * 1024u;
-  int grid8 = ctx->num_sms * 3;  // idct8_kernel: __launch_bounds__(256, 3)
+  int grid8 = ctx->num_sms * 4;  // idct8_kernel: __launch_bounds__(256, 4)
   if ((uint32_t)grid8 > px_blocks / 32u + 1u) grid8 = (int)(px_blocks / 32u + 1u);
   int grid_mid = ctx->num_sms * 2, grid_large = ctx->num_sms * 2;
   if ((uint32_t)grid_mid > px_blocks / 32u + 1u) grid_mid = (int)(px_blocks / 32u + 1u);

@@ -150,17 +150,16 @@ __device__ __forceinline__ void dct1d(float* v) {
 // ---------------------------------------------------------------------------
 // dequantisation (dec_group.cc:115-181, quantizer-inl.h:35-67)
 // ---------------------------------------------------------------------------
-// Correctly rounded 1/x for the integer-valued x the dequantiser sees: MUFU.RCP + one FMA Newton
-// step equals __frcp_rn(x) for every integer 2 <= |x| <= 2^24 (exhaustively checked on B200 by
-// tools/probe/rcp_probe.cu) and has no special-case branch.  Larger magnitudes (int32 only, never
-// seen in practice) take the library routine.
+// Correctly rounded 1/x for the dequantiser: MUFU.RCP + one FMA Newton step equals __frcp_rn(x)
+// for every integer 2 <= |x| < 2^24 (exhaustively checked on B200 by tools/probe/rcp_probe.cu).
+// [2^23, 2^24) contains every 24-bit significand, MUFU.RCP and FMA are exponent-invariant for
+// normal numbers, and 1/x stays normal for |x| <= 2^31, so the identity holds for every int32
+// coefficient; no special-case branch is needed.  (x = 0 yields NaN, which callers discard.)
 __device__ __forceinline__ float rcp_int(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   const float e = fmaf(-x, r, 1.0f);
-  r = fmaf(r, e, r);
-  if (fabsf(x) > 16777216.0f) r = __frcp_rn(x);
-  return r;
+  return fmaf(r, e, r);
 }
 
 // AdjustQuantBias (quantizer-inl.h:35-67), branch-free: q in {-1,0,1} -> q*biases[c] (exact),
@@ -169,18 +168,6 @@ __device__ __forceinline__ float adjust_quant_bias(int q, float bias_c, float bi
   const float fq = (float)q;
   const float small = bias_c * fq;
   const float big = fmaf(-bias3, rcp_int(fq), fq);
-  return fabsf(fq) < 1.125f ? small : big;
-}
-
-// Same without the |q| > 2^24 guard: the caller checks that once per row (never true in practice).
-__device__ __forceinline__ float adjust_quant_bias_nr(int q, float bias_c, float bias3) {
-  const float fq = (float)q;
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fq));
-  const float e = fmaf(-fq, r, 1.0f);
-  r = fmaf(r, e, r);
-  const float small = bias_c * fq;
-  const float big = fmaf(-bias3, r, fq);
   return fabsf(fq) < 1.125f ? small : big;
 }
 
@@ -461,32 +448,14 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint32_
     load_row8f(P.dq + P.dq_off[3 * kind + 1] + l * 8, my);
     load_row8f(P.dq + P.dq_off[3 * kind + 0] + l * 8, mx);
     load_row8f(P.dq + P.dq_off[3 * kind + 2] + l * 8, mb);
-    bool huge = false;  // |q| > 2^24: outside the range rcp_nr was validated on (int32 only)
-    if constexpr (I32) {
-      unsigned m = 0;
-#pragma unroll
-      for (int e = 0; e < 8; e++) m |= (unsigned)abs(qy[e]) | (unsigned)abs(qx[e]) | (unsigned)abs(qb[e]);
-      huge = m > (1u << 24);
-    }
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-      const float dy = adjust_quant_bias_nr(qy[e], P.qbias[1], P.qbias[3]) * (my[e] * vb.sy);
-      const float dx = adjust_quant_bias_nr(qx[e], P.qbias[0], P.qbias[3]) * (mx[e] * vb.sx);
-      const float db = adjust_quant_bias_nr(qb[e], P.qbias[2], P.qbias[3]) * (mb[e] * vb.sb);
+      const float dy = adjust_quant_bias(qy[e], P.qbias[1], P.qbias[3]) * (my[e] * vb.sy);
+      const float dx = adjust_quant_bias(qx[e], P.qbias[0], P.qbias[3]) * (mx[e] * vb.sx);
+      const float db = adjust_quant_bias(qb[e], P.qbias[2], P.qbias[3]) * (mb[e] * vb.sb);
       val[1][e] = dy;
       val[0][e] = fmaf(vb.x_cc, dy, dx);
       val[2][e] = fmaf(vb.b_cc, dy, db);
-    }
-    if (huge) {
-#pragma unroll
-      for (int e = 0; e < 8; e++) {
-        const float dy = adjust_quant_bias(qy[e], P.qbias[1], P.qbias[3]) * (my[e] * vb.sy);
-        const float dx = adjust_quant_bias(qx[e], P.qbias[0], P.qbias[3]) * (mx[e] * vb.sx);
-        const float db = adjust_quant_bias(qb[e], P.qbias[2], P.qbias[3]) * (mb[e] * vb.sb);
-        val[1][e] = dy;
-        val[0][e] = fmaf(vb.x_cc, dy, dx);
-        val[2][e] = fmaf(vb.b_cc, dy, db);
-      }
     }
     if (l == 0) {  // LowestFrequenciesFromDC for the 8x8 class: llf[0] = dc[0]
       const size_t bi = (size_t)vb.aby * P.xb + vb.abx;
@@ -753,7 +722,7 @@ __device__ __forceinline__ int small_slots(int s) {
 
 // 8x8-class strategies (DCT, IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4, AFV0-3).
 template <bool I32>
-__global__ void __launch_bounds__(kSmallWarpsPerCta * 32, 3) idct8_kernel(const __grid_constant__ FrameDev P) {
+__global__ void __launch_bounds__(kSmallWarpsPerCta * 32, 4) idct8_kernel(const __grid_constant__ FrameDev P) {
   __shared__ __align__(16) float smem[kSmallWarpsPerCta * 1056];
   float* sm = smem + (threadIdx.x >> 5) * 1056;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -88,6 +88,21 @@ def test_zero_coefficients_and_extremes(pipe):
     assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), "int16 extremes")
 
 
+def test_int32_large_magnitudes(pipe):
+    """int32 coefficients far beyond int16 (the Newton reciprocal in the dequantiser must stay
+    correctly rounded for every magnitude)."""
+    desc, coeffs = wl.synthetic_frame(300, 200, seed=8, ac_type=abi.AC_INT32)
+    rng = np.random.default_rng(0)
+    big = rng.integers(-(1 << 30), 1 << 30, coeffs.shape, dtype=np.int64).astype(np.int32)
+    mask = rng.random(coeffs.shape) < 0.02
+    coeffs = np.where(mask, big, coeffs).astype(np.int32)
+    desc.stage_mask = abi.STAGE_EXPLICIT | 0      # post-IDCT XYB: keeps the huge values finite
+    desc.out_format = abi.OUT_PLANAR_F32
+    got = pipe.decode_frame(desc, coeffs)
+    assert np.isfinite(got).all()
+    assert_same(got, oracle(desc, coeffs), "int32 large magnitudes")
+
+
 def test_golden_frame_against_reference_pixels(pipe):
     """Real bitstream (tests/golden/frame_small.npz): coefficients as the reference's entropy
     decoder produced them; pixels vs the reference decoder. Tolerances in absolute units."""

@@ -12,7 +12,7 @@ __global__ void k(unsigned long long* bad, unsigned* first) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2^24 + extra
   float x;
   if (i < (1u << 24)) x = (float)(i + 2);
-  else x = (float)(1u << 24) * (1.0f + (float)(i - (1u << 24)) * (1.0f / 1048576.0f)) * 64.0f;  // sparse large values
+  else x = __int_as_float(0x4e800000 + (i - (1u << 24)) * 8);  // exponent 2^30, every 8th significand
   for (int sgn = 0; sgn < 2; sgn++) {
     const float v = sgn ? -x : x;
     if (rcp_nr(v) != __frcp_rn(v)) {
