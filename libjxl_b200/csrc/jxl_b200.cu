@@ -460,7 +460,7 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
     P.list_base[s] = (uint32_t)total;
     total += nblocks / (covered_x(s) * covered_y(s)) + 1;
   }
-  CU(ctx->list.ensure(total * 4));
+  CU(ctx->list.ensure(total * sizeof(uint4)));
   P.row_stride = xb * 8;
   P.plane_stride = P.row_stride * yb * 8;
   CU(ctx->xyb.ensure(3 * P.plane_stride * 4));
@@ -490,7 +490,7 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   }
   P.coeff_off = (uint16_t*)ctx->coeff_off.p;
   P.sigma = (float*)ctx->sigma.p;
-  P.list = (uint32_t*)ctx->list.p;
+  P.list = (uint4*)ctx->list.p;
   P.counts = (uint32_t*)ctx->counts.p;
   P.xyb = (float*)ctx->xyb.p;
   P.inv_global_scale = f->inv_global_scale;

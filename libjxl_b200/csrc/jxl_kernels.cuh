@@ -73,7 +73,7 @@ struct FrameDev {
   // produced by the plan kernel
   uint16_t* coeff_off;       // [yb][xb] offset/64 of the varblock inside its group (first blocks)
   float* sigma;              // [yb][xb] inverse sigma
-  uint32_t* list;            // work lists, entry = (aby << 16) | abx
+  uint4* list;               // work lists: {(aby<<16)|abx, coefficient base / 64, raw quant, ytox | ytob<<8}
   uint32_t* counts;          // [27]
   uint32_t list_base[kNumStrategies];
   // planes
@@ -184,20 +184,17 @@ struct VarblockCtx {
   float x_cc, b_cc;
 };
 
-__device__ __forceinline__ VarblockCtx make_ctx(const FrameDev& P, uint32_t entry) {
+__device__ __forceinline__ VarblockCtx make_ctx(const FrameDev& P, uint4 entry) {
   VarblockCtx v;
-  v.abx = entry & 0xffffu;
-  v.aby = entry >> 16;
-  const size_t bi = (size_t)v.aby * P.xb + v.abx;
-  const uint32_t g = (v.aby >> 5) * P.xg + (v.abx >> 5);
-  v.cbase = (size_t)g * P.coeff_gstride + (size_t)P.coeff_off[bi] * 64u;
-  const float s = P.inv_global_scale / (float)P.quant[bi];
+  v.abx = entry.x & 0xffffu;
+  v.aby = entry.x >> 16;
+  v.cbase = (size_t)entry.y * 64u;
+  const float s = P.inv_global_scale / (float)(int)entry.z;
   v.sx = s * P.x_dm;
   v.sy = s;
   v.sb = s * P.b_dm;
-  const size_t ti = (size_t)(v.aby >> 3) * P.cmap_stride + (v.abx >> 3);
-  v.x_cc = P.cfl_base_x + (float)P.ytox[ti] * P.cfl_scale;
-  v.b_cc = P.cfl_base_b + (float)P.ytob[ti] * P.cfl_scale;
+  v.x_cc = P.cfl_base_x + (float)(int)(int8_t)(entry.w & 0xffu) * P.cfl_scale;
+  v.b_cc = P.cfl_base_b + (float)(int)(int8_t)((entry.w >> 8) & 0xffu) * P.cfl_scale;
   return v;
 }
 
@@ -262,7 +259,12 @@ __global__ void __launch_bounds__(1024) plan_kernel(const __grid_constant__ Fram
   if (t < kNumStrategies && local_count[t]) local_base[t] = atomicAdd(&P.counts[t], local_count[t]);
   __syncthreads();
   if (wanted) {
-    P.list[P.list_base[s] + local_base[s] + rank] = (aby << 16) | abx;
+    // everything an IDCT warp needs about the varblock in one 16-byte record (one load instead of
+    // a dependent chain list -> coeff_off / quant / cmap)
+    const size_t ti = (size_t)(aby >> 3) * P.cmap_stride + (abx >> 3);
+    const uint32_t cfl = (uint32_t)(uint8_t)P.ytox[ti] | ((uint32_t)(uint8_t)P.ytob[ti] << 8);
+    P.list[P.list_base[s] + local_base[s] + rank] =
+        make_uint4((aby << 16) | abx, (uint32_t)((size_t)g * (P.coeff_gstride >> 6) + off), (uint32_t)P.quant[bi], cfl);
     if (want_sigma) {
       // ComputeSigma (epf.cc:39-133)
       const float kInvSigmaNum = -1.1715728752538099024f;
@@ -340,7 +342,7 @@ __device__ __forceinline__ void small_dct_item(const FrameDev& P, int kind, uint
   float* llf = T + TS;
   float* llf_tmp = llf + CY * CX;
   VarblockCtx vb;
-  if (active) vb = make_ctx(P, P.list[P.list_base[kind] + eidx]);
+  if (active) vb = make_ctx(P, __ldg(P.list + P.list_base[kind] + eidx));
   else vb = VarblockCtx{};
 #pragma unroll 1
   for (int c = 0; c < 3; c++) {
@@ -438,7 +440,7 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint32_
   VarblockCtx vb;
   float val[3][8];
   if (active) {
-    vb = make_ctx(P, P.list[P.list_base[kind] + eidx]);
+    vb = make_ctx(P, __ldg(P.list + P.list_base[kind] + eidx));
     int qx[8], qy[8], qb[8];
     float mx[8], my[8], mb[8];
     const size_t e0 = vb.cbase + (size_t)l * 8;
@@ -842,7 +844,7 @@ template <int N>
 __device__ __forceinline__ constexpr bool in_regs() { return N <= 64; }
 
 template <int R, int C, bool I32>
-__device__ __forceinline__ void large_item(const FrameDev& P, int kind, uint32_t entry, float* sm) {
+__device__ __forceinline__ void large_item(const FrameDev& P, int kind, uint4 entry, float* sm) {
   constexpr int CY = R / 8, CX = C / 8;
   const int tid = threadIdx.x;
   float* llf = sm;                 // 3 * CY*CX
@@ -931,7 +933,7 @@ __global__ void __launch_bounds__(256) idct_large_kernel(const __grid_constant__
     uint32_t it = (blockIdx.x + gridDim.x - (base % gridDim.x)) % gridDim.x;
 #pragma unroll 1
     for (; it < count; it += gridDim.x) {
-      const uint32_t entry = P.list[P.list_base[s] + it];
+      const uint4 entry = __ldg(P.list + P.list_base[s] + it);
       switch (s) {
         case 18: large_item<64, 64, I32>(P, s, entry, sm); break;
         case 19: large_item<64, 32, I32>(P, s, entry, sm); break;
