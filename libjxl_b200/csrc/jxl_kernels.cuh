@@ -1245,6 +1245,9 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_con
 // ===========================================================================
 namespace jxlb {
 
+template <int V>
+using IC = std::integral_constant<int, V>;
+
 constexpr int kStripThreads = 256;
 constexpr int kStripPad = 4;  // floats of padding before/after the rings
 
@@ -1329,32 +1332,6 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
       out[2 * plane + (size_t)yo * out_row_stride + x] = c3;
     }
   };
-  // Hand a stage's result to the next stage's ring, or emit it when it was the last stage.
-  // `which`: 0 = output of the loader, 1 = Gaborish, 2 = EPF0, 3 = EPF1, 4 = EPF2.
-  auto deliver = [&](auto which_tag, int r, float X, float Y, float B) {
-    constexpr int which = decltype(which_tag)::value;
-    constexpr bool toG = which < 1 && C::G;
-    constexpr bool to0 = !toG && which < 2 && C::E0;
-    constexpr bool to1 = !toG && !to0 && which < 3 && C::E1;
-    constexpr bool to2 = !toG && !to0 && !to1 && which < 4 && C::E2;
-    if constexpr (toG) {
-      ring_row(ringG, C::NG, r, 0)[t] = X; ring_row(ringG, C::NG, r, 1)[t] = Y; ring_row(ringG, C::NG, r, 2)[t] = B;
-    } else if constexpr (to0) {
-      ring_row(ring0, C::N0, r, 0)[t] = X; ring_row(ring0, C::N0, r, 1)[t] = Y; ring_row(ring0, C::N0, r, 2)[t] = B;
-    } else if constexpr (to1) {
-      ring_row(ring1, C::N1, r, 0)[t] = X; ring_row(ring1, C::N1, r, 1)[t] = Y; ring_row(ring1, C::N1, r, 2)[t] = B;
-    } else if constexpr (to2) {
-      ring_row(ring2, C::N2, r, 0)[t] = X; ring_row(ring2, C::N2, r, 1)[t] = Y; ring_row(ring2, C::N2, r, 2)[t] = B;
-    } else {
-      emit(r, X, Y, B);
-    }
-  };
-  using T0 = std::integral_constant<int, 0>;
-  using T1 = std::integral_constant<int, 1>;
-  using T2 = std::integral_constant<int, 2>;
-  using T3 = std::integral_constant<int, 3>;
-  using T4 = std::integral_constant<int, 4>;
-
   // cumulative delays (steps between loading row r and the stage producing row r)
   constexpr int dG = C::G ? 2 : 0;
   constexpr int d0 = dG + (C::E0 ? 4 : 0);
@@ -1363,11 +1340,45 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
   const int r_in_lo = lo(H), r_in_hi = hi(H);
   const int r_end = hi(0) + d2;  // after this many input-row steps the last output row is out
 
-  // One pipeline step. ST (steady): every stage has an in-range, unmirrored row; lanes are not
-  // range-checked (only `xin` in edge strips, where garbage lanes would read global memory).
-  auto step = [&](auto steady_tag, int rin) {
+  // One pipeline step.
+  //   ST (steady): every stage has an in-range, unmirrored row; lanes are not range-checked (only
+  //     `xin` in edge strips, where garbage lanes would read global memory).
+  //   J >= 0 (aligned): rin == 8*m + J, so every ring slot (row & (n-1)) is a compile-time constant
+  //     and shared-memory addresses are `lane base + immediate`; J == -1: slots computed at run time.
+  auto step = [&](auto steady_tag, auto jtag, int rin) {
     constexpr bool ST = decltype(steady_tag)::value;
+    constexpr int J = decltype(jtag)::value;
+    static_assert(J < 0 || ST, "aligned steps are steady steps");
     auto mr = [&](int r) { return ST ? r : mrow(r); };
+    // channel-0 row pointer of ring row (rin + dk); r_dyn is that row (mirrored in generic mode)
+    auto RP = [&](float* ring, auto ntag, auto dktag, int r_dyn) -> float* {
+      constexpr int n = decltype(ntag)::value;
+      constexpr int dk = decltype(dktag)::value;
+      if constexpr (J >= 0) return ring + ((((J + dk) % n + n) % n) * 3) * kStripThreads;
+      else return ring + ((r_dyn & (n - 1)) * 3) * kStripThreads;
+    };
+    // Hand a stage's result (row rin - D) to the next stage's ring, or emit it after the last stage.
+    // `which`: 0 = loader output, 1 = Gaborish, 2 = EPF0, 3 = EPF1, 4 = EPF2.
+    auto deliver = [&](auto which_tag, int r, float X, float Y, float B) {
+      constexpr int which = decltype(which_tag)::value;
+      constexpr int D = which == 0 ? 0 : (which == 1 ? dG : (which == 2 ? d0 : (which == 3 ? d1 : d2)));
+      constexpr bool toG = which < 1 && C::G;
+      constexpr bool to0 = !toG && which < 2 && C::E0;
+      constexpr bool to1 = !toG && !to0 && which < 3 && C::E1;
+      constexpr bool to2 = !toG && !to0 && !to1 && which < 4 && C::E2;
+      float* dst = nullptr;
+      if constexpr (toG) dst = RP(ringG, IC<C::NG ? C::NG : 1>(), IC<-D>(), r);
+      else if constexpr (to0) dst = RP(ring0, IC<C::N0 ? C::N0 : 1>(), IC<-D>(), r);
+      else if constexpr (to1) dst = RP(ring1, IC<C::N1 ? C::N1 : 1>(), IC<-D>(), r);
+      else if constexpr (to2) dst = RP(ring2, IC<C::N2 ? C::N2 : 1>(), IC<-D>(), r);
+      if constexpr (toG || to0 || to1 || to2) {
+        dst[t] = X;
+        dst[kStripThreads + t] = Y;
+        dst[2 * kStripThreads + t] = B;
+      } else {
+        emit(r, X, Y, B);
+      }
+    };
     const bool lane_ok = (ST && !EDGE) ? true : xin;
     // ---- loader: XYB row rin ----
     if ((ST || rin < r_in_hi) && xin) {
@@ -1375,24 +1386,26 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
       const float a = __ldg(P.xyb + off);
       const float b = __ldg(P.xyb + P.plane_stride + off);
       const float c3 = __ldg(P.xyb + 2 * P.plane_stride + off);
-      deliver(T0(), rin, a, b, c3);
+      deliver(IC<0>(), rin, a, b, c3);
     }
     // ---- Gaborish (stage_gaborish.cc:56-100) ----
     if constexpr (C::G) {
       const int r = rin - dG;
       if ((ST || (r >= lo(H - hG) && r < hi(H - hG) && t >= hG && t < kStripThreads - hG)) && lane_ok) {
-        const int rt = mr(r - 1), rb = mr(r + 1);
+        const float* pT0 = RP(ringG, IC<C::NG>(), IC<-dG - 1>(), mr(r - 1));
+        const float* pM0 = RP(ringG, IC<C::NG>(), IC<-dG>(), r);
+        const float* pB0 = RP(ringG, IC<C::NG>(), IC<-dG + 1>(), mr(r + 1));
         float v[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          const float* pT = ring_row(ringG, C::NG, rt, c);
-          const float* pM = ring_row(ringG, C::NG, r, c);
-          const float* pB = ring_row(ringG, C::NG, rb, c);
+          const float* pT = pT0 + c * kStripThreads;
+          const float* pM = pM0 + c * kStripThreads;
+          const float* pB = pB0 + c * kStripThreads;
           const float sum1 = (pM[cn[2]] + pM[cn[4]]) + (pT[t] + pB[t]);
           const float sum2 = (pT[cn[2]] + pT[cn[4]]) + (pB[cn[2]] + pB[cn[4]]);
           v[c] = fmaf(sum2, P.gab_w[3 * c + 2], fmaf(sum1, P.gab_w[3 * c + 1], pM[t] * P.gab_w[3 * c]));
         }
-        deliver(T1(), r, v[0], v[1], v[2]);
+        deliver(IC<1>(), r, v[0], v[1], v[2]);
       }
     }
     // ---- EPF0 (stage_epf.cc:54-193) ----
@@ -1400,17 +1413,22 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
       const int r = rin - d0;
       if ((ST || (r >= lo(H - h0) && r < hi(H - h0) && t >= h0 && t < kStripThreads - h0)) && lane_ok) {
         const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + xs);
-        float X = ring_row(ring0, C::N0, r, 0)[t];
-        float Y = ring_row(ring0, C::N0, r, 1)[t];
-        float B = ring_row(ring0, C::N0, r, 2)[t];
+        const float* rows[7];
+        rows[0] = RP(ring0, IC<C::N0>(), IC<-d0 - 3>(), mr(r - 3));
+        rows[1] = RP(ring0, IC<C::N0>(), IC<-d0 - 2>(), mr(r - 2));
+        rows[2] = RP(ring0, IC<C::N0>(), IC<-d0 - 1>(), mr(r - 1));
+        rows[3] = RP(ring0, IC<C::N0>(), IC<-d0>(), r);
+        rows[4] = RP(ring0, IC<C::N0>(), IC<-d0 + 1>(), mr(r + 1));
+        rows[5] = RP(ring0, IC<C::N0>(), IC<-d0 + 2>(), mr(r + 2));
+        rows[6] = RP(ring0, IC<C::N0>(), IC<-d0 + 3>(), mr(r + 3));
+        float X = rows[3][t];
+        float Y = rows[3][kStripThreads + t];
+        float B = rows[3][2 * kStripThreads + t];
         if (!(s < kMinSigma)) {
           const int iy = r & 7;
           const float sm_ = P.epf_sm[0];
           const float vsm = (iy == 0 || iy == 7 || xborder) ? sm_ * P.epf_border_mul : sm_;
           const float inv_sigma = s * vsm;
-          int rr[7];
-#pragma unroll
-          for (int k = 0; k < 7; k++) rr[k] = mr(r + k - 3);
           const int dy12[12] = {-2, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 2};
           const int dx12[12] = {0, -1, 0, 1, -2, -1, 1, 2, -1, 0, 1, 0};
           const int py5[5] = {0, -1, 0, 1, 0};
@@ -1428,7 +1446,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
 #pragma unroll
               for (int b = 0; b < 7; b++)
                 if ((a > 3 ? a - 3 : 3 - a) + (b > 3 ? b - 3 : 3 - b) <= 3)
-                  v[a][b] = ring_row(ring0, C::N0, rr[a], c)[cn[b]];
+                  v[a][b] = rows[a][c * kStripThreads + cn[b]];
             const float scale = P.epf_scale[c];
 #pragma unroll
             for (int k = 0; k < 12; k++) {
@@ -1452,7 +1470,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
           const float inv_w = 1.0f / w;
           X = X * inv_w; Y = Y * inv_w; B = B * inv_w;
         }
-        deliver(T2(), r, X, Y, B);
+        deliver(IC<2>(), r, X, Y, B);
       }
     }
     // ---- EPF1 (stage_epf.cc:197-379) ----
@@ -1460,7 +1478,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
       const int r = rin - d1;
       if ((ST || (r >= lo(H - h1) && r < hi(H - h1) && t >= h1 && t < kStripThreads - h1)) && lane_ok) {
         const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + xs);
-        const float* q2x = ring_row(ring1, C::N1, r, 0);
+        const float* q2x = RP(ring1, IC<C::N1>(), IC<-d1>(), r);
         float X = q2x[t];
         float Y = q2x[kStripThreads + t];
         float B = q2x[2 * kStripThreads + t];
@@ -1469,10 +1487,10 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
           const float sm_ = P.epf_sm[1];
           const float vsm = (iy == 0 || iy == 7 || xborder) ? sm_ * P.epf_border_mul : sm_;
           const float inv_sigma = s * vsm;
-          const float* q0x = ring_row(ring1, C::N1, mr(r - 2), 0);
-          const float* q1x = ring_row(ring1, C::N1, mr(r - 1), 0);
-          const float* q3x = ring_row(ring1, C::N1, mr(r + 1), 0);
-          const float* q4x = ring_row(ring1, C::N1, mr(r + 2), 0);
+          const float* q0x = RP(ring1, IC<C::N1>(), IC<-d1 - 2>(), mr(r - 2));
+          const float* q1x = RP(ring1, IC<C::N1>(), IC<-d1 - 1>(), mr(r - 1));
+          const float* q3x = RP(ring1, IC<C::N1>(), IC<-d1 + 1>(), mr(r + 1));
+          const float* q4x = RP(ring1, IC<C::N1>(), IC<-d1 + 2>(), mr(r + 2));
           float sad0 = 0.0f, sad1 = 0.0f, sad2 = 0.0f, sad3 = 0.0f;
           float nb[3][4];  // neighbour pixels N, W, E, S per channel
 #pragma unroll
@@ -1530,7 +1548,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
           const float inv_w = 1.0f / w;
           X = X * inv_w; Y = Y * inv_w; B = B * inv_w;
         }
-        deliver(T3(), r, X, Y, B);
+        deliver(IC<3>(), r, X, Y, B);
       }
     }
     // ---- EPF2 (stage_epf.cc:383-506) ----
@@ -1538,23 +1556,26 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
       const int r = rin - d2;
       if ((ST || (r >= lo(0) && r < hi(0) && t >= h2 && t < kStripThreads - h2)) && lane_ok) {
         const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + xs);
-        float X = ring_row(ring2, C::N2, r, 0)[t];
-        float Y = ring_row(ring2, C::N2, r, 1)[t];
-        float B = ring_row(ring2, C::N2, r, 2)[t];
+        const float* pM = RP(ring2, IC<C::N2>(), IC<-d2>(), r);
+        float X = pM[t];
+        float Y = pM[kStripThreads + t];
+        float B = pM[2 * kStripThreads + t];
         if (!(s < kMinSigma)) {
           const int iy = r & 7;
           const float sm_ = P.epf_sm[2];
           const float vsm = (iy == 0 || iy == 7 || xborder) ? sm_ * P.epf_border_mul : sm_;
           const float inv_sigma = s * vsm;
-          const int nr[4] = {mr(r - 1), r, r, mr(r + 1)};
+          const float* pT = RP(ring2, IC<C::N2>(), IC<-d2 - 1>(), mr(r - 1));
+          const float* pB = RP(ring2, IC<C::N2>(), IC<-d2 + 1>(), mr(r + 1));
+          const float* nr[4] = {pT, pM, pM, pB};
           const int nc[4] = {t, cn[2], cn[4], t};
           const float rx = X, ry = Y, rb = B;
           float w = 1.0f;
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            const float cx = ring_row(ring2, C::N2, nr[k], 0)[nc[k]];
-            const float cy = ring_row(ring2, C::N2, nr[k], 1)[nc[k]];
-            const float cb = ring_row(ring2, C::N2, nr[k], 2)[nc[k]];
+            const float cx = nr[k][nc[k]];
+            const float cy = nr[k][kStripThreads + nc[k]];
+            const float cb = nr[k][2 * kStripThreads + nc[k]];
             float sad = fabsf(cx - rx) * P.epf_scale[0];
             sad = fmaf(fabsf(cy - ry), P.epf_scale[1], sad);
             sad = fmaf(fabsf(cb - rb), P.epf_scale[2], sad);
@@ -1567,7 +1588,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
           const float inv_w = 1.0f / w;
           X = X * inv_w; Y = Y * inv_w; B = B * inv_w;
         }
-        deliver(T4(), r, X, Y, B);
+        deliver(IC<4>(), r, X, Y, B);
       }
     }
     if constexpr (H > 0) __syncthreads();
@@ -1585,10 +1606,27 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
   if (C::E1) constrain(d1, 2, H - h1);
   if (C::E2) constrain(d2, 1, 0);
   if (s_hi < s_lo) s_hi = s_lo;
+  const int s_begin = min(s_lo, r_end), s_end = min(s_hi, r_end);
+  using F = std::false_type;
+  using T = std::true_type;
   int rin = r_in_lo;
-  for (; rin < min(s_lo, r_end); rin++) step(std::false_type(), rin);
-  for (; rin < min(s_hi, r_end); rin++) step(std::true_type(), rin);
-  for (; rin < r_end; rin++) step(std::false_type(), rin);
+  for (; rin < s_begin; rin++) step(F(), IC<-1>(), rin);
+  if constexpr (H > 0 && !C::E0) {
+    // 8x unrolled steady loop with compile-time ring slots (EPF0 chains are too large to replicate)
+    for (; rin < s_end && (rin & 7); rin++) step(T(), IC<-1>(), rin);
+    for (; rin + 8 <= s_end; rin += 8) {
+      step(T(), IC<0>(), rin);
+      step(T(), IC<1>(), rin + 1);
+      step(T(), IC<2>(), rin + 2);
+      step(T(), IC<3>(), rin + 3);
+      step(T(), IC<4>(), rin + 4);
+      step(T(), IC<5>(), rin + 5);
+      step(T(), IC<6>(), rin + 6);
+      step(T(), IC<7>(), rin + 7);
+    }
+  }
+  for (; rin < s_end; rin++) step(T(), IC<-1>(), rin);
+  for (; rin < r_end; rin++) step(F(), IC<-1>(), rin);
 }
 
 template <uint32_t MASK>
