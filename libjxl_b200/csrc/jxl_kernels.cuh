@@ -1340,6 +1340,22 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
   const int r_in_lo = lo(H), r_in_hi = hi(H);
   const int r_end = hi(0) + d2;  // after this many input-row steps the last output row is out
 
+  // row r_in_lo is fetched up front, every later row one step ahead of its use
+  float pre_a = 0.0f, pre_b = 0.0f, pre_c = 0.0f;
+  if (r_in_lo < r_in_hi && xin) {
+    const size_t off = (size_t)r_in_lo * P.row_stride + x;
+    pre_a = __ldg(P.xyb + off);
+    pre_b = __ldg(P.xyb + P.plane_stride + off);
+    pre_c = __ldg(P.xyb + 2 * P.plane_stride + off);
+  }
+
+  // inverse sigma of each EPF stage's next row, fetched one step ahead as well.  A stage's first
+  // produced row is max(0, y_begin - rem) (its `lo`), reached at step lo + delay.
+  float sg0 = 0.0f, sg1 = 0.0f, sg2 = 0.0f;
+  if (C::E0) sg0 = __ldg(P.sigma + (size_t)(lo(H - h0) >> 3) * P.xb + xs);
+  if (C::E1) sg1 = __ldg(P.sigma + (size_t)(lo(H - h1) >> 3) * P.xb + xs);
+  if (C::E2) sg2 = __ldg(P.sigma + (size_t)(lo(0) >> 3) * P.xb + xs);
+
   // One pipeline step.
   //   ST (steady): every stage has an in-range, unmirrored row; lanes are not range-checked (only
   //     `xin` in edge strips, where garbage lanes would read global memory).
@@ -1380,13 +1396,14 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
       }
     };
     const bool lane_ok = (ST && !EDGE) ? true : xin;
-    // ---- loader: XYB row rin ----
-    if ((ST || rin < r_in_hi) && xin) {
-      const size_t off = (size_t)rin * P.row_stride + x;
-      const float a = __ldg(P.xyb + off);
-      const float b = __ldg(P.xyb + P.plane_stride + off);
-      const float c3 = __ldg(P.xyb + 2 * P.plane_stride + off);
-      deliver(IC<0>(), rin, a, b, c3);
+    // ---- loader: XYB row rin was fetched during the previous step (its latency hid behind that
+    // step's arithmetic); hand it on and start fetching row rin + 1 ----
+    if ((ST || rin < r_in_hi) && xin) deliver(IC<0>(), rin, pre_a, pre_b, pre_c);
+    if (rin + 1 < r_in_hi && xin) {
+      const size_t off = (size_t)(rin + 1) * P.row_stride + x;
+      pre_a = __ldg(P.xyb + off);
+      pre_b = __ldg(P.xyb + P.plane_stride + off);
+      pre_c = __ldg(P.xyb + 2 * P.plane_stride + off);
     }
     // ---- Gaborish (stage_gaborish.cc:56-100) ----
     if constexpr (C::G) {
@@ -1412,7 +1429,8 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
     if constexpr (C::E0) {
       const int r = rin - d0;
       if ((ST || (r >= lo(H - h0) && r < hi(H - h0) && t >= h0 && t < kStripThreads - h0)) && lane_ok) {
-        const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + xs);
+        const float s = sg0;
+        sg0 = __ldg(P.sigma + (size_t)(min(max(r + 1, 0), HI - 1) >> 3) * P.xb + xs);
         const float* rows[7];
         rows[0] = RP(ring0, IC<C::N0>(), IC<-d0 - 3>(), mr(r - 3));
         rows[1] = RP(ring0, IC<C::N0>(), IC<-d0 - 2>(), mr(r - 2));
@@ -1477,7 +1495,8 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
     if constexpr (C::E1) {
       const int r = rin - d1;
       if ((ST || (r >= lo(H - h1) && r < hi(H - h1) && t >= h1 && t < kStripThreads - h1)) && lane_ok) {
-        const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + xs);
+        const float s = sg1;
+        sg1 = __ldg(P.sigma + (size_t)(min(max(r + 1, 0), HI - 1) >> 3) * P.xb + xs);
         const float* q2x = RP(ring1, IC<C::N1>(), IC<-d1>(), r);
         float X = q2x[t];
         float Y = q2x[kStripThreads + t];
@@ -1555,7 +1574,8 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
     if constexpr (C::E2) {
       const int r = rin - d2;
       if ((ST || (r >= lo(0) && r < hi(0) && t >= h2 && t < kStripThreads - h2)) && lane_ok) {
-        const float s = __ldg(P.sigma + (size_t)(r >> 3) * P.xb + xs);
+        const float s = sg2;
+        sg2 = __ldg(P.sigma + (size_t)(min(max(r + 1, 0), HI - 1) >> 3) * P.xb + xs);
         const float* pM = RP(ring2, IC<C::N2>(), IC<-d2>(), r);
         float X = pM[t];
         float Y = pM[kStripThreads + t];
