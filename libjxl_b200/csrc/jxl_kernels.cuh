@@ -1470,8 +1470,16 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
             for (int k = 0; k < 12; k++) {
               float sad = 0.0f;
 #pragma unroll
-              for (int o = 0; o < 5; o++)
-                sad = sad + fabsf(v[3 + py5[o]][3 + px5[o]] - v[3 + dy12[k] + py5[o]][3 + dx12[k] + px5[o]]);
+              for (int o = 0; o < 5; o++) {
+                // |a-b| == |b-a| exactly: always subtract in (row, column) order so that the 60
+                // terms collapse to the ~32 distinct pixel pairs under common-subexpression elimination
+                const int a0 = 3 + py5[o], b0 = 3 + px5[o];
+                const int a1 = a0 + dy12[k], b1 = b0 + dx12[k];
+                const bool sw = (a1 < a0) || (a1 == a0 && b1 < b0);
+                const float lhs = sw ? v[a1][b1] : v[a0][b0];
+                const float rhs = sw ? v[a0][b0] : v[a1][b1];
+                sad = sad + fabsf(lhs - rhs);
+              }
               sads[k] = fmaf(sad, scale, sads[k]);
               nbv[c][k] = v[3 + dy12[k]][3 + dx12[k]];
             }
