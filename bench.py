@@ -186,6 +186,9 @@ def main() -> int:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="8k-d1", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "p2p", "nccl"],
+                    help="N>1: how the bands are all-gathered (auto: fused multicast stores if the switch "
+                         "supports them, else fused peer stores, else NCCL)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -244,17 +247,48 @@ def main() -> int:
         ptrs = [dev_part[c].data_ptr() - g0 * abi.GROUP_COEFFS * es for c in range(3)]
     pipe.set_device_coefficients(ptrs)
     pipe.frame_begin(desc)
+    gather_mode = "none"
+    hdl = None
     if world == 1:
         gathered = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
         my_out = gathered
     else:
-        gathered = torch.empty((world, max_rows, W, 3), dtype=torch.float32, device="cuda")
+        slot = max_rows * W * 3
+        gathered = None
+        if args.gather != "nccl":
+            try:
+                # Fused compute + all-gather: the frame buffer of every rank is symmetric memory; the
+                # filter kernel stores each finished pixel straight into every peer's buffer (NVLink
+                # peer stores, or one multimem.st through the NVSwitch multicast mapping).
+                import torch.distributed._symmetric_memory as symm
+                flat = symm.empty(world * slot, dtype=torch.float32, device=torch.device("cuda", local_rank))
+                hdl = symm.rendezvous(flat, dist.group.WORLD)
+                gathered = flat.view(world, max_rows, W, 3)
+                mc = int(hdl.multicast_ptr) if args.gather in ("auto", "multicast") else 0
+                if args.gather == "multicast" and not mc:
+                    raise RuntimeError("multicast not supported here")
+                if mc:
+                    pipe.set_output_replicas([], mc + rank * slot * 4)
+                    gather_mode = "fused multimem.st (NVSwitch multicast) in the filter epilogue"
+                else:
+                    pipe.set_output_replicas([int(hdl.buffer_ptrs[p]) + rank * slot * 4 for p in range(world)])
+                    gather_mode = "fused NVLink peer stores in the filter epilogue"
+            except Exception as e:  # noqa: BLE001
+                log(f"symmetric memory unavailable ({e!r}): falling back to NCCL all-gather")
+                hdl = None
+                gathered = None
+        if gathered is None:
+            gathered = torch.empty((world, max_rows, W, 3), dtype=torch.float32, device="cuda")
+            gather_mode = "NCCL all_gather_into_tensor after the filter kernel"
         my_out = gathered[rank]
 
     def step():
         pipe.render_device(my_out.data_ptr(), W * 12, stream.cuda_stream)
         if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), my_out.reshape(-1))
+            if hdl is not None:
+                hdl.barrier(channel=0)      # publishes the peers' stores: the frame is complete everywhere
+            else:
+                dist.all_gather_into_tensor(gathered.view(-1), my_out.reshape(-1))
 
     for _ in range(args.warmup):
         step()
@@ -282,6 +316,9 @@ def main() -> int:
     value = W * H / (ms_step * 1e-3) / 1e6
 
     # per-kernel times (separate pass, CUDA events inside the library on the same stream)
+    pipe.set_output_replicas([], 0)   # per-kernel times and the e2e arm run without the gather
+    if world > 1:
+        my_out = torch.empty((max_rows, W, 3), dtype=torch.float32, device="cuda")
     pipe.set_profiling(True)
     ktimes = {"plan": [], "idct8": [], "idct_mid": [], "idct_large": [], "filter": []}
     for _ in range(max(5, min(args.steps, 20))):
@@ -294,10 +331,15 @@ def main() -> int:
     # correctness spot check of the timed output against the reference decoder's pixels
     parity = None
     if fr.get("decoded") is not None and rank == 0:
-        got = (gathered if world == 1 else gathered[0, :sharding.band_pixel_rows(desc, *bands[0])[1]]).cpu().numpy()
+        if world == 1:
+            got = gathered.cpu().numpy()
+        else:  # every band, as it arrived in rank 0's frame buffer
+            got = np.concatenate([gathered[r, :sharding.band_pixel_rows(desc, *bands[r])[1]].cpu().numpy()
+                                  for r in range(world)])
         want = fr["decoded"][:got.shape[0]]
         d = np.abs(got - want)
-        parity = {"peak_abs_err_vs_reference": float(d.max()), "rmse_vs_reference": float(np.sqrt(np.mean(d * d)))}
+        parity = {"peak_abs_err_vs_reference": float(d.max()), "rmse_vs_reference": float(np.sqrt(np.mean(d * d))),
+                  "rows_checked": int(got.shape[0])}
 
     # ---------------- end-to-end arm: host buffers through the C ABI ----------------
     pipe.set_device_coefficients(None)
@@ -422,7 +464,7 @@ def main() -> int:
         "config": {"workload": f"{args.workload}: {W}x{H} VarDCT d{dist_} e{effort_}, gab={desc.gab} epf_iters={desc.epf_iters}, "
                                f"{source}, coefficients {'int16' if es == 2 else 'int32'} as the reference decoder chose, "
                                "output interleaved linear RGB f32",
-                   "groups": desc.num_groups, "parallelism": f"band-sharded x{world} + NCCL all-gather" if world > 1 else "1 GPU",
+                   "groups": desc.num_groups, "parallelism": f"band-sharded x{world}; all-gather: {gather_mode}" if world > 1 else "1 GPU",
                    "strategy_histogram": fr["hist"], "bpp": fr["bpp"],
                    "l2": "inputs larger than L2 (coefficients + XYB planes + output >> 126 MB per step)"},
         "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d_t[0].item()),

@@ -697,6 +697,15 @@ int jxlgpu_frame_finish(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes) {
   return JXLGPU_OK;
 }
 
+int jxlgpu_set_output_replicas(jxlgpu_ctx* ctx, uint32_t n, void* const* dev_ptrs, void* multicast_ptr) {
+  if (!ctx || n > 8 || (n && !dev_ptrs)) return JXLGPU_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->P.nrep = multicast_ptr ? 0 : n;
+  for (uint32_t i = 0; i < 8; i++) ctx->P.rep[i] = i < n ? (float*)dev_ptrs[i] : nullptr;
+  ctx->P.mc = (float*)multicast_ptr;
+  return JXLGPU_OK;
+}
+
 int jxlgpu_device_output(jxlgpu_ctx* ctx, void** dev_ptr, size_t* stride_bytes) {
   if (!ctx || !dev_ptr || !stride_bytes) return JXLGPU_ERR_INVALID_ARGUMENT;
   *dev_ptr = ctx->out.p;

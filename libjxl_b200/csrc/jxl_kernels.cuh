@@ -56,6 +56,11 @@ struct FrameDev {
   uint32_t out_format;
   uint32_t band_y0, band_y1; // pixel rows [band_y0, band_y1) rendered by the filter kernel
   uint32_t out_y0, out_h;    // output addressing: image row stored at output row 0, rows per plane
+  // fused all-gather (multi-GPU): every finished pixel is also stored to the same offset of
+  // `nrep` peer-mapped buffers over NVLink, or once through an NVSwitch multicast address
+  uint32_t nrep;
+  float* rep[8];
+  float* mc;
   uint32_t need_y0, need_y1; // pixel rows of post-IDCT data the band's filters read (band +- halo)
   uint32_t plan_g0;          // first AC group handled by the plan kernel (band sharding)
   // side info (device)
@@ -958,6 +963,46 @@ __global__ void __launch_bounds__(256) idct_large_kernel(const __grid_constant__
 // (Mirror(), lib/jxl/image_ops.h:184-196 -- every stage's input is mirrored about the
 // true image size, simple_render_pipeline.cc:129-164).
 // ---------------------------------------------------------------------------
+// Pixel store of the filter epilogues.  Single GPU: plain stores.  Multi-GPU: the band is
+// all-gathered BY the stores -- each value goes to this rank's slot in every peer's frame buffer
+// (peer-mapped pointers, NVLink P2P), or once to the slot's NVSwitch multicast address
+// (multimem.st: the switch replicates it), so the transfer overlaps the filtering row by row.
+__device__ __forceinline__ void mc_store(float* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ void store_px(const FrameDev& P, float* __restrict__ out, size_t out_row_stride,
+                                         int yo, int x, int band_h, float a, float b, float c3) {
+  size_t o0, o1, o2;
+  if (P.out_format == 0) {
+    o0 = (size_t)yo * out_row_stride + (size_t)x * 3;
+    o1 = o0 + 1;
+    o2 = o0 + 2;
+  } else {
+    const size_t plane = (size_t)band_h * out_row_stride;
+    o0 = (size_t)yo * out_row_stride + x;
+    o1 = o0 + plane;
+    o2 = o1 + plane;
+  }
+  if (P.mc) {
+    mc_store(P.mc + o0, a);
+    mc_store(P.mc + o1, b);
+    mc_store(P.mc + o2, c3);
+  } else if (P.nrep) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < P.nrep; i++) {
+      float* d = P.rep[i];
+      d[o0] = a;
+      d[o1] = b;
+      d[o2] = c3;
+    }
+  } else {
+    out[o0] = a;
+    out[o1] = b;
+    out[o2] = c3;
+  }
+}
+
 constexpr int kTW = 64, kTH = 32, kMaxHalo = 7;
 constexpr int kSW = kTW + 2 * kMaxHalo;       // 78
 constexpr int kSH = kTH + 2 * kMaxHalo;       // 46
@@ -1207,16 +1252,7 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_con
       lr = fmaf(P.opsin_m[2], mb, lr); lg = fmaf(P.opsin_m[5], mb, lg); lb = fmaf(P.opsin_m[8], mb, lb);
       a = lr; b = lg; c3 = lb;
     }
-    const int yo = y - (int)P.out_y0;
-    if (P.out_format == 0) {
-      float* o = out + (size_t)yo * out_row_stride + (size_t)x * 3;
-      o[0] = a; o[1] = b; o[2] = c3;
-    } else {
-      const size_t plane = (size_t)band_h * out_row_stride;
-      out[(size_t)yo * out_row_stride + x] = a;
-      out[plane + (size_t)yo * out_row_stride + x] = b;
-      out[2 * plane + (size_t)yo * out_row_stride + x] = c3;
-    }
+    store_px(P, out, out_row_stride, y - (int)P.out_y0, x, band_h, a, b, c3);
   }
 }
 
@@ -1321,16 +1357,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
       lr = fmaf(P.opsin_m[2], mb, lr); lg = fmaf(P.opsin_m[5], mb, lg); lb = fmaf(P.opsin_m[8], mb, lb);
       a = lr; b = lg; c3 = lb;
     }
-    const int yo = r - (int)P.out_y0;
-    if (P.out_format == 0) {
-      float* o = out + (size_t)yo * out_row_stride + (size_t)x * 3;
-      o[0] = a; o[1] = b; o[2] = c3;
-    } else {
-      const size_t plane = (size_t)band_h * out_row_stride;
-      out[(size_t)yo * out_row_stride + x] = a;
-      out[plane + (size_t)yo * out_row_stride + x] = b;
-      out[2 * plane + (size_t)yo * out_row_stride + x] = c3;
-    }
+    store_px(P, out, out_row_stride, r - (int)P.out_y0, x, band_h, a, b, c3);
   };
   // cumulative delays (steps between loading row r and the stage producing row r)
   constexpr int dG = C::G ? 2 : 0;

@@ -27,7 +27,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTS = ["jxlgpu_abi_version", "jxlgpu_error_string", "jxlgpu_last_error", "jxlgpu_create",
            "jxlgpu_destroy", "jxlgpu_frame_begin", "jxlgpu_frame_set_output", "jxlgpu_submit_group",
            "jxlgpu_submit_groups", "jxlgpu_frame_finish",
-           "jxlgpu_set_device_coefficients", "jxlgpu_render_device", "jxlgpu_device_output",
+           "jxlgpu_set_device_coefficients", "jxlgpu_render_device", "jxlgpu_set_output_replicas", "jxlgpu_device_output",
            "jxlgpu_device_xyb", "jxlgpu_synchronize", "jxlgpu_launch_count", "jxlgpu_alloc_pinned",
            "jxlgpu_free_pinned", "jxlgpu_set_profiling", "jxlgpu_kernel_times"]
 
@@ -73,6 +73,7 @@ def lib():
         L.jxlgpu_frame_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.jxlgpu_set_device_coefficients.argtypes = [C.c_void_p, C.c_void_p]
         L.jxlgpu_render_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.jxlgpu_set_output_replicas.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.jxlgpu_device_output.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.jxlgpu_device_xyb.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                         C.POINTER(C.c_size_t)]
@@ -204,6 +205,13 @@ class TransformPipeline:
     def render_device(self, dev_out: int = 0, out_stride_bytes: int = 0, stream: int = 0):
         self._check(lib().jxlgpu_render_device(self._h, dev_out or None, out_stride_bytes, stream or None),
                     "jxlgpu_render_device")
+
+    def set_output_replicas(self, ptrs, multicast_ptr: int = 0):
+        """Fused all-gather: device addresses (peer-mapped) of this band's slot in every rank's frame."""
+        ptrs = list(ptrs or [])
+        arr = (C.c_void_p * max(1, len(ptrs)))(*ptrs) if ptrs else None
+        self._check(lib().jxlgpu_set_output_replicas(self._h, len(ptrs), arr, multicast_ptr or None),
+                    "jxlgpu_set_output_replicas")
 
     def device_output(self) -> tuple[int, int]:
         p, s = C.c_void_p(), C.c_size_t()
