@@ -1295,8 +1295,7 @@ struct StripCfg {
   // ring sizes (rows, power of two >= 2*border+2) of each stage's input; 0 when absent
   static constexpr int NG = G ? 4 : 0, N0 = E0 ? 8 : 0, N1 = E1 ? 8 : 0, N2 = E2 ? 4 : 0;
   static constexpr int kRows = NG + N0 + N1 + N2;
-  // rings + padding + one 96-float RGB staging line per warp
-  static constexpr size_t kSmemBytes = ((size_t)kRows * 3 * kStripThreads + 2 * kStripPad + (kStripThreads / 32) * 96) * sizeof(float);
+  static constexpr size_t kSmemBytes = ((size_t)(kRows ? kRows : 1) * 3 * kStripThreads + 2 * kStripPad) * sizeof(float);
   static constexpr int kOutCols = kStripThreads - 2 * H;
 };
 
@@ -1342,30 +1341,8 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
   const bool emit_lane = xin && t >= H && t < kStripThreads - H;
 
   // Final step of the chain: XYB -> linear RGB (dec_xyb-inl.h:38-86) and the global store.
-  // Final step of the chain: XYB -> linear RGB (dec_xyb-inl.h:38-86) and the global store.  The
-  // last stage only parks its pixel in (ev, er, ea, eb, ec); flush_emit() runs at the end of the
-  // step with the whole warp converged, so the interleaved RGB row segment of a warp (32 px = 384
-  // contiguous bytes) can go through a 96-float shared staging line and leave as three fully
-  // coalesced 128-byte stores -- full sectors for HBM, and full packets for the NVLink / multicast
-  // stores of the fused all-gather.
-  bool ev = false;
-  int er = 0;
-  float ea = 0.0f, eb = 0.0f, ec = 0.0f;
-  float* stage_line = smem + kStripPad + C::kRows * 3 * kStripThreads + kStripPad + (t >> 5) * 96;
-  auto store_elem = [&](size_t o, float v) {
-    if (P.mc) {
-      mc_store(P.mc + o, v);
-    } else if (P.nrep) {
-#pragma unroll 1
-      for (uint32_t i = 0; i < P.nrep; i++) P.rep[i][o] = v;
-    } else {
-      out[o] = v;
-    }
-  };
-  auto flush_emit = [&]() {
-    const unsigned m = __ballot_sync(0xffffffffu, ev);
-    if (m == 0) return;  // warp-uniform
-    float a = ea, b = eb, c3 = ec;
+  auto emit = [&](int r, float a, float b, float c3) {
+    if (!emit_lane) return;
     if constexpr (C::XYB) {
       float gr = b + a, gg = b - a, gb = c3;
       gr = gr - P.opsin_cbrt[0];
@@ -1380,36 +1357,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
       lr = fmaf(P.opsin_m[2], mb, lr); lg = fmaf(P.opsin_m[5], mb, lg); lb = fmaf(P.opsin_m[8], mb, lb);
       a = lr; b = lg; c3 = lb;
     }
-    // all participating lanes of a warp emit the same row this step
-    const int row = __shfl_sync(0xffffffffu, er, __ffs(m) - 1);
-    const int yo = row - (int)P.out_y0;
-    const int lane = t & 31;
-    if (P.out_format == 0) {
-      stage_line[3 * lane] = a;
-      stage_line[3 * lane + 1] = b;
-      stage_line[3 * lane + 2] = c3;
-      __syncwarp();
-      const size_t base = (size_t)yo * out_row_stride + (size_t)(x - lane) * 3;  // x - lane may be < 0: masked below
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const int e = k * 32 + lane;
-        if ((m >> (e / 3)) & 1u) store_elem(base + e, stage_line[e]);
-      }
-      __syncwarp();
-    } else if (ev) {
-      const size_t plane = (size_t)band_h * out_row_stride;
-      const size_t o0 = (size_t)yo * out_row_stride + x;
-      store_elem(o0, a);
-      store_elem(o0 + plane, b);
-      store_elem(o0 + 2 * plane, c3);
-    }
-    ev = false;
-  };
-  auto emit = [&](int r, float a, float b, float c3) {
-    if (!emit_lane) return;
-    ev = true;
-    er = r;
-    ea = a; eb = b; ec = c3;
+    store_px(P, out, out_row_stride, r - (int)P.out_y0, x, band_h, a, b, c3);
   };
   // cumulative delays (steps between loading row r and the stage producing row r)
   constexpr int dG = C::G ? 2 : 0;
@@ -1698,7 +1646,6 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
         deliver(IC<4>(), r, X, Y, B);
       }
     }
-    flush_emit();
     if constexpr (H > 0) __syncthreads();
   };
 
@@ -1738,7 +1685,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
 }
 
 template <uint32_t MASK>
-__global__ void __launch_bounds__(kStripThreads, StripCfg<MASK>::E0 ? 2 : 4) filter_strip_kernel(const __grid_constant__ FrameDev P,
+__global__ void __launch_bounds__(kStripThreads) filter_strip_kernel(const __grid_constant__ FrameDev P,
                                                                     float* __restrict__ out,
                                                                     size_t out_row_stride, int seg_rows) {
   extern __shared__ __align__(16) float fsm[];
