@@ -257,9 +257,9 @@ def main() -> int:
         gathered = None
         if args.gather != "nccl":
             try:
-                # Fused compute + all-gather: the frame buffer of every rank is symmetric memory; the
-                # filter kernel stores each finished pixel straight into every peer's buffer (NVLink
-                # peer stores, or one multimem.st through the NVSwitch multicast mapping).
+                # Fused compute + all-gather: the frame buffer of every rank is symmetric memory; a filter
+                # CTA writes its strip segment into the local slot and replays it to every peer with wide
+                # stores (multimem.st.v2 through the NVSwitch multicast mapping, or NVLink peer stores).
                 import torch.distributed._symmetric_memory as symm
                 flat = symm.empty(world * slot, dtype=torch.float32, device=torch.device("cuda", local_rank))
                 hdl = symm.rendezvous(flat, dist.group.WORLD)
@@ -269,10 +269,10 @@ def main() -> int:
                     raise RuntimeError("multicast not supported here")
                 if mc:
                     pipe.set_output_replicas([], mc + rank * slot * 4)
-                    gather_mode = "fused multimem.st (NVSwitch multicast) in the filter epilogue"
+                    gather_mode = "fused in the filter kernel: each CTA replays its finished region with multimem.st.v2 (NVSwitch multicast)"
                 else:
-                    pipe.set_output_replicas([int(hdl.buffer_ptrs[p]) + rank * slot * 4 for p in range(world)])
-                    gather_mode = "fused NVLink peer stores in the filter epilogue"
+                    pipe.set_output_replicas([int(hdl.buffer_ptrs[p]) + rank * slot * 4 for p in range(world) if p != rank])
+                    gather_mode = "fused in the filter kernel: each CTA replays its finished region to the peers (NVLink P2P float2 stores)"
             except Exception as e:  # noqa: BLE001
                 log(f"symmetric memory unavailable ({e!r}): falling back to NCCL all-gather")
                 hdl = None

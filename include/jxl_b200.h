@@ -190,11 +190,13 @@ JXLGPU_API int jxlgpu_set_device_coefficients(jxlgpu_ctx* ctx, const void* const
 JXLGPU_API int jxlgpu_render_device(jxlgpu_ctx* ctx, void* dev_out, size_t out_stride_bytes,
                                     void* cuda_stream);
 /* Multi-GPU fused all-gather.  dev_ptrs[i] (i < n <= 8) are addresses -- valid on THIS device, i.e.
- * peer-mapped over NVLink -- of this band's slot inside rank i's frame buffer (own rank included);
- * the filter kernel then stores every finished pixel to all of them instead of `dev_out`, so the
- * gather overlaps the filtering.  If multicast_ptr is non-NULL it is the slot's NVSwitch multicast
- * address and one multimem.st per value replaces the n stores.  n = 0 and NULL switch it off.
- * The caller owns the cross-GPU barrier that publishes the frame (bench.py: symmetric-memory barrier). */
+ * peer-mapped over NVLink -- of this band's slot inside the other ranks' frame buffers; `dev_out` of
+ * jxlgpu_render_device is the same slot in the local frame buffer.  Every filter CTA, after writing its
+ * strip segment locally, replays it to all of them with wide coalesced stores, so the gather overlaps
+ * the filtering and no collective kernel runs.  If multicast_ptr is non-NULL it is the slot's NVSwitch
+ * multicast address and one multimem.st.v2 per 8 bytes replaces the n stores.  n = 0 and NULL switch it
+ * off.  The caller owns the cross-GPU barrier that publishes the frame (bench.py: symmetric-memory
+ * barrier).  Only the production stage chains (filter_strip_kernel) replicate. */
 JXLGPU_API int jxlgpu_set_output_replicas(jxlgpu_ctx* ctx, uint32_t n, void* const* dev_ptrs, void* multicast_ptr);
 /* Context-owned output buffer of the last render (device pointer) and its row stride. */
 JXLGPU_API int jxlgpu_device_output(jxlgpu_ctx* ctx, void** dev_ptr, size_t* stride_bytes);

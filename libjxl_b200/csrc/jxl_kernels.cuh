@@ -963,43 +963,60 @@ __global__ void __launch_bounds__(256) idct_large_kernel(const __grid_constant__
 // (Mirror(), lib/jxl/image_ops.h:184-196 -- every stage's input is mirrored about the
 // true image size, simple_render_pipeline.cc:129-164).
 // ---------------------------------------------------------------------------
-// Pixel store of the filter epilogues.  Single GPU: plain stores.  Multi-GPU: the band is
-// all-gathered BY the stores -- each value goes to this rank's slot in every peer's frame buffer
-// (peer-mapped pointers, NVLink P2P), or once to the slot's NVSwitch multicast address
-// (multimem.st: the switch replicates it), so the transfer overlaps the filtering row by row.
-__device__ __forceinline__ void mc_store(float* p, float v) {
+// Fused all-gather (multi-GPU).  A filter CTA first writes its strip segment into this rank's slot
+// of the LOCAL frame buffer, then -- while other CTAs are still filtering -- replays that region
+// (hot in L2) to every peer with wide, fully coalesced stores: one multimem.st.v2 per 8 bytes through
+// the NVSwitch multicast mapping (the switch replicates it to all GPUs), or plain peer stores over
+// NVLink P2P.  The transfer therefore overlaps the math segment by segment and no separate
+// collective kernel runs.
+__device__ __forceinline__ void mc_store2(float* p, float2 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void mc_store1(float* p, float v) {
   asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// replicate `n` floats starting at float offset `off` of the local buffer `src` (all threads of the CTA)
+__device__ __forceinline__ void replicate_span(const FrameDev& P, const float* src, size_t off, int n) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int head = (int)(off & 1);  // make the vector part 8-byte aligned
+  const int nv = (n - head) >> 1;
+  if (tid == 0) {
+    if (head) {
+      const float v = src[off];
+      if (P.mc) mc_store1(P.mc + off, v);
+      else for (uint32_t i = 0; i < P.nrep; i++) P.rep[i][off] = v;
+    }
+    if ((n - head) & 1) {
+      const size_t o = off + n - 1;
+      const float v = src[o];
+      if (P.mc) mc_store1(P.mc + o, v);
+      else for (uint32_t i = 0; i < P.nrep; i++) P.rep[i][o] = v;
+    }
+  }
+  const float2* s2 = reinterpret_cast<const float2*>(src + off + head);
+  for (int i = tid; i < nv; i += nt) {
+    const float2 v = s2[i];
+    const size_t o = off + head + 2 * (size_t)i;
+    if (P.mc) {
+      mc_store2(P.mc + o, v);
+    } else {
+#pragma unroll 1
+      for (uint32_t k = 0; k < P.nrep; k++) *reinterpret_cast<float2*>(P.rep[k] + o) = v;
+    }
+  }
 }
 
 __device__ __forceinline__ void store_px(const FrameDev& P, float* __restrict__ out, size_t out_row_stride,
                                          int yo, int x, int band_h, float a, float b, float c3) {
-  size_t o0, o1, o2;
   if (P.out_format == 0) {
-    o0 = (size_t)yo * out_row_stride + (size_t)x * 3;
-    o1 = o0 + 1;
-    o2 = o0 + 2;
+    float* o = out + (size_t)yo * out_row_stride + (size_t)x * 3;
+    o[0] = a; o[1] = b; o[2] = c3;
   } else {
     const size_t plane = (size_t)band_h * out_row_stride;
-    o0 = (size_t)yo * out_row_stride + x;
-    o1 = o0 + plane;
-    o2 = o1 + plane;
-  }
-  if (P.mc) {
-    mc_store(P.mc + o0, a);
-    mc_store(P.mc + o1, b);
-    mc_store(P.mc + o2, c3);
-  } else if (P.nrep) {
-#pragma unroll 1
-    for (uint32_t i = 0; i < P.nrep; i++) {
-      float* d = P.rep[i];
-      d[o0] = a;
-      d[o1] = b;
-      d[o2] = c3;
-    }
-  } else {
-    out[o0] = a;
-    out[o1] = b;
-    out[o2] = c3;
+    out[(size_t)yo * out_row_stride + x] = a;
+    out[plane + (size_t)yo * out_row_stride + x] = b;
+    out[2 * plane + (size_t)yo * out_row_stride + x] = c3;
   }
 }
 
@@ -1697,6 +1714,21 @@ __global__ void __launch_bounds__(kStripThreads) filter_strip_kernel(const __gri
   const bool edge = (x0 - C::H < 0) || (x0 - C::H + kStripThreads > (int)P.xsize);
   if (edge) filter_strip_body<MASK, true>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
   else filter_strip_body<MASK, false>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
+  if (P.mc || P.nrep) {
+    // fused all-gather: replay this CTA's finished region to the peers
+    __syncthreads();  // the CTA's own global writes are visible to all its threads
+    const int ncols = min(C::kOutCols, (int)P.xsize - x0);
+    const int band_h = (int)P.out_h;
+    for (int y = y_begin; y < y_end; y++) {
+      const size_t yo = (size_t)(y - (int)P.out_y0);
+      if (P.out_format == 0) {
+        replicate_span(P, out, yo * out_row_stride + (size_t)x0 * 3, ncols * 3);
+      } else {
+        for (int c = 0; c < 3; c++)
+          replicate_span(P, out, ((size_t)c * band_h + yo) * out_row_stride + x0, ncols);
+      }
+    }
+  }
 }
 
 }  // namespace jxlb
