@@ -1681,6 +1681,24 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
   const int s_begin = min(s_lo, r_end), s_end = min(s_hi, r_end);
   using F = std::false_type;
   using T = std::true_type;
+  // Fused all-gather: rows this CTA has finished (and that a __syncthreads() made visible) are
+  // replayed to the peers every few steps, so the NVLink traffic is spread over the whole kernel.
+  const bool replicate = P.mc != nullptr || P.nrep != 0;
+  const int ncols_out = min(C::kOutCols, W - x0);
+  int replayed = y_begin;
+  auto replay_to = [&](int row_excl) {
+    if constexpr (H == 0) __syncthreads();  // (chains with filters end every step with a barrier)
+    row_excl = min(row_excl, y_end);
+    for (int y = replayed; y < row_excl; y++) {
+      const size_t yo = (size_t)(y - (int)P.out_y0);
+      if (P.out_format == 0) {
+        replicate_span(P, out, yo * out_row_stride + (size_t)x0 * 3, ncols_out * 3);
+      } else {
+        for (int c = 0; c < 3; c++) replicate_span(P, out, ((size_t)c * band_h + yo) * out_row_stride + x0, ncols_out);
+      }
+    }
+    if (row_excl > replayed) replayed = row_excl;
+  };
   int rin = r_in_lo;
   for (; rin < s_begin; rin++) step(F(), IC<-1>(), rin);
   if constexpr (H > 0 && !C::E0) {
@@ -1695,10 +1713,15 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
       step(T(), IC<5>(), rin + 5);
       step(T(), IC<6>(), rin + 6);
       step(T(), IC<7>(), rin + 7);
+      if (replicate) replay_to(rin + 8 - d2);  // rows < rin + 8 - d2 have been emitted
     }
   }
-  for (; rin < s_end; rin++) step(T(), IC<-1>(), rin);
+  for (; rin < s_end; rin++) {
+    step(T(), IC<-1>(), rin);
+    if (replicate && (rin & 7) == 7) replay_to(rin + 1 - d2);
+  }
   for (; rin < r_end; rin++) step(F(), IC<-1>(), rin);
+  if (replicate) replay_to(y_end);
 }
 
 template <uint32_t MASK>
@@ -1714,21 +1737,6 @@ __global__ void __launch_bounds__(kStripThreads) filter_strip_kernel(const __gri
   const bool edge = (x0 - C::H < 0) || (x0 - C::H + kStripThreads > (int)P.xsize);
   if (edge) filter_strip_body<MASK, true>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
   else filter_strip_body<MASK, false>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
-  if (P.mc || P.nrep) {
-    // fused all-gather: replay this CTA's finished region to the peers
-    __syncthreads();  // the CTA's own global writes are visible to all its threads
-    const int ncols = min(C::kOutCols, (int)P.xsize - x0);
-    const int band_h = (int)P.out_h;
-    for (int y = y_begin; y < y_end; y++) {
-      const size_t yo = (size_t)(y - (int)P.out_y0);
-      if (P.out_format == 0) {
-        replicate_span(P, out, yo * out_row_stride + (size_t)x0 * 3, ncols * 3);
-      } else {
-        for (int c = 0; c < 3; c++)
-          replicate_span(P, out, ((size_t)c * band_h + yo) * out_row_stride + x0, ncols);
-      }
-    }
-  }
 }
 
 }  // namespace jxlb
