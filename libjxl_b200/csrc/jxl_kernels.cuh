@@ -1725,7 +1725,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
 }
 
 template <uint32_t MASK>
-__global__ void __launch_bounds__(kStripThreads) filter_strip_kernel(const __grid_constant__ FrameDev P,
+__global__ void __launch_bounds__(kStripThreads, StripCfg<MASK>::E0 ? 2 : 4) filter_strip_kernel(const __grid_constant__ FrameDev P,
                                                                     float* __restrict__ out,
                                                                     size_t out_row_stride, int seg_rows) {
   extern __shared__ __align__(16) float fsm[];
