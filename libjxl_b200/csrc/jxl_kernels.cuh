@@ -431,12 +431,10 @@ __device__ __forceinline__ void load_row8f(const float* p, float* m) {
 // vector loads and dequantises them in registers (CfL needs Y next to X and B anyway).
 // Phase B, per channel: rows go to shared memory, the strategy's transform runs on them.
 template <bool I32>
-__device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint32_t first_entry_idx,
-                                            uint32_t count, float* sm) {
+__device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 entry, bool active,
+                                            uint4 entry_next, bool next_active, float* sm) {
   const int lane = threadIdx.x & 31;
   const int slot = lane >> 3, l = lane & 7;
-  const uint32_t eidx = first_entry_idx + slot;
-  const bool active = eidx < count;
   // Inactive slots (tail of a list) run the same instruction stream on scratch data so that
   // every __syncwarp() is reached by all 32 lanes; only their loads and stores are masked.
   float* co = sm + slot * 264;   // 264 = 96 + 96 + 64 + 8: slot bases 8 banks apart
@@ -445,7 +443,7 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint32_
   VarblockCtx vb;
   float val[3][8];
   if (active) {
-    vb = make_ctx(P, __ldg(P.list + P.list_base[kind] + eidx));
+    vb = make_ctx(P, entry);
     int qx[8], qy[8], qb[8];
     float mx[8], my[8], mb[8];
     const size_t e0 = vb.cbase + (size_t)l * 8;
@@ -475,6 +473,17 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint32_
     for (int c = 0; c < 3; c++)
 #pragma unroll
       for (int e = 0; e < 8; e++) val[c][e] = 0.0f;
+  }
+  // Pull the NEXT item's coefficient lines (streamed from HBM exactly once) into L2 while this
+  // item is being transformed: no registers are held, the next item's loads become L2 hits.
+  if (next_active) {
+    constexpr int kLines = I32 ? 2 : 1;  // a block-channel is 256 / 128 contiguous bytes
+    if (l < 3 * kLines) {
+      const int ch = l / kLines, half = l % kLines;
+      const char* p = reinterpret_cast<const char*>(P.coeff[ch]) +
+                      ((size_t)entry_next.y * 64u) * (I32 ? 4 : 2) + half * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
   }
 #pragma unroll
   for (int c = 0; c < 3; c++) {
@@ -742,8 +751,20 @@ __global__ void __launch_bounds__(kSmallWarpsPerCta * 32, 4) idct8_kernel(const 
     const uint32_t count = P.counts[s];
     const uint32_t items = (count + 3) / 4;
     uint32_t it = (warp + nwarps - (base % nwarps)) % nwarps;
+    const int slot = (threadIdx.x & 31) >> 3;
+    const uint4* list = P.list + P.list_base[s];
+    const uint4 zero = make_uint4(0, 0, 1, 0);
+    bool act = it < items && it * 4 + slot < count;
+    uint4 cur = act ? __ldg(list + it * 4 + slot) : zero;
 #pragma unroll 1
-    for (; it < items; it += nwarps) block8_item<I32>(P, s, it * 4, count, sm);
+    for (; it < items; it += nwarps) {
+      const uint32_t nx = (it + nwarps) * 4 + slot;  // the record of this warp's next item is fetched now
+      const bool nact = (it + nwarps) < items && nx < count;
+      const uint4 next = nact ? __ldg(list + nx) : zero;
+      block8_item<I32>(P, s, cur, act, next, nact, sm);
+      cur = next;
+      act = nact;
+    }
     base += items;
   }
 }
