@@ -141,7 +141,7 @@ void launch_strip_mask(jxlgpu_ctx* ctx, const FrameDev& P, float* dev_out, size_
   // wave would double the kernel time), segments long enough to amortise the pipeline fill.
   static int blocks_per_sm = 0;
   if (!blocks_per_sm) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, filter_strip_kernel<MASK>, kStripThreads,
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, filter_strip_kernel<MASK, false>, kStripThreads,
                                                   C::kSmemBytes);
     if (blocks_per_sm < 1) blocks_per_sm = 1;
   }
@@ -152,7 +152,10 @@ void launch_strip_mask(jxlgpu_ctx* ctx, const FrameDev& P, float* dev_out, size_
   if (seg_rows < 64) seg_rows = 64;
   seg_rows = (seg_rows + 7) & ~7;
   segs = (band_h + seg_rows - 1) / seg_rows;
-  filter_strip_kernel<MASK><<<dim3(strips, segs), kStripThreads, C::kSmemBytes, s>>>(P, dev_out, out_stride_floats, seg_rows);
+  if (P.mc || P.nrep)  // multi-GPU: the instantiation with the fused all-gather replay
+    filter_strip_kernel<MASK, true><<<dim3(strips, segs), kStripThreads, C::kSmemBytes, s>>>(P, dev_out, out_stride_floats, seg_rows);
+  else
+    filter_strip_kernel<MASK, false><<<dim3(strips, segs), kStripThreads, C::kSmemBytes, s>>>(P, dev_out, out_stride_floats, seg_rows);
 }
 
 // the stage chains PreparePipeline can build for a VarDCT XYB frame (dec_cache.cc:151-170)
@@ -173,7 +176,10 @@ bool launch_strip(jxlgpu_ctx* ctx, const FrameDev& P, float* dev_out, size_t out
 
 template <uint32_t MASK>
 cudaError_t strip_attr() {
-  return cudaFuncSetAttribute(filter_strip_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(filter_strip_kernel<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)StripCfg<MASK>::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(filter_strip_kernel<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)StripCfg<MASK>::kSmemBytes);
 }
 

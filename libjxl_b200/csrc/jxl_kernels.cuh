@@ -1341,7 +1341,7 @@ __device__ __forceinline__ float* ring_row(float* ring, int n, int r, int c) {
   return ring + ((r & (n - 1)) * 3 + c) * kStripThreads;
 }
 
-template <uint32_t MASK, bool EDGE>
+template <uint32_t MASK, bool EDGE, bool REPL>
 __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __restrict__ out,
                                                   size_t out_row_stride, int x0, int y_begin, int y_end,
                                                   float* smem) {
@@ -1704,7 +1704,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
   using T = std::true_type;
   // Fused all-gather: rows this CTA has finished (and that a __syncthreads() made visible) are
   // replayed to the peers every few steps, so the NVLink traffic is spread over the whole kernel.
-  const bool replicate = P.mc != nullptr || P.nrep != 0;
+  constexpr bool replicate = REPL;  // separate instantiation: the single-GPU kernel carries none of this
   const int ncols_out = min(C::kOutCols, W - x0);
   int replayed = y_begin;
   auto replay_to = [&](int row_excl) {
@@ -1734,18 +1734,20 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
       step(T(), IC<5>(), rin + 5);
       step(T(), IC<6>(), rin + 6);
       step(T(), IC<7>(), rin + 7);
-      if (replicate) replay_to(rin + 8 - d2);  // rows < rin + 8 - d2 have been emitted
+      if constexpr (replicate) replay_to(rin + 8 - d2);  // rows < rin + 8 - d2 have been emitted
     }
   }
   for (; rin < s_end; rin++) {
     step(T(), IC<-1>(), rin);
-    if (replicate && (rin & 7) == 7) replay_to(rin + 1 - d2);
+    if constexpr (replicate) {
+      if ((rin & 7) == 7) replay_to(rin + 1 - d2);
+    }
   }
   for (; rin < r_end; rin++) step(F(), IC<-1>(), rin);
-  if (replicate) replay_to(y_end);
+  if constexpr (replicate) replay_to(y_end);
 }
 
-template <uint32_t MASK>
+template <uint32_t MASK, bool REPL>
 __global__ void __launch_bounds__(kStripThreads, StripCfg<MASK>::E0 ? 2 : 4) filter_strip_kernel(const __grid_constant__ FrameDev P,
                                                                     float* __restrict__ out,
                                                                     size_t out_row_stride, int seg_rows) {
@@ -1756,8 +1758,8 @@ __global__ void __launch_bounds__(kStripThreads, StripCfg<MASK>::E0 ? 2 : 4) fil
   const int y_end = min((int)P.band_y1, y_begin + seg_rows);
   if (y_begin >= y_end) return;
   const bool edge = (x0 - C::H < 0) || (x0 - C::H + kStripThreads > (int)P.xsize);
-  if (edge) filter_strip_body<MASK, true>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
-  else filter_strip_body<MASK, false>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
+  if (edge) filter_strip_body<MASK, true, REPL>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
+  else filter_strip_body<MASK, false, REPL>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
 }
 
 }  // namespace jxlb
