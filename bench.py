@@ -45,6 +45,10 @@ WORKLOADS = {
 }
 
 
+OUTPUT_TEXT = {"f32": "interleaved linear RGB f32 (12 B/px)",
+               "srgb8": "interleaved sRGB 8-bit, FromLinear + dithered WriteToOutput as djxl writes it (3 B/px)"}
+
+
 def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
@@ -124,13 +128,13 @@ def prepare_frame(name: str, rank: int, world: int, barrier):
     return fr, source
 
 
-def algorithmic_bytes(desc, rows: int) -> dict:
+def algorithmic_bytes(desc, rows: int, out_px_bytes: int = 12) -> dict:
     """bytes one launch must move, per kernel, for `rows` pixel rows."""
     px = desc.xsize * rows
     es = 2 if desc.ac_type == 0 else 4
     side = 21.0 / 64.0  # acs 1 + quant 4 + sigma 4 + dc 12 bytes per 8x8 block
-    return {"idct": px * (3 * es + side + 12), "filter": px * (12 + 12 + 4.0 / 64),
-            "fused_path": px * (3 * es + side + 12)}
+    return {"idct": px * (3 * es + side + 12), "filter": px * (12 + out_px_bytes + 4.0 / 64),
+            "fused_path": px * (3 * es + side + out_px_bytes)}
 
 
 def run_reference(args, rank: int) -> int:
@@ -145,11 +149,22 @@ def run_reference(args, rank: int) -> int:
     cores = os.cpu_count() or 1
     fr = wl.reference_frame(w, h, dist, effort, gab, epf, seed=1234, kind=kind, cache=True)
     frame = ref.Frame(fr["jxl"], cores)
-    _, _ = frame.render(-1, reps=max(1, args.warmup), want_output=False)
-    _, secs = frame.render(-1, reps=args.steps, want_output=False)
+
+    def hot(kind, reps):
+        if kind == "f32":   # ... XYB -> linear RGB, planar float image (the path's §8 scope)
+            return frame.render(-1, reps=reps, want_output=False)[1]
+        # ... + FromLinear (sRGB) + WriteToOutput into an interleaved 8-bit buffer (what djxl writes)
+        return frame.render_out(-33, 2, reps=reps, want_output=False)[1]
+
+    hot(args.output, max(1, args.warmup))
+    secs = hot(args.output, args.steps)
+    other = "srgb8" if args.output == "f32" else "f32"
+    hot(other, 1)
+    other_secs = hot(other, max(3, min(args.steps, 8)))
     frame.close()
     total = float(np.sum(secs))
     mps = w * h * args.steps / total / 1e6
+    other_mps = w * h * len(other_secs) / float(np.sum(other_secs)) / 1e6
     # whole decoder (entropy decode included) for context
     runner = ref.Runner(cores)
     out = np.empty((h, w, 3), np.float32)
@@ -166,7 +181,9 @@ def run_reference(args, rank: int) -> int:
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{name}: {w}x{h} VarDCT d{dist} e{effort}, hot path only "
-                               "(DecodeGroupForRoundtrip + reference Gaborish/EPF/XYB stages) on host CPU"},
+                               "(DecodeGroupForRoundtrip + reference Gaborish/EPF/XYB stages) on host CPU, "
+                               f"output {OUTPUT_TEXT[args.output]}"},
+        "variants": {other: {"value": other_mps, "unit": "Mpixel/s", "output": OUTPUT_TEXT[other]}},
         "cpu_baseline": {"value": mps, "unit": "Mpixel/s", "cores": cores, "kind": "reference",
                          "sample": f"{args.steps} passes over the full {w}x{h} frame",
                          "full_decode_mpixels_per_s": full},
@@ -185,6 +202,11 @@ def main() -> int:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="8k-d1", choices=list(WORKLOADS))
+    ap.add_argument("--output", default="f32", choices=["f32", "srgb8"],
+                    help="pixel format the path ends in: linear f32 (the §8 scope, default) or sRGB 8-bit "
+                         "(sRGB transfer function + WriteToOutput packing fused into the filter kernel's store); "
+                         "the other one is measured too and reported under \"variants\"")
+    ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "p2p", "nccl"],
                     help="N>1: how the bands are all-gathered (auto: fused multicast stores if the switch "
@@ -234,179 +256,220 @@ def main() -> int:
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
 
-    # ---------------- device-resident arm ----------------
-    dev_coeff = torch.zeros((3, desc.num_groups, abi.GROUP_COEFFS), dtype=torch.int16 if es == 2 else torch.int32,
-                            device="cuda") if world == 1 else None
-    if world == 1:
-        dev_coeff.copy_(torch.from_numpy(coeffs))
-        ptrs = [dev_coeff[c].data_ptr() for c in range(3)]
-    else:
-        # only the groups this rank needs live on its GPU; the planes keep frame-wide indexing
-        g0, g1 = min(need), max(need) + 1
-        dev_part = torch.from_numpy(np.ascontiguousarray(coeffs[:, g0:g1])).cuda()
-        ptrs = [dev_part[c].data_ptr() - g0 * abi.GROUP_COEFFS * es for c in range(3)]
-    pipe.set_device_coefficients(ptrs)
-    pipe.frame_begin(desc)
-    gather_mode = "none"
-    hdl = None
-    if world == 1:
-        gathered = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
-        my_out = gathered
-    else:
-        slot = max_rows * W * 3
-        gathered = None
-        if args.gather != "nccl":
-            try:
-                # Fused compute + all-gather: the frame buffer of every rank is symmetric memory; a filter
-                # CTA writes its strip segment into the local slot and replays it to every peer with wide
-                # stores (multimem.st.v2 through the NVSwitch multicast mapping, or NVLink peer stores).
-                import torch.distributed._symmetric_memory as symm
-                flat = symm.empty(world * slot, dtype=torch.float32, device=torch.device("cuda", local_rank))
-                hdl = symm.rendezvous(flat, dist.group.WORLD)
-                gathered = flat.view(world, max_rows, W, 3)
-                # measured on this box (N=2): peer stores 0.84 ms/step, multimem.st.v2 1.16 ms -> auto = p2p
-                mc = int(hdl.multicast_ptr) if args.gather == "multicast" else 0
-                if args.gather == "multicast" and not mc:
-                    raise RuntimeError("multicast not supported here")
-                if mc:
-                    pipe.set_output_replicas([], mc + rank * slot * 4)
-                    gather_mode = "fused in the filter kernel: each CTA replays its finished region with multimem.st.v2 (NVSwitch multicast)"
-                else:
-                    pipe.set_output_replicas([int(hdl.buffer_ptrs[p]) + rank * slot * 4 for p in range(world) if p != rank])
-                    gather_mode = "fused in the filter kernel: each CTA replays its finished region to the peers (NVLink P2P float2 stores)"
-            except Exception as e:  # noqa: BLE001
-                log(f"symmetric memory unavailable ({e!r}): falling back to NCCL all-gather")
-                hdl = None
-                gathered = None
-        if gathered is None:
-            gathered = torch.empty((world, max_rows, W, 3), dtype=torch.float32, device="cuda")
-            gather_mode = "NCCL all_gather_into_tensor after the filter kernel"
-        my_out = gathered[rank]
-
-    def step():
-        pipe.render_device(my_out.data_ptr(), W * 12, stream.cuda_stream)
-        if world > 1:
-            if hdl is not None:
-                hdl.barrier(channel=0)      # publishes the peers' stores: the frame is complete everywhere
+    def measure(kind: str, full: bool) -> dict:
+        """Device-resident arm + (full: per-kernel pass, parity) + end-to-end arm for one output kind."""
+        out_fmt = abi.OUT_RGB_F32 if kind == "f32" else abi.OUT_RGB_U8
+        desc.out_format = out_fmt
+        desc.stage_mask = 0 if kind == "f32" else abi.STAGE_SRGB
+        tdtype = torch.float32 if kind == "f32" else torch.uint8
+        ndtype = np.float32 if kind == "f32" else np.uint8
+        isz = 4 if kind == "f32" else 1          # bytes per sample
+        row_bytes = W * 3 * isz
+        # ---------------- device-resident arm ----------------
+        if "ptrs" not in shared:
+            if world == 1:
+                dev = torch.zeros((3, desc.num_groups, abi.GROUP_COEFFS), dtype=torch.int16 if es == 2 else torch.int32,
+                                  device="cuda")
+                dev.copy_(torch.from_numpy(coeffs))
+                shared["ptrs"] = [dev[c].data_ptr() for c in range(3)]
             else:
-                dist.all_gather_into_tensor(gathered.view(-1), my_out.reshape(-1))
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = pipe.launch_count()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step()
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = pipe.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = W * H / (ms_step * 1e-3) / 1e6
-
-    # per-kernel times (separate pass, CUDA events inside the library on the same stream)
-    pipe.set_output_replicas([], 0)   # per-kernel times and the e2e arm run without the gather
-    if world > 1:
-        my_out = torch.empty((max_rows, W, 3), dtype=torch.float32, device="cuda")
-    pipe.set_profiling(True)
-    ktimes = {"plan": [], "idct8": [], "idct_mid": [], "idct_large": [], "filter": []}
-    for _ in range(max(5, min(args.steps, 20))):
-        pipe.render_device(my_out.data_ptr(), W * 12, stream.cuda_stream)
-        for k, v in pipe.kernel_times_ms().items():
-            ktimes[k].append(v)
-    pipe.set_profiling(False)
-    kavg = {k: float(np.mean(v)) for k, v in ktimes.items()}
-
-    # correctness spot check of the timed output against the reference decoder's pixels
-    parity = None
-    if fr.get("decoded") is not None and rank == 0:
-        if world == 1:
-            got = gathered.cpu().numpy()
-        else:  # every band, as it arrived in rank 0's frame buffer
-            got = np.concatenate([gathered[r, :sharding.band_pixel_rows(desc, *bands[r])[1]].cpu().numpy()
-                                  for r in range(world)])
-        want = fr["decoded"][:got.shape[0]]
-        d = np.abs(got - want)
-        parity = {"peak_abs_err_vs_reference": float(d.max()), "rmse_vs_reference": float(np.sqrt(np.mean(d * d))),
-                  "rows_checked": int(got.shape[0])}
-
-    # ---------------- end-to-end arm: host buffers through the C ABI ----------------
-    pipe.set_device_coefficients(None)
-    # Host layout: one pinned [3][65536] block per AC group (what a pinned ACImage subclass gives
-    # libjxl's entropy decoder to write into) -> each group is one DMA.
-    host_all = pipeline.pinned_array((len(need), 3, abi.GROUP_COEFFS), coeffs.dtype)
-    host_groups = {}
-    h2d = 0
-    for i, g in enumerate(need):
-        n = desc.group_ncoeff(g)
-        host_all[i] = coeffs[:, g]
-        host_groups[g] = [host_all[i, c, :n] for c in range(3)]
-        h2d += (2 * abi.GROUP_COEFFS + n) * coeffs.dtype.itemsize
-    yb, xb = desc.ysize_blocks, desc.xsize_blocks
-    h2d += yb * xb * (1 + 4 + 1 + 12) + desc.dequant.nbytes + 2 * desc.ytox.size
-    host_out = pipeline.pinned_array((band_rows, W, 3), np.float32)
-    d2h = host_out.nbytes
-
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(n_submit_threads)
-
-    # what libjxl's worker threads do after entropy-decoding their groups (dec_frame.cc:707-730);
-    # the argument arrays are marshalled once, outside the timed region (ctypes overhead is not
-    # part of the path)
-    # each thread hands over whole AC-group rows (30 adjacent blocks at 8K -> one 23.6 MB DMA)
-    xg = desc.xsize_groups
-    rows_of = sorted({g // xg for g in need})
-    batches = [pipe.make_batch([g for r in rows_of[tid::n_submit_threads] for g in need if g // xg == r], host_groups)
-               for tid in range(n_submit_threads)]
-
-    def submit_slice(tid):
-        pipe.submit_batch(batches[tid], tid)
-
-    phase = [0.0, 0.0, 0.0]
-
-    def e2e_step():
-        t0 = time.perf_counter()
+                # only the groups this rank needs live on its GPU; the planes keep frame-wide indexing
+                g0, g1 = min(need), max(need) + 1
+                dev = torch.from_numpy(np.ascontiguousarray(coeffs[:, g0:g1])).cuda()
+                shared["ptrs"] = [dev[c].data_ptr() - g0 * abi.GROUP_COEFFS * es for c in range(3)]
+            shared["dev"] = dev
+        pipe.set_device_coefficients(shared["ptrs"])
         pipe.frame_begin(desc)
-        pipe.frame_set_output(host_out)          # rows stream back as they finish
-        t1 = time.perf_counter()
-        list(pool.map(submit_slice, range(n_submit_threads)))
-        t2 = time.perf_counter()
-        pipe.frame_finish(host_out)
-        t3 = time.perf_counter()
-        phase[0] += t1 - t0
-        phase[1] += t2 - t1
-        phase[2] += t3 - t2
+        gather_mode = "none"
+        hdl = None
+        if world == 1:
+            gathered = torch.empty((H, W, 3), dtype=tdtype, device="cuda")
+            my_out = gathered
+        else:
+            slot = max_rows * W * 3
+            gathered = None
+            if args.gather != "nccl":
+                try:
+                    # Fused compute + all-gather: the frame buffer of every rank is symmetric memory; a filter
+                    # CTA writes its strip segment into the local slot and replays it to every peer with wide
+                    # stores (multimem.st.v2 through the NVSwitch multicast mapping, or NVLink peer stores).
+                    import torch.distributed._symmetric_memory as symm
+                    flat = symm.empty(world * slot, dtype=tdtype, device=torch.device("cuda", local_rank))
+                    hdl = symm.rendezvous(flat, dist.group.WORLD)
+                    gathered = flat.view(world, max_rows, W, 3)
+                    # measured on this box (N=2): peer stores 0.84 ms/step, multimem.st.v2 1.16 ms -> auto = p2p
+                    mc = int(hdl.multicast_ptr) if args.gather == "multicast" else 0
+                    if args.gather == "multicast" and not mc:
+                        raise RuntimeError("multicast not supported here")
+                    if mc:
+                        pipe.set_output_replicas([], mc + rank * slot * isz)
+                        gather_mode = "fused in the filter kernel: each CTA replays its finished region with multimem.st.v2 (NVSwitch multicast)"
+                    else:
+                        pipe.set_output_replicas([int(hdl.buffer_ptrs[p]) + rank * slot * isz for p in range(world) if p != rank])
+                        gather_mode = "fused in the filter kernel: each CTA replays its finished region to the peers (NVLink P2P float2 stores)"
+                except Exception as e:  # noqa: BLE001
+                    log(f"symmetric memory unavailable ({e!r}): falling back to NCCL all-gather")
+                    hdl = None
+                    gathered = None
+            if gathered is None:
+                gathered = torch.empty((world, max_rows, W, 3), dtype=tdtype, device="cuda")
+                gather_mode = "NCCL all_gather_into_tensor after the filter kernel"
+            my_out = gathered[rank]
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    n_e2e = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / n_e2e
-    log(f"e2e phases (ms, avg incl. 2 warm-ups): begin {1e3 * phase[0] / (n_e2e + 2):.2f} "
-        f"submit {1e3 * phase[1] / (n_e2e + 2):.2f} finish {1e3 * phase[2] / (n_e2e + 2):.2f}")
-    te = torch.tensor([e2e_s], device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = W * H / float(te.item()) / 1e6
-    h2d_t = torch.tensor([float(h2d), float(d2h)], device="cuda")
-    if world > 1:
-        dist.all_reduce(h2d_t)
+        def step():
+            pipe.render_device(my_out.data_ptr(), row_bytes, stream.cuda_stream)
+            if world > 1:
+                if hdl is not None:
+                    hdl.barrier(channel=0)      # publishes the peers' stores: the frame is complete everywhere
+                else:
+                    dist.all_gather_into_tensor(gathered.view(-1), my_out.reshape(-1))
+
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = pipe.launch_count()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        launches = pipe.launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        t = torch.tensor([ms_total], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item()) / args.steps
+        value = W * H / (ms_step * 1e-3) / 1e6
+
+        res = {"value": value, "ms_per_step": ms_step, "launches": int(launches), "clocks": clocks,
+               "gather_mode": gather_mode}
+        # per-kernel times (separate pass, CUDA events inside the library on the same stream)
+        pipe.set_output_replicas([], 0)   # per-kernel times and the e2e arm run without the gather
+        if world > 1:
+            my_out = torch.empty((max_rows, W, 3), dtype=tdtype, device="cuda")
+        pipe.set_profiling(True)
+        ktimes = {"plan": [], "idct8": [], "idct_mid": [], "idct_large": [], "filter": []}
+        for _ in range(max(5, min(args.steps, 20))):
+            pipe.render_device(my_out.data_ptr(), row_bytes, stream.cuda_stream)
+            for k, v in pipe.kernel_times_ms().items():
+                ktimes[k].append(v)
+        pipe.set_profiling(False)
+        res["kernel_ms"] = {k: float(np.mean(v)) for k, v in ktimes.items()}
+
+        # correctness spot check of the timed output against the reference decoder's pixels
+        parity = None
+        if fr.get("decoded") is not None and rank == 0 and full:
+            if world == 1:
+                got = gathered.cpu().numpy()
+            else:  # every band, as it arrived in rank 0's frame buffer
+                got = np.concatenate([gathered[r, :sharding.band_pixel_rows(desc, *bands[r])[1]].cpu().numpy()
+                                      for r in range(world)])
+            if kind == "f32":
+                want = fr["decoded"][:got.shape[0]]
+                d = np.abs(got - want)
+                parity = {"peak_abs_err_vs_reference": float(d.max()),
+                          "rmse_vs_reference": float(np.sqrt(np.mean(d * d))), "rows_checked": int(got.shape[0])}
+            else:
+                from oracle import ref
+                if ref.available() and fr.get("jxl") is not None:
+                    frame = ref.Frame(fr["jxl"], os.cpu_count() or 1)
+                    want, _ = frame.render_out(-33, 2)        # the reference's own 8-bit sRGB bytes
+                    frame.close()
+                    d = np.abs(got.astype(np.int16) - want[:got.shape[0]].astype(np.int16))
+                    parity = {"max_code_diff_vs_reference": int(d.max()),
+                              "fraction_differing": float((d != 0).mean()), "rows_checked": int(got.shape[0])}
+        res["parity"] = parity
+        del gathered, my_out
+
+        # ---------------- end-to-end arm: host buffers through the C ABI ----------------
+        pipe.set_device_coefficients(None)
+        # Host layout: one pinned [3][65536] block per AC group (what a pinned ACImage subclass gives
+        # libjxl's entropy decoder to write into) -> each group is one DMA.
+        if "host_groups" not in shared:
+            host_all = pipeline.pinned_array((len(need), 3, abi.GROUP_COEFFS), coeffs.dtype)
+            host_groups = {}
+            h2d = 0
+            for i, g in enumerate(need):
+                n = desc.group_ncoeff(g)
+                host_all[i] = coeffs[:, g]
+                host_groups[g] = [host_all[i, c, :n] for c in range(3)]
+                h2d += (2 * abi.GROUP_COEFFS + n) * coeffs.dtype.itemsize
+            yb, xb = desc.ysize_blocks, desc.xsize_blocks
+            h2d += yb * xb * (1 + 4 + 1 + 12) + desc.dequant.nbytes + 2 * desc.ytox.size
+            shared["host_groups"], shared["h2d"] = host_groups, h2d
+        host_groups, h2d = shared["host_groups"], shared["h2d"]
+        host_out = pipeline.pinned_array((band_rows, W, 3), ndtype)
+        d2h = host_out.nbytes
+
+        from concurrent.futures import ThreadPoolExecutor
+        if "pool" not in shared:
+            shared["pool"] = ThreadPoolExecutor(n_submit_threads)
+        pool = shared["pool"]
+
+        # what libjxl's worker threads do after entropy-decoding their groups (dec_frame.cc:707-730);
+        # the argument arrays are marshalled once, outside the timed region (ctypes overhead is not
+        # part of the path)
+        # each thread hands over whole AC-group rows (30 adjacent blocks at 8K -> one 23.6 MB DMA)
+        xg = desc.xsize_groups
+        rows_of = sorted({g // xg for g in need})
+        batches = [pipe.make_batch([g for r in rows_of[tid::n_submit_threads] for g in need if g // xg == r], host_groups)
+                   for tid in range(n_submit_threads)]
+
+        def submit_slice(tid):
+            pipe.submit_batch(batches[tid], tid)
+
+        phase = [0.0, 0.0, 0.0]
+
+        def e2e_step():
+            t0 = time.perf_counter()
+            pipe.frame_begin(desc)
+            pipe.frame_set_output(host_out)          # rows stream back as they finish
+            t1 = time.perf_counter()
+            list(pool.map(submit_slice, range(n_submit_threads)))
+            t2 = time.perf_counter()
+            pipe.frame_finish(host_out)
+            t3 = time.perf_counter()
+            phase[0] += t1 - t0
+            phase[1] += t2 - t1
+            phase[2] += t3 - t2
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        n_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        log(f"[{kind}] e2e phases (ms, avg incl. 2 warm-ups): begin {1e3 * phase[0] / (n_e2e + 2):.2f} "
+            f"submit {1e3 * phase[1] / (n_e2e + 2):.2f} finish {1e3 * phase[2] / (n_e2e + 2):.2f}")
+        te = torch.tensor([e2e_s], device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_value = W * H / float(te.item()) / 1e6
+        h2d_t = torch.tensor([float(h2d), float(d2h)], device="cuda")
+        if world > 1:
+            dist.all_reduce(h2d_t)
+        res["e2e"] = {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d_t[0].item()),
+                      "d2h_bytes_per_step": int(h2d_t[1].item()), "steps": n_e2e}
+        return res
+
+    shared = {}
+    primary = measure(args.output, True)
+    other_kind = "srgb8" if args.output == "f32" else "f32"
+    variant = None if args.no_variants else measure(other_kind, True)
+    desc.out_format = abi.OUT_RGB_F32 if args.output == "f32" else abi.OUT_RGB_U8
+    value, ms_step, launches, clocks = primary["value"], primary["ms_per_step"], primary["launches"], primary["clocks"]
+    kavg, parity, gather_mode = primary["kernel_ms"], primary["parity"], primary["gather_mode"]
     pipe.close()
 
     if rank != 0:
@@ -421,7 +484,7 @@ def main() -> int:
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    ab = algorithmic_bytes(desc, band_rows)
+    ab = algorithmic_bytes(desc, band_rows, 12 if args.output == "f32" else 3)
     k_idct = kavg["idct8"] + kavg["idct_mid"] + kavg["idct_large"]
     dominant = "filter" if kavg["filter"] >= k_idct else "idct"
     dom_ms = kavg["filter"] if dominant == "filter" else k_idct
@@ -439,11 +502,18 @@ def main() -> int:
         from oracle import ref
         cores = os.cpu_count() or 1
         frame = ref.Frame(fr["jxl"], cores)
-        frame.render(-1, reps=1, want_output=False)
         reps = 8
-        _, secs = frame.render(-1, reps=reps, want_output=False)
+        hot_by_kind = {}
+        for kind in ("f32", "srgb8"):
+            if kind == "f32":
+                frame.render(-1, reps=1, want_output=False)
+                _, secs = frame.render(-1, reps=reps, want_output=False)
+            else:
+                frame.render_out(-33, 2, reps=1, want_output=False)
+                _, secs = frame.render_out(-33, 2, reps=reps, want_output=False)
+            hot_by_kind[kind] = W * H * reps / float(np.sum(secs)) / 1e6
         frame.close()
-        hot = W * H * reps / float(np.sum(secs)) / 1e6
+        hot = hot_by_kind[args.output]
         runner = ref.Runner(cores)
         out = np.empty((H, W, 3), np.float32)
         ref.decode_linear_f32(fr["jxl"], cores, out, runner)
@@ -455,7 +525,7 @@ def main() -> int:
         cpu_baseline = {"value": hot, "unit": "Mpixel/s", "cores": cores, "kind": "reference",
                         "sample": f"{reps} passes of the reference's own hot-path code over the same {W}x{H} frame "
                                   "(coefficients pre-decoded); full_decode = whole libjxl decoder incl. entropy decode, 3 passes",
-                        "full_decode_mpixels_per_s": full}
+                        "full_decode_mpixels_per_s": full, "by_output": hot_by_kind}
 
     w_, h_, dist_, effort_, _, _, _ = WORKLOADS[args.workload]
     line = {
@@ -464,18 +534,23 @@ def main() -> int:
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {W}x{H} VarDCT d{dist_} e{effort_}, gab={desc.gab} epf_iters={desc.epf_iters}, "
                                f"{source}, coefficients {'int16' if es == 2 else 'int32'} as the reference decoder chose, "
-                               "output interleaved linear RGB f32",
+                               f"output {OUTPUT_TEXT[args.output]}",
                    "groups": desc.num_groups, "parallelism": f"band-sharded x{world}; all-gather: {gather_mode}" if world > 1 else "1 GPU",
                    "strategy_histogram": fr["hist"], "bpp": fr["bpp"],
                    "l2": "inputs larger than L2 (coefficients + XYB planes + output >> 126 MB per step)"},
-        "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d_t[0].item()),
-                "d2h_bytes_per_step": int(h2d_t[1].item()), "steps": n_e2e,
+        "e2e": {**primary["e2e"],
                 "how": f"frame_begin + frame_set_output + submit_groups (one AC-group row per call, {n_submit_threads} host "
                        "threads, pinned [group][3][65536] host blocks) + frame_finish; H2D / kernels / D2H overlap per row"},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "parity": parity,
     }
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
+    if variant is not None:
+        # the same frame with the other output kind (same kernels; only the fused store differs)
+        line["variants"] = {other_kind: {"output": OUTPUT_TEXT[other_kind], "value": variant["value"],
+                                         "ms_per_step": variant["ms_per_step"], "kernel_ms": variant["kernel_ms"],
+                                         "e2e": variant["e2e"], "parity": variant["parity"],
+                                         "cpu_reference_hot_path": (cpu_baseline or {}).get("by_output", {}).get(other_kind)}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

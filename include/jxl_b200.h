@@ -12,6 +12,9 @@
  *   EPF pass 0 / 1 / 2 (+ sigma)                                    (replaces render_pipeline/stage_epf.cc, epf.cc:39-133)
  *   XYB -> linear RGB                                               (replaces render_pipeline/stage_xyb.cc:78-98,
  *                                                                    dec_xyb-inl.h:38-86)
+ *   optional: linear -> sRGB transfer function                      (replaces render_pipeline/stage_from_linear.cc:42-53,
+ *                                                                    cms/transfer_functions-inl.h:244-267)
+ *   output packing f32 / f16 / u16 / dithered u8, RGB or RGBA       (replaces render_pipeline/stage_write.cc:455-640)
  *
  * as hand-written sm_100a CUDA kernels and returns the finished frame.
  *
@@ -41,7 +44,7 @@ extern "C" {
 #define JXLGPU_API
 #endif
 
-#define JXLGPU_ABI_VERSION 1
+#define JXLGPU_ABI_VERSION 2
 
 enum {
   JXLGPU_OK = 0,
@@ -62,7 +65,14 @@ enum { JXLGPU_AC_INT16 = 0, JXLGPU_AC_INT32 = 1 };
 enum {
   JXLGPU_OUT_RGB_F32 = 0,       /* interleaved linear RGB float32, what JxlDecoderSetImageOutBuffer
                                    delivers for {3, JXL_TYPE_FLOAT} (decode.h:1021, types.h:80-104) */
-  JXLGPU_OUT_PLANAR_F32 = 1     /* 3 planes [c][y][x]; also used for intermediate-stage taps */
+  JXLGPU_OUT_PLANAR_F32 = 1,    /* 3 planes [c][y][x]; also used for intermediate-stage taps */
+  /* The packed formats of WriteToOutputStage (stage_write.cc:455-640), native endianness, no
+   * orientation change.  Unsigned: v*(2^bits-1), clamp, round-half-even (MakeUnsigned, :455-479);
+   * 8-bit adds the reference's 32x32 ordered dither (:466-471).  Row stride >= xsize * pixel bytes. */
+  JXLGPU_OUT_RGB_U8 = 2,        /* {3, JXL_TYPE_UINT8}: what djxl writes for 8-bit images */
+  JXLGPU_OUT_RGBA_U8 = 3,       /* {4, JXL_TYPE_UINT8}, opaque alpha (no alpha channel on this path) */
+  JXLGPU_OUT_RGB_U16 = 4,       /* {3, JXL_TYPE_UINT16} */
+  JXLGPU_OUT_RGB_F16 = 5        /* {3, JXL_TYPE_FLOAT16}: round-to-nearest-even demotion (:590-640) */
 };
 
 /* Stage selection bits for jxlgpu_frame.stage_mask (0 = derive from gab/epf_iters,
@@ -73,6 +83,10 @@ enum {
   JXLGPU_STAGE_EPF1 = 4,
   JXLGPU_STAGE_EPF2 = 8,
   JXLGPU_STAGE_XYB = 16,
+  JXLGPU_STAGE_SRGB = 32,  /* FromLinearStage<OpRgb>: sRGB OETF after XYB (stage_from_linear.cc:42-53).
+                              Not part of the derived chain: OR it into stage_mask (alone, = derived
+                              chain + transfer function, or together with EXPLICIT) when the output
+                              colour encoding's transfer function is sRGB (stage_from_linear.cc:161-166) */
   JXLGPU_STAGE_EXPLICIT = 1u << 31 /* set to make stage_mask authoritative (test taps) */
 };
 
@@ -137,7 +151,7 @@ typedef struct jxlgpu_frame {
   float opsin_biases_cbrt[3];
 
   uint32_t out_format;          /* JXLGPU_OUT_* */
-  uint32_t stage_mask;          /* 0, or JXLGPU_STAGE_EXPLICIT | bits */
+  uint32_t stage_mask;          /* 0, JXLGPU_STAGE_SRGB, or JXLGPU_STAGE_EXPLICIT | bits */
 } jxlgpu_frame;
 
 JXLGPU_API uint32_t jxlgpu_abi_version(void);

@@ -12,15 +12,18 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NUM_STRATEGIES = 27
 GROUP_DIM = 256
 GROUP_COEFFS = 65536
 
 OK, ERR_INVALID_ARGUMENT, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_STATE = range(7)
 AC_INT16, AC_INT32 = 0, 1
-OUT_RGB_F32, OUT_PLANAR_F32 = 0, 1
-STAGE_GAB, STAGE_EPF0, STAGE_EPF1, STAGE_EPF2, STAGE_XYB = 1, 2, 4, 8, 16
+OUT_RGB_F32, OUT_PLANAR_F32, OUT_RGB_U8, OUT_RGBA_U8, OUT_RGB_U16, OUT_RGB_F16 = range(6)
+STAGE_GAB, STAGE_EPF0, STAGE_EPF1, STAGE_EPF2, STAGE_XYB, STAGE_SRGB = 1, 2, 4, 8, 16, 32
+# out_format -> (numpy dtype, channels per pixel); OUT_PLANAR_F32 is the one planar layout
+OUT_LAYOUT = {OUT_RGB_F32: ("float32", 3), OUT_PLANAR_F32: ("float32", 1), OUT_RGB_U8: ("uint8", 3),
+              OUT_RGBA_U8: ("uint8", 4), OUT_RGB_U16: ("uint16", 3), OUT_RGB_F16: ("float16", 3)}
 STAGE_EXPLICIT = 1 << 31
 
 # AcStrategy geometry, lib/jxl/ac_strategy.h:148-173
@@ -131,6 +134,23 @@ class FrameDesc:
     @property
     def num_groups(self) -> int:
         return self.xsize_groups * self.ysize_groups
+
+    def out_shape(self, rows: int | None = None) -> tuple:
+        """Shape of the (dense) output array for `rows` pixel rows (default: this band's rows)."""
+        if rows is None:
+            rows = self.band_rows()[1]
+        if self.out_format == OUT_PLANAR_F32:
+            return (3, rows, self.xsize)
+        return (rows, self.xsize, OUT_LAYOUT[self.out_format][1])
+
+    @property
+    def out_dtype(self):
+        return np.dtype(OUT_LAYOUT[self.out_format][0])
+
+    @property
+    def out_row_bytes(self) -> int:
+        dt, ch = OUT_LAYOUT[self.out_format]
+        return self.xsize * ch * np.dtype(dt).itemsize
 
     def band_rows(self) -> tuple[int, int]:
         """(first pixel row, number of pixel rows) this band renders."""

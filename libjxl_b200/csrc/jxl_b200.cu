@@ -80,7 +80,7 @@ struct jxlgpu_ctx {
   size_t host_out_stride = 0;
   int stream_error = 0;
   DevBuf acs, quant, sharp, ytox, ytob, dc, dq, coeff, coeff_off, sigma, list, counts, xyb, out;
-  size_t out_stride_floats = 0;
+  size_t out_row_bytes = 0;   // dense row of the context-owned output buffer
   std::atomic<uint64_t> launches{0};
   bool force_generic_filter = false;  // JXLGPU_FORCE_GENERIC_FILTER=1: tile kernel for every chain
   bool profile = false;               // record CUDA events around every kernel (bench roofline)
@@ -102,8 +102,15 @@ int fail_cuda(jxlgpu_ctx* ctx, cudaError_t e, const char* what) {
     if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call); \
   } while (0)
 
-size_t out_floats_per_row(const jxlgpu_frame& f) {
-  return f.out_format == JXLGPU_OUT_RGB_F32 ? (size_t)f.xsize * 3 : (size_t)f.xsize;
+size_t out_bytes_per_row(const jxlgpu_frame& f) { return (size_t)f.xsize * out_pixel_bytes(f.out_format); }
+size_t out_planes(uint32_t out_format) { return out_format == JXLGPU_OUT_PLANAR_F32 ? 3 : 1; }
+// alignment the store instructions of a layout need from the row stride (and base pointer)
+size_t out_align(uint32_t out_format) {
+  switch (out_format) {
+    case JXLGPU_OUT_RGB_U8: return 1;
+    case JXLGPU_OUT_RGB_U16: case JXLGPU_OUT_RGB_F16: return 2;
+    default: return 4;
+  }
 }
 
 // copies a strided host plane into a dense device plane (one linear DMA when it is dense)
@@ -122,8 +129,8 @@ cudaError_t download_rows(void* dst, size_t dst_stride, const void* src, size_t 
 }
 
 uint32_t effective_mask(const jxlgpu_frame& f) {
-  if (f.stage_mask & JXLGPU_STAGE_EXPLICIT) return f.stage_mask & 31u;
-  uint32_t m = JXLGPU_STAGE_XYB;  // PassesDecoderState::PreparePipeline order, dec_cache.cc:151-170
+  if (f.stage_mask & JXLGPU_STAGE_EXPLICIT) return f.stage_mask & 63u;
+  uint32_t m = JXLGPU_STAGE_XYB | (f.stage_mask & JXLGPU_STAGE_SRGB);  // PassesDecoderState::PreparePipeline order, dec_cache.cc:151-170
   if (f.gab) m |= JXLGPU_STAGE_GAB;
   if (f.epf_iters >= 3) m |= JXLGPU_STAGE_EPF0;
   if (f.epf_iters >= 1) m |= JXLGPU_STAGE_EPF1;
@@ -131,56 +138,21 @@ uint32_t effective_mask(const jxlgpu_frame& f) {
   return m;
 }
 
-template <uint32_t MASK>
-void launch_strip_mask(jxlgpu_ctx* ctx, const FrameDev& P, float* dev_out, size_t out_stride_floats,
-                       cudaStream_t s) {
-  using C = StripCfg<MASK>;
-  const int band_h = (int)(P.band_y1 - P.band_y0);
-  const int strips = ((int)P.xsize + C::kOutCols - 1) / C::kOutCols;
-  // Exactly one wave: as many CTAs as fit on the chip at this kernel's occupancy (a 5% second
-  // wave would double the kernel time), segments long enough to amortise the pipeline fill.
-  static int blocks_per_sm = 0;
-  if (!blocks_per_sm) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, filter_strip_kernel<MASK, false>, kStripThreads,
-                                                  C::kSmemBytes);
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-  }
-  const int slots = ctx->num_sms * blocks_per_sm;
-  int segs = slots / strips;
-  if (segs < 1) segs = 1;
-  int seg_rows = (band_h + segs - 1) / segs;
-  if (seg_rows < 64) seg_rows = 64;
-  seg_rows = (seg_rows + 7) & ~7;
-  segs = (band_h + seg_rows - 1) / seg_rows;
-  if (P.mc || P.nrep)  // multi-GPU: the instantiation with the fused all-gather replay
-    filter_strip_kernel<MASK, true><<<dim3(strips, segs), kStripThreads, C::kSmemBytes, s>>>(P, dev_out, out_stride_floats, seg_rows);
-  else
-    filter_strip_kernel<MASK, false><<<dim3(strips, segs), kStripThreads, C::kSmemBytes, s>>>(P, dev_out, out_stride_floats, seg_rows);
-}
-
 // the stage chains PreparePipeline can build for a VarDCT XYB frame (dec_cache.cc:151-170)
-bool launch_strip(jxlgpu_ctx* ctx, const FrameDev& P, float* dev_out, size_t out_stride_floats, cudaStream_t s) {
+bool launch_strip(jxlgpu_ctx* ctx, const FrameDev& P, char* dev_out, size_t out_row_stride, cudaStream_t s,
+                  cudaError_t* err) {
   if (ctx->force_generic_filter) return false;
-  switch (P.stage_mask) {
-    case 16: launch_strip_mask<16>(ctx, P, dev_out, out_stride_floats, s); return true;
-    case 17: launch_strip_mask<17>(ctx, P, dev_out, out_stride_floats, s); return true;
-    case 20: launch_strip_mask<20>(ctx, P, dev_out, out_stride_floats, s); return true;
-    case 21: launch_strip_mask<21>(ctx, P, dev_out, out_stride_floats, s); return true;
-    case 28: launch_strip_mask<28>(ctx, P, dev_out, out_stride_floats, s); return true;
-    case 29: launch_strip_mask<29>(ctx, P, dev_out, out_stride_floats, s); return true;
-    case 30: launch_strip_mask<30>(ctx, P, dev_out, out_stride_floats, s); return true;
-    case 31: launch_strip_mask<31>(ctx, P, dev_out, out_stride_floats, s); return true;
+  switch (P.stage_mask & 31u) {  // (bit 32, the transfer function, is a run-time branch of the store)
+    case 16: *err = launch_strip_mask<16>(P, dev_out, out_row_stride, ctx->num_sms, s); return true;
+    case 17: *err = launch_strip_mask<17>(P, dev_out, out_row_stride, ctx->num_sms, s); return true;
+    case 20: *err = launch_strip_mask<20>(P, dev_out, out_row_stride, ctx->num_sms, s); return true;
+    case 21: *err = launch_strip_mask<21>(P, dev_out, out_row_stride, ctx->num_sms, s); return true;
+    case 28: *err = launch_strip_mask<28>(P, dev_out, out_row_stride, ctx->num_sms, s); return true;
+    case 29: *err = launch_strip_mask<29>(P, dev_out, out_row_stride, ctx->num_sms, s); return true;
+    case 30: *err = launch_strip_mask<30>(P, dev_out, out_row_stride, ctx->num_sms, s); return true;
+    case 31: *err = launch_strip_mask<31>(P, dev_out, out_row_stride, ctx->num_sms, s); return true;
     default: return false;
   }
-}
-
-template <uint32_t MASK>
-cudaError_t strip_attr() {
-  cudaError_t e = cudaFuncSetAttribute(filter_strip_kernel<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)StripCfg<MASK>::kSmemBytes);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(filter_strip_kernel<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)StripCfg<MASK>::kSmemBytes);
 }
 
 // plan + inverse transforms of AC-group rows [row0, row1), restricted to the varblocks that
@@ -240,19 +212,21 @@ int launch_idct(jxlgpu_ctx* ctx, uint32_t row0, uint32_t row1, uint32_t need_y0,
 }
 
 // filters pixel rows [y0, y1) into dev_out, whose row 0 is image row out_y0.
-int launch_filter(jxlgpu_ctx* ctx, uint32_t y0, uint32_t y1, uint32_t out_y0, uint32_t out_h, float* dev_out,
-                  size_t out_stride_floats, cudaStream_t s) {
+int launch_filter(jxlgpu_ctx* ctx, uint32_t y0, uint32_t y1, uint32_t out_y0, uint32_t out_h, char* dev_out,
+                  size_t out_row_stride, cudaStream_t s) {
   if (y1 <= y0) return JXLGPU_OK;
   FrameDev P = ctx->P;
   P.band_y0 = y0;
   P.band_y1 = y1;
   P.out_y0 = out_y0;
   P.out_h = out_h;
-  if (!launch_strip(ctx, P, dev_out, out_stride_floats, s)) {
+  cudaError_t strip_err = cudaSuccess;
+  if (!launch_strip(ctx, P, dev_out, out_row_stride, s, &strip_err)) {
     // stage chains outside the production set (test taps): generic tile kernel
     dim3 grid((P.xsize + kTW - 1) / kTW, (y1 - y0 + kTH - 1) / kTH);
-    filter_kernel<<<grid, kFilterThreads, kFilterSmemFloats * sizeof(float), s>>>(P, dev_out, out_stride_floats);
+    filter_kernel<<<grid, kFilterThreads, kFilterSmemFloats * sizeof(float), s>>>(P, dev_out, out_row_stride);
   }
+  CU(strip_err);
   if (ctx->profile) CU(cudaEventRecord(ctx->prof_ev[5], s));
   ctx->launches += 1;
   CU(cudaGetLastError());
@@ -261,8 +235,7 @@ int launch_filter(jxlgpu_ctx* ctx, uint32_t y0, uint32_t y1, uint32_t out_y0, ui
 
 int ensure_out(jxlgpu_ctx* ctx) {
   const uint32_t band_h = ctx->P.band_y1 - ctx->P.band_y0;
-  const size_t planes = ctx->P.out_format == JXLGPU_OUT_RGB_F32 ? 1 : 3;
-  CU(ctx->out.ensure(planes * band_h * ctx->out_stride_floats * 4));
+  CU(ctx->out.ensure(out_planes(ctx->P.out_format) * band_h * ctx->out_row_bytes));
   return JXLGPU_OK;
 }
 
@@ -295,14 +268,14 @@ int pump(jxlgpu_ctx* ctx) {
     if (y1 > P.band_y1) y1 = P.band_y1;
     int rc = ensure_out(ctx);
     if (rc) return rc;
-    rc = launch_filter(ctx, y0, y1, P.band_y0, band_h, (float*)ctx->out.p, ctx->out_stride_floats, s);
+    rc = launch_filter(ctx, y0, y1, P.band_y0, band_h, (char*)ctx->out.p, ctx->out_row_bytes, s);
     if (rc) return rc;
     ctx->row_filtered[g] = 1;
     if (ctx->host_out && y1 > y0) {  // copy the finished rows back while later rows still arrive
       CU(cudaEventRecord(ctx->ev_filter, s));
       CU(cudaStreamWaitEvent(ctx->s_down, ctx->ev_filter, 0));
-      const size_t row_bytes = ctx->out_stride_floats * 4;
-      const size_t planes = P.out_format == JXLGPU_OUT_RGB_F32 ? 1 : 3;
+      const size_t row_bytes = ctx->out_row_bytes;
+      const size_t planes = out_planes(P.out_format);
       for (size_t pl = 0; pl < planes; pl++) {
         const size_t row = pl * band_h + (y0 - P.band_y0);
         CU(download_rows((uint8_t*)ctx->host_out + row * ctx->host_out_stride, ctx->host_out_stride,
@@ -365,8 +338,9 @@ int jxlgpu_create(jxlgpu_ctx** out, const jxlgpu_config* cfg) {
   if ((e = cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(kFilterSmemFloats * sizeof(float)))) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(filter_kernel)");
-  for (cudaError_t ea : {strip_attr<16>(), strip_attr<17>(), strip_attr<20>(), strip_attr<21>(), strip_attr<28>(),
-                         strip_attr<29>(), strip_attr<30>(), strip_attr<31>()})
+  for (cudaError_t ea : {prepare_strip_mask<16>(), prepare_strip_mask<17>(), prepare_strip_mask<20>(),
+                         prepare_strip_mask<21>(), prepare_strip_mask<28>(), prepare_strip_mask<29>(),
+                         prepare_strip_mask<30>(), prepare_strip_mask<31>()})
     if (ea != cudaSuccess) return bail(ea, "cudaFuncSetAttribute(filter_strip_kernel)");
   {
     const char* env = getenv("JXLGPU_FORCE_GENERIC_FILTER");
@@ -409,7 +383,7 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   if (!f->ac_strategy || !f->raw_quant || !f->ytox_map || !f->ytob_map || !f->dc[0] || !f->dc[1] ||
       !f->dc[2] || !f->dequant_table)
     return JXLGPU_ERR_INVALID_ARGUMENT;
-  if (f->ac_type > JXLGPU_AC_INT32 || f->out_format > JXLGPU_OUT_PLANAR_F32) return JXLGPU_ERR_INVALID_ARGUMENT;
+  if (f->ac_type > JXLGPU_AC_INT32 || f->out_format > JXLGPU_OUT_RGB_F16) return JXLGPU_ERR_INVALID_ARGUMENT;
   const uint32_t mask = effective_mask(*f);
   if ((mask & 14u) && !f->epf_sharpness) return JXLGPU_ERR_INVALID_ARGUMENT;
   for (int i = 0; i < 3 * kNumStrategies; i++) {
@@ -521,7 +495,7 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   memcpy(P.opsin_m, f->inverse_opsin_matrix, sizeof(P.opsin_m));
   memcpy(P.opsin_bias, f->opsin_biases, sizeof(P.opsin_bias));
   memcpy(P.opsin_cbrt, f->opsin_biases_cbrt, sizeof(P.opsin_cbrt));
-  ctx->out_stride_floats = out_floats_per_row(*f);
+  ctx->out_row_bytes = out_bytes_per_row(*f);
   ctx->submitted.assign(ctx->num_groups, ctx->coeff_external ? 1 : 0);
   ctx->row_count.assign(P.yg, ctx->coeff_external ? P.xg : 0);
   ctx->row_idct.assign(P.yg, 0);
@@ -543,7 +517,7 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
 int jxlgpu_frame_set_output(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes) {
   if (!ctx) return JXLGPU_ERR_INVALID_ARGUMENT;
   if (!ctx->in_frame) return JXLGPU_ERR_STATE;
-  if (out && out_stride_bytes < ctx->out_stride_floats * 4) return JXLGPU_ERR_INVALID_ARGUMENT;
+  if (out && out_stride_bytes < ctx->out_row_bytes) return JXLGPU_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->host_out = out;
   ctx->host_out_stride = out_stride_bytes;
@@ -654,15 +628,22 @@ int jxlgpu_render_device(jxlgpu_ctx* ctx, void* dev_out, size_t out_stride_bytes
   }
   const FrameDev& P = ctx->P;
   const uint32_t band_h = P.band_y1 - P.band_y0;
-  float* o = (float*)dev_out;
-  size_t stride = out_stride_bytes / 4;
+  char* o = (char*)dev_out;
+  size_t stride = out_stride_bytes;
   if (!o) {
     int rc = ensure_out(ctx);
     if (rc) return rc;
-    o = (float*)ctx->out.p;
-    stride = ctx->out_stride_floats;
-  } else if (out_stride_bytes % 4 || stride < ctx->out_stride_floats) {
+    o = (char*)ctx->out.p;
+    stride = ctx->out_row_bytes;
+  } else if (stride % out_align(P.out_format) || (uintptr_t)o % out_align(P.out_format) ||
+             stride < ctx->out_row_bytes) {
     return JXLGPU_ERR_INVALID_ARGUMENT;
+  }
+  if (P.nrep || P.mc) {
+    // fused all-gather: the 8-byte vector stores to the replicas mirror the local byte offsets (all
+    // bases 8-byte aligned), and the multicast mapping moves 4-byte granules (f32 layouts only)
+    if ((uintptr_t)o % 8) return JXLGPU_ERR_INVALID_ARGUMENT;
+    if (P.mc && P.out_format > JXLGPU_OUT_PLANAR_F32) return JXLGPU_ERR_UNSUPPORTED;
   }
   int rc = launch_idct(ctx, ctx->need_row0, ctx->need_row1, P.need_y0, P.need_y1, s);
   if (rc) return rc;
@@ -692,9 +673,9 @@ int jxlgpu_frame_finish(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes) {
   }
   if (out && out != ctx->host_out) {
     const uint32_t band_h = ctx->P.band_y1 - ctx->P.band_y0;
-    const size_t row_bytes = ctx->out_stride_floats * 4;
+    const size_t row_bytes = ctx->out_row_bytes;
     if (out_stride_bytes < row_bytes) return JXLGPU_ERR_INVALID_ARGUMENT;
-    const size_t planes = ctx->P.out_format == JXLGPU_OUT_RGB_F32 ? 1 : 3;
+    const size_t planes = out_planes(ctx->P.out_format);
     CU(download_rows(out, out_stride_bytes, ctx->out.p, row_bytes, planes * band_h, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
@@ -706,16 +687,19 @@ int jxlgpu_frame_finish(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes) {
 int jxlgpu_set_output_replicas(jxlgpu_ctx* ctx, uint32_t n, void* const* dev_ptrs, void* multicast_ptr) {
   if (!ctx || n > 8 || (n && !dev_ptrs)) return JXLGPU_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  for (uint32_t i = 0; i < n; i++)
+    if ((uintptr_t)dev_ptrs[i] % 8) return JXLGPU_ERR_INVALID_ARGUMENT;
+  if ((uintptr_t)multicast_ptr % 8) return JXLGPU_ERR_INVALID_ARGUMENT;
   ctx->P.nrep = multicast_ptr ? 0 : n;
-  for (uint32_t i = 0; i < 8; i++) ctx->P.rep[i] = i < n ? (float*)dev_ptrs[i] : nullptr;
-  ctx->P.mc = (float*)multicast_ptr;
+  for (uint32_t i = 0; i < 8; i++) ctx->P.rep[i] = i < n ? (char*)dev_ptrs[i] : nullptr;
+  ctx->P.mc = (char*)multicast_ptr;
   return JXLGPU_OK;
 }
 
 int jxlgpu_device_output(jxlgpu_ctx* ctx, void** dev_ptr, size_t* stride_bytes) {
   if (!ctx || !dev_ptr || !stride_bytes) return JXLGPU_ERR_INVALID_ARGUMENT;
   *dev_ptr = ctx->out.p;
-  *stride_bytes = ctx->out_stride_floats * 4;
+  *stride_bytes = ctx->out_row_bytes;
   return ctx->out.p ? JXLGPU_OK : JXLGPU_ERR_STATE;
 }
 

@@ -25,12 +25,14 @@
 //   filter        one CTA per 64x32 output tile (+halo), all enabled stages fused through two
 //                 shared-memory ping-pong tiles, XYB->RGB in the epilogue.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <type_traits>
 
 #define JXT_CONST __device__ __constant__ const
+#define JXT_CONST_GMEM __device__ const
 #include "jxl_tables.h"
 
 namespace jxlb {
@@ -59,8 +61,8 @@ struct FrameDev {
   // fused all-gather (multi-GPU): every finished pixel is also stored to the same offset of
   // `nrep` peer-mapped buffers over NVLink, or once through an NVSwitch multicast address
   uint32_t nrep;
-  float* rep[8];
-  float* mc;
+  char* rep[8];
+  char* mc;
   uint32_t need_y0, need_y1; // pixel rows of post-IDCT data the band's filters read (band +- halo)
   uint32_t plan_g0;          // first AC group handled by the plan kernel (band sharding)
   // side info (device)
@@ -220,6 +222,7 @@ __device__ __forceinline__ float dequant(const FrameDev& P, const VarblockCtx& v
 // ---------------------------------------------------------------------------
 // plan kernel: one CTA (1024 threads) per AC group
 // ---------------------------------------------------------------------------
+#ifndef JXLB_STRIP_TU  // (the strip translation units compile the row-streaming filter kernel only)
 __global__ void __launch_bounds__(1024) plan_kernel(const __grid_constant__ FrameDev P, int want_sigma) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t local_count[kNumStrategies];
@@ -284,6 +287,8 @@ __global__ void __launch_bounds__(1024) plan_kernel(const __grid_constant__ Fram
     }
   }
 }
+
+#endif  // JXLB_STRIP_TU
 
 // ---------------------------------------------------------------------------
 // LLF from DC for multi-block DCTs (dec_transforms-inl.h:35-64): forward
@@ -997,30 +1002,34 @@ __device__ __forceinline__ void mc_store1(float* p, float v) {
   asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-// replicate `n` floats starting at float offset `off` of the local buffer `src` (all threads of the CTA)
-__device__ __forceinline__ void replicate_span(const FrameDev& P, const float* src, size_t off, int n) {
+// replicate `n` bytes starting at byte offset `off` of the local buffer `src` (all threads of the
+// CTA): bytes up to the first 8-byte boundary, an 8-byte vector body, the remaining bytes.  The
+// multicast mapping takes 4-byte granules only (f32 layouts; the host rejects it otherwise).
+__device__ __forceinline__ void replicate_span(const FrameDev& P, const char* src, size_t off, int n) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int head = (int)(off & 1);  // make the vector part 8-byte aligned
-  const int nv = (n - head) >> 1;
-  if (tid == 0) {
-    if (head) {
-      const float v = src[off];
-      if (P.mc) mc_store1(P.mc + off, v);
-      else for (uint32_t i = 0; i < P.nrep; i++) P.rep[i][off] = v;
+  int head = (int)((8 - (off & 7)) & 7);
+  if (head > n) head = n;
+  const int nv = (n - head) >> 3;
+  const int tail = n - head - 8 * nv;
+  if (P.mc) {
+    if (tid == 0) {
+      if (head) mc_store1(reinterpret_cast<float*>(P.mc + off), *reinterpret_cast<const float*>(src + off));
+      if (tail) {
+        const size_t o = off + head + 8 * (size_t)nv;
+        mc_store1(reinterpret_cast<float*>(P.mc + o), *reinterpret_cast<const float*>(src + o));
+      }
     }
-    if ((n - head) & 1) {
-      const size_t o = off + n - 1;
-      const float v = src[o];
-      if (P.mc) mc_store1(P.mc + o, v);
-      else for (uint32_t i = 0; i < P.nrep; i++) P.rep[i][o] = v;
-    }
+  } else if (tid < head + tail) {
+    const size_t o = tid < head ? off + tid : off + head + 8 * (size_t)nv + (tid - head);
+    const char v = src[o];
+    for (uint32_t i = 0; i < P.nrep; i++) P.rep[i][o] = v;
   }
   const float2* s2 = reinterpret_cast<const float2*>(src + off + head);
   for (int i = tid; i < nv; i += nt) {
     const float2 v = s2[i];
-    const size_t o = off + head + 2 * (size_t)i;
+    const size_t o = off + head + 8 * (size_t)i;
     if (P.mc) {
-      mc_store2(P.mc + o, v);
+      mc_store2(reinterpret_cast<float*>(P.mc + o), v);
     } else {
 #pragma unroll 1
       for (uint32_t k = 0; k < P.nrep; k++) *reinterpret_cast<float2*>(P.rep[k] + o) = v;
@@ -1028,16 +1037,92 @@ __device__ __forceinline__ void replicate_span(const FrameDev& P, const float* s
   }
 }
 
-__device__ __forceinline__ void store_px(const FrameDev& P, float* __restrict__ out, size_t out_row_stride,
+// bytes per pixel of the interleaved JXLGPU_OUT_* layouts (bytes per sample for the planar one)
+__host__ __device__ constexpr int out_pixel_bytes(uint32_t fmt) {
+  return fmt == 0 ? 12 : fmt == 1 ? 4 : fmt == 2 ? 3 : fmt == 3 ? 4 : 6;
+}
+
+// TF_SRGB::EncodedFromDisplay (cms/transfer_functions-inl.h:244-267): what FromLinearStage<OpRgb>
+// applies with JXL_HIGH_PRECISION (stage_from_linear.cc:42-53).  IEEE sqrt and division, Horner
+// with FMAs (rational_polynomial-inl.h:59-97) -- bit-exact against the CPU.
+__device__ __forceinline__ float srgb_from_linear(float v) {
+  const float x = fabsf(v);
+  const float s = __fsqrt_rn(x);
+  float yp = 7.352629620e-01f, yq = 2.424867759e-02f;
+  yp = fmaf(yp, s, 1.474205315e+00f); yq = fmaf(yq, s, 9.258482155e-01f);
+  yp = fmaf(yp, s, 3.903842876e-01f); yq = fmaf(yq, s, 1.340816930e+00f);
+  yp = fmaf(yp, s, 5.287254571e-03f); yq = fmaf(yq, s, 3.036675394e-01f);
+  yp = fmaf(yp, s, -5.135152395e-04f); yq = fmaf(yq, s, 1.004519624e-02f);
+  const float poly = __fdiv_rn(yp, yq);
+  const float mag = x > 0.0031308f ? poly : x * 12.92f;
+  return copysignf(fabsf(mag), v);
+}
+
+// MakeUnsigned (stage_write.cc:455-479): scale, 8-bit ordered dither, clamp (NaN -> 0 as maxps
+// does), round half to even.
+template <int BITS>
+__device__ __forceinline__ uint32_t make_unsigned(float v, int x, int y, int c) {
+  constexpr float mul = (float)((1u << BITS) - 1u);
+  v = v * mul;
+  if constexpr (BITS == 8) v = v + __ldg(&JXT_DITHER[(y + 13 * c) & 31][(x + 23 * c) & 31]);
+  float t = v > 0.0f ? v : 0.0f;
+  t = t < mul ? t : mul;
+  return (uint32_t)__float2int_rn(t);
+}
+
+// Last two stages of the pipeline for one pixel: optional sRGB transfer function and the
+// WriteToOutputStage conversion + interleave (stage_write.cc:455-640).  `yo` = row inside `out`.
+// OUTK 0: the instantiation for linear interleaved f32 (no run-time format dispatch in the loop);
+// OUTK 1: every other transfer function / layout, selected at run time.
+template <int OUTK>
+__device__ __forceinline__ void store_px(const FrameDev& P, char* __restrict__ out, size_t out_row_bytes,
                                          int yo, int x, int band_h, float a, float b, float c3) {
-  if (P.out_format == 0) {
-    float* o = out + (size_t)yo * out_row_stride + (size_t)x * 3;
+  if constexpr (OUTK == 0) {
+    float* o = reinterpret_cast<float*>(out + (size_t)yo * out_row_bytes) + (size_t)x * 3;
     o[0] = a; o[1] = b; o[2] = c3;
-  } else {
-    const size_t plane = (size_t)band_h * out_row_stride;
-    out[(size_t)yo * out_row_stride + x] = a;
-    out[plane + (size_t)yo * out_row_stride + x] = b;
-    out[2 * plane + (size_t)yo * out_row_stride + x] = c3;
+    return;
+  }
+  if (P.stage_mask & 32u) {
+    a = srgb_from_linear(a);
+    b = srgb_from_linear(b);
+    c3 = srgb_from_linear(c3);
+  }
+  char* row = out + (size_t)yo * out_row_bytes;
+  const int y = yo + (int)P.out_y0;
+  switch (P.out_format) {
+    case 0: {
+      float* o = reinterpret_cast<float*>(row) + (size_t)x * 3;
+      o[0] = a; o[1] = b; o[2] = c3;
+    } break;
+    case 1: {
+      const size_t plane = (size_t)band_h * out_row_bytes;
+      reinterpret_cast<float*>(row)[x] = a;
+      reinterpret_cast<float*>(row + plane)[x] = b;
+      reinterpret_cast<float*>(row + 2 * plane)[x] = c3;
+    } break;
+    case 2: {
+      uint8_t* o = reinterpret_cast<uint8_t*>(row) + (size_t)x * 3;
+      o[0] = (uint8_t)make_unsigned<8>(a, x, y, 0);
+      o[1] = (uint8_t)make_unsigned<8>(b, x, y, 1);
+      o[2] = (uint8_t)make_unsigned<8>(c3, x, y, 2);
+    } break;
+    case 3: {  // opaque alpha: MakeUnsigned(1.0) = 255 for every dither value
+      const uint32_t w = make_unsigned<8>(a, x, y, 0) | (make_unsigned<8>(b, x, y, 1) << 8) |
+                         (make_unsigned<8>(c3, x, y, 2) << 16) | 0xff000000u;
+      reinterpret_cast<uint32_t*>(row)[x] = w;
+    } break;
+    case 4: {
+      uint16_t* o = reinterpret_cast<uint16_t*>(row) + (size_t)x * 3;
+      o[0] = (uint16_t)make_unsigned<16>(a, x, y, 0);
+      o[1] = (uint16_t)make_unsigned<16>(b, x, y, 1);
+      o[2] = (uint16_t)make_unsigned<16>(c3, x, y, 2);
+    } break;
+    default: {  // binary16, round to nearest even (stage_write.cc:590-640)
+      __half* o = reinterpret_cast<__half*>(row) + (size_t)x * 3;
+      o[0] = __float2half_rn(a);
+      o[1] = __float2half_rn(b);
+      o[2] = __float2half_rn(c3);
+    } break;
   }
 }
 
@@ -1073,9 +1158,10 @@ __device__ __forceinline__ float epf_weight(float sad, float inv_sigma) {
   return v < 0.0f ? 0.0f : v;
 }
 
+#ifndef JXLB_STRIP_TU
 __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_constant__ FrameDev P,
-                                                               float* __restrict__ out,
-                                                               size_t out_row_stride /*floats*/) {
+                                                               char* __restrict__ out,
+                                                               size_t out_row_stride /*bytes*/) {
   extern __shared__ __align__(16) float fsm[];
   float* bufA = fsm;
   float* bufB = fsm + 3 * kTilePlane;
@@ -1290,9 +1376,11 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_con
       lr = fmaf(P.opsin_m[2], mb, lr); lg = fmaf(P.opsin_m[5], mb, lg); lb = fmaf(P.opsin_m[8], mb, lb);
       a = lr; b = lg; c3 = lb;
     }
-    store_px(P, out, out_row_stride, y - (int)P.out_y0, x, band_h, a, b, c3);
+    store_px<1>(P, out, out_row_stride, y - (int)P.out_y0, x, band_h, a, b, c3);
   }
 }
+
+#endif  // JXLB_STRIP_TU
 
 }  // namespace jxlb
 
@@ -1341,9 +1429,9 @@ __device__ __forceinline__ float* ring_row(float* ring, int n, int r, int c) {
   return ring + ((r & (n - 1)) * 3 + c) * kStripThreads;
 }
 
-template <uint32_t MASK, bool EDGE, bool REPL>
-__device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __restrict__ out,
-                                                  size_t out_row_stride, int x0, int y_begin, int y_end,
+template <uint32_t MASK, bool EDGE, bool REPL, int OUTK>
+__device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __restrict__ out,
+                                                  size_t out_row_stride /*bytes*/, int x0, int y_begin, int y_end,
                                                   float* smem) {
   using C = StripCfg<MASK>;
   constexpr int H = C::H;
@@ -1395,7 +1483,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
       lr = fmaf(P.opsin_m[2], mb, lr); lg = fmaf(P.opsin_m[5], mb, lg); lb = fmaf(P.opsin_m[8], mb, lb);
       a = lr; b = lg; c3 = lb;
     }
-    store_px(P, out, out_row_stride, r - (int)P.out_y0, x, band_h, a, b, c3);
+    store_px<OUTK>(P, out, out_row_stride, r - (int)P.out_y0, x, band_h, a, b, c3);
   };
   // cumulative delays (steps between loading row r and the stage producing row r)
   constexpr int dG = C::G ? 2 : 0;
@@ -1712,10 +1800,12 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
     row_excl = min(row_excl, y_end);
     for (int y = replayed; y < row_excl; y++) {
       const size_t yo = (size_t)(y - (int)P.out_y0);
-      if (P.out_format == 0) {
-        replicate_span(P, out, yo * out_row_stride + (size_t)x0 * 3, ncols_out * 3);
+      if (P.out_format == 1) {
+        for (int c = 0; c < 3; c++)
+          replicate_span(P, out, ((size_t)c * band_h + yo) * out_row_stride + (size_t)x0 * 4, ncols_out * 4);
       } else {
-        for (int c = 0; c < 3; c++) replicate_span(P, out, ((size_t)c * band_h + yo) * out_row_stride + x0, ncols_out);
+        const int pxb = out_pixel_bytes(P.out_format);
+        replicate_span(P, out, yo * out_row_stride + (size_t)x0 * pxb, ncols_out * pxb);
       }
     }
     if (row_excl > replayed) replayed = row_excl;
@@ -1747,9 +1837,9 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, float* __re
   if constexpr (replicate) replay_to(y_end);
 }
 
-template <uint32_t MASK, bool REPL>
+template <uint32_t MASK, bool REPL, int OUTK>
 __global__ void __launch_bounds__(kStripThreads, StripCfg<MASK>::E0 ? 2 : 4) filter_strip_kernel(const __grid_constant__ FrameDev P,
-                                                                    float* __restrict__ out,
+                                                                    char* __restrict__ out,
                                                                     size_t out_row_stride, int seg_rows) {
   extern __shared__ __align__(16) float fsm[];
   using C = StripCfg<MASK>;
@@ -1758,8 +1848,24 @@ __global__ void __launch_bounds__(kStripThreads, StripCfg<MASK>::E0 ? 2 : 4) fil
   const int y_end = min((int)P.band_y1, y_begin + seg_rows);
   if (y_begin >= y_end) return;
   const bool edge = (x0 - C::H < 0) || (x0 - C::H + kStripThreads > (int)P.xsize);
-  if (edge) filter_strip_body<MASK, true, REPL>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
-  else filter_strip_body<MASK, false, REPL>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
+  if (edge) filter_strip_body<MASK, true, REPL, OUTK>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
+  else filter_strip_body<MASK, false, REPL, OUTK>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
 }
+
+// Host launcher of one stage chain; each explicit specialisation lives in its own translation unit
+// (jxl_strip_inst.cu compiled with -DSTRIP_MASK=<mask>), so that the eight chains build in parallel.
+template <uint32_t MASK>
+cudaError_t launch_strip_mask(const FrameDev& P, char* dev_out, size_t out_row_bytes, int num_sms, cudaStream_t s);
+// per device, once: opt in to the dynamic shared memory the rings need
+template <uint32_t MASK>
+__attribute__((visibility("hidden"))) cudaError_t prepare_strip_mask();
+#define JXLB_DECLARE_STRIP(M)                                                            \
+  template <>                                                                            \
+  cudaError_t launch_strip_mask<M>(const FrameDev&, char*, size_t, int, cudaStream_t);   \
+  template <>                                                                            \
+  __attribute__((visibility("hidden"))) cudaError_t prepare_strip_mask<M>();
+JXLB_DECLARE_STRIP(16) JXLB_DECLARE_STRIP(17) JXLB_DECLARE_STRIP(20) JXLB_DECLARE_STRIP(21)
+JXLB_DECLARE_STRIP(28) JXLB_DECLARE_STRIP(29) JXLB_DECLARE_STRIP(30) JXLB_DECLARE_STRIP(31)
+#undef JXLB_DECLARE_STRIP
 
 }  // namespace jxlb

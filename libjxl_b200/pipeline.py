@@ -10,6 +10,7 @@ constructor raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -22,7 +23,10 @@ SO = PKG / "libjxl_b200.so"
 CSRC = PKG / "csrc"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared"]
+              "-fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
+OBJ = PKG / "build"
+# the stage chains with their own row-streaming filter instantiation (one translation unit each)
+STRIP_MASKS = (16, 17, 20, 21, 28, 29, 30, 31)
 
 EXPORTS = ["jxlgpu_abi_version", "jxlgpu_error_string", "jxlgpu_last_error", "jxlgpu_create",
            "jxlgpu_destroy", "jxlgpu_frame_begin", "jxlgpu_frame_set_output", "jxlgpu_submit_group",
@@ -38,14 +42,35 @@ class JxlGpuError(RuntimeError):
         super().__init__(f"{where}: error {code}" + (f" ({detail})" if detail else ""))
 
 
-def build(force: bool = False) -> Path:
-    """Compile csrc/jxl_b200.cu for sm_100a into libjxl_b200.so (in-tree)."""
-    srcs = [CSRC / "jxl_b200.cu", CSRC / "jxl_kernels.cuh", CSRC / "jxl_tables.h",
-            PKG.parent / "include" / "jxl_b200.h"]
-    if not force and SO.exists() and all(SO.stat().st_mtime >= s.stat().st_mtime for s in srcs):
-        return SO
-    cmd = ["nvcc", *NVCC_FLAGS, str(CSRC / "jxl_b200.cu"), "-o", str(SO)]
-    subprocess.check_call(cmd)
+def build(force: bool = False, verbose_ptxas: bool = False) -> Path:
+    """Compile csrc/*.cu for sm_100a into libjxl_b200.so (in-tree): the main translation unit and one
+    per filter stage chain, compiled in parallel, then linked."""
+    from concurrent.futures import ThreadPoolExecutor
+    hdrs = [CSRC / "jxl_kernels.cuh", CSRC / "jxl_tables.h", PKG.parent / "include" / "jxl_b200.h"]
+    units = [(CSRC / "jxl_b200.cu", OBJ / "jxl_b200.o", [])]
+    units += [(CSRC / "jxl_strip_inst.cu", OBJ / f"jxl_strip_{m}.o", [f"-DSTRIP_MASK={m}"]) for m in STRIP_MASKS]
+    newest_hdr = max(h.stat().st_mtime for h in hdrs)
+    OBJ.mkdir(exist_ok=True)
+
+    def compile_unit(u):
+        src, obj, defs = u
+        if not force and obj.exists() and obj.stat().st_mtime >= max(newest_hdr, src.stat().st_mtime):
+            return False
+        cmd = ["nvcc", *NVCC_FLAGS, *defs, "-c", str(src), "-o", str(obj)]
+        if verbose_ptxas:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose_ptxas:
+            (obj.with_suffix(".ptxas.txt")).write_text(r.stderr)
+        if r.returncode:
+            raise RuntimeError(f"nvcc failed for {src.name} {defs}:\n{r.stderr[-4000:]}")
+        return True
+
+    with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 4)) as ex:
+        rebuilt = list(ex.map(compile_unit, units))
+    if any(rebuilt) or not SO.exists():
+        subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
+                               *[str(u[1]) for u in units], "-o", str(SO)])
     return SO
 
 
@@ -138,10 +163,8 @@ class TransformPipeline:
     def frame_set_output(self, out: np.ndarray):
         """Announce the (ideally pinned) host output array: rows stream back as they finish."""
         d = self.desc
-        _, rows = d.band_rows()
-        shape = (rows, d.xsize, 3) if d.out_format == abi.OUT_RGB_F32 else (3, rows, d.xsize)
-        assert out.shape == shape and out.dtype == np.float32 and out.flags.c_contiguous
-        stride = d.xsize * 4 * (3 if d.out_format == abi.OUT_RGB_F32 else 1)
+        assert out.shape == d.out_shape() and out.dtype == d.out_dtype and out.flags.c_contiguous
+        stride = d.out_row_bytes
         self._check(lib().jxlgpu_frame_set_output(self._h, out.ctypes.data, stride), "jxlgpu_frame_set_output")
 
     def submit_group(self, group_idx: int, coeff_xyb, thread_id: int = 0, ncoeff: int | None = None):
@@ -168,12 +191,10 @@ class TransformPipeline:
 
     def frame_finish(self, out: np.ndarray | None = None) -> np.ndarray:
         d = self.desc
-        _, rows = d.band_rows()
-        shape = (rows, d.xsize, 3) if d.out_format == abi.OUT_RGB_F32 else (3, rows, d.xsize)
         if out is None:
-            out = np.empty(shape, np.float32)
-        assert out.shape == shape and out.dtype == np.float32 and out.flags.c_contiguous
-        stride = d.xsize * 4 * (3 if d.out_format == abi.OUT_RGB_F32 else 1)
+            out = np.empty(d.out_shape(), d.out_dtype)
+        assert out.shape == d.out_shape() and out.dtype == d.out_dtype and out.flags.c_contiguous
+        stride = d.out_row_bytes
         self._check(lib().jxlgpu_frame_finish(self._h, out.ctypes.data, stride), "jxlgpu_frame_finish")
         return out
 
@@ -185,9 +206,7 @@ class TransformPipeline:
         self.frame_begin(desc)
         if stream_output:
             if out is None:
-                _, rows = desc.band_rows()
-                shape = (rows, desc.xsize, 3) if desc.out_format == abi.OUT_RGB_F32 else (3, rows, desc.xsize)
-                out = np.empty(shape, np.float32)
+                out = np.empty(desc.out_shape(), desc.out_dtype)
             self.frame_set_output(out)
         for g in (order if order is not None else range(desc.num_groups)):
             self.submit_group(g, [coeffs[c, g] for c in range(3)])

@@ -34,6 +34,12 @@ def lib():
         L.jxo_adjust_quant_bias.argtypes = [C.c_int, C.c_int32, C.c_void_p, C.c_int]
         L.jxo_compute_sigma.argtypes = [C.POINTER(abi.JxlGpuFrame), C.c_void_p]
         L.jxo_render_frame.argtypes = [C.POINTER(abi.JxlGpuFrame), C.c_void_p * 3, C.c_int, C.c_void_p]
+        L.jxo_srgb_from_linear.restype = C.c_float
+        L.jxo_srgb_from_linear.argtypes = [C.c_float]
+        L.jxo_make_unsigned.restype = C.c_uint32
+        L.jxo_make_unsigned.argtypes = [C.c_float, C.c_int, C.c_size_t, C.c_size_t, C.c_int]
+        L.jxo_f16_from_f32.restype = C.c_uint16
+        L.jxo_f16_from_f32.argtypes = [C.c_float]
         _lib = L
     return _lib
 
@@ -84,12 +90,28 @@ def render_frame(desc: abi.FrameDesc, coeffs: np.ndarray, rcp_mode: int = 0) -> 
     assert co.shape == (3, desc.num_groups, abi.GROUP_COEFFS), co.shape
     s = desc.to_struct()
     ptrs = (C.c_void_p * 3)(*[co.ctypes.data + c * co[0].nbytes for c in range(3)])
-    shape = (3, desc.ysize, desc.xsize) if desc.out_format == abi.OUT_PLANAR_F32 else (desc.ysize, desc.xsize, 3)
-    out = np.zeros(shape, np.float32)
+    out = np.zeros(desc.out_shape(desc.ysize), desc.out_dtype)
     rc = lib().jxo_render_frame(C.byref(s), ptrs, rcp_mode, out.ctypes.data)
     if rc:
         raise RuntimeError(f"jxo_render_frame rc={rc}")
     return out
+
+
+def srgb_from_linear(v: np.ndarray) -> np.ndarray:
+    """TF_SRGB::EncodedFromDisplay, element-wise (small arrays: scalar calls)."""
+    fn = lib().jxo_srgb_from_linear
+    flat = np.ascontiguousarray(v, np.float32).ravel()
+    return np.array([fn(float(x)) for x in flat], np.float32).reshape(np.shape(v))
+
+
+def make_unsigned(v: float, bits: int, x: int, y: int, c: int) -> int:
+    return int(lib().jxo_make_unsigned(float(v), bits, x, y, c))
+
+
+def f16_from_f32(v: np.ndarray) -> np.ndarray:
+    fn = lib().jxo_f16_from_f32
+    flat = np.ascontiguousarray(v, np.float32).ravel()
+    return np.array([fn(float(x)) for x in flat], np.uint16).reshape(np.shape(v))
 
 
 def desc_from_dump(d, **overrides) -> abi.FrameDesc:

@@ -432,8 +432,8 @@ static inline int64_t mirror(int64_t x, int64_t size) {
 }
 
 uint32_t jxo_effective_stage_mask(const jxlgpu_frame* f) {
-  if (f->stage_mask & JXLGPU_STAGE_EXPLICIT) return f->stage_mask & 31u;
-  uint32_t m = JXLGPU_STAGE_XYB; /* order: dec_cache.cc:151-170,259-260 */
+  if (f->stage_mask & JXLGPU_STAGE_EXPLICIT) return f->stage_mask & 63u;
+  uint32_t m = JXLGPU_STAGE_XYB | (f->stage_mask & JXLGPU_STAGE_SRGB); /* order: dec_cache.cc:151-170,259-260 */
   if (f->gab) m |= JXLGPU_STAGE_GAB;
   if (f->epf_iters >= 3) m |= JXLGPU_STAGE_EPF0;
   if (f->epf_iters >= 1) m |= JXLGPU_STAGE_EPF1;
@@ -725,7 +725,88 @@ static void xyb_to_linear(const jxlgpu_frame* f, float* const p[3], size_t ps) {
     }
 }
 
-int jxo_render_frame(const jxlgpu_frame* f, const void* const coeff[3], int rcp_mode, float* out) {
+/* TF_SRGB::EncodedFromDisplay (lib/jxl/cms/transfer_functions-inl.h:244-267): the branch OpRgb takes
+ * with JXL_HIGH_PRECISION (stage_from_linear.cc:42-53, common.h:15-16).  Rational polynomial in
+ * sqrt(|x|), Horner with fused multiply-adds (rational_polynomial-inl.h:59-97), true division
+ * (FastDivision<float>, :36-52), linear segment below 0.0031308, sign carried over. */
+float jxo_srgb_from_linear(float v) {
+  static const float p[5] = {-5.135152395e-04f, 5.287254571e-03f, 3.903842876e-01f, 1.474205315e+00f,
+                             7.352629620e-01f};
+  static const float q[5] = {1.004519624e-02f, 3.036675394e-01f, 1.340816930e+00f, 9.258482155e-01f,
+                             2.424867759e-02f};
+  const float x = fabsf(v);
+  const float linear = x * 12.92f;
+  const float s = sqrtf(x);
+  float yp = p[4], yq = q[4];
+  for (int i = 3; i >= 0; i--) {
+    yp = fmaf(yp, s, p[i]);
+    yq = fmaf(yq, s, q[i]);
+  }
+  const float poly = yp / yq;
+  const float mag = x > 0.0031308f ? poly : linear;
+  return copysignf(fabsf(mag), v);
+}
+
+/* MakeUnsigned (lib/jxl/render_pipeline/stage_write.cc:455-479): scale, ordered dither for 8-bit
+ * (x/y/channel offsets :466-471; the 48-wide padded rows make the lane index wrap mod 32), clamp
+ * (Min(Max(v, 0), mul); a NaN becomes 0 as with maxps), round half to even (NearestInt). */
+uint32_t jxo_make_unsigned(float v, int bits, size_t x, size_t y, int c) {
+  const float mul = (float)((1u << bits) - 1u);
+  v = v * mul;
+  if (bits == 8) v = v + JXT_DITHER[(y + 13 * (size_t)c) & 31][(x + 23 * (size_t)c) & 31];
+  float t = v > 0.0f ? v : 0.0f;
+  t = t < mul ? t : mul;
+  return (uint32_t)(int32_t)nearbyintf(t);
+}
+
+/* DemoteTo(float16) as StoreFloat16Row uses it (stage_write.cc:590-640): IEEE round-to-nearest-even
+ * (vcvtps2ph with rounding control 0), overflow to infinity, gradual underflow, NaN stays NaN. */
+uint16_t jxo_f16_from_f32(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const uint32_t a = u & 0x7fffffffu;
+  if (a >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (a > 0x7f800000u ? 0x200u | ((a >> 13) & 0x3ffu) : 0u));
+  if (a >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u); /* >= 65520 rounds to infinity */
+  if (a < 0x33000001u) return (uint16_t)sign;               /* <= 2^-25 rounds to zero (tie to even) */
+  const int e = (int)(a >> 23) - 127;
+  uint32_t m = (a & 0x7fffffu) | 0x800000u;
+  int shift = 13;
+  uint32_t h_exp = (uint32_t)(e + 15);
+  if (e < -14) { /* subnormal half */
+    shift += -14 - e;
+    h_exp = 0;
+  }
+  const uint32_t halfway = 1u << (shift - 1);
+  const uint32_t rem = m & ((1u << shift) - 1u);
+  uint32_t r = m >> shift;
+  if (rem > halfway || (rem == halfway && (r & 1u))) r++;
+  /* r carries the implicit bit for normals: adding it to (h_exp - 1) << 10 lets a mantissa carry
+   * roll into the exponent */
+  const uint32_t h = h_exp ? ((h_exp - 1u) << 10) + r : r;
+  return (uint16_t)(sign | h);
+}
+
+/* FromLinearStage<OpRgb> over the whole frame, in place (stage_from_linear.cc:86-96) */
+static void srgb_from_linear(const jxlgpu_frame* f, float* const p[3], size_t ps) {
+#pragma omp parallel for schedule(static)
+  for (int64_t y = 0; y < (int64_t)f->ysize; y++)
+    for (int c = 0; c < 3; c++)
+      for (size_t x = 0; x < f->xsize; x++) p[c][(size_t)y * ps + x] = jxo_srgb_from_linear(p[c][(size_t)y * ps + x]);
+}
+
+size_t jxo_out_bytes(const jxlgpu_frame* f) {
+  const size_t n = (size_t)f->xsize * f->ysize;
+  switch (f->out_format) {
+    case JXLGPU_OUT_RGB_U8: return n * 3;
+    case JXLGPU_OUT_RGBA_U8: return n * 4;
+    case JXLGPU_OUT_RGB_U16: case JXLGPU_OUT_RGB_F16: return n * 6;
+    default: return n * 12;
+  }
+}
+
+int jxo_render_frame(const jxlgpu_frame* f, const void* const coeff[3], int rcp_mode, void* out_v) {
+  float* out = (float*)out_v;
   const size_t xb = f->xsize_blocks, yb = f->ysize_blocks;
   const size_t ps = xb * 8, plane = ps * yb * 8;
   const size_t xg = (xb + 31) / 32, yg = (yb + 31) / 32;
@@ -759,9 +840,28 @@ int jxo_render_frame(const jxlgpu_frame* f, const void* const coeff[3], int rcp_
   if (mask & JXLGPU_STAGE_EPF1) { epf(f, 1, sigma, cur, nxt, ps); SWAP(); }
   if (mask & JXLGPU_STAGE_EPF2) { epf(f, 2, sigma, cur, nxt, ps); SWAP(); }
   if (mask & JXLGPU_STAGE_XYB) xyb_to_linear(f, cur, ps);
+  if (mask & JXLGPU_STAGE_SRGB) srgb_from_linear(f, cur, ps);
 #undef SWAP
   const size_t W = f->xsize, H = f->ysize;
-  if (f->out_format == JXLGPU_OUT_PLANAR_F32) {
+  if (f->out_format >= JXLGPU_OUT_RGB_U8 && f->out_format <= JXLGPU_OUT_RGB_F16) {
+    /* WriteToOutputStage (stage_write.cc:455-640): interleave + convert; opaque alpha = all ones */
+    uint8_t* o8 = (uint8_t*)out_v;
+    uint16_t* o16 = (uint16_t*)out_v;
+    const uint32_t fmt = f->out_format;
+#pragma omp parallel for schedule(static)
+    for (int64_t y = 0; y < (int64_t)H; y++)
+      for (size_t x = 0; x < W; x++)
+        for (int c = 0; c < 3; c++) {
+          const float v = cur[c][(size_t)y * ps + x];
+          const size_t i = (size_t)y * W + x;
+          if (fmt == JXLGPU_OUT_RGB_U8) o8[i * 3 + c] = (uint8_t)jxo_make_unsigned(v, 8, x, (size_t)y, c);
+          else if (fmt == JXLGPU_OUT_RGBA_U8) {
+            o8[i * 4 + c] = (uint8_t)jxo_make_unsigned(v, 8, x, (size_t)y, c);
+            if (c == 2) o8[i * 4 + 3] = (uint8_t)jxo_make_unsigned(1.0f, 8, x, (size_t)y, 3);
+          } else if (fmt == JXLGPU_OUT_RGB_U16) o16[i * 3 + c] = (uint16_t)jxo_make_unsigned(v, 16, x, (size_t)y, c);
+          else o16[i * 3 + c] = jxo_f16_from_f32(v);
+        }
+  } else if (f->out_format == JXLGPU_OUT_PLANAR_F32) {
     for (int c = 0; c < 3; c++)
       for (size_t y = 0; y < H; y++) memcpy(out + (c * H + y) * W, cur[c] + y * ps, W * sizeof(float));
   } else {

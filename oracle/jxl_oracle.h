@@ -23,9 +23,16 @@ float jxo_adjust_quant_bias(int c, int32_t q, const float* biases, int rcp_mode)
 uint32_t jxo_effective_stage_mask(const jxlgpu_frame* f);
 /* ComputeSigma (epf.cc:39-133): (ysize_blocks+4) x (xsize_blocks+4) inverse sigmas. */
 void jxo_compute_sigma(const jxlgpu_frame* f, float* sigma);
+/* TF_SRGB::EncodedFromDisplay (cms/transfer_functions-inl.h:244-267). */
+float jxo_srgb_from_linear(float v);
+/* MakeUnsigned (stage_write.cc:455-479), bits = 8 (dithered) or 16. */
+uint32_t jxo_make_unsigned(float v, int bits, size_t x, size_t y, int c);
+/* float -> binary16, round to nearest even (stage_write.cc:590-640). */
+uint16_t jxo_f16_from_f32(float v);
+size_t jxo_out_bytes(const jxlgpu_frame* f);
 /* Whole frame: coeff[c] = [num_groups][65536] host planes of f->ac_type.
- * out: xsize*ysize*3 floats in f->out_format. Returns 0 on success. */
-int jxo_render_frame(const jxlgpu_frame* f, const void* const coeff[3], int rcp_mode, float* out);
+ * out: jxo_out_bytes(f) bytes, dense rows, in f->out_format. Returns 0 on success. */
+int jxo_render_frame(const jxlgpu_frame* f, const void* const coeff[3], int rcp_mode, void* out);
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,8 @@ def lib():
         L.ref_frame_info.argtypes = [C.c_void_p, C.POINTER(RefFrameInfo)]
         L.ref_frame_get_plane.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.ref_frame_render.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.ref_frame_render_out.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                           C.POINTER(C.c_double)]
         L.ref_encode_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_uint8)),
                                       C.POINTER(C.c_size_t)]
@@ -214,6 +216,23 @@ class Frame:
                                     reps, secs)
         if rc:
             raise RuntimeError(f"ref_frame_render rc={rc}")
+        return out, list(secs)
+
+
+    _OUT = {0: ("float32", 3), 2: ("uint8", 3), 3: ("uint8", 4), 4: ("uint16", 3), 5: ("float16", 3)}
+
+    def render_out(self, stage_mask: int = -1, out_format: int = 0, reps: int = 1, want_output: bool = True):
+        """Hot path ending in the reference's FromLinear (stage_mask bit 32; -33 = derived chain +
+        sRGB) and WriteToOutput stages.  out_format as JXLGPU_OUT_* (interleaved ones).
+        Returns ((H, W, ch) array or None, [seconds per rep])."""
+        i = self.info
+        dt, ch = self._OUT[out_format]
+        out = np.zeros((i.ysize, i.xsize, ch), dt) if want_output else None
+        secs = (C.c_double * max(reps, 1))()
+        rc = lib().ref_frame_render_out(self.h, stage_mask, out_format, out.ctypes.data if want_output else None,
+                                        reps, secs)
+        if rc:
+            raise RuntimeError(f"ref_frame_render_out rc={rc}")
         return out, list(secs)
 
 

@@ -59,6 +59,7 @@
 #include "lib/jxl/quantizer.h"
 #include "lib/jxl/render_pipeline/render_pipeline.h"
 #include "lib/jxl/render_pipeline/stage_epf.h"
+#include "lib/jxl/render_pipeline/stage_from_linear.h"
 #include "lib/jxl/render_pipeline/stage_gaborish.h"
 #include "lib/jxl/render_pipeline/stage_write.h"
 #include "lib/jxl/render_pipeline/stage_xyb.h"
@@ -617,6 +618,105 @@ REF_API int ref_frame_render(void* h, int stage_mask, float* out, int reps, doub
       for (size_t y = 0; y < d.ysize; y++)
         if (memcmp(out + (c * d.ysize + y) * d.xsize, result.ConstPlaneRow(c, y), d.xsize * sizeof(float)))
           return 9;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// (4b) same loop, but ending the way the decoder's real pipeline ends
+// (dec_cache.cc:259-330): optional FromLinearStage with an sRGB output encoding
+// (stage_mask bit 32, stage_from_linear.cc:161-166) and WriteToOutputStage
+// into a caller buffer of a JxlPixelFormat (stage_write.cc:455-700).
+// out_format: 0 = {3, FLOAT}, 2 = {3, UINT8}, 3 = {4, UINT8}, 4 = {3, UINT16},
+// 5 = {3, FLOAT16}; native endianness, dense rows.  out may be NULL (timing).
+// ---------------------------------------------------------------------------
+REF_API int ref_frame_render_out(void* h, int stage_mask, int out_format, void* out, int reps,
+                                 double* seconds) {
+  auto* f = static_cast<RefFrame*>(h);
+  PassesDecoderState* ds = f->dec_state.get();
+  const FrameHeader& fh = *f->frame_header;
+  const LoopFilter& lf = fh.loop_filter;
+  const FrameDimensions& d = ds->shared->frame_dim;
+  if (stage_mask < 0) {
+    const int srgb = (-stage_mask) & 32 ? 32 : 0;  // -1: derived chain; -33: derived chain + sRGB
+    stage_mask = 16 | srgb | (lf.gab ? 1 : 0);
+    if (lf.epf_iters >= 3) stage_mask |= 2;
+    if (lf.epf_iters >= 1) stage_mask |= 4;
+    if (lf.epf_iters >= 2) stage_mask |= 8;
+  }
+  if ((stage_mask & 14) && lf.epf_iters == 0) return 7;
+  if (reps < 1) reps = 1;
+  JxlPixelFormat format = {3, JXL_TYPE_FLOAT, JXL_NATIVE_ENDIAN, 0};
+  size_t bits = 32, px_bytes = 12;
+  switch (out_format) {
+    case 0: break;
+    case 2: format = {3, JXL_TYPE_UINT8, JXL_NATIVE_ENDIAN, 0}; bits = 8; px_bytes = 3; break;
+    case 3: format = {4, JXL_TYPE_UINT8, JXL_NATIVE_ENDIAN, 0}; bits = 8; px_bytes = 4; break;
+    case 4: format = {3, JXL_TYPE_UINT16, JXL_NATIVE_ENDIAN, 0}; bits = 16; px_bytes = 6; break;
+    case 5: format = {3, JXL_TYPE_FLOAT16, JXL_NATIVE_ENDIAN, 0}; bits = 16; px_bytes = 6; break;
+    default: return 8;
+  }
+  std::vector<uint8_t> own;
+  const size_t stride = d.xsize * px_bytes;
+  if (!out) {
+    own.resize(stride * d.ysize);
+    out = own.data();
+  }
+  ImageOutput main_output = {};
+  main_output.format = format;
+  main_output.bits_per_sample = bits;
+  main_output.buffer = out;
+  main_output.buffer_size = stride * d.ysize;
+  main_output.stride = stride;
+  std::vector<ImageOutput> extra;
+  AlignedArray<GroupDecCache> caches;
+  size_t caches_n = 0;
+  const auto init = [&](size_t num_threads) -> Status {
+    if (caches_n >= num_threads) return true;
+    caches_n = num_threads;
+    JXL_RETURN_IF_ERROR(ds->render_pipeline->PrepareForThreads(num_threads, false));
+    JXL_ASSIGN_OR_RETURN(caches, AlignedArray<GroupDecCache>::Create(&f->mm, num_threads));
+    return true;
+  };
+  const auto group = [&](uint32_t g, size_t thread) -> Status {
+    RenderPipelineInput input = ds->render_pipeline->GetInputBuffers(g, thread);
+    JXL_RETURN_IF_ERROR(DecodeGroupForRoundtrip(fh, f->ac32, g, ds, &caches[thread], thread, input,
+                                                nullptr, nullptr));
+    JXL_RETURN_IF_ERROR(input.Done());
+    return true;
+  };
+  Status st = [&]() -> Status {
+    RenderPipeline::Builder builder(&f->mm, 3);
+    if (stage_mask & 1) JXL_RETURN_IF_ERROR(builder.AddStage(GetGaborishStage(lf)));
+    if (stage_mask & 2)
+      JXL_RETURN_IF_ERROR(builder.AddStage(GetEPFStage(lf, ds->sigma, EpfStage::Zero)));
+    if (stage_mask & 4)
+      JXL_RETURN_IF_ERROR(builder.AddStage(GetEPFStage(lf, ds->sigma, EpfStage::One)));
+    if (stage_mask & 8)
+      JXL_RETURN_IF_ERROR(builder.AddStage(GetEPFStage(lf, ds->sigma, EpfStage::Two)));
+    if (stage_mask & 16)
+      JXL_RETURN_IF_ERROR(builder.AddStage(GetXYBStage(ds->output_encoding_info)));
+    if (stage_mask & 32) {
+      OutputEncodingInfo info = ds->output_encoding_info;
+      info.color_encoding = ColorEncoding::SRGB(/*is_gray=*/false);
+      JXL_RETURN_IF_ERROR(builder.AddStage(GetFromLinearStage(info)));
+    }
+    JXL_RETURN_IF_ERROR(builder.AddStage(GetWriteToOutputStage(main_output, d.xsize, d.ysize,
+                                                               /*has_alpha=*/false, /*unpremul_alpha=*/false,
+                                                               /*alpha_c=*/0, Orientation::kIdentity, extra,
+                                                               &f->mm)));
+    JXL_ASSIGN_OR_RETURN(ds->render_pipeline, std::move(builder).Finalize(d));
+    JXL_RETURN_IF_ERROR(RunOnPool(f->pool.get(), 0, d.num_groups, init, group, "hot path"));
+    return true;
+  }();
+  if (!st) return 1;
+  for (int rep = 0; rep < reps; rep++) {
+    for (size_t g = 0; g < d.num_groups; g++) ds->render_pipeline->ClearDone(g);
+    double t0 = NowSec();
+    Status s2 = RunOnPool(f->pool.get(), 0, d.num_groups, init, group, "hot path");
+    double t1 = NowSec();
+    if (!s2) return 1;
+    if (seconds) seconds[rep] = t1 - t0;
   }
   return 0;
 }

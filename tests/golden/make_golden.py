@@ -12,6 +12,8 @@ Fixtures
                    coefficient hand-off (quantised coefficients + all side info) and the reference
                    pixels: full decode (default build, public API) and stage taps of the strict
                    build rendered with the reference's own DecodeGroupForRoundtrip + stages.
+  outputs_small.npz the same frame through the reference's FromLinearStage (sRGB) and WriteToOutputStage
+                   in every packed pixel format (strict build); `--outputs-only` regenerates just this.
 """
 from __future__ import annotations
 
@@ -41,7 +43,30 @@ def transform_inputs(strategy: int):
     return coeffs, dc
 
 
+OUTPUTS = {"srgb_f32": (abi.OUT_RGB_F32, -33), "srgb_u8": (abi.OUT_RGB_U8, -33), "srgb_rgba8": (abi.OUT_RGBA_U8, -33),
+           "srgb_u16": (abi.OUT_RGB_U16, -33), "srgb_f16": (abi.OUT_RGB_F16, -33), "linear_u8": (abi.OUT_RGB_U8, -1),
+           "linear_f16": (abi.OUT_RGB_F16, -1)}
+
+
+def outputs() -> None:
+    """outputs_small.npz: the frame of frame_small.npz rendered by the strict reference build through
+    its FromLinear (sRGB) and WriteToOutput stages in every packed format."""
+    ref.use_variant("strict")
+    data = np.load(HERE / "frame_small.npz")["jxl"].tobytes()
+    fr = ref.Frame(data, 1)
+    fx = {}
+    for name, (fmt, mask) in OUTPUTS.items():
+        img, _ = fr.render_out(mask, fmt)
+        fx[name] = img.view(np.uint16) if img.dtype == np.float16 else img
+    fr.close()
+    np.savez_compressed(HERE / "outputs_small.npz", **fx)
+    print("outputs_small.npz", (HERE / "outputs_small.npz").stat().st_size, "bytes")
+
+
 def main() -> int:
+    if "--outputs-only" in sys.argv:
+        outputs()
+        return 0
     ref.use_variant("strict")
     out = {}
     for s in range(27):
@@ -85,6 +110,7 @@ def main() -> int:
     np.savez_compressed(HERE / "frame_small.npz", **fx)
     for f in ("transforms.npz", "frame_small.npz"):
         print(f, (HERE / f).stat().st_size, "bytes")
+    outputs()
     return 0
 
 

@@ -25,7 +25,16 @@ def oracle(desc, coeffs):
 
 
 def assert_same(got, want, what=""):
-    assert got.shape == want.shape
+    assert got.shape == want.shape and got.dtype == want.dtype
+    if got.dtype != np.float32:   # packed output formats: compare the stored code values
+        if got.dtype == np.float16:
+            got, want = got.view(np.uint16), want.view(np.uint16)
+        if not np.array_equal(got, want):
+            d = np.abs(got.astype(np.int64) - want.astype(np.int64))
+            idx = np.unravel_index(np.argmax(d), d.shape)
+            raise AssertionError(f"{what}: max code diff {d.max()} at {idx} ({got[idx]} vs {want[idx]}), "
+                                 f"{int((d > 0).sum())} of {d.size} differ")
+        return
     if not np.array_equal(got, want):
         d = np.abs(got - want)
         idx = np.unravel_index(np.argmax(d), d.shape)
@@ -117,6 +126,71 @@ def test_golden_frame_against_reference_pixels(pipe):
         desc.out_format = abi.OUT_PLANAR_F32
         got = pipe.decode_frame(desc, coeffs)
         assert np.abs(got - g.taps[tap]).max() <= 2e-5, tap
+
+
+PACKED = [abi.OUT_RGB_U8, abi.OUT_RGBA_U8, abi.OUT_RGB_U16, abi.OUT_RGB_F16]
+
+
+@pytest.mark.parametrize("srgb", [0, abi.STAGE_SRGB])
+@pytest.mark.parametrize("fmt", [abi.OUT_RGB_F32, abi.OUT_PLANAR_F32] + PACKED)
+def test_output_stages_bit_exact(pipe, fmt, srgb):
+    """sRGB transfer function (FromLinearStage<OpRgb>) and WriteToOutput packing fused into the
+    filter kernel's store: identical bytes to the oracle, strip kernel (derived chain) and generic
+    tile kernel (a chain outside the production set), odd width so rows are not 4-byte multiples."""
+    if fmt in (abi.OUT_RGB_F32, abi.OUT_PLANAR_F32) and not srgb:
+        pytest.skip("covered by the tests above")
+    desc, coeffs = wl.synthetic_frame(773, 530, seed=fmt * 2 + (1 if srgb else 0))
+    desc.out_format = fmt
+    desc.stage_mask = srgb
+    assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), "strip kernel")
+    desc.stage_mask = abi.STAGE_EXPLICIT | abi.STAGE_GAB | abi.STAGE_EPF2 | abi.STAGE_XYB | srgb
+    assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), "tile kernel")
+
+
+@pytest.mark.parametrize("case", ["srgb_f32", "srgb_u8", "srgb_rgba8", "srgb_u16", "srgb_f16", "linear_u8",
+                                  "linear_f16"])
+def test_golden_frame_packed_outputs(pipe, case):
+    """Real bitstream, the reference's own FromLinear + WriteToOutput bytes (tests/golden/
+    outputs_small.npz): at most one code value off where the reference's 12-bit rcpps moved a sample
+    across a rounding boundary; bit-exact against the oracle."""
+    from tests.test_oracle_golden import OUTPUT_CASES
+    fmt, mask = OUTPUT_CASES[case]
+    desc, coeffs, _ = support.golden_desc(out_format=fmt, stage_mask=mask)
+    got = pipe.decode_frame(desc, coeffs)
+    assert_same(got, oracle(desc, coeffs), case)
+    want = np.load(support.GOLDEN / "outputs_small.npz")[case]
+    if got.dtype == np.float32:
+        assert np.abs(got - want).max() <= 2e-5
+        return
+    if got.dtype == np.float16:
+        got = got.view(np.uint16)
+    d = np.abs(got.astype(np.int64) - want.astype(np.int64))
+    if case.endswith("f16"):
+        d = d[(got & 0x7fff) > 0x0400]
+    assert d.max() <= 1 and (d != 0).mean() <= (2e-3 if got.dtype == np.uint8 else 5e-2)
+
+
+def test_packed_output_streaming_and_bands(pipe):
+    """8-bit sRGB output through the streaming path (rows copied back as they finish, shuffled
+    submission) and rendered band by band: same bytes as the one-shot whole-frame call."""
+    desc, coeffs = wl.synthetic_frame(901, 1300, seed=34)
+    desc.out_format, desc.stage_mask = abi.OUT_RGB_U8, abi.STAGE_SRGB
+    want = pipe.decode_frame(desc, coeffs)
+    assert want.dtype == np.uint8 and want.shape == (1300, 901, 3)
+    out = pipeline.pinned_array((desc.ysize, desc.xsize, 3), np.uint8)
+    out[:] = 7
+    order = np.random.default_rng(5).permutation(desc.num_groups)
+    assert_same(pipe.decode_frame(desc, coeffs, out=out, order=order, stream_output=True), want, "streamed")
+    rows = []
+    for (y0, ny) in sharding.band_partition(desc.ysize_groups, 3):
+        desc.band_y0_groups, desc.band_ny_groups = y0, ny
+        pipe.set_device_coefficients(None)
+        pipe.frame_begin(desc)
+        for gidx in sharding.groups_needed(desc, y0, ny):
+            pipe.submit_group(gidx, [coeffs[c, gidx] for c in range(3)])
+        rows.append(pipe.frame_finish())
+    desc.band_y0_groups = desc.band_ny_groups = 0
+    assert_same(np.concatenate(rows, axis=0), want, "bands")
 
 
 def test_band_sharded_equals_whole_frame(pipe):

@@ -105,3 +105,77 @@ def test_sigma_against_reference():
     desc, _, g = support.golden_desc()
     sg = cpu.compute_sigma(desc)[2:-2, 2:-2]
     assert np.array_equal(sg, g.sigma_interior)
+
+
+OUTPUT_CASES = {"srgb_f32": (abi.OUT_RGB_F32, abi.STAGE_SRGB), "srgb_u8": (abi.OUT_RGB_U8, abi.STAGE_SRGB),
+                "srgb_rgba8": (abi.OUT_RGBA_U8, abi.STAGE_SRGB), "srgb_u16": (abi.OUT_RGB_U16, abi.STAGE_SRGB),
+                "srgb_f16": (abi.OUT_RGB_F16, abi.STAGE_SRGB), "linear_u8": (abi.OUT_RGB_U8, 0),
+                "linear_f16": (abi.OUT_RGB_F16, 0)}
+
+
+@pytest.mark.parametrize("case", list(OUTPUT_CASES))
+def test_packed_outputs_against_reference(case):
+    """sRGB transfer function + WriteToOutput packing (8-bit dither, 16-bit, binary16, RGBA) against
+    the reference's own FromLinear/WriteToOutput stages.  Exact-reciprocal mode, so the 12-bit rcpps of
+    the reference's AdjustQuantBias may move a value across a rounding boundary: at most one code
+    value, on a small fraction of the samples (f32: absolute 2e-5).  tests/test_oracle_vs_reference.py
+    holds the bit-exact version of this comparison (host-rcpss mode, needs oracle/_ref)."""
+    from oracle import cpu
+    fmt, mask = OUTPUT_CASES[case]
+    desc, coeffs, _ = support.golden_desc(out_format=fmt, stage_mask=mask)
+    got = cpu.render_frame(desc, coeffs, rcp_mode=0)
+    want = np.load(support.GOLDEN / "outputs_small.npz")[case]
+    if got.dtype == np.float32:
+        assert np.abs(got - want).max() <= 2e-5
+        return
+    if got.dtype == np.float16:
+        got = got.view(np.uint16)
+        ok = (got & 0x7fff) > 0x0400          # leave binary16 subnormals (|v| < 6.1e-5) out of the ULP count
+        d = np.abs(got.astype(np.int64) - want.astype(np.int64))[ok]
+    else:
+        d = np.abs(got.astype(np.int64) - want.astype(np.int64))
+    assert got.shape == want.shape
+    # one 16-bit code value (1.5e-5) is the size of the rcpps effect itself: more samples move
+    frac = 2e-3 if got.dtype == np.uint8 else 5e-2
+    assert d.max() <= 1 and (d != 0).mean() <= frac, (int(d.max()), float((d != 0).mean()))
+
+
+def test_srgb_transfer_function_properties():
+    """TF_SRGB::EncodedFromDisplay: 0 -> 0, odd symmetry, linear segment below 0.0031308, within the
+    5e-7 the reference documents of the analytic curve (transfer_functions-inl.h:243)."""
+    from oracle import cpu
+    x = np.concatenate([np.linspace(0, 1, 2001), [0.0031308, 0.00313081, 2.0, 10.0]]).astype(np.float32)
+    y = cpu.srgb_from_linear(x)
+    xd = x.astype(np.float64)
+    analytic = np.where(xd <= 0.0031308, 12.92 * xd, 1.055 * np.power(xd, 1 / 2.4) - 0.055)
+    assert np.abs(y[:2003] - analytic[:2003]).max() <= 1e-6
+    assert np.array_equal(cpu.srgb_from_linear(-x), -y)
+    assert y[0] == 0.0 and np.all(np.diff(y[:2001]) >= 0)
+    lin = x[x <= np.float32(0.0031308)]
+    assert np.array_equal(cpu.srgb_from_linear(lin), lin * np.float32(12.92))
+
+
+def test_binary16_demotion_matches_ieee():
+    from oracle import cpu
+    rng = np.random.default_rng(3)
+    v = np.concatenate([rng.standard_normal(4000).astype(np.float32) * s for s in (1e-8, 1e-5, 1e-3, 1, 300, 7e4)] +
+                       [np.array([0, -0.0, 65504, 65519.99, 65520, 1e10, -1e10, np.inf, -np.inf, 5.9604645e-8,
+                                  2.9802322e-8, 2.9802326e-8, 6.1e-5, 6.0975552e-5], np.float32)])
+    with np.errstate(over="ignore"):
+        want = v.astype(np.float16).view(np.uint16)
+    assert np.array_equal(cpu.f16_from_f32(v), want)
+
+
+def test_make_unsigned_dither_and_rounding():
+    """MakeUnsigned: round-half-even, clamp, and the dither indexed (x + 23c, y + 13c) mod 32."""
+    from oracle import cpu
+    assert cpu.make_unsigned(0.5, 16, 0, 0, 0) == 32768          # 32767.5 -> even
+    assert cpu.make_unsigned(1.5 / 65535, 16, 5, 9, 1) == 2      # 1.5 -> 2
+    assert cpu.make_unsigned(2.5 / 65535, 16, 5, 9, 1) == 2      # 2.5 -> 2
+    assert cpu.make_unsigned(-3.0, 8, 1, 2, 0) == 0 and cpu.make_unsigned(7.0, 8, 1, 2, 0) == 255
+    assert cpu.make_unsigned(float("nan"), 16, 0, 0, 0) == 0
+    # periodicity and the channel offsets
+    for (x, y, c) in ((0, 0, 0), (7, 30, 1), (31, 31, 2)):
+        a = cpu.make_unsigned(0.5, 8, x, y, c)
+        assert a == cpu.make_unsigned(0.5, 8, x + 32, y + 64, c)
+        assert a == cpu.make_unsigned(0.5, 8, (x + 23 * c) % 32, (y + 13 * c) % 32, 0)

@@ -89,3 +89,23 @@ def test_hot_path_render_equals_public_decode(refmod):
         fr.close()
     finally:
         refmod.use_variant("strict")
+
+
+@pytest.mark.parametrize("fmt,srgb", [(abi.OUT_RGB_F32, True), (abi.OUT_RGB_U8, True), (abi.OUT_RGBA_U8, True),
+                                      (abi.OUT_RGB_U16, True), (abi.OUT_RGB_F16, True), (abi.OUT_RGB_U8, False),
+                                      (abi.OUT_RGB_F16, False)])
+def test_output_stages_bit_exact(fmt, srgb, refmod):
+    """FromLinearStage<OpRgb> + WriteToOutputStage (dithered u8, RGBA, u16, binary16, f32) of the strict
+    reference build vs the restatement, whole frame, host-rcpss mode: identical bytes."""
+    from oracle import cpu
+    img = wl.synth_image(333, 277, 5)
+    data = refmod.encode_rgb8(img, 1.0, 7, -1, 2, 2)
+    fr = refmod.Frame(data, 2)
+    d = fr.dump()
+    want, _ = fr.render_out(-33 if srgb else -1, fmt)
+    desc = cpu.desc_from_dump(d, out_format=fmt, stage_mask=abi.STAGE_SRGB if srgb else 0)
+    got = cpu.render_frame(desc, d.coeffs, rcp_mode=1)
+    assert got.dtype == want.dtype and got.shape == want.shape
+    assert np.array_equal(got.view(np.uint16) if got.dtype == np.float16 else got,
+                          want.view(np.uint16) if want.dtype == np.float16 else want)
+    fr.close()
