@@ -206,6 +206,10 @@ def main() -> int:
                     help="pixel format the path ends in: linear f32 (the §8 scope, default) or sRGB 8-bit "
                          "(sRGB transfer function + WriteToOutput packing fused into the filter kernel's store); "
                          "the other one is measured too and reported under \"variants\"")
+    ap.add_argument("--submit", default="sparse", choices=["dense", "sparse"],
+                    help="e2e arm: the non-zero lists of jxlgpu_submit_groups_sparse (default), or dense "
+                         "[group][3][65536] coefficient blocks (libjxl's ACImage layout); the other one is measured "
+                         "too and reported under \"variants\"")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "p2p", "nccl"],
@@ -423,47 +427,66 @@ def main() -> int:
         batches = [pipe.make_batch([g for r in rows_of[tid::n_submit_threads] for g in need if g // xg == r], host_groups)
                    for tid in range(n_submit_threads)]
 
-        def submit_slice(tid):
-            pipe.submit_batch(batches[tid], tid)
+        # sparse hand-off: one batch (= one DMA of non-zero lists) per AC-group row
+        if "sparse_batches" not in shared:
+            sb = [[pipe.make_sparse_batch([g for g in need if g // xg == r], coeffs) for r in rows_of[tid::n_submit_threads]]
+                  for tid in range(n_submit_threads)]
+            shared["sparse_batches"] = sb
+            shared["h2d_sparse"] = sum(b[3] for per in sb for b in per) + (shared["h2d"] - sum(
+                (2 * abi.GROUP_COEFFS + desc.group_ncoeff(g)) * coeffs.dtype.itemsize for g in need))
 
-        phase = [0.0, 0.0, 0.0]
+        def run_e2e(mode: str) -> dict:
+            def submit_slice(tid):
+                if mode == "sparse":
+                    for b in shared["sparse_batches"][tid]:
+                        pipe.submit_sparse_batch(b, tid)
+                else:
+                    pipe.submit_batch(batches[tid], tid)
 
-        def e2e_step():
+            phase = [0.0, 0.0, 0.0]
+
+            def e2e_step():
+                t0 = time.perf_counter()
+                pipe.frame_begin(desc)
+                pipe.frame_set_output(host_out)          # rows stream back as they finish
+                t1 = time.perf_counter()
+                list(pool.map(submit_slice, range(n_submit_threads)))
+                t2 = time.perf_counter()
+                pipe.frame_finish(host_out)
+                t3 = time.perf_counter()
+                phase[0] += t1 - t0
+                phase[1] += t2 - t1
+                phase[2] += t3 - t2
+
+            for _ in range(2):
+                e2e_step()
+            barrier()
+            phase[:] = [0.0, 0.0, 0.0]
+            n_e2e = max(3, min(args.steps, 10))
             t0 = time.perf_counter()
-            pipe.frame_begin(desc)
-            pipe.frame_set_output(host_out)          # rows stream back as they finish
-            t1 = time.perf_counter()
-            list(pool.map(submit_slice, range(n_submit_threads)))
-            t2 = time.perf_counter()
-            pipe.frame_finish(host_out)
-            t3 = time.perf_counter()
-            phase[0] += t1 - t0
-            phase[1] += t2 - t1
-            phase[2] += t3 - t2
+            for _ in range(n_e2e):
+                e2e_step()
+            barrier()
+            e2e_s = (time.perf_counter() - t0) / n_e2e
+            log(f"[{kind}/{mode}] e2e phases (ms): begin {1e3 * phase[0] / n_e2e:.2f} "
+                f"submit {1e3 * phase[1] / n_e2e:.2f} finish {1e3 * phase[2] / n_e2e:.2f}")
+            te = torch.tensor([e2e_s], device="cuda")
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            h2d_t = torch.tensor([float(shared["h2d_sparse"] if mode == "sparse" else h2d), float(d2h)], device="cuda")
+            if world > 1:
+                dist.all_reduce(h2d_t)
+            return {"value": W * H / float(te.item()) / 1e6, "unit": "Mpixel/s",
+                    "h2d_bytes_per_step": int(h2d_t[0].item()), "d2h_bytes_per_step": int(h2d_t[1].item()),
+                    "steps": n_e2e, "submit": mode}
 
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        n_e2e = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            e2e_step()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / n_e2e
-        log(f"[{kind}] e2e phases (ms, avg incl. 2 warm-ups): begin {1e3 * phase[0] / (n_e2e + 2):.2f} "
-            f"submit {1e3 * phase[1] / (n_e2e + 2):.2f} finish {1e3 * phase[2] / (n_e2e + 2):.2f}")
-        te = torch.tensor([e2e_s], device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_value = W * H / float(te.item()) / 1e6
-        h2d_t = torch.tensor([float(h2d), float(d2h)], device="cuda")
-        if world > 1:
-            dist.all_reduce(h2d_t)
-        res["e2e"] = {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d_t[0].item()),
-                      "d2h_bytes_per_step": int(h2d_t[1].item()), "steps": n_e2e}
+        res["e2e"] = run_e2e(args.submit)
+        if not args.no_variants:
+            res["e2e_other_submit"] = run_e2e("dense" if args.submit == "sparse" else "sparse")
         return res
 
     shared = {}
+    pipeline.pin_side_info(desc)   # side info in page-locked memory, as the coefficient blocks are
     primary = measure(args.output, True)
     other_kind = "srgb8" if args.output == "f32" else "f32"
     variant = None if args.no_variants else measure(other_kind, True)
@@ -539,8 +562,12 @@ def main() -> int:
                    "strategy_histogram": fr["hist"], "bpp": fr["bpp"],
                    "l2": "inputs larger than L2 (coefficients + XYB planes + output >> 126 MB per step)"},
         "e2e": {**primary["e2e"],
-                "how": f"frame_begin + frame_set_output + submit_groups (one AC-group row per call, {n_submit_threads} host "
-                       "threads, pinned [group][3][65536] host blocks) + frame_finish; H2D / kernels / D2H overlap per row"},
+                "how": (f"frame_begin + frame_set_output + submit_groups (one AC-group row per call, {n_submit_threads} host "
+                        "threads, pinned [group][3][65536] host blocks) + frame_finish; H2D / kernels / D2H overlap per row")
+                if args.submit == "dense" else
+                       (f"frame_begin + frame_set_output + submit_groups_sparse (one AC-group row per call, {n_submit_threads} "
+                        "host threads, pinned non-zero lists as the entropy decoder would append them; zero-fill + "
+                        "scatter kernel on the device) + frame_finish; H2D / kernels / D2H overlap per batch of rows")},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "parity": parity,
     }
     if cpu_baseline:
@@ -549,8 +576,10 @@ def main() -> int:
         # the same frame with the other output kind (same kernels; only the fused store differs)
         line["variants"] = {other_kind: {"output": OUTPUT_TEXT[other_kind], "value": variant["value"],
                                          "ms_per_step": variant["ms_per_step"], "kernel_ms": variant["kernel_ms"],
-                                         "e2e": variant["e2e"], "parity": variant["parity"],
-                                         "cpu_reference_hot_path": (cpu_baseline or {}).get("by_output", {}).get(other_kind)}}
+                                         "e2e": variant["e2e"], "e2e_other_submit": variant.get("e2e_other_submit"),
+                                         "parity": variant["parity"],
+                                         "cpu_reference_hot_path": (cpu_baseline or {}).get("by_output", {}).get(other_kind)},
+                            "e2e_other_submit": primary.get("e2e_other_submit")}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

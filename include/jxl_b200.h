@@ -105,7 +105,9 @@ typedef struct jxlgpu_config {
 
 /* Everything the hot path reads, as it sits in PassesSharedState / PassesDecoderState
  * after ProcessACGlobal (passes_state.h:48-96, dec_cache.h:86-188).  All plane
- * pointers are HOST pointers here (copied during frame_begin); strides in elements. */
+ * pointers are HOST pointers here; strides in elements.  Pageable planes are copied before
+ * frame_begin returns; page-locked ones (jxlgpu_alloc_pinned) are read asynchronously and must stay
+ * unchanged until frame_finish. */
 typedef struct jxlgpu_frame {
   /* geometry: FrameDimensions (frame_dimensions.h:34-60) */
   uint32_t xsize, ysize;                /* true image size = mirror boundary of the filters */
@@ -187,6 +189,29 @@ JXLGPU_API int jxlgpu_submit_group(jxlgpu_ctx* ctx, uint32_t group_idx, size_t t
 /* Same, for `n` groups in one call: coeff[3*i + c] is channel c of group group_idx[i]. */
 JXLGPU_API int jxlgpu_submit_groups(jxlgpu_ctx* ctx, size_t n, const uint32_t* group_idx, size_t thread_id,
                                     const void* const* coeff, const size_t* ncoeff);
+
+/* Sparse hand-off: only the NON-ZERO quantised coefficients of an AC group cross PCIe (at d >= 1
+ * about 85-90% of them are zero, so this is 5-8x fewer bytes than the dense planes).  It is what
+ * the entropy decoder's inner loop produces anyway: DecodeACVarBlock visits the non-zeros one by
+ * one (`block[order[k]] += coeff`, dec_group.cc:515-534) into a block it had to zero-fill first
+ * (:341-355); with this entry point it appends `(offset + order[k]) << 16 | (uint16_t)coeff` to a
+ * per-group list instead and skips the zero-fill.
+ *   nz16[c]: n16[c] words `(pos << 16) | (uint16_t)value`, -32768 <= value <= 32767
+ *   nz32[c]: n32[c] pairs of words `{pos, (uint32_t)value}` for larger values (int32 frames only)
+ * pos = index of the coefficient inside the group's channel plane (< 65536; same order as the dense
+ * layout of jxlgpu_submit_group), entries in any order, every pos at most once (single pass).  The
+ * library zero-fills the group's dense planes in HBM, copies the lists (adjacent host arrays travel
+ * as one DMA) and expands them with a scatter kernel on the upload stream. */
+typedef struct jxlgpu_sparse_group {
+  uint32_t group_idx;
+  uint32_t n16[3];
+  uint32_t n32[3];
+  const uint32_t* nz16[3];
+  const uint32_t* nz32[3];
+} jxlgpu_sparse_group;
+
+JXLGPU_API int jxlgpu_submit_groups_sparse(jxlgpu_ctx* ctx, size_t n, const jxlgpu_sparse_group* groups,
+                                           size_t thread_id);
 
 /* Runs the kernels for every submitted group of the band and copies the band's pixels to
  * `out` (host; row stride in bytes).  out == NULL keeps the result on the device

@@ -74,6 +74,25 @@ def _f32(a, n=None):
     return a
 
 
+class JxlGpuSparseGroup(C.Structure):
+    """jxlgpu_sparse_group (include/jxl_b200.h)."""
+    _fields_ = [("group_idx", C.c_uint32), ("n16", C.c_uint32 * 3), ("n32", C.c_uint32 * 3),
+                ("nz16", C.c_void_p * 3), ("nz32", C.c_void_p * 3)]
+
+
+def pack_sparse(plane: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """One (group, channel) plane of quantised coefficients -> (nz16 words, nz32 word pairs), the two
+    lists of jxlgpu_sparse_group -- what an entropy decoder that appends instead of scattering emits."""
+    idx = np.flatnonzero(plane)
+    v = plane[idx].astype(np.int64)
+    small = (v >= -32768) & (v <= 32767)
+    w16 = ((idx[small].astype(np.uint32) << np.uint32(16)) | (v[small] & 0xffff).astype(np.uint32)).astype(np.uint32)
+    big = np.empty((int((~small).sum()), 2), np.uint32)
+    big[:, 0] = idx[~small]
+    big[:, 1] = (v[~small] & 0xffffffff).astype(np.uint32)
+    return w16, big.ravel()
+
+
 @dataclass
 class FrameDesc:
     """Host-side description of one VarDCT frame's hot-path inputs (see module doc)."""

@@ -15,6 +15,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -75,11 +76,16 @@ struct jxlgpu_ctx {
   // streaming state (guarded by mu)
   std::vector<uint8_t> submitted;
   std::vector<uint32_t> row_count;               // groups submitted per group row
+  std::vector<size_t> row_bytes;                 // coefficient bytes uploaded per group row
+  size_t launch_bytes = 10u << 20;
+  uint32_t groups_in = 0;                        // submitted groups among the rows this band needs
   std::vector<uint8_t> row_idct, row_filtered;
   void* host_out = nullptr;
   size_t host_out_stride = 0;
   int stream_error = 0;
   DevBuf acs, quant, sharp, ytox, ytob, dc, dq, coeff, coeff_off, sigma, list, counts, xyb, out;
+  DevBuf sparse;              // staging for the non-zero lists of jxlgpu_submit_groups_sparse
+  size_t sparse_used = 0;     // words handed out this frame (bump allocation, guarded by mu)
   size_t out_row_bytes = 0;   // dense row of the context-owned output buffer
   std::atomic<uint64_t> launches{0};
   bool force_generic_filter = false;  // JXLGPU_FORCE_GENERIC_FILTER=1: tile kernel for every chain
@@ -240,37 +246,66 @@ int ensure_out(jxlgpu_ctx* ctx) {
 }
 
 // Streaming scheduler, called with ctx->mu held: enqueue whatever became runnable.
-int pump(jxlgpu_ctx* ctx) {
+// Granularity: kernels are launched over runs of complete AC-group rows.  A run is launched once
+// the coefficient bytes uploaded for it amount to kLaunchBytes (~0.2 ms of PCIe time: with dense 8K
+// rows that is every row, with sparse lists every ~3 rows; measured best of 3/8/20 MB), when
+// the band's last group has arrived, or when frame_finish forces it -- so a PCIe-bound feed keeps
+// its per-row overlap and a light feed does not pay 17 under-filled launches per frame.
+constexpr size_t kLaunchBytes = 10u << 20;  // (JXLGPU_LAUNCH_MB overrides it: tuning knob)
+
+int pump(jxlgpu_ctx* ctx, bool force) {
   const FrameDev& P = ctx->P;
   cudaStream_t s = ctx->stream;
-  for (uint32_t g = ctx->need_row0; g < ctx->need_row1; g++) {
-    if (ctx->row_idct[g] || ctx->row_count[g] < P.xg) continue;
-    // the row's coefficients are in flight on the upload streams
+  if (ctx->coeff_external || ctx->groups_in == (ctx->need_row1 - ctx->need_row0) * P.xg) force = true;
+  for (uint32_t g = ctx->need_row0; g < ctx->need_row1;) {
+    if (ctx->row_idct[g] || ctx->row_count[g] < P.xg) {
+      g++;
+      continue;
+    }
+    uint32_t h = g;
+    size_t bytes = 0;
+    while (h < ctx->need_row1 && !ctx->row_idct[h] && ctx->row_count[h] == P.xg) bytes += ctx->row_bytes[h++];
+    if (!force && bytes < ctx->launch_bytes) {
+      g = h;
+      continue;
+    }
+    // the rows' coefficients are in flight on the upload stream
     if (!ctx->coeff_external)
-      if (ctx->row_event_used[g]) CU(cudaStreamWaitEvent(s, ctx->row_events[g], 0));
-    uint32_t ny0 = g * 256u, ny1 = (g + 1) * 256u;
+      for (uint32_t r = g; r < h; r++)
+        if (ctx->row_event_used[r]) CU(cudaStreamWaitEvent(s, ctx->row_events[r], 0));
+    uint32_t ny0 = g * 256u, ny1 = h * 256u;
     if (ny0 < P.need_y0) ny0 = P.need_y0;
-    if (ny1 > P.need_y1 || g + 1 == ctx->need_row1) ny1 = P.need_y1;
-    int rc = launch_idct(ctx, g, g + 1, ny0, ny1, s);
+    if (ny1 > P.need_y1 || h == ctx->need_row1) ny1 = P.need_y1;
+    int rc = launch_idct(ctx, g, h, ny0, ny1, s);
     if (rc) return rc;
-    ctx->row_idct[g] = 1;
+    for (uint32_t r = g; r < h; r++) ctx->row_idct[r] = 1;
+    g = h;
   }
+  // filter every run of rows whose neighbours (the 7-row halo) are transformed
   const uint32_t band_h = P.band_y1 - P.band_y0;
-  for (uint32_t g = ctx->band_row0; g < ctx->band_row1; g++) {
-    if (ctx->row_filtered[g]) continue;
+  auto ready = [&](uint32_t g) {
+    if (ctx->row_filtered[g]) return false;
     const uint32_t lo = g > ctx->need_row0 ? g - 1 : g;
     const uint32_t hi = g + 1 < ctx->need_row1 ? g + 1 : g;
-    bool ready = true;
-    for (uint32_t r = lo; r <= hi; r++) ready = ready && ctx->row_idct[r];
-    if (!ready) continue;
-    uint32_t y0 = g * 256u, y1 = (g + 1) * 256u;
+    for (uint32_t r = lo; r <= hi; r++)
+      if (!ctx->row_idct[r]) return false;
+    return true;
+  };
+  for (uint32_t g = ctx->band_row0; g < ctx->band_row1;) {
+    if (!ready(g)) {
+      g++;
+      continue;
+    }
+    uint32_t h = g + 1;
+    while (h < ctx->band_row1 && ready(h)) h++;
+    uint32_t y0 = g * 256u, y1 = h * 256u;
     if (y0 < P.band_y0) y0 = P.band_y0;
     if (y1 > P.band_y1) y1 = P.band_y1;
     int rc = ensure_out(ctx);
     if (rc) return rc;
     rc = launch_filter(ctx, y0, y1, P.band_y0, band_h, (char*)ctx->out.p, ctx->out_row_bytes, s);
     if (rc) return rc;
-    ctx->row_filtered[g] = 1;
+    for (uint32_t r = g; r < h; r++) ctx->row_filtered[r] = 1;
     if (ctx->host_out && y1 > y0) {  // copy the finished rows back while later rows still arrive
       CU(cudaEventRecord(ctx->ev_filter, s));
       CU(cudaStreamWaitEvent(ctx->s_down, ctx->ev_filter, 0));
@@ -282,6 +317,7 @@ int pump(jxlgpu_ctx* ctx) {
                          (uint8_t*)ctx->out.p + row * row_bytes, row_bytes, y1 - y0, ctx->s_down));
       }
     }
+    g = h;
   }
   return JXLGPU_OK;
 }
@@ -345,6 +381,8 @@ int jxlgpu_create(jxlgpu_ctx** out, const jxlgpu_config* cfg) {
   {
     const char* env = getenv("JXLGPU_FORCE_GENERIC_FILTER");
     ctx->force_generic_filter = env && env[0] == '1';
+    ctx->launch_bytes = kLaunchBytes;
+    if (const char* mb = getenv("JXLGPU_LAUNCH_MB")) ctx->launch_bytes = (size_t)atoi(mb) << 20;
   }
   if ((e = ctx->counts.ensure(kNumStrategies * sizeof(uint32_t))) != cudaSuccess) return bail(e, "alloc");
   for (auto& ev : ctx->prof_ev)
@@ -359,7 +397,7 @@ void jxlgpu_destroy(jxlgpu_ctx* ctx) {
   cudaDeviceSynchronize();
   for (DevBuf* b : {&ctx->acs, &ctx->quant, &ctx->sharp, &ctx->ytox, &ctx->ytob, &ctx->dc, &ctx->dq,
                     &ctx->coeff, &ctx->coeff_off, &ctx->sigma,
-                    &ctx->list, &ctx->counts, &ctx->xyb, &ctx->out})
+                    &ctx->list, &ctx->counts, &ctx->xyb, &ctx->out, &ctx->sparse})
     b->release();
   for (auto s : ctx->up_streams) cudaStreamDestroy(s);
   for (auto ev : ctx->up_events) cudaEventDestroy(ev);
@@ -496,8 +534,11 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   memcpy(P.opsin_bias, f->opsin_biases, sizeof(P.opsin_bias));
   memcpy(P.opsin_cbrt, f->opsin_biases_cbrt, sizeof(P.opsin_cbrt));
   ctx->out_row_bytes = out_bytes_per_row(*f);
+  ctx->sparse_used = 0;
   ctx->submitted.assign(ctx->num_groups, ctx->coeff_external ? 1 : 0);
   ctx->row_count.assign(P.yg, ctx->coeff_external ? P.xg : 0);
+  ctx->row_bytes.assign(P.yg, 0);
+  ctx->groups_in = 0;
   ctx->row_idct.assign(P.yg, 0);
   ctx->row_filtered.assign(P.yg, 0);
   if (P.yg > ctx->row_cap) {
@@ -525,15 +566,18 @@ int jxlgpu_frame_set_output(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes)
 }
 
 // bookkeeping after the DMA(s) of group g were enqueued on the upload stream; ctx->mu is held
-static int mark_submitted(jxlgpu_ctx* ctx, uint32_t g) {
+static int mark_submitted(jxlgpu_ctx* ctx, uint32_t g, size_t bytes) {
   const uint32_t row = g / ctx->P.xg;
+  ctx->row_bytes[row] += bytes;
   cudaError_t e = cudaEventRecord(ctx->row_events[row], ctx->up_streams[0]);
   if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaEventRecord(row)");
   ctx->row_event_used[row] = 1;
   if (ctx->submitted[g]) return JXLGPU_OK;  // a re-submission is not streamed again
   ctx->submitted[g] = 1;
-  if (++ctx->row_count[row] == ctx->P.xg && row >= ctx->need_row0 && row < ctx->need_row1) {
-    int rc = pump(ctx);
+  const bool needed = row >= ctx->need_row0 && row < ctx->need_row1;
+  if (needed) ctx->groups_in++;
+  if (++ctx->row_count[row] == ctx->P.xg && needed) {
+    int rc = pump(ctx, false);
     if (rc) {
       ctx->stream_error = rc;
       return rc;
@@ -587,10 +631,117 @@ int jxlgpu_submit_groups(jxlgpu_ctx* ctx, size_t n, const uint32_t* group_idx, s
       }
     }
     for (size_t k = i; k <= j; k++) {
-      int rc = mark_submitted(ctx, group_idx[k]);
+      int rc = mark_submitted(ctx, group_idx[k], 3 * ncoeff[k] * es);
       if (rc) return rc;
     }
     i = j + 1;
+  }
+  return JXLGPU_OK;
+}
+
+int jxlgpu_submit_groups_sparse(jxlgpu_ctx* ctx, size_t n, const jxlgpu_sparse_group* groups, size_t thread_id) {
+  if (!ctx || (n && !groups)) return JXLGPU_ERR_INVALID_ARGUMENT;
+  if (!ctx->in_frame || ctx->coeff_external) return JXLGPU_ERR_STATE;
+  if (thread_id >= ctx->num_threads) return JXLGPU_ERR_INVALID_ARGUMENT;
+  size_t words = 0;
+  for (size_t i = 0; i < n; i++) {
+    const jxlgpu_sparse_group& g = groups[i];
+    if (g.group_idx >= ctx->num_groups) return JXLGPU_ERR_INVALID_ARGUMENT;
+    for (int c = 0; c < 3; c++) {
+      if (g.n16[c] > 65536 || g.n32[c] > 65536 || (g.n16[c] && !g.nz16[c]) || (g.n32[c] && !g.nz32[c]))
+        return JXLGPU_ERR_INVALID_ARGUMENT;
+      if (g.n32[c] && !ctx->P.ac_is32) return JXLGPU_ERR_INVALID_ARGUMENT;  // would not fit the int16 planes
+      words += g.n16[c] + 2 * (size_t)g.n32[c] + 1;  // (+1: pair lists start on an 8-byte boundary)
+    }
+  }
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return JXLGPU_ERR_CUDA;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaStream_t s = ctx->up_streams[0];  // the FIFO upload stream (see jxlgpu_submit_groups)
+  const size_t es = ctx->elem_size, gelems = 3 * 65536, gbytes = gelems * es;
+  // staging: worst case (every coefficient non-zero) is one word per coefficient + slack
+  const size_t cap_words = (size_t)ctx->num_groups * (gelems + 8);
+  if (!ctx->sparse.p) {
+    e = ctx->sparse.ensure(cap_words * 4);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "alloc(sparse staging)");
+  }
+  if (ctx->sparse_used + words > cap_words) {
+    ctx->last_error = "sparse lists larger than the dense planes: submit dense groups instead";
+    return JXLGPU_ERR_INVALID_ARGUMENT;
+  }
+  // 1. zero-fill the dense planes of these groups (runs of consecutive groups in one memset).  Zero-fill
+  //    and scatter run on the compute stream, so that the upload stream carries DMAs only and the
+  //    next batch's lists travel while this one is expanded.
+  cudaStream_t cs = ctx->stream;
+  for (size_t i = 0; i < n;) {
+    size_t j = i;
+    while (j + 1 < n && groups[j + 1].group_idx == groups[j].group_idx + 1) j++;
+    e = cudaMemsetAsync((uint8_t*)ctx->coeff.p + (size_t)groups[i].group_idx * gbytes, 0, (j - i + 1) * gbytes, cs);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaMemsetAsync(coefficient groups)");
+    i = j + 1;
+  }
+  // 2. copy the lists; host arrays that follow each other in memory travel as one DMA
+  std::vector<SparseSeg> segs;
+  segs.reserve(6 * n);
+  uint32_t* stage = (uint32_t*)ctx->sparse.p;
+  const uint32_t* run_src = nullptr;
+  size_t run_words = 0, run_dst = 0;
+  auto flush = [&]() -> cudaError_t {
+    if (!run_words) return cudaSuccess;
+    cudaError_t r = cudaMemcpyAsync(stage + run_dst, run_src, run_words * 4, cudaMemcpyHostToDevice, s);
+    run_words = 0;
+    return r;
+  };
+  auto add = [&](const uint32_t* src, size_t nwords, uint32_t entries, uint32_t dst_off, uint32_t wide) -> cudaError_t {
+    if (!entries) return cudaSuccess;
+    const bool joins = run_words && src == run_src + run_words && (!wide || ((run_dst + run_words) % 2 == 0));
+    if (!joins) {
+      cudaError_t r = flush();
+      if (r != cudaSuccess) return r;
+      if (wide && ctx->sparse_used % 2) ctx->sparse_used++;
+      run_src = src;
+      run_dst = ctx->sparse_used;
+    }
+    segs.push_back(SparseSeg{(uint32_t)(run_dst + run_words), entries, dst_off, wide});
+    run_words += nwords;
+    ctx->sparse_used = run_dst + run_words;
+    return cudaSuccess;
+  };
+  for (size_t i = 0; i < n; i++) {
+    const jxlgpu_sparse_group& g = groups[i];
+    for (int c = 0; c < 3; c++) {
+      const uint32_t dst_off = (uint32_t)((size_t)g.group_idx * gelems + (size_t)c * 65536);
+      if ((e = add(g.nz16[c], g.n16[c], g.n16[c], dst_off, 0)) != cudaSuccess) return fail_cuda(ctx, e, "cudaMemcpyAsync(sparse)");
+      if ((e = add(g.nz32[c], 2 * (size_t)g.n32[c], g.n32[c], dst_off, 1)) != cudaSuccess) return fail_cuda(ctx, e, "cudaMemcpyAsync(sparse)");
+    }
+  }
+  if ((e = flush()) != cudaSuccess) return fail_cuda(ctx, e, "cudaMemcpyAsync(sparse)");
+  if (n) {
+    cudaEvent_t ev = ctx->row_events[groups[0].group_idx / ctx->P.xg];
+    if ((e = cudaEventRecord(ev, s)) != cudaSuccess || (e = cudaStreamWaitEvent(cs, ev, 0)) != cudaSuccess)
+      return fail_cuda(ctx, e, "event(sparse lists)");
+  }
+  // 3. scatter into the dense planes
+  for (size_t s0 = 0; s0 < segs.size(); s0 += kMaxSparseSegs) {
+    SparseBatch B;
+    const size_t cnt = std::min((size_t)kMaxSparseSegs, segs.size() - s0);
+    uint32_t max_n = 1;
+    for (size_t k = 0; k < cnt; k++) {
+      B.seg[k] = segs[s0 + k];
+      max_n = std::max(max_n, B.seg[k].n);
+    }
+    const dim3 grid(std::min<uint32_t>((max_n + 1023) / 1024, 16), (unsigned)cnt);
+    if (ctx->P.ac_is32) sparse_expand_kernel<true><<<grid, 256, 0, cs>>>(B, stage, ctx->coeff.p);
+    else sparse_expand_kernel<false><<<grid, 256, 0, cs>>>(B, stage, ctx->coeff.p);
+    ctx->launches += 1;
+  }
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail_cuda(ctx, e, "sparse_expand_kernel");
+  for (size_t i = 0; i < n; i++) {
+    const jxlgpu_sparse_group& g = groups[i];
+    size_t gw = 0;
+    for (int c = 0; c < 3; c++) gw += g.n16[c] + 2 * (size_t)g.n32[c];
+    int rc = mark_submitted(ctx, g.group_idx, gw * 4);
+    if (rc) return rc;
   }
   return JXLGPU_OK;
 }
@@ -663,7 +814,7 @@ int jxlgpu_frame_finish(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes) {
         ctx->last_error = "missing group";
         return JXLGPU_ERR_STATE;
       }
-    int rc = pump(ctx);  // device-resident coefficients: nothing was streamed yet
+    int rc = pump(ctx, true);  // whatever the scheduler still holds back, and device-resident coefficients
     if (rc) return rc;
     for (uint32_t g = ctx->band_row0; g < ctx->band_row1; g++)
       if (!ctx->row_filtered[g]) {

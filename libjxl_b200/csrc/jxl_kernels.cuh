@@ -982,6 +982,49 @@ __global__ void __launch_bounds__(256) idct_large_kernel(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------
+// Sparse coefficient hand-off (jxlgpu_submit_groups_sparse): scatter the non-zero entries of up to
+// kMaxSparseSegs (group, channel) lists into the zero-filled dense planes.  HBM-bound: 4 bytes read
+// and one 2/4-byte store per non-zero; the stores of one varblock fall into few 32-byte sectors
+// because the low frequencies, where the non-zeros are, sit together in the natural order.
+// ---------------------------------------------------------------------------
+struct SparseSeg {
+  uint32_t src_off;  // first word of the list inside the staging buffer
+  uint32_t n;        // entries
+  uint32_t dst_off;  // first element of the (group, channel) plane inside the dense buffer
+  uint32_t wide;     // 0: (pos << 16) | u16 value words; 1: {pos, value} word pairs
+};
+constexpr int kMaxSparseSegs = 192;
+struct SparseBatch {
+  SparseSeg seg[kMaxSparseSegs];
+};
+
+#ifndef JXLB_STRIP_TU
+template <bool I32>
+__global__ void __launch_bounds__(256) sparse_expand_kernel(const __grid_constant__ SparseBatch B,
+                                                            const uint32_t* __restrict__ staging,
+                                                            void* __restrict__ coeff) {
+  const SparseSeg sg = B.seg[blockIdx.y];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += gridDim.x * blockDim.x) {
+    uint32_t pos;
+    int32_t val;
+    if (sg.wide) {
+      const uint2 w = *reinterpret_cast<const uint2*>(staging + sg.src_off + 2 * (size_t)i);
+      pos = w.x;
+      val = (int32_t)w.y;
+    } else {
+      const uint32_t w = staging[sg.src_off + i];
+      pos = w >> 16;
+      val = (int32_t)(int16_t)(w & 0xffffu);
+    }
+    if (pos < 65536u) {
+      if constexpr (I32) reinterpret_cast<int32_t*>(coeff)[(size_t)sg.dst_off + pos] = val;
+      else reinterpret_cast<int16_t*>(coeff)[(size_t)sg.dst_off + pos] = (int16_t)val;
+    }
+  }
+}
+#endif  // JXLB_STRIP_TU
+
+// ---------------------------------------------------------------------------
 // fused filter kernel: [Gaborish] -> [EPF0] -> [EPF1] -> [EPF2] -> [XYB->linear RGB]
 // One CTA per TW x TH output tile; every enabled stage is evaluated on a shrinking
 // halo inside two shared-memory ping-pong tiles.  Positions outside the image are

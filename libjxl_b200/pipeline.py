@@ -30,7 +30,7 @@ STRIP_MASKS = (16, 17, 20, 21, 28, 29, 30, 31)
 
 EXPORTS = ["jxlgpu_abi_version", "jxlgpu_error_string", "jxlgpu_last_error", "jxlgpu_create",
            "jxlgpu_destroy", "jxlgpu_frame_begin", "jxlgpu_frame_set_output", "jxlgpu_submit_group",
-           "jxlgpu_submit_groups", "jxlgpu_frame_finish",
+           "jxlgpu_submit_groups", "jxlgpu_submit_groups_sparse", "jxlgpu_frame_finish",
            "jxlgpu_set_device_coefficients", "jxlgpu_render_device", "jxlgpu_set_output_replicas", "jxlgpu_device_output",
            "jxlgpu_device_xyb", "jxlgpu_synchronize", "jxlgpu_launch_count", "jxlgpu_alloc_pinned",
            "jxlgpu_free_pinned", "jxlgpu_set_profiling", "jxlgpu_kernel_times"]
@@ -95,6 +95,7 @@ def lib():
         L.jxlgpu_frame_set_output.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.jxlgpu_submit_group.argtypes = [C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p * 3, C.c_size_t]
         L.jxlgpu_submit_groups.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.jxlgpu_submit_groups_sparse.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.jxlgpu_frame_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.jxlgpu_set_device_coefficients.argtypes = [C.c_void_p, C.c_void_p]
         L.jxlgpu_render_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -125,6 +126,23 @@ def pinned_array(shape, dtype) -> np.ndarray:
         raise JxlGpuError(abi.ERR_OOM, "jxlgpu_alloc_pinned")
     buf = (C.c_uint8 * n).from_address(p)
     return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def pin_side_info(desc: abi.FrameDesc) -> abi.FrameDesc:
+    """Move the frame's side-information planes into page-locked memory (what a host gets by handing
+    libjxl a JxlMemoryManager that allocates pinned memory): frame_begin then enqueues their uploads
+    asynchronously instead of paying the driver's staging copy.  They must stay untouched until
+    frame_finish."""
+    for name, dt in (("ac_strategy", np.uint8), ("raw_quant", np.int32), ("epf_sharpness", np.uint8),
+                     ("ytox", np.int8), ("ytob", np.int8), ("dc", np.float32), ("dequant", np.float32)):
+        a = getattr(desc, name)
+        if a is None:
+            continue
+        a = np.ascontiguousarray(a, dt)
+        p = pinned_array(a.shape, dt)
+        p[...] = a
+        setattr(desc, name, p)
+    return desc
 
 
 class TransformPipeline:
@@ -189,6 +207,32 @@ class TransformPipeline:
         n, idx, ptrs, nco = batch
         self._check(lib().jxlgpu_submit_groups(self._h, n, idx, thread_id, ptrs, nco), "jxlgpu_submit_groups")
 
+    def make_sparse_batch(self, groups, coeffs, pinned: bool = True):
+        """Sparse hand-off of `groups` (jxlgpu_submit_groups_sparse): the non-zero lists of every
+        (group, channel), packed back to back into one (pinned) host buffer so that the batch is one
+        DMA.  coeffs: (3, num_groups, 65536).  Returns (n, struct array, buffer, bytes)."""
+        lists = []
+        for g in groups:
+            n = self.desc.group_ncoeff(g)
+            lists.append([abi.pack_sparse(coeffs[c, g, :n]) for c in range(3)])
+        total = sum(a.size + b.size for gl in lists for (a, b) in gl)
+        buf = pinned_array((max(total, 1),), np.uint32) if pinned else np.empty(max(total, 1), np.uint32)
+        arr = (abi.JxlGpuSparseGroup * len(groups))()
+        off = 0
+        for i, (g, gl) in enumerate(zip(groups, lists)):
+            arr[i].group_idx = int(g)
+            for c, (a, b) in enumerate(gl):
+                for name, cnt_name, lst, per in (("nz16", "n16", a, 1), ("nz32", "n32", b, 2)):
+                    buf[off:off + lst.size] = lst
+                    getattr(arr[i], cnt_name)[c] = lst.size // per
+                    getattr(arr[i], name)[c] = buf.ctypes.data + 4 * off if lst.size else None
+                    off += lst.size
+        return len(groups), arr, buf, 4 * total
+
+    def submit_sparse_batch(self, batch, thread_id: int = 0):
+        n, arr = batch[0], batch[1]
+        self._check(lib().jxlgpu_submit_groups_sparse(self._h, n, arr, thread_id), "jxlgpu_submit_groups_sparse")
+
     def frame_finish(self, out: np.ndarray | None = None) -> np.ndarray:
         d = self.desc
         if out is None:
@@ -200,15 +244,26 @@ class TransformPipeline:
 
     # convenience: whole frame from a (3, num_groups, 65536) host array
     def decode_frame(self, desc: abi.FrameDesc, coeffs: np.ndarray, out: np.ndarray | None = None,
-                     order=None, stream_output: bool = False) -> np.ndarray:
-        """frame_begin + submit_group for every group (`order`: submission order) + frame_finish."""
+                     order=None, stream_output: bool = False, sparse: bool = False) -> np.ndarray:
+        """frame_begin + submit_group for every group (`order`: submission order) + frame_finish.
+        sparse: hand the groups over as non-zero lists, one AC-group row per call."""
         self.set_device_coefficients(None)
         self.frame_begin(desc)
         if stream_output:
             if out is None:
                 out = np.empty(desc.out_shape(), desc.out_dtype)
             self.frame_set_output(out)
-        for g in (order if order is not None else range(desc.num_groups)):
+        order = list(order if order is not None else range(desc.num_groups))
+        if sparse:
+            keep = []
+            xg = desc.xsize_groups
+            for i in range(0, len(order), xg):
+                keep.append(self.make_sparse_batch(order[i:i + xg], coeffs, pinned=False))
+                self.submit_sparse_batch(keep[-1])
+            res = self.frame_finish(out)
+            del keep
+            return res
+        for g in order:
             self.submit_group(g, [coeffs[c, g] for c in range(3)])
         return self.frame_finish(out)
 

@@ -37,13 +37,14 @@ def test_struct_layout_matches_header():
     """sizeof(jxlgpu_frame) computed by the C compiler == ctypes mirror."""
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include "jxl_b200.h"\nint main(){printf("%zu %zu\\n", sizeof(jxlgpu_frame), sizeof(jxlgpu_config));return 0;}\n'
+    src = '#include <stdio.h>\n#include "jxl_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(jxlgpu_frame), sizeof(jxlgpu_config), sizeof(jxlgpu_sparse_group));return 0;}\n'
     with tempfile.TemporaryDirectory() as td:
         (Path(td) / "t.c").write_text(src)
         subprocess.check_call(["/usr/bin/gcc", "-I", str(ROOT / "include"), str(Path(td) / "t.c"), "-o", str(Path(td) / "t")])
         out = subprocess.check_output([str(Path(td) / "t")]).split()
     assert int(out[0]) == C.sizeof(abi.JxlGpuFrame)
     assert int(out[1]) == C.sizeof(abi.JxlGpuConfig)
+    assert int(out[2]) == C.sizeof(abi.JxlGpuSparseGroup)
 
 
 def test_no_cpu_fallback_without_device():

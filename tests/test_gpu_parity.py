@@ -258,6 +258,64 @@ def test_streaming_any_submission_order(pipe):
     assert_same(got, want, "pinned streamed output")
 
 
+@pytest.mark.parametrize("ac_type", [abi.AC_INT16, abi.AC_INT32])
+def test_sparse_submit_equals_dense(pipe, ac_type):
+    """jxlgpu_submit_groups_sparse (non-zero lists + scatter kernel) produces the same pixels as the
+    dense hand-off: all 27 strategies, ragged size, shuffled group order, streamed output; the int32
+    frame carries values beyond 16 bits (the {pos, value} pair lists)."""
+    desc, coeffs = wl.synthetic_frame(1100, 777, seed=77 + ac_type, ac_type=ac_type)
+    if ac_type == abi.AC_INT32:
+        coeffs = coeffs.copy()
+        rng = np.random.default_rng(2)
+        for c in range(3):
+            g = rng.integers(0, desc.num_groups, 200)
+            k = rng.integers(64, 4096, 200)
+            coeffs[c, g, k] = rng.integers(-300000, 300000, 200)
+        assert np.abs(coeffs).max() > 40000
+    want = pipe.decode_frame(desc, coeffs)
+    assert_same(pipe.decode_frame(desc, coeffs, sparse=True), want, "sparse, in order")
+    order = np.random.default_rng(9).permutation(desc.num_groups).tolist()
+    assert_same(pipe.decode_frame(desc, coeffs, sparse=True, order=order, stream_output=True), want, "sparse, shuffled")
+    # a frame of zeros after a frame with content: the planes really are re-zeroed
+    zeros = np.zeros_like(coeffs)
+    assert_same(pipe.decode_frame(desc, zeros, sparse=True), pipe.decode_frame(desc, zeros), "all-zero frame")
+    # mixing both hand-offs inside one frame
+    pipe.set_device_coefficients(None)
+    pipe.frame_begin(desc)
+    xg = desc.xsize_groups
+    keep = []
+    for row in range(desc.ysize_groups):
+        gs = list(range(row * xg, (row + 1) * xg))
+        if row % 2:
+            keep.append(pipe.make_sparse_batch(gs, coeffs, pinned=False))
+            pipe.submit_sparse_batch(keep[-1])
+        else:
+            for g in gs:
+                pipe.submit_group(g, [coeffs[c, g] for c in range(3)])
+    assert_same(pipe.frame_finish(), want, "mixed")
+
+
+def test_sparse_submit_errors(pipe):
+    desc, coeffs = wl.synthetic_frame(300, 300, seed=1)          # int16 frame
+    pipe.set_device_coefficients(None)
+    pipe.frame_begin(desc)
+    n, arr, buf, _ = pipe.make_sparse_batch([0], coeffs, pinned=False)
+    arr[0].group_idx = 99
+    with pytest.raises(pipeline.JxlGpuError):      # group index out of range
+        pipe.submit_sparse_batch((n, arr))
+    arr[0].group_idx = 0
+    arr[0].n32[0] = 1
+    arr[0].nz32[0] = buf.ctypes.data
+    with pytest.raises(pipeline.JxlGpuError):      # wide values cannot go into int16 planes
+        pipe.submit_sparse_batch((n, arr))
+    arr[0].n32[0] = 0
+    arr[0].n16[1] = 70000
+    with pytest.raises(pipeline.JxlGpuError):      # more entries than the plane has coefficients
+        pipe.submit_sparse_batch((n, arr))
+    with pytest.raises(pipeline.JxlGpuError):      # the frame is still incomplete
+        pipe.frame_finish()
+
+
 def test_submit_errors(pipe):
     desc, coeffs = wl.synthetic_frame(300, 300, seed=1)
     pipe.set_device_coefficients(None)

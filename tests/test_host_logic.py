@@ -82,3 +82,22 @@ def test_groups_needed_includes_halo_rows():
     desc.gab, desc.epf_iters = 0, 0
     assert sharding.filter_halo(desc) == 0
     assert sharding.groups_needed(desc, 2, 1) == list(range(2 * xg, 3 * xg))
+
+
+def test_pack_sparse_round_trip():
+    """abi.pack_sparse: the two non-zero lists of jxlgpu_sparse_group re-expand to the dense plane
+    (16-bit words for |v| < 2^15, {pos, value} pairs beyond)."""
+    rng = np.random.default_rng(11)
+    plane = np.zeros(65536, np.int32)
+    idx = rng.choice(65536, 9000, replace=False)
+    plane[idx] = rng.integers(-40, 41, idx.size)
+    plane[idx[:50]] = rng.integers(-2**31, 2**31 - 1, 50)
+    plane[idx[50:54]] = (32767, -32768, 32768, -32769)
+    w16, w32 = abi.pack_sparse(plane)
+    assert w16.dtype == np.uint32 and w32.dtype == np.uint32 and w32.size % 2 == 0
+    back = np.zeros_like(plane)
+    back[w16 >> 16] = (w16 & 0xffff).astype(np.uint16).view(np.int16)
+    back[w32[0::2]] = w32[1::2].view(np.int32)
+    assert np.array_equal(back, plane)
+    assert w16.size + w32.size // 2 == np.count_nonzero(plane)
+    assert set(np.abs(plane[w32[0::2]]).tolist()) and np.all((plane[w32[0::2]] > 32767) | (plane[w32[0::2]] < -32768))
