@@ -517,8 +517,15 @@ def main() -> int:
     dominant = "filter" if kavg["filter"] >= k_idct else "idct"
     dom_ms = kavg["filter"] if dominant == "filter" else k_idct
     achieved = ab[dominant] / (dom_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:   # DRAM bytes of the dominant kernel from the committed ncu capture of this workload, if there is one
+        t = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())[args.workload][args.output][dominant]
+        if world == 1:
+            traffic, traffic_src = float(t["bytes"]), t["capture"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "kernel": "filter_strip_kernel" if dominant == "filter" else "idct8_kernel+idct_mid_kernel+idct_large_kernel",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ab[dominant],
                 "kernel_ms": kavg,
                 "pipeline": {"algorithmic_bytes": ab["fused_path"],
