@@ -50,6 +50,9 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> Path:
     units = [(CSRC / "jxl_b200.cu", OBJ / "jxl_b200.o", [])]
     units += [(CSRC / "jxl_strip_inst.cu", OBJ / f"jxl_strip_{m}.o", [f"-DSTRIP_MASK={m}"]) for m in STRIP_MASKS]
     newest_hdr = max(h.stat().st_mtime for h in hdrs)
+    newest_src = max(newest_hdr, *(u[0].stat().st_mtime for u in units))
+    if not force and SO.exists() and SO.stat().st_mtime >= newest_src:
+        return SO   # up to date (the objects need not be around: only the .so travels to the GPU box)
     OBJ.mkdir(exist_ok=True)
 
     def compile_unit(u):
