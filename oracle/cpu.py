@@ -34,6 +34,10 @@ def lib():
         L.jxo_adjust_quant_bias.argtypes = [C.c_int, C.c_int32, C.c_void_p, C.c_int]
         L.jxo_compute_sigma.argtypes = [C.POINTER(abi.JxlGpuFrame), C.c_void_p]
         L.jxo_render_frame.argtypes = [C.POINTER(abi.JxlGpuFrame), C.c_void_p * 3, C.c_int, C.c_void_p]
+        L.jxo_dequant_dc.restype = None
+        L.jxo_dequant_dc.argtypes = [C.c_void_p * 3, C.c_size_t, C.c_size_t, C.c_float * 3, C.c_float,
+                                     C.c_float * 3, C.c_void_p]
+        L.jxo_adaptive_dc_smoothing.argtypes = [C.c_float * 3, C.c_void_p, C.c_size_t, C.c_size_t]
         L.jxo_srgb_from_linear.restype = C.c_float
         L.jxo_srgb_from_linear.argtypes = [C.c_float]
         L.jxo_make_unsigned.restype = C.c_uint32
@@ -112,6 +116,28 @@ def f16_from_f32(v: np.ndarray) -> np.ndarray:
     fn = lib().jxo_f16_from_f32
     flat = np.ascontiguousarray(v, np.float32).ravel()
     return np.array([fn(float(x)) for x in flat], np.uint16).reshape(np.shape(v))
+
+
+def dequant_dc(q: np.ndarray, dc_factors, mul: float, cfl_factors) -> np.ndarray:
+    """q: (3, ys, xs) int32 quantised DC (X, Y, B). Returns (3, ys, xs) float32."""
+    q = np.ascontiguousarray(q, np.int32)
+    _, ys, xs = q.shape
+    out = np.zeros(q.shape, np.float32)
+    ptrs = (C.c_void_p * 3)(*[q.ctypes.data + c * q[0].nbytes for c in range(3)])
+    f = (C.c_float * 3)(*dc_factors)
+    cf = (C.c_float * 3)(*cfl_factors)
+    lib().jxo_dequant_dc(ptrs, xs, ys, f, mul, cf, out.ctypes.data)
+    return out
+
+
+def adaptive_dc_smoothing(dc: np.ndarray, dc_factors) -> np.ndarray:
+    dc = np.array(dc, np.float32, order="C")
+    _, ys, xs = dc.shape
+    f = (C.c_float * 3)(*dc_factors)
+    rc = lib().jxo_adaptive_dc_smoothing(f, dc.ctypes.data, xs, ys)
+    if rc:
+        raise RuntimeError(f"jxo_adaptive_dc_smoothing rc={rc}")
+    return dc
 
 
 def desc_from_dump(d, **overrides) -> abi.FrameDesc:

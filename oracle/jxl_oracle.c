@@ -725,6 +725,62 @@ static void xyb_to_linear(const jxlgpu_frame* f, float* const p[3], size_t ps) {
     }
 }
 
+/* ---- the DC stage in front of the hot path (not yet on the GPU) ---- */
+
+/* DequantDC, 4:4:4 branch (lib/jxl/compressed_dc.cc:199-232): q[c] = quantised DC planes (X, Y, B),
+ * fac_c = dc_factors[c] * mul (one float product, as `Set(df, dc_factors[0] * mul)`), Y stored as is,
+ * X and B get the chroma-from-luma term with one FMA each.  out: [3][ys][xs]. */
+void jxo_dequant_dc(const int32_t* const q[3], size_t xs, size_t ys, const float* dc_factors, float mul,
+                    const float* cfl_factors, float* out) {
+  const float fac_x = dc_factors[0] * mul, fac_y = dc_factors[1] * mul, fac_b = dc_factors[2] * mul;
+  const size_t n = xs * ys;
+  for (size_t i = 0; i < n; i++) {
+    const float in_x = (float)q[0][i] * fac_x;
+    const float in_y = (float)q[1][i] * fac_y;
+    const float in_b = (float)q[2][i] * fac_b;
+    out[n + i] = in_y;
+    out[i] = fmaf(in_y, cfl_factors[0], in_x);
+    out[2 * n + i] = fmaf(in_y, cfl_factors[2], in_b);
+  }
+}
+
+/* AdaptiveDCSmoothing (lib/jxl/compressed_dc.cc:50-197): 3x3 smoothing of the interior, weighted by how
+ * far (in quantisation steps) the smoothed value is from the original in the worst channel.
+ * dc: [3][ys][xs] in place; images with a side <= 2 are left alone (:133). */
+int jxo_adaptive_dc_smoothing(const float* dc_factors, float* dc, size_t xs, size_t ys) {
+  if (ys <= 2 || xs <= 2) return 0;
+  const float w1 = 0.20345139757231578f, w2 = 0.0334829185968739f;
+  const float w0 = 1.0f - 4.0f * (w1 + w2);
+  const size_t n = xs * ys;
+  float* sm_out = (float*)malloc(3 * n * sizeof(float));
+  if (!sm_out) return 2;
+  memcpy(sm_out, dc, 3 * n * sizeof(float)); /* borders stay (:143-148, :170-174) */
+#pragma omp parallel for schedule(static)
+  for (int64_t y = 1; y < (int64_t)ys - 1; y++)
+    for (size_t x = 1; x + 1 < xs; x++) {
+      float mc[3], sm[3];
+      float gap = 0.5f;
+      for (int c = 0; c < 3; c++) {
+        const float* p = dc + (size_t)c * n + (size_t)y * xs + x;
+        const float tl = p[-(ptrdiff_t)xs - 1], tc = p[-(ptrdiff_t)xs], tr = p[-(ptrdiff_t)xs + 1];
+        const float ml = p[-1], mr = p[1];
+        const float bl = p[xs - 1], bc = p[xs], br = p[xs + 1];
+        mc[c] = p[0];
+        const float corner = (tl + tr) + (bl + br);
+        const float side = (ml + mr) + (tc + bc);
+        sm[c] = fmaf(corner, w2, fmaf(side, w1, mc[c] * w0));
+        const float g = fabsf((mc[c] - sm[c]) / dc_factors[c]);
+        gap = gap > g ? gap : g; /* Max(gap, g): maxps(a, b) = a > b ? a : b */
+      }
+      float factor = fmaf(-4.0f, gap, 3.0f);
+      if (factor < 0.0f) factor = 0.0f; /* ZeroIfNegative */
+      for (int c = 0; c < 3; c++) sm_out[(size_t)c * n + (size_t)y * xs + x] = fmaf(sm[c] - mc[c], factor, mc[c]);
+    }
+  memcpy(dc, sm_out, 3 * n * sizeof(float));
+  free(sm_out);
+  return 0;
+}
+
 /* TF_SRGB::EncodedFromDisplay (lib/jxl/cms/transfer_functions-inl.h:244-267): the branch OpRgb takes
  * with JXL_HIGH_PRECISION (stage_from_linear.cc:42-53, common.h:15-16).  Rational polynomial in
  * sqrt(|x|), Horner with fused multiply-adds (rational_polynomial-inl.h:59-97), true division

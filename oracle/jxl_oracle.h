@@ -23,6 +23,11 @@ float jxo_adjust_quant_bias(int c, int32_t q, const float* biases, int rcp_mode)
 uint32_t jxo_effective_stage_mask(const jxlgpu_frame* f);
 /* ComputeSigma (epf.cc:39-133): (ysize_blocks+4) x (xsize_blocks+4) inverse sigmas. */
 void jxo_compute_sigma(const jxlgpu_frame* f, float* sigma);
+/* DC stage in front of the path: DequantDC 4:4:4 (compressed_dc.cc:199-232) and
+ * AdaptiveDCSmoothing (:50-197); planes [3][ys][xs], X/Y/B order. */
+void jxo_dequant_dc(const int32_t* const q[3], size_t xs, size_t ys, const float* dc_factors, float mul,
+                    const float* cfl_factors, float* out);
+int jxo_adaptive_dc_smoothing(const float* dc_factors, float* dc, size_t xs, size_t ys);
 /* TF_SRGB::EncodedFromDisplay (cms/transfer_functions-inl.h:244-267). */
 float jxo_srgb_from_linear(float v);
 /* MakeUnsigned (stage_write.cc:455-479), bits = 8 (dithered) or 16. */

@@ -76,6 +76,9 @@ def lib():
         L.ref_frame_info.argtypes = [C.c_void_p, C.POINTER(RefFrameInfo)]
         L.ref_frame_get_plane.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.ref_frame_render.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.ref_dequant_dc.argtypes = [C.c_void_p * 3, C.c_size_t, C.c_size_t, C.c_float * 3, C.c_float,
+                                     C.c_float * 3, C.c_void_p]
+        L.ref_adaptive_dc_smoothing.argtypes = [C.c_float * 3, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
         L.ref_frame_render_out.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                            C.POINTER(C.c_double)]
         L.ref_encode_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
@@ -262,3 +265,26 @@ def llf_from_dc(strategy: int, dc: np.ndarray, block: np.ndarray) -> np.ndarray:
     if rc:
         raise RuntimeError(f"ref_llf_from_dc rc={rc}")
     return block
+
+
+def dequant_dc(q: np.ndarray, dc_factors, mul: float, cfl_factors) -> np.ndarray:
+    """jxl::DequantDC (4:4:4) on one DC group; q: (3, ys, xs) int32 in X, Y, B order."""
+    q = np.ascontiguousarray(q, np.int32)
+    _, ys, xs = q.shape
+    out = np.zeros(q.shape, np.float32)
+    ptrs = (C.c_void_p * 3)(*[q.ctypes.data + c * q[0].nbytes for c in range(3)])
+    rc = lib().ref_dequant_dc(ptrs, xs, ys, (C.c_float * 3)(*dc_factors), mul, (C.c_float * 3)(*cfl_factors),
+                              out.ctypes.data)
+    if rc:
+        raise RuntimeError(f"ref_dequant_dc rc={rc}")
+    return out
+
+
+def adaptive_dc_smoothing(dc: np.ndarray, dc_factors, threads: int = 1) -> np.ndarray:
+    """jxl::AdaptiveDCSmoothing on a (3, ys, xs) DC image (returns a new array)."""
+    dc = np.array(dc, np.float32, order="C")
+    _, ys, xs = dc.shape
+    rc = lib().ref_adaptive_dc_smoothing((C.c_float * 3)(*dc_factors), dc.ctypes.data, xs, ys, threads)
+    if rc:
+        raise RuntimeError(f"ref_adaptive_dc_smoothing rc={rc}")
+    return dc

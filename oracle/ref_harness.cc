@@ -38,6 +38,8 @@
 #include "lib/jxl/base/span.h"
 #include "lib/jxl/chroma_from_luma.h"
 #include "lib/jxl/color_encoding_internal.h"
+#include "lib/jxl/compressed_dc.h"
+#include "lib/jxl/modular/modular_image.h"
 #include "lib/jxl/dct_util.h"
 #include "lib/jxl/dec_bit_reader.h"
 #include "lib/jxl/dec_cache.h"
@@ -769,6 +771,53 @@ REF_API int ref_llf_from_dc(int strategy, const float* dc, size_t dc_stride, flo
   memcpy(c, block, ncoeff * sizeof(float));
   LowestFrequenciesFromDC(static_cast<AcStrategyType>(strategy), dc, dc_stride, c, scratch);
   memcpy(block, c, ncoeff * sizeof(float));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// (6) DC stage, the step right before the hot path:
+// DequantDC (lib/jxl/compressed_dc.cc:199-300, 4:4:4 branch) on one DC group and
+// AdaptiveDCSmoothing (:128-197) on the whole DC image, with the reference's code.
+// q[c]: quantised DC planes xs*ys in X, Y, B order; out/dc: [3][ys][xs] floats.
+// ---------------------------------------------------------------------------
+REF_API int ref_dequant_dc(const int32_t* const q[3], size_t xs, size_t ys, const float* dc_factors, float mul,
+                           const float* cfl_factors, float* out) {
+  JxlMemoryManager mm;
+  if (!MemoryManagerInit(&mm, nullptr)) return 1;
+  auto img = Image::Create(&mm, xs, ys, 16, 3);
+  auto dc = Image3F::Create(&mm, xs, ys);
+  auto qdc = ImageB::Create(&mm, xs, ys);
+  if (!img.ok() || !dc.ok() || !qdc.ok()) return 2;
+  Image image = std::move(img).value_();
+  Image3F dc3 = std::move(dc).value_();
+  ImageB quant_dc = std::move(qdc).value_();
+  for (size_t c = 0; c < 3; c++) {
+    Channel& ch = image.channel[c < 2 ? c ^ 1 : c];  // modular channel order is Y, X, B (dec_modular.cc:448)
+    for (size_t y = 0; y < ys; y++) memcpy(ch.plane.Row(y), q[c] + y * xs, xs * sizeof(int32_t));
+  }
+  BlockCtxMap bctx;
+  YCbCrChromaSubsampling cs;
+  DequantDC(Rect(0, 0, xs, ys), &dc3, &quant_dc, image, dc_factors, mul, cfl_factors, cs, bctx);
+  for (size_t c = 0; c < 3; c++)
+    for (size_t y = 0; y < ys; y++) memcpy(out + (c * ys + y) * xs, dc3.ConstPlaneRow(c, y), xs * sizeof(float));
+  return 0;
+}
+
+REF_API int ref_adaptive_dc_smoothing(const float* dc_factors, float* dc, size_t xs, size_t ys, int threads) {
+  JxlMemoryManager mm;
+  if (!MemoryManagerInit(&mm, nullptr)) return 1;
+  auto im = Image3F::Create(&mm, xs, ys);
+  if (!im.ok()) return 2;
+  Image3F dc3 = std::move(im).value_();
+  for (size_t c = 0; c < 3; c++)
+    for (size_t y = 0; y < ys; y++) memcpy(dc3.PlaneRow(c, y), dc + (c * ys + y) * xs, xs * sizeof(float));
+  void* runner = threads > 1 ? JxlThreadParallelRunnerCreate(nullptr, threads) : nullptr;
+  ThreadPool pool(runner ? JxlThreadParallelRunner : nullptr, runner);
+  Status st = AdaptiveDCSmoothing(&mm, dc_factors, &dc3, &pool);
+  if (runner) JxlThreadParallelRunnerDestroy(runner);
+  if (!st) return 3;
+  for (size_t c = 0; c < 3; c++)
+    for (size_t y = 0; y < ys; y++) memcpy(dc + (c * ys + y) * xs, dc3.ConstPlaneRow(c, y), xs * sizeof(float));
   return 0;
 }
 

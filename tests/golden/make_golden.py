@@ -14,6 +14,8 @@ Fixtures
                    build rendered with the reference's own DecodeGroupForRoundtrip + stages.
   outputs_small.npz the same frame through the reference's FromLinearStage (sRGB) and WriteToOutputStage
                    in every packed pixel format (strict build); `--outputs-only` regenerates just this.
+  dc_stage.npz     DequantDC + AdaptiveDCSmoothing outputs (the step in front of the path)
+                   for seeded inputs; `--dc-only` regenerates just this.
 """
 from __future__ import annotations
 
@@ -63,9 +65,28 @@ def outputs() -> None:
     print("outputs_small.npz", (HERE / "outputs_small.npz").stat().st_size, "bytes")
 
 
+def dc_stage() -> None:
+    """dc_stage.npz: jxl::DequantDC + jxl::AdaptiveDCSmoothing (strict build) on the seeded inputs of
+    tests/support.py:dc_stage_input (inputs are not stored)."""
+    sys.path.insert(0, str(ROOT))
+    from tests import support
+    ref.use_variant("strict")
+    fx = {}
+    for xs, ys in support.DC_STAGE_CASES:
+        q = support.dc_stage_input(xs, ys)
+        for mul in (1.0, 0.25):
+            fx[f"dequant_{xs}x{ys}_mul{mul}"] = ref.dequant_dc(q, support.DC_FACTORS, mul, support.DC_CFL)
+        fx[f"smooth_{xs}x{ys}"] = ref.adaptive_dc_smoothing(fx[f"dequant_{xs}x{ys}_mul1.0"], support.DC_FACTORS, 2)
+    np.savez_compressed(HERE / "dc_stage.npz", **fx)
+    print("dc_stage.npz", (HERE / "dc_stage.npz").stat().st_size, "bytes")
+
+
 def main() -> int:
     if "--outputs-only" in sys.argv:
         outputs()
+        return 0
+    if "--dc-only" in sys.argv:
+        dc_stage()
         return 0
     ref.use_variant("strict")
     out = {}
@@ -111,6 +132,7 @@ def main() -> int:
     for f in ("transforms.npz", "frame_small.npz"):
         print(f, (HERE / f).stat().st_size, "bytes")
     outputs()
+    dc_stage()
     return 0
 
 

@@ -49,3 +49,19 @@ def ulp_diff(a: np.ndarray, b: np.ndarray) -> int:
 
 
 TAP_MASKS = {"idct": 0, "gab_epf012": 15, "full": 31}
+
+
+DC_STAGE_CASES = [(37, 21), (64, 48), (3, 3), (2, 9)]
+DC_FACTORS = (3.1 / 4096, 1.7 / 512, 0.9 / 256)
+DC_CFL = (0.0117, 0.0, 0.935)
+
+
+def dc_stage_input(xs: int, ys: int) -> np.ndarray:
+    """Seeded quantised DC planes (X, Y, B): smooth gradients (adaptive smoothing engages) with one busy
+    quadrant (it must switch itself off there)."""
+    rng = np.random.default_rng(1000 * xs + ys)
+    yy, xx = np.mgrid[0:ys, 0:xs]
+    q = np.stack([np.round(20 * np.sin(xx / 17 + c) + 15 * np.cos(yy / 23 + c) + rng.random((ys, xs)) * 1.2)
+                  for c in range(3)]).astype(np.int32)
+    q[:, ys // 2:, xs // 2:] += rng.integers(-40, 40, (3, ys - ys // 2, xs - xs // 2))
+    return q

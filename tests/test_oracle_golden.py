@@ -179,3 +179,28 @@ def test_make_unsigned_dither_and_rounding():
         a = cpu.make_unsigned(0.5, 8, x, y, c)
         assert a == cpu.make_unsigned(0.5, 8, x + 32, y + 64, c)
         assert a == cpu.make_unsigned(0.5, 8, (x + 23 * c) % 32, (y + 13 * c) % 32, 0)
+
+
+@pytest.mark.parametrize("xs,ys", support.DC_STAGE_CASES)
+def test_dc_stage_against_reference(xs, ys):
+    """DequantDC (4:4:4) and AdaptiveDCSmoothing -- the step in front of the path, restated for the
+    next row of SURVEY §8f -- bit-exact against the reference's outputs (tests/golden/dc_stage.npz)."""
+    from oracle import cpu
+    z = np.load(support.GOLDEN / "dc_stage.npz")
+    q = support.dc_stage_input(xs, ys)
+    for mul in (1.0, 0.25):
+        got = cpu.dequant_dc(q, support.DC_FACTORS, mul, support.DC_CFL)
+        assert np.array_equal(got, z[f"dequant_{xs}x{ys}_mul{mul}"]), mul
+    dc = z[f"dequant_{xs}x{ys}_mul1.0"]
+    got = cpu.adaptive_dc_smoothing(dc, support.DC_FACTORS)
+    want = z[f"smooth_{xs}x{ys}"]
+    assert np.array_equal(got, want)
+    if xs > 2 and ys > 2:
+        # borders untouched; the smooth region changes, the busy quadrant mostly does not
+        assert np.array_equal(got[:, 0], dc[:, 0]) and np.array_equal(got[:, :, -1], dc[:, :, -1])
+        if xs >= 16:
+            changed = got != dc
+            assert changed[:, 1:ys // 2 - 1, 1:xs // 2 - 1].mean() > 0.5
+            assert changed[:, ys // 2 + 1:-1, xs // 2 + 1:-1].mean() < 0.2
+    else:
+        assert np.array_equal(got, dc)

@@ -6,6 +6,7 @@ import pytest
 
 import jxl_workload as wl
 from libjxl_b200 import abi
+from tests import support
 
 pytestmark = pytest.mark.usefixtures("built")
 
@@ -109,3 +110,21 @@ def test_output_stages_bit_exact(fmt, srgb, refmod):
     assert np.array_equal(got.view(np.uint16) if got.dtype == np.float16 else got,
                           want.view(np.uint16) if want.dtype == np.float16 else want)
     fr.close()
+
+
+@pytest.mark.parametrize("xs,ys", [(256, 256), (960, 540), (37, 21)])
+def test_dc_stage_bit_exact(xs, ys, refmod):
+    """DequantDC + AdaptiveDCSmoothing of the reference (both builds) vs the restatement."""
+    from oracle import cpu
+    q = support.dc_stage_input(xs, ys)
+    for variant in ("strict", "default"):
+        refmod.use_variant(variant)
+        try:
+            for mul in (1.0, 0.5):
+                assert np.array_equal(refmod.dequant_dc(q, support.DC_FACTORS, mul, support.DC_CFL),
+                                      cpu.dequant_dc(q, support.DC_FACTORS, mul, support.DC_CFL))
+            dc = cpu.dequant_dc(q, support.DC_FACTORS, 1.0, support.DC_CFL)
+            assert np.array_equal(refmod.adaptive_dc_smoothing(dc, support.DC_FACTORS, 3),
+                                  cpu.adaptive_dc_smoothing(dc, support.DC_FACTORS))
+        finally:
+            refmod.use_variant("strict")
