@@ -44,7 +44,7 @@ extern "C" {
 #define JXLGPU_API
 #endif
 
-#define JXLGPU_ABI_VERSION 2
+#define JXLGPU_ABI_VERSION 3
 
 enum {
   JXLGPU_OK = 0,
@@ -154,6 +154,20 @@ typedef struct jxlgpu_frame {
 
   uint32_t out_format;          /* JXLGPU_OUT_* */
   uint32_t stage_mask;          /* 0, JXLGPU_STAGE_SRGB, or JXLGPU_STAGE_EXPLICIT | bits */
+
+  /* Optional DC stage on the device (the step in front of the path).  When quant_dc[0] != NULL the
+   * `dc` planes above are not read: the library runs DequantDC (4:4:4 branch, compressed_dc.cc:199-232)
+   * and, if dc_smoothing, AdaptiveDCSmoothing (compressed_dc.cc:50-197; FinalizeDC, dec_frame.cc:342-360)
+   * itself.  quant_dc[c]: quantised DC of channel X, Y, B per 8x8 block = modular channels 1, 0, 2 of
+   * the VarDCT DC groups (dec_modular.cc:446-449), frame-wide planes. */
+  const int32_t* quant_dc[3];
+  size_t quant_dc_stride;       /* elements */
+  float dc_factors[3];          /* quantizer.MulDC() (quantizer.h:140) */
+  float dc_cfl_factors[3];      /* cmap.base().DCFactors() (dec_modular.cc:462) */
+  const float* dc_group_mul;    /* per DC group (2048x2048 px, raster order) 1 / (1 << extra_precision)
+                                   (dec_modular.cc:443-444); NULL = 1 everywhere */
+  uint32_t dc_smoothing;        /* 0 when kSkipAdaptiveDCSmoothing or kUseDcFrame is set */
+  uint32_t reserved0;
 } jxlgpu_frame;
 
 JXLGPU_API uint32_t jxlgpu_abi_version(void);

@@ -12,7 +12,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 NUM_STRATEGIES = 27
 GROUP_DIM = 256
 GROUP_COEFFS = 65536
@@ -65,6 +65,9 @@ class JxlGpuFrame(C.Structure):
         ("inverse_opsin_matrix", C.c_float * 9),
         ("opsin_biases", C.c_float * 3), ("opsin_biases_cbrt", C.c_float * 3),
         ("out_format", C.c_uint32), ("stage_mask", C.c_uint32),
+        ("quant_dc", C.c_void_p * 3), ("quant_dc_stride", C.c_size_t),
+        ("dc_factors", C.c_float * 3), ("dc_cfl_factors", C.c_float * 3),
+        ("dc_group_mul", C.c_void_p), ("dc_smoothing", C.c_uint32), ("reserved0", C.c_uint32),
     ]
 
 
@@ -132,6 +135,12 @@ class FrameDesc:
     stage_mask: int = 0
     band_y0_groups: int = 0
     band_ny_groups: int = 0
+    # optional DC stage on the device: quantised DC (3, yb, xb) int32 instead of `dc`
+    quant_dc: np.ndarray | None = None
+    dc_factors: tuple = (0.0, 0.0, 0.0)
+    dc_cfl_factors: tuple = (0.0, 0.0, 1.0)
+    dc_group_mul: np.ndarray | None = None    # f32 (ceil(yb/256), ceil(xb/256)) or None
+    dc_smoothing: int = 1
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -209,12 +218,28 @@ class FrameDesc:
         cm = ((yb + 7) // 8, (xb + 7) // 8)
         s.ytox_map, s.ytob_map = pin(self.ytox, np.int8, cm), pin(self.ytob, np.int8, cm)
         s.cmap_stride = cm[1]
-        dc = np.ascontiguousarray(self.dc, np.float32)
-        assert dc.shape == (3, yb, xb), dc.shape
-        keep.append(dc)
-        for c in range(3):
-            s.dc[c] = dc.ctypes.data + c * yb * xb * 4
-        s.dc_stride = xb
+        if self.quant_dc is None:
+            dc = np.ascontiguousarray(self.dc, np.float32)
+            assert dc.shape == (3, yb, xb), dc.shape
+            keep.append(dc)
+            for c in range(3):
+                s.dc[c] = dc.ctypes.data + c * yb * xb * 4
+            s.dc_stride = xb
+        else:
+            qdc = np.ascontiguousarray(self.quant_dc, np.int32)
+            assert qdc.shape == (3, yb, xb), qdc.shape
+            keep.append(qdc)
+            for c in range(3):
+                s.quant_dc[c] = qdc.ctypes.data + c * yb * xb * 4
+            s.quant_dc_stride = xb
+            s.dc_factors[:] = list(_f32(self.dc_factors, 3))
+            s.dc_cfl_factors[:] = list(_f32(self.dc_cfl_factors, 3))
+            if self.dc_group_mul is not None:
+                gm = np.ascontiguousarray(self.dc_group_mul, np.float32)
+                assert gm.shape == ((yb + 255) // 256, (xb + 255) // 256), gm.shape
+                keep.append(gm)
+                s.dc_group_mul = gm.ctypes.data
+            s.dc_smoothing = int(self.dc_smoothing)
         s.dequant_table = pin(self.dequant, np.float32)
         s.dequant_table_floats = int(np.asarray(self.dequant).size)
         offs = np.asarray(self.dequant_offsets, np.uint32).reshape(NUM_STRATEGIES * 3)

@@ -84,6 +84,7 @@ struct jxlgpu_ctx {
   size_t host_out_stride = 0;
   int stream_error = 0;
   DevBuf acs, quant, sharp, ytox, ytob, dc, dq, coeff, coeff_off, sigma, list, counts, xyb, out;
+  DevBuf qdc, dc_deq;         // DC stage on the device: quantised planes (+ per-group mul), dequantised planes
   DevBuf sparse;              // staging for the non-zero lists of jxlgpu_submit_groups_sparse
   size_t sparse_used = 0;     // words handed out this frame (bump allocation, guarded by mu)
   size_t out_row_bytes = 0;   // dense row of the context-owned output buffer
@@ -397,7 +398,7 @@ void jxlgpu_destroy(jxlgpu_ctx* ctx) {
   cudaDeviceSynchronize();
   for (DevBuf* b : {&ctx->acs, &ctx->quant, &ctx->sharp, &ctx->ytox, &ctx->ytob, &ctx->dc, &ctx->dq,
                     &ctx->coeff, &ctx->coeff_off, &ctx->sigma,
-                    &ctx->list, &ctx->counts, &ctx->xyb, &ctx->out, &ctx->sparse})
+                    &ctx->list, &ctx->counts, &ctx->xyb, &ctx->out, &ctx->sparse, &ctx->qdc, &ctx->dc_deq})
     b->release();
   for (auto s : ctx->up_streams) cudaStreamDestroy(s);
   for (auto ev : ctx->up_events) cudaEventDestroy(ev);
@@ -418,8 +419,11 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   if (f->xsize == 0 || f->ysize == 0 || f->xsize_blocks != (f->xsize + 7) / 8 ||
       f->ysize_blocks != (f->ysize + 7) / 8 || f->xsize_blocks > 65535 || f->ysize_blocks > 65535)
     return JXLGPU_ERR_INVALID_ARGUMENT;
-  if (!f->ac_strategy || !f->raw_quant || !f->ytox_map || !f->ytob_map || !f->dc[0] || !f->dc[1] ||
-      !f->dc[2] || !f->dequant_table)
+  const bool dc_on_device = f->quant_dc[0] != nullptr;
+  if (!f->ac_strategy || !f->raw_quant || !f->ytox_map || !f->ytob_map || !f->dequant_table)
+    return JXLGPU_ERR_INVALID_ARGUMENT;
+  if (dc_on_device ? (!f->quant_dc[1] || !f->quant_dc[2] || f->quant_dc_stride < f->xsize_blocks)
+                   : (!f->dc[0] || !f->dc[1] || !f->dc[2]))
     return JXLGPU_ERR_INVALID_ARGUMENT;
   if (f->ac_type > JXLGPU_AC_INT32 || f->out_format > JXLGPU_OUT_RGB_F16) return JXLGPU_ERR_INVALID_ARGUMENT;
   const uint32_t mask = effective_mask(*f);
@@ -490,8 +494,38 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   if (f->epf_sharpness) CU(upload_plane<uint8_t>(ctx->sharp.p, f->epf_sharpness, f->epf_sharpness_stride, xb, yb, s));
   CU(upload_plane<int8_t>(ctx->ytox.p, f->ytox_map, f->cmap_stride, cmw, cmh, s));
   CU(upload_plane<int8_t>(ctx->ytob.p, f->ytob_map, f->cmap_stride, cmw, cmh, s));
-  for (int c = 0; c < 3; c++)
-    CU(upload_plane<float>((float*)ctx->dc.p + c * nblocks, f->dc[c], f->dc_stride, xb, yb, s));
+  if (!dc_on_device) {
+    for (int c = 0; c < 3; c++)
+      CU(upload_plane<float>((float*)ctx->dc.p + c * nblocks, f->dc[c], f->dc_stride, xb, yb, s));
+  } else {
+    // DC stage on the device: quantised planes up, dequantise, smooth (two small launches)
+    const uint32_t xdg = (uint32_t)((xb + 255) / 256), ydg = (uint32_t)((yb + 255) / 256);
+    CU(ctx->qdc.ensure(3 * nblocks * 4 + (size_t)xdg * ydg * 4));
+    CU(ctx->dc_deq.ensure(3 * nblocks * 4));
+    DcStage S{};
+    S.xb = (uint32_t)xb;
+    S.yb = (uint32_t)yb;
+    S.xdg = xdg;
+    for (int c = 0; c < 3; c++) {
+      CU(upload_plane<int32_t>((int32_t*)ctx->qdc.p + c * nblocks, f->quant_dc[c], f->quant_dc_stride, xb, yb, s));
+      S.q[c] = (const int32_t*)ctx->qdc.p + c * nblocks;
+      S.deq[c] = (float*)ctx->dc_deq.p + c * nblocks;
+      S.out[c] = (float*)ctx->dc.p + c * nblocks;
+      S.dc_factors[c] = f->dc_factors[c];
+    }
+    S.cfl_x = f->dc_cfl_factors[0];
+    S.cfl_b = f->dc_cfl_factors[2];
+    if (f->dc_group_mul) {
+      float* gm = (float*)((int32_t*)ctx->qdc.p + 3 * nblocks);
+      CU(cudaMemcpyAsync(gm, f->dc_group_mul, (size_t)xdg * ydg * 4, cudaMemcpyHostToDevice, s));
+      S.group_mul = gm;
+    }
+    const dim3 grid((unsigned)((xb + 31) / 32), (unsigned)((yb + 7) / 8));
+    dc_dequant_kernel<<<grid, 256, 0, s>>>(S);
+    dc_smooth_kernel<<<grid, 256, 0, s>>>(S, f->dc_smoothing ? 1 : 0);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+  }
   CU(cudaMemcpyAsync(ctx->dq.p, f->dequant_table, f->dequant_table_floats * 4, cudaMemcpyHostToDevice, s));
   P.acs = (const uint8_t*)ctx->acs.p;
   P.quant = (const int32_t*)ctx->quant.p;

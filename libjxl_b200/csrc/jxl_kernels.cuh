@@ -34,6 +34,7 @@
 #define JXT_CONST __device__ __constant__ const
 #define JXT_CONST_GMEM __device__ const
 #include "jxl_tables.h"
+#include "jxl_dc_stage.h"
 
 namespace jxlb {
 
@@ -980,6 +981,22 @@ __global__ void __launch_bounds__(256) idct_large_kernel(const __grid_constant__
     base += count;
   }
 }
+
+// ---------------------------------------------------------------------------
+// DC stage (optional): dequantise the quantised DC image and smooth it on the
+// device instead of uploading finished float planes.  One thread per 8x8 block; the arithmetic lives
+// in jxl_dc_stage.h (shared with a host-side test).  Tiny: 0.5 M blocks at 8K.
+// ---------------------------------------------------------------------------
+#ifndef JXLB_STRIP_TU
+__global__ void __launch_bounds__(256) dc_dequant_kernel(const __grid_constant__ DcStage S) {
+  const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x < S.xb && y < S.yb) dc_dequant_px(S, x, y);
+}
+__global__ void __launch_bounds__(256) dc_smooth_kernel(const __grid_constant__ DcStage S, int smoothing) {
+  const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x < S.xb && y < S.yb) dc_smooth_px(S, x, y, smoothing != 0);
+}
+#endif  // JXLB_STRIP_TU
 
 // ---------------------------------------------------------------------------
 // Sparse coefficient hand-off (jxlgpu_submit_groups_sparse): scatter the non-zero entries of up to

@@ -861,15 +861,39 @@ size_t jxo_out_bytes(const jxlgpu_frame* f) {
   }
 }
 
-int jxo_render_frame(const jxlgpu_frame* f, const void* const coeff[3], int rcp_mode, void* out_v) {
+int jxo_render_frame(const jxlgpu_frame* f_in, const void* const coeff[3], int rcp_mode, void* out_v) {
   float* out = (float*)out_v;
+  /* optional DC stage (quant_dc given): DequantDC per DC group + AdaptiveDCSmoothing, then as usual */
+  jxlgpu_frame f_local = *f_in;
+  const jxlgpu_frame* f = &f_local;
+  float* dc_own = NULL;
+  if (f_in->quant_dc[0]) {
+    const size_t xbb = f_in->xsize_blocks, ybb = f_in->ysize_blocks, nb = xbb * ybb;
+    dc_own = (float*)malloc(3 * nb * sizeof(float));
+    if (!dc_own) return 2;
+    const size_t xdg = (xbb + 255) / 256;
+    for (size_t y = 0; y < ybb; y++)
+      for (size_t x = 0; x < xbb; x++) { /* one block at a time: the group factor may change every 256 blocks */
+        const int32_t qx = f_in->quant_dc[0][y * f_in->quant_dc_stride + x];
+        const int32_t qy = f_in->quant_dc[1][y * f_in->quant_dc_stride + x];
+        const int32_t qb = f_in->quant_dc[2][y * f_in->quant_dc_stride + x];
+        const int32_t* q1[3] = {&qx, &qy, &qb};
+        const float mul = f_in->dc_group_mul ? f_in->dc_group_mul[(y >> 8) * xdg + (x >> 8)] : 1.0f;
+        float o[3];
+        jxo_dequant_dc(q1, 1, 1, f_in->dc_factors, mul, f_in->dc_cfl_factors, o);
+        for (int c = 0; c < 3; c++) dc_own[(size_t)c * nb + y * xbb + x] = o[c];
+      }
+    if (f_in->dc_smoothing && jxo_adaptive_dc_smoothing(f_in->dc_factors, dc_own, xbb, ybb)) { free(dc_own); return 2; }
+    for (int c = 0; c < 3; c++) f_local.dc[c] = dc_own + (size_t)c * nb;
+    f_local.dc_stride = xbb;
+  }
   const size_t xb = f->xsize_blocks, yb = f->ysize_blocks;
   const size_t ps = xb * 8, plane = ps * yb * 8;
   const size_t xg = (xb + 31) / 32, yg = (yb + 31) / 32;
   float* a = (float*)calloc(3 * plane, sizeof(float));
   float* b = (float*)calloc(3 * plane, sizeof(float));
   float* sigma = (float*)calloc((yb + 4) * (xb + 4), sizeof(float));
-  if (!a || !b || !sigma) { free(a); free(b); free(sigma); return 2; }
+  if (!a || !b || !sigma) { free(a); free(b); free(sigma); free(dc_own); return 2; }
   float* A[3] = {a, a + plane, a + 2 * plane};
   float* B[3] = {b, b + plane, b + 2 * plane};
   int failed = 0;
@@ -885,7 +909,7 @@ int jxo_render_frame(const jxlgpu_frame* f, const void* const coeff[3], int rcp_
       if (work) dequant_idct_group(f, coeff, (size_t)g, rcp_mode, A, ps, work);
     free(work);
   }
-  if (failed) { free(a); free(b); free(sigma); return 2; }
+  if (failed) { free(a); free(b); free(sigma); free(dc_own); return 2; }
   const uint32_t mask = jxo_effective_stage_mask(f);
   float** cur = A;
   float** nxt = B;
@@ -925,6 +949,6 @@ int jxo_render_frame(const jxlgpu_frame* f, const void* const coeff[3], int rcp_
       for (size_t x = 0; x < W; x++)
         for (int c = 0; c < 3; c++) out[(y * W + x) * 3 + c] = cur[c][y * ps + x];
   }
-  free(a); free(b); free(sigma);
+  free(a); free(b); free(sigma); free(dc_own);
   return 0;
 }

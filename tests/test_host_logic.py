@@ -101,3 +101,58 @@ def test_pack_sparse_round_trip():
     assert np.array_equal(back, plane)
     assert w16.size + w32.size // 2 == np.count_nonzero(plane)
     assert set(np.abs(plane[w32[0::2]]).tolist()) and np.all((plane[w32[0::2]] > 32767) | (plane[w32[0::2]] < -32768))
+
+
+def _build_dc_stage_host(tmp_path):
+    """The product's per-block DC-stage functions (libjxl_b200/csrc/jxl_dc_stage.h -- the code the CUDA
+    kernels call) compiled for the host, contraction off like the device build."""
+    import ctypes as C
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    src = tmp_path / "dc_host.cc"
+    src.write_text('''
+#include "jxl_dc_stage.h"
+extern "C" void run_dc_stage(const int32_t* q, uint32_t xb, uint32_t yb, const float* fac, float cfl_x, float cfl_b,
+                             const float* gm, int smoothing, float* deq, float* out) {
+  jxlb::DcStage S{};
+  S.xb = xb; S.yb = yb; S.xdg = (xb + 255) / 256; S.group_mul = gm; S.cfl_x = cfl_x; S.cfl_b = cfl_b;
+  const size_t n = (size_t)xb * yb;
+  for (int c = 0; c < 3; c++) { S.q[c] = q + c * n; S.deq[c] = deq + c * n; S.out[c] = out + c * n; S.dc_factors[c] = fac[c]; }
+  for (uint32_t y = 0; y < yb; y++) for (uint32_t x = 0; x < xb; x++) jxlb::dc_dequant_px(S, x, y);
+  for (uint32_t y = 0; y < yb; y++) for (uint32_t x = 0; x < xb; x++) jxlb::dc_smooth_px(S, x, y, smoothing != 0);
+}
+''')
+    so = tmp_path / "dc_host.so"
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(root / "libjxl_b200" / "csrc"),
+                           str(src), "-o", str(so)])
+    lib = C.CDLL(str(so))
+    lib.run_dc_stage.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float * 3, C.c_float, C.c_float, C.c_void_p,
+                                 C.c_int, C.c_void_p, C.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("xs,ys,smoothing", [(37, 21, 1), (300, 270, 1), (300, 270, 0), (2, 9, 1), (3, 3, 1)])
+def test_dc_stage_device_functions_on_host(tmp_path, xs, ys, smoothing):
+    """dc_dequant_px / dc_smooth_px (what dc_dequant_kernel / dc_smooth_kernel execute per block) against
+    the CPU restatement of DequantDC + AdaptiveDCSmoothing, bit for bit, including the per-DC-group
+    precision factor (300 blocks = two DC groups per row)."""
+    import ctypes as C
+    from oracle import cpu
+    from tests import support
+    lib = _build_dc_stage_host(tmp_path)
+    q = support.dc_stage_input(xs, ys)
+    gm = np.array([[1.0, 0.5], [0.25, 0.125]], np.float32)[:(ys + 255) // 256, :(xs + 255) // 256].copy()
+    deq, out = np.zeros((3, ys, xs), np.float32), np.zeros((3, ys, xs), np.float32)
+    lib.run_dc_stage(q.ctypes.data, xs, ys, (C.c_float * 3)(*support.DC_FACTORS), support.DC_CFL[0], support.DC_CFL[2],
+                     gm.ctypes.data, smoothing, deq.ctypes.data, out.ctypes.data)
+    want = np.zeros_like(deq)
+    for gy in range(gm.shape[0]):
+        for gx in range(gm.shape[1]):
+            sl = (slice(None), slice(gy * 256, (gy + 1) * 256), slice(gx * 256, (gx + 1) * 256))
+            want[sl] = cpu.dequant_dc(q[sl], support.DC_FACTORS, float(gm[gy, gx]), support.DC_CFL)
+    assert np.array_equal(deq, want)
+    want_sm = cpu.adaptive_dc_smoothing(want, support.DC_FACTORS) if smoothing else want
+    assert np.array_equal(out, want_sm)
+    if smoothing and xs > 16:
+        assert (out != deq).mean() > 0.1

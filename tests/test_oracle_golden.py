@@ -204,3 +204,24 @@ def test_dc_stage_against_reference(xs, ys):
             assert changed[:, ys // 2 + 1:-1, xs // 2 + 1:-1].mean() < 0.2
     else:
         assert np.array_equal(got, dc)
+
+
+def test_render_frame_with_quantised_dc_matches_prepared_dc():
+    """jxo_render_frame's optional DC stage (quant_dc given) == rendering with the DC planes that
+    DequantDC + AdaptiveDCSmoothing produce, on a synthetic all-strategy frame with two DC groups."""
+    import jxl_workload as wl
+    from oracle import cpu
+    desc, coeffs = wl.synthetic_frame(2100, 300, seed=5)
+    yb, xb = desc.ysize_blocks, desc.xsize_blocks
+    q = support.dc_stage_input(xb, yb)
+    gm = np.array([[1.0, 0.5]], np.float32)
+    dc = np.zeros((3, yb, xb), np.float32)
+    for gx in range(2):
+        sl = (slice(None), slice(None), slice(gx * 256, (gx + 1) * 256))
+        dc[sl] = cpu.dequant_dc(q[sl], support.DC_FACTORS, float(gm[0, gx]), support.DC_CFL)
+    desc.dc = cpu.adaptive_dc_smoothing(dc, support.DC_FACTORS)
+    want = cpu.render_frame(desc, coeffs, rcp_mode=0)
+    desc.dc = None
+    desc.quant_dc, desc.dc_group_mul = q, gm
+    desc.dc_factors, desc.dc_cfl_factors = support.DC_FACTORS, support.DC_CFL
+    assert np.array_equal(cpu.render_frame(desc, coeffs, rcp_mode=0), want)
