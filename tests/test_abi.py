@@ -62,3 +62,41 @@ def test_product_never_imports_oracle():
         if f.suffix in (".py", ".cu", ".cuh", ".h"):
             txt = f.read_text()
             assert "oracle" not in txt.replace("oracle/jxl_oracle.c (rcp_mode 0)", ""), f
+
+
+def _build_host_feed(tmp_path):
+    import subprocess
+    root = Path(__file__).resolve().parents[1]
+    exe = tmp_path / "host_feed"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", str(root / "include"),
+                           str(root / "examples" / "host_feed.cc"), "-L", str(root / "libjxl_b200"), "-ljxl_b200",
+                           "-pthread", "-o", str(exe)])
+    return exe
+
+
+def test_cpp_host_example_builds_and_parses(tmp_path, built):
+    """examples/host_feed.cc -- the C ABI driven from plain C++ worker threads, as libjxl would -- compiles
+    against include/jxl_b200.h alone, links against the library, reads the frame dump correctly, and
+    without a device fails loudly in jxlgpu_create (exit code 3) instead of computing anything."""
+    import os
+    import subprocess
+    import sys
+    import numpy as np
+    root = Path(__file__).resolve().parents[1]
+    sys.path.insert(0, str(root / "examples"))
+    import dump_frame
+    import jxl_workload as wl
+    exe = _build_host_feed(tmp_path)
+    desc, coeffs = wl.synthetic_frame(300, 200, seed=500)
+    dump = tmp_path / "frame.bin"
+    dump_frame.write_dump(dump, desc, coeffs)
+    env = dict(os.environ, LD_LIBRARY_PATH=str(root / "libjxl_b200"), HOST_FEED_PARSE_ONLY="1")
+    out = subprocess.run([str(exe), str(dump), str(tmp_path / "out.raw")], env=env, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    nz = sum(int(np.count_nonzero(coeffs[c, g, :desc.group_ncoeff(g)])) for g in range(desc.num_groups) for c in range(3))
+    assert f"groups={desc.num_groups} " in out.stdout and f"nonzero={nz} " in out.stdout, out.stdout
+    import torch
+    if not torch.cuda.is_available():
+        env.pop("HOST_FEED_PARSE_ONLY")
+        out = subprocess.run([str(exe), str(dump), str(tmp_path / "out.raw")], env=env, capture_output=True, text=True)
+        assert out.returncode == 3 and "no CUDA device" in out.stderr, (out.returncode, out.stderr)

@@ -46,3 +46,34 @@ def test_dc_stage_on_device(w, h, smoothing):
         assert np.array_equal(got, want), float(np.abs(got - want).max())
     finally:
         pipe.close()
+
+
+@pytest.mark.parametrize("kind,mode", [("f32", "dense"), ("f32", "sparse"), ("srgb8", "sparse")])
+def test_cpp_host_example_matches_python_host(tmp_path, kind, mode):
+    """examples/host_feed.cc (C++ worker threads, shuffled group order, streamed output) produces the
+    same bytes as the Python mirror for the same frame."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    from libjxl_b200 import abi
+    from tests.test_abi import _build_host_feed
+    root = Path(__file__).resolve().parents[1]
+    sys.path.insert(0, str(root / "examples"))
+    import dump_frame
+    exe = _build_host_feed(tmp_path)
+    desc, coeffs = wl.synthetic_frame(1100, 777, seed=1877)
+    if kind == "srgb8":
+        desc.out_format, desc.stage_mask = abi.OUT_RGB_U8, abi.STAGE_SRGB
+    dump, raw = tmp_path / "frame.bin", tmp_path / "out.raw"
+    dump_frame.write_dump(dump, desc, coeffs)
+    env = dict(os.environ, LD_LIBRARY_PATH=str(root / "libjxl_b200"))
+    out = subprocess.run([str(exe), str(dump), str(raw), "6", mode], env=env, capture_output=True, text=True)
+    assert out.returncode == 0, (out.stdout, out.stderr)
+    got = np.fromfile(raw, desc.out_dtype).reshape(desc.out_shape())
+    pipe = pipeline.TransformPipeline(device=0)
+    try:
+        want = pipe.decode_frame(desc, coeffs)
+    finally:
+        pipe.close()
+    assert np.array_equal(got, want)
