@@ -76,6 +76,8 @@ def lib():
         L.ref_frame_info.argtypes = [C.c_void_p, C.POINTER(RefFrameInfo)]
         L.ref_frame_get_plane.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.ref_frame_render.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.ref_decode_native.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                        C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ref_dequant_dc.argtypes = [C.c_void_p * 3, C.c_size_t, C.c_size_t, C.c_float * 3, C.c_float,
                                      C.c_float * 3, C.c_void_p]
         L.ref_adaptive_dc_smoothing.argtypes = [C.c_float * 3, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
@@ -288,3 +290,20 @@ def adaptive_dc_smoothing(dc: np.ndarray, dc_factors, threads: int = 1) -> np.nd
     if rc:
         raise RuntimeError(f"ref_adaptive_dc_smoothing rc={rc}")
     return dc
+
+
+_NATIVE = {"float32": 0, "uint8": 2, "uint16": 3, "float16": 5}   # JxlDataType, jxl/types.h
+
+
+def decode_native(data: bytes, shape, dtype, threads: int = 1) -> np.ndarray:
+    """Public-API decode with no output colour profile override (what djxl does by default) into an
+    (H, W, channels) array of `dtype`."""
+    out = np.zeros(shape, dtype)
+    w, h = C.c_int(0), C.c_int(0)
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    rc = lib().ref_decode_native(buf, len(data), threads, _NATIVE[np.dtype(dtype).name], shape[2], out.ctypes.data,
+                                 out.nbytes, C.byref(w), C.byref(h))
+    if rc:
+        raise RuntimeError(f"ref_decode_native rc={rc}")
+    assert (h.value, w.value) == tuple(shape[:2]), (h.value, w.value, shape)
+    return out

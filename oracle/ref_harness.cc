@@ -204,6 +204,44 @@ REF_API int ref_decode_linear_f32(const uint8_t* jxl, size_t n, void* runner_opa
   return rc == -1 ? 0 : rc;
 }
 
+// (2b) public API, the way djxl decodes by default: no output colour profile override (an sRGB image
+// comes out sRGB-encoded), caller-chosen JxlPixelFormat: data_type 0 = FLOAT, 2 = UINT8, 3 = UINT16,
+// 5 = FLOAT16 (jxl/types.h:35-60), num_channels 3 or 4.  out_bytes = capacity of out.
+REF_API int ref_decode_native(const uint8_t* jxl, size_t n, int threads, int data_type, int num_channels,
+                              void* out, size_t out_bytes, int* w, int* h) {
+  Runner runner(threads);
+  JxlDecoder* dec = JxlDecoderCreate(nullptr);
+  if (!dec) return 1;
+  int rc = 0;
+  JxlPixelFormat pf = {static_cast<uint32_t>(num_channels), static_cast<JxlDataType>(data_type), JXL_NATIVE_ENDIAN, 0};
+  do {
+    if (JxlDecoderSetParallelRunner(dec, JxlThreadParallelRunner, runner.opaque) != JXL_DEC_SUCCESS) { rc = 2; break; }
+    JxlDecoderSubscribeEvents(dec, JXL_DEC_BASIC_INFO | JXL_DEC_FULL_IMAGE);
+    JxlDecoderSetInput(dec, jxl, n);
+    JxlDecoderCloseInput(dec);
+    for (;;) {
+      JxlDecoderStatus st = JxlDecoderProcessInput(dec);
+      if (st == JXL_DEC_BASIC_INFO) {
+        JxlBasicInfo info;
+        JxlDecoderGetBasicInfo(dec, &info);
+        *w = info.xsize;
+        *h = info.ysize;
+      } else if (st == JXL_DEC_NEED_IMAGE_OUT_BUFFER) {
+        size_t need = 0;
+        JxlDecoderImageOutBufferSize(dec, &pf, &need);
+        if (need > out_bytes) { rc = 4; break; }
+        JxlDecoderSetImageOutBuffer(dec, &pf, out, need);
+      } else if (st == JXL_DEC_FULL_IMAGE) {
+        continue;
+      } else if (st == JXL_DEC_SUCCESS) {
+        break;
+      } else { rc = 10 + static_cast<int>(st); break; }
+    }
+  } while (false);
+  JxlDecoderDestroy(dec);
+  return rc;
+}
+
 // ---------------------------------------------------------------------------
 // (3) frame opened with reference internals, coefficients retained
 // ---------------------------------------------------------------------------

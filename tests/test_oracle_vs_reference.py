@@ -128,3 +128,30 @@ def test_dc_stage_bit_exact(xs, ys, refmod):
                                   cpu.adaptive_dc_smoothing(dc, support.DC_FACTORS))
         finally:
             refmod.use_variant("strict")
+
+
+@pytest.mark.parametrize("fmt,dtype,ch", [(abi.OUT_RGB_U8, np.uint8, 3), (abi.OUT_RGBA_U8, np.uint8, 4),
+                                          (abi.OUT_RGB_U16, np.uint16, 3), (abi.OUT_RGB_F16, np.float16, 3),
+                                          (abi.OUT_RGB_F32, np.float32, 3)])
+def test_full_chain_equals_default_public_decode(fmt, dtype, ch, refmod):
+    """The path with JXLGPU_STAGE_SRGB and a packed output format is, byte for byte, what the reference's
+    PUBLIC decoder delivers by default for an sRGB image (what `djxl in.jxl out.png` writes): public API
+    == hot path + FromLinear + WriteToOutput (reference stages) == the restatement (strict build)."""
+    from oracle import cpu
+    img = wl.synth_image(333, 277, 5)
+    data = refmod.encode_rgb8(img, 1.0, 7, -1, -1, 2)
+    public = refmod.decode_native(data, (277, 333, ch), dtype, 2)
+    fr = refmod.Frame(data, 2)
+    d = fr.dump()
+    hot, _ = fr.render_out(-33, fmt)
+    fr.close()
+    desc = cpu.desc_from_dump(d, out_format=fmt, stage_mask=abi.STAGE_SRGB)
+    restated = cpu.render_frame(desc, d.coeffs, rcp_mode=1)
+
+    def bits(a):
+        return a.view(np.uint16) if a.dtype == np.float16 else a
+    assert np.array_equal(bits(public), bits(hot))
+    assert np.array_equal(bits(public), bits(restated))
+    # and it is a decode of the image that went in (8-bit sRGB in, d1.0): mean abs error < 2 %
+    scale = {np.uint8: 255.0, np.uint16: 65535.0}.get(dtype, 1.0)
+    assert np.abs(public[..., :3].astype(np.float64) / scale - img / 255.0).mean() < 0.02
