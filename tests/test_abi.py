@@ -47,6 +47,22 @@ def test_struct_layout_matches_header():
     assert int(out[2]) == C.sizeof(abi.JxlGpuSparseGroup)
 
 
+def test_field_offsets_match_header(tmp_path):
+    """offsetof() of every jxlgpu_frame field, by the C compiler, == the ctypes mirror."""
+    import subprocess
+    root = Path(__file__).resolve().parents[1]
+    names = [n for n, _ in abi.JxlGpuFrame._fields_]
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "jxl_b200.h"\nint main(){' + "".join(
+        f'printf("{n} %zu\\n", offsetof(jxlgpu_frame, {n}));' for n in names) + "return 0;}\n"
+    src = tmp_path / "off.c"
+    src.write_text(prog)
+    exe = tmp_path / "off"
+    subprocess.check_call(["gcc", "-I", str(root / "include"), str(src), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for n in names:
+        assert int(got[n]) == getattr(abi.JxlGpuFrame, n).offset, n
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
