@@ -72,6 +72,9 @@ def lib():
         L = C.CDLL(str(so))
         L.ref_frame_open.restype = C.c_void_p
         L.ref_frame_open.argtypes = [C.c_char_p, C.c_size_t, C.c_int]
+        L.ref_frame_open_storage.restype = C.c_void_p
+        L.ref_frame_open_storage.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int]
+        L.ref_frame_raw_coeffs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.ref_frame_close.argtypes = [C.c_void_p]
         L.ref_frame_info.argtypes = [C.c_void_p, C.POINTER(RefFrameInfo)]
         L.ref_frame_get_plane.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
@@ -167,12 +170,24 @@ class FrameDump:
 class Frame:
     """A frame opened with the reference's FrameDecoder, coefficients retained."""
 
-    def __init__(self, data: bytes, threads: int = 1):
-        self.h = lib().ref_frame_open(data, len(data), threads)
+    def __init__(self, data: bytes, threads: int = 1, storage: int = 0):
+        """storage 1: the reference's entropy decoder writes through integration/pinned_ac_image.h
+        (group-major layout) instead of its own ACImageT."""
+        self.h = lib().ref_frame_open_storage(data, len(data), threads, storage)
         if not self.h:
             raise RuntimeError("ref_frame_open failed (frame not eligible for the hot path?)")
         self.info = RefFrameInfo()
         lib().ref_frame_info(self.h, C.byref(self.info))
+
+    def raw_group_major_coeffs(self) -> np.ndarray:
+        """storage 1 only: the allocation itself, viewed as (num_groups, 3, 65536) -- exactly the host
+        blocks jxlgpu_submit_group(s) would be handed."""
+        base, nbytes = C.c_void_p(), C.c_size_t()
+        if lib().ref_frame_raw_coeffs(self.h, C.byref(base), C.byref(nbytes)):
+            raise RuntimeError("frame was not opened with storage=1")
+        dt = np.int16 if self.info.ac_is16 else np.int32
+        buf = (C.c_uint8 * nbytes.value).from_address(base.value)
+        return np.frombuffer(buf, dt).reshape(self.info.num_groups, 3, 65536)
 
     def close(self):
         if self.h:

@@ -37,6 +37,7 @@
 #include "lib/jxl/base/data_parallel.h"
 #include "lib/jxl/base/span.h"
 #include "lib/jxl/chroma_from_luma.h"
+#include "../integration/pinned_ac_image.h"
 #include "lib/jxl/color_encoding_internal.h"
 #include "lib/jxl/compressed_dc.h"
 #include "lib/jxl/modular/modular_image.h"
@@ -256,6 +257,9 @@ struct RefFrame {
   std::unique_ptr<FrameHeader> frame_header;
   void* runner = nullptr;
   std::unique_ptr<ThreadPool> pool;
+  int storage = 0;            // 0: ACImageT (reference), 1: integration/pinned_ac_image.h
+  void* raw_base = nullptr;   // storage 1: the group-major allocation
+  size_t raw_bytes = 0;
   // int32 copy of the coefficients for DecodeGroupForRoundtrip
   // (GetBlockFromEncoder requires k32: lib/jxl/dec_group.cc:668).
   std::vector<std::unique_ptr<ACImage>> ac32;
@@ -345,7 +349,23 @@ Status OpenImpl(RefFrame* f, const uint8_t* data, size_t n) {
     // Switch on accumulate-mode storage: every group's coefficients land in
     // dec_state->coefficients->PlaneRow(c, group, offset).
     f->is16 = f->dec_state->coefficients->Type() == ACType::k16;
-    if (f->is16) {
+    if (f->storage == 1) {
+      // the host-integration storage class (integration/pinned_ac_image.h) through libjxl's own
+      // abstract ACImage interface: group-major [group][3][65536], malloc here, pinned in production
+      if (f->is16) {
+        auto im = jxlb_integration::GroupMajorACImage<int16_t>::Make(fdim.num_groups, malloc, free);
+        if (!im) return JXL_FAILURE("alloc");
+        f->raw_base = im->data();
+        f->raw_bytes = im->size_bytes();
+        f->dec_state->coefficients = std::move(im);
+      } else {
+        auto im = jxlb_integration::GroupMajorACImage<int32_t>::Make(fdim.num_groups, malloc, free);
+        if (!im) return JXL_FAILURE("alloc");
+        f->raw_base = im->data();
+        f->raw_bytes = im->size_bytes();
+        f->dec_state->coefficients = std::move(im);
+      }
+    } else if (f->is16) {
       JXL_ASSIGN_OR_RETURN(f->dec_state->coefficients,
                            ACImageT<int16_t>::Make(&f->mm, kGroupDim * kGroupDim,
                                                    fdim.num_groups));
@@ -410,8 +430,23 @@ struct RefFrameInfo {
   int32_t dequant_offsets[27 * 3];          // float offset of Matrix(kind,c)
 };
 
+REF_API void* ref_frame_open_storage(const uint8_t* jxl, size_t n, int threads, int storage);
 REF_API void* ref_frame_open(const uint8_t* jxl, size_t n, int threads) {
+  return ref_frame_open_storage(jxl, n, threads, 0);
+}
+
+// the raw group-major coefficient allocation of a frame opened with storage == 1
+REF_API int ref_frame_raw_coeffs(void* h, void** base, size_t* bytes) {
+  auto* f = static_cast<RefFrame*>(h);
+  if (!f->raw_base) return 1;
+  *base = f->raw_base;
+  *bytes = f->raw_bytes;
+  return 0;
+}
+
+REF_API void* ref_frame_open_storage(const uint8_t* jxl, size_t n, int threads, int storage) {
   auto* f = new RefFrame();
+  f->storage = storage;
   f->runner = JxlThreadParallelRunnerCreate(nullptr, threads < 1 ? 1 : threads);
   f->pool.reset(new ThreadPool(JxlThreadParallelRunner, f->runner));
   Status st = OpenImpl(f, jxl, n);

@@ -155,3 +155,23 @@ def test_full_chain_equals_default_public_decode(fmt, dtype, ch, refmod):
     # and it is a decode of the image that went in (8-bit sRGB in, d1.0): mean abs error < 2 %
     scale = {np.uint8: 255.0, np.uint16: 65535.0}.get(dtype, 1.0)
     assert np.abs(public[..., :3].astype(np.float64) / scale - img / 255.0).mean() < 0.02
+
+
+@pytest.mark.parametrize("distance", [1.0, 8.0])
+def test_group_major_ac_image_is_a_drop_in(distance, refmod):
+    """integration/pinned_ac_image.h (the storage class a libjxl host installs for a GPU frame) driven by
+    the UNMODIFIED reference decoder through libjxl's abstract ACImage interface: same coefficients,
+    same pixels, and the allocation is the [group][channel][65536] layout the C ABI takes as is."""
+    img = wl.synth_image(600, 300, 21)
+    data = refmod.encode_rgb8(img, distance, 7, -1, -1, 2)
+    a = refmod.Frame(data, 2)
+    b = refmod.Frame(data, 2, storage=1)
+    da, db = a.dump(), b.dump()
+    assert da.coeffs.dtype == db.coeffs.dtype and np.array_equal(da.coeffs, db.coeffs)
+    assert np.array_equal(da.decoded, db.decoded)
+    raw = b.raw_group_major_coeffs()
+    assert raw.shape == (da.info.num_groups, 3, 65536)
+    assert np.array_equal(raw.transpose(1, 0, 2), da.coeffs)
+    assert np.count_nonzero(raw) > 0
+    a.close()
+    b.close()
