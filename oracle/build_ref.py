@@ -189,7 +189,7 @@ def build_variant(variant: str) -> int:
     subprocess.check_call(["ar", "rcs", str(lib), *map(str, objs)])
     harness = HERE / "ref_harness.cc"
     so = OUT / so_name
-    cmd = ["g++", *CXXFLAGS, *vflags, *COMMON_DEFS, *includes(), "-shared", str(harness),
+    cmd = ["g++", *CXXFLAGS, *vflags, *COMMON_DEFS, *includes(), f"-I{HERE.parent / 'include'}", "-shared", str(harness),
            "-Wl,--whole-archive", str(lib), "-Wl,--no-whole-archive",
            "-Wl,--exclude-libs,ALL", "-lpthread", "-lm", "-o", str(so)]
     cmd.remove("-w")

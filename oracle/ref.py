@@ -74,6 +74,8 @@ def lib():
         L.ref_frame_open.argtypes = [C.c_char_p, C.c_size_t, C.c_int]
         L.ref_frame_open_storage.restype = C.c_void_p
         L.ref_frame_open_storage.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int]
+        from libjxl_b200 import abi as _abi
+        L.ref_frame_bind_gpu_frame.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(_abi.JxlGpuFrame)]
         L.ref_frame_raw_coeffs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.ref_frame_close.argtypes = [C.c_void_p]
         L.ref_frame_info.argtypes = [C.c_void_p, C.POINTER(RefFrameInfo)]
@@ -178,6 +180,16 @@ class Frame:
             raise RuntimeError("ref_frame_open failed (frame not eligible for the hot path?)")
         self.info = RefFrameInfo()
         lib().ref_frame_info(self.h, C.byref(self.info))
+
+    def bind_gpu_frame(self, out_format: int = 0, stage_mask: int = 0):
+        """integration/gpu_frame_binding.h applied to the live decoder state: the jxlgpu_frame a libjxl
+        host would pass to jxlgpu_frame_begin (pointers into the reference's images; valid until close)."""
+        from libjxl_b200 import abi as _abi
+        s = _abi.JxlGpuFrame()
+        rc = lib().ref_frame_bind_gpu_frame(self.h, out_format, stage_mask, C.byref(s))
+        if rc:
+            raise RuntimeError(f"ref_frame_bind_gpu_frame rc={rc}")
+        return s
 
     def raw_group_major_coeffs(self) -> np.ndarray:
         """storage 1 only: the allocation itself, viewed as (num_groups, 3, 65536) -- exactly the host

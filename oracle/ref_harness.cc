@@ -37,6 +37,7 @@
 #include "lib/jxl/base/data_parallel.h"
 #include "lib/jxl/base/span.h"
 #include "lib/jxl/chroma_from_luma.h"
+#include "../integration/gpu_frame_binding.h"
 #include "../integration/pinned_ac_image.h"
 #include "lib/jxl/color_encoding_internal.h"
 #include "lib/jxl/compressed_dc.h"
@@ -257,6 +258,7 @@ struct RefFrame {
   std::unique_ptr<FrameHeader> frame_header;
   void* runner = nullptr;
   std::unique_ptr<ThreadPool> pool;
+  jxlb_integration::GpuFrameBinding binding;  // integration/gpu_frame_binding.h, see ref_frame_bind_gpu_frame
   int storage = 0;            // 0: ACImageT (reference), 1: integration/pinned_ac_image.h
   void* raw_base = nullptr;   // storage 1: the group-major allocation
   size_t raw_bytes = 0;
@@ -433,6 +435,19 @@ struct RefFrameInfo {
 REF_API void* ref_frame_open_storage(const uint8_t* jxl, size_t n, int threads, int storage);
 REF_API void* ref_frame_open(const uint8_t* jxl, size_t n, int threads) {
   return ref_frame_open_storage(jxl, n, threads, 0);
+}
+
+// The libjxl-side binding of the product ABI (integration/gpu_frame_binding.h) applied to this frame's
+// live decoder state: *out points into the reference's own images (valid until ref_frame_close).
+REF_API int ref_frame_bind_gpu_frame(void* h, uint32_t out_format, uint32_t stage_mask, jxlgpu_frame* out) {
+  auto* f = static_cast<RefFrame*>(h);
+  if (!jxlb_integration::IsEligible(*f->frame_header, f->metadata)) return 2;
+  if (!jxlb_integration::BindGpuFrame(*f->dec_state, *f->frame_header, out_format, stage_mask, &f->binding)) return 1;
+  // this harness parked the coefficient image elsewhere after decoding (OpenImpl), so the type the
+  // binding read from dec_state->coefficients is the placeholder's: restore the frame's own
+  f->binding.frame.ac_type = f->is16 ? JXLGPU_AC_INT16 : JXLGPU_AC_INT32;
+  *out = f->binding.frame;
+  return 0;
 }
 
 // the raw group-major coefficient allocation of a frame opened with storage == 1

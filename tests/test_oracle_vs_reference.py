@@ -175,3 +175,39 @@ def test_group_major_ac_image_is_a_drop_in(distance, refmod):
     assert np.count_nonzero(raw) > 0
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("cfg", [dict(w=517, h=331, distance=1.0, gaborish=1, epf=3), dict(w=300, h=520, distance=0.5, gaborish=0, epf=0)])
+def test_gpu_frame_binding_from_decoder_state(cfg, refmod):
+    """integration/gpu_frame_binding.h -- the C++ a libjxl maintainer adds to fill jxlgpu_frame from
+    PassesDecoderState -- applied to the unmodified reference's live decoder state: every scalar equals
+    the description the tests build by hand, and the oracle rendered straight from the bound struct
+    (zero-copy pointers + strides into libjxl's images) gives the reference's pixels."""
+    import ctypes as C
+    from oracle import cpu
+    img = wl.synth_image(cfg["w"], cfg["h"], 31)
+    data = refmod.encode_rgb8(img, cfg["distance"], 7, cfg["gaborish"], cfg["epf"], 2)
+    fr = refmod.Frame(data, 2)
+    d = fr.dump()
+    bound = fr.bind_gpu_frame(abi.OUT_RGB_F32, 0)
+    by_hand = cpu.desc_from_dump(d).to_struct()
+    pointer_fields = {"ac_strategy", "raw_quant", "epf_sharpness", "ytox_map", "ytob_map", "dc", "dequant_table",
+                      "quant_dc", "dc_group_mul"}
+    stride_fields = {"ac_strategy_stride", "raw_quant_stride", "epf_sharpness_stride", "cmap_stride", "dc_stride"}
+    for name, _ in abi.JxlGpuFrame._fields_:
+        if name in pointer_fields or name in stride_fields:
+            continue
+        a, b = getattr(bound, name), getattr(by_hand, name)
+        if hasattr(a, "__len__"):
+            assert list(a) == list(b), name
+        else:
+            assert a == b, name
+    assert bound.raw_quant_stride >= bound.xsize_blocks and bound.dc_stride >= bound.xsize_blocks
+    # render with the oracle straight from the bound struct
+    co = np.ascontiguousarray(d.coeffs)
+    ptrs = (C.c_void_p * 3)(*[co.ctypes.data + c * co[0].nbytes for c in range(3)])
+    out = np.zeros((d.info.ysize, d.info.xsize, 3), np.float32)
+    assert cpu.lib().jxo_render_frame(C.byref(bound), ptrs, 1, out.ctypes.data) == 0
+    want, _ = fr.render(-1)
+    assert np.array_equal(out, want.transpose(1, 2, 0))
+    fr.close()
