@@ -31,6 +31,15 @@
 
 #include <type_traits>
 
+// tests/emu compiles this very source for the host (a SIMT emulation shim provides threadIdx,
+// __syncthreads, ... ) to check the kernels on a machine without a GPU; inline PTX is the one thing
+// that cannot travel, so each use has a host-equivalent behind JXLB_HOST_EMU.  nvcc never defines it.
+#ifdef JXLB_HOST_EMU
+#define JXLB_PTX 0
+#else
+#define JXLB_PTX 1
+#endif
+
 #define JXT_CONST __device__ __constant__ const
 #define JXT_CONST_GMEM __device__ const
 #include "jxl_tables.h"
@@ -164,10 +173,14 @@ __device__ __forceinline__ void dct1d(float* v) {
 // normal numbers, and 1/x stays normal for |x| <= 2^31, so the identity holds for every int32
 // coefficient; no special-case branch is needed.  (x = 0 yields NaN, which callers discard.)
 __device__ __forceinline__ float rcp_int(float x) {
+#if JXLB_PTX
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   const float e = fmaf(-x, r, 1.0f);
   return fmaf(r, e, r);
+#else
+  return 1.0f / x;  // the correctly rounded reciprocal, which is what the sequence above yields
+#endif
 }
 
 // AdjustQuantBias (quantizer-inl.h:35-67), branch-free: q in {-1,0,1} -> q*biases[c] (exact),
@@ -488,7 +501,11 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 e
       const int ch = l / kLines, half = l % kLines;
       const char* p = reinterpret_cast<const char*>(P.coeff[ch]) +
                       ((size_t)entry_next.y * 64u) * (I32 ? 4 : 2) + half * 128;
+#if JXLB_PTX
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+      (void)p;
+#endif
     }
   }
 #pragma unroll
@@ -1056,10 +1073,18 @@ __global__ void __launch_bounds__(256) sparse_expand_kernel(const __grid_constan
 // NVLink P2P.  The transfer therefore overlaps the math segment by segment and no separate
 // collective kernel runs.
 __device__ __forceinline__ void mc_store2(float* p, float2 v) {
+#if JXLB_PTX
   asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+#else
+  reinterpret_cast<float2*>(p)[0] = v;  // (no switch to replicate it: a plain store)
+#endif
 }
 __device__ __forceinline__ void mc_store1(float* p, float v) {
+#if JXLB_PTX
   asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+#else
+  *p = v;
+#endif
 }
 
 // replicate `n` bytes starting at byte offset `off` of the local buffer `src` (all threads of the

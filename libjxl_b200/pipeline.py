@@ -80,13 +80,9 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> Path:
 _lib = None
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not SO.exists():
-            raise RuntimeError(f"{SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                               "(there is no CPU fallback)")
-        L = C.CDLL(str(SO))
+def bind(L):
+    """Declare the argument types of every entry point of include/jxl_b200.h on a loaded library."""
+    if True:
         L.jxlgpu_abi_version.restype = C.c_uint32
         L.jxlgpu_error_string.restype = C.c_char_p
         L.jxlgpu_error_string.argtypes = [C.c_int]
@@ -116,7 +112,16 @@ def lib():
         L.jxlgpu_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float * 5)]
         if L.jxlgpu_abi_version() != abi.ABI_VERSION:
             raise RuntimeError("libjxl_b200.so ABI version mismatch: rebuild")
-        _lib = L
+    return L
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not SO.exists():
+            raise RuntimeError(f"{SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        _lib = bind(C.CDLL(str(SO)))
     return _lib
 
 

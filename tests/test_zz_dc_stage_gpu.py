@@ -10,11 +10,8 @@ from tests import support
 
 pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("built")]
 
-# Written after round 1's GPU budget was spent: the code under test is verified on the host (device
-# functions compiled for the CPU against the oracle; the C++ example's reader and build), but these tests
-# have not run on hardware yet.  Non-strict xfail: an XPASS ("X") is the expected outcome, a failure
-# shows as "x" without hiding the rest of the suite.  Remove the marker once confirmed.
-unconfirmed = pytest.mark.xfail(strict=False, reason="new in round 1, not yet run on a GPU")
+# Written after round 1's GPU budget was spent: not yet run on hardware, but the same product source runs
+# these very scenarios bit-exactly under the SIMT emulation of tests/emu (tests/test_emulated_cuda.py).
 
 
 def with_quant_dc(desc, smoothing=1):
@@ -33,7 +30,6 @@ def with_quant_dc(desc, smoothing=1):
     return q, gm, dc
 
 
-@unconfirmed
 @pytest.mark.parametrize("w,h,smoothing", [(520, 264, 1), (2100, 600, 1), (2100, 600, 0), (17, 9, 1)])
 def test_dc_stage_on_device(w, h, smoothing):
     from oracle import cpu
@@ -55,7 +51,6 @@ def test_dc_stage_on_device(w, h, smoothing):
         pipe.close()
 
 
-@unconfirmed
 @pytest.mark.parametrize("kind,mode", [("f32", "dense"), ("f32", "sparse"), ("srgb8", "sparse")])
 def test_cpp_host_example_matches_python_host(tmp_path, kind, mode):
     """examples/host_feed.cc (C++ worker threads, shuffled group order, streamed output) produces the
