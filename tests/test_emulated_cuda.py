@@ -162,3 +162,62 @@ def test_emulated_cpp_host_example(emu_pipe, tmp_path, kind, mode):
     assert out.returncode == 0, (out.stdout, out.stderr)
     got = np.fromfile(raw, desc.out_dtype).reshape(desc.out_shape())
     assert same(got, emu_pipe.decode_frame(desc, coeffs))
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("fmt,srgb", [(abi.OUT_RGB_F32, 0), (abi.OUT_RGB_U8, abi.STAGE_SRGB), (abi.OUT_RGB_U16, 0),
+                                      (abi.OUT_PLANAR_F32, 0)])
+def test_emulated_fused_all_gather_replay(emu_pipe, fmt, srgb):
+    """REPL=1 instantiation of the strip kernel: every finished row is replayed into the `replica`
+    buffers (peer GPUs' frame slots in production) with 8-byte stores plus byte head/tail pieces.  Odd
+    width and packed formats make strips start at arbitrary byte offsets; the replicas must end up
+    identical to the local output, and nothing outside the band may be touched."""
+    desc, coeffs = wl.synthetic_frame(301, 203, seed=90 + fmt)
+    desc.out_format, desc.stage_mask = fmt, srgb
+    want = oracle(desc, coeffs)
+    dev = np.ascontiguousarray(coeffs)                      # "device" memory is host memory here
+    emu_pipe.set_device_coefficients([dev[c].ctypes.data for c in range(3)])
+    emu_pipe.frame_begin(desc)
+    nbytes = want.nbytes
+    guard = 64
+    local = np.full(nbytes + 2 * guard, 0xAB, np.uint8)
+    reps = [np.full(nbytes + 2 * guard, 0xCD, np.uint8) for _ in range(3)]
+    base = lambda a: a.ctypes.data + (-a.ctypes.data) % 8 + 8       # 8-byte aligned, inside the guard
+    off = base(local) - local.ctypes.data
+    emu_pipe.set_output_replicas([base(r) for r in reps])
+    try:
+        emu_pipe.render_device(base(local), desc.out_row_bytes)
+    finally:
+        emu_pipe.set_output_replicas([])
+        emu_pipe.set_device_coefficients(None)
+    flat = want.view(np.uint8).ravel()
+    assert np.array_equal(local[off:off + nbytes], flat)
+    for r in reps:
+        o = base(r) - r.ctypes.data
+        assert np.array_equal(r[o:o + nbytes], flat)
+        assert (r[:o] == 0xCD).all() and (r[o + nbytes:] == 0xCD).all()
+
+
+@pytest.mark.timeout(900)
+def test_emulated_multicast_replay_and_its_limits(emu_pipe):
+    """The multimem.st variant of the replay (emulated as a plain store to the one multicast address):
+    4-byte granules for the f32 layouts; packed layouts are refused."""
+    desc, coeffs = wl.synthetic_frame(203, 131, seed=123)
+    want = oracle(desc, coeffs)
+    dev = np.ascontiguousarray(coeffs)
+    emu_pipe.set_device_coefficients([dev[c].ctypes.data for c in range(3)])
+    emu_pipe.frame_begin(desc)
+    local, mc = np.zeros(want.nbytes + 16, np.uint8), np.zeros(want.nbytes + 16, np.uint8)
+    base = lambda a: a.ctypes.data + (-a.ctypes.data) % 8
+    emu_pipe.set_output_replicas([], base(mc))
+    try:
+        emu_pipe.render_device(base(local), desc.out_row_bytes)
+        o = base(mc) - mc.ctypes.data
+        assert np.array_equal(mc[o:o + want.nbytes], want.view(np.uint8).ravel())
+        desc.out_format = abi.OUT_RGB_U8
+        emu_pipe.frame_begin(desc)
+        with pytest.raises(pipeline.JxlGpuError):
+            emu_pipe.render_device(base(local), desc.out_row_bytes)
+    finally:
+        emu_pipe.set_output_replicas([])
+        emu_pipe.set_device_coefficients(None)
