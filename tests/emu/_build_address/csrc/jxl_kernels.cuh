@@ -1247,7 +1247,7 @@ __device__ __forceinline__ float epf_weight(float sad, float inv_sigma) {
 __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_constant__ FrameDev P,
                                                                char* __restrict__ out,
                                                                size_t out_row_stride /*bytes*/) {
-  extern __shared__ __align__(16) float fsm[];
+  float* fsm = (float*)emu::dynamic_smem();
   float* bufA = fsm;
   float* bufB = fsm + 3 * kTilePlane;
   const int tid = threadIdx.x;
@@ -1529,13 +1529,6 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
   int cn[7];
 #pragma unroll
   for (int d = -3; d <= 3; d++) cn[d + 3] = EDGE ? (mirror_i(x + d, W) - (x0 - H)) : (t + d);
-#ifdef JXLB_EMU_CLAMP_GARBAGE_LANES
-  // ThreadSanitizer build of tests/emu only: the outermost H lanes of a strip compute values nobody reads
-  // and, with cn = t + d, read a few floats of the neighbouring ring row while its owner writes them -- a
-  // deliberate, harmless overlap (the rings are padded for it) that would drown real reports.  Keeping
-  // those lanes inside their own row changes no lane whose result is used.
-  for (int k = 0; k < 7; k++) cn[k] = min(max(cn[k], 0), kStripThreads - 1);
-#endif
   auto mrow = [&](int r) { return r < 0 ? -r - 1 : (r >= HI ? 2 * HI - 1 - r : r); };
 
   float* ringG = smem + kStripPad;
@@ -1933,7 +1926,7 @@ template <uint32_t MASK, bool REPL, int OUTK>
 __global__ void __launch_bounds__(kStripThreads, StripCfg<MASK>::E0 ? 2 : 4) filter_strip_kernel(const __grid_constant__ FrameDev P,
                                                                     char* __restrict__ out,
                                                                     size_t out_row_stride, int seg_rows) {
-  extern __shared__ __align__(16) float fsm[];
+  float* fsm = (float*)emu::dynamic_smem();
   using C = StripCfg<MASK>;
   const int x0 = blockIdx.x * C::kOutCols;
   const int y_begin = (int)P.band_y0 + blockIdx.y * seg_rows;

@@ -1247,7 +1247,7 @@ __device__ __forceinline__ float epf_weight(float sad, float inv_sigma) {
 __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_constant__ FrameDev P,
                                                                char* __restrict__ out,
                                                                size_t out_row_stride /*bytes*/) {
-  extern __shared__ __align__(16) float fsm[];
+  float* fsm = (float*)emu::dynamic_smem();
   float* bufA = fsm;
   float* bufB = fsm + 3 * kTilePlane;
   const int tid = threadIdx.x;
@@ -1933,7 +1933,7 @@ template <uint32_t MASK, bool REPL, int OUTK>
 __global__ void __launch_bounds__(kStripThreads, StripCfg<MASK>::E0 ? 2 : 4) filter_strip_kernel(const __grid_constant__ FrameDev P,
                                                                     char* __restrict__ out,
                                                                     size_t out_row_stride, int seg_rows) {
-  extern __shared__ __align__(16) float fsm[];
+  float* fsm = (float*)emu::dynamic_smem();
   using C = StripCfg<MASK>;
   const int x0 = blockIdx.x * C::kOutCols;
   const int y_begin = (int)P.band_y0 + blockIdx.y * seg_rows;

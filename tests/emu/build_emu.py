@@ -34,7 +34,14 @@ def rewrite(text: str) -> str:
     return text
 
 
-def build(force: bool = False) -> Path:
+def build(force: bool = False, sanitize: str = "") -> Path:
+    """sanitize: "" | "address" | "thread" -> a separate library built with -fsanitize=<...> (a memcheck /
+    racecheck substitute: CUDA threads are OS threads here, shared memory and "device" buffers are host
+    memory).  Load it in a process started with the matching runtime preloaded (see tests/emu/README.md)."""
+    global OUT, SO
+    if sanitize:
+        OUT = HERE / f"_build_{sanitize}"
+        SO = OUT / "libjxl_b200_emu.so"
     srcs = sorted(CSRC.glob("*")) + [HERE / "cuda_runtime.h", HERE / "cuda_fp16.h", Path(__file__)]
     if not force and SO.exists() and all(SO.stat().st_mtime >= s.stat().st_mtime for s in srcs):
         return SO
@@ -44,6 +51,10 @@ def build(force: bool = False) -> Path:
         (gen / (f.stem + ".cc" if f.suffix == ".cu" else f.name)).write_text(rewrite(f.read_text()))
     flags = ["-std=c++20", "-O1", "-g0", "-ffp-contract=off", "-fPIC", "-pthread", "-fvisibility=hidden", "-w",
              "-DJXLB_HOST_EMU=1", f"-I{HERE}", f"-I{ROOT / 'include'}", f"-I{gen}"]
+    if sanitize:
+        flags += [f"-fsanitize={sanitize}", "-g", "-fno-omit-frame-pointer"]
+    if sanitize == "thread":
+        flags += ["-DJXLB_EMU_CLAMP_GARBAGE_LANES=1"]   # see filter_strip_body in jxl_kernels.cuh
     units = [(gen / "jxl_b200.cc", OUT / "jxl_b200.o", [])]
     units += [(gen / "jxl_strip_inst.cc", OUT / f"strip_{m}.o", [f"-DSTRIP_MASK={m}"]) for m in MASKS]
 
@@ -55,9 +66,11 @@ def build(force: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 4)) as ex:
         list(ex.map(cc, units))
-    subprocess.check_call(["g++", "-shared", "-pthread", *[str(u[1]) for u in units], "-o", str(SO)])
+    subprocess.check_call(["g++", "-shared", "-pthread", *([f"-fsanitize={sanitize}"] if sanitize else []),
+                           *[str(u[1]) for u in units], "-o", str(SO)])
     return SO
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    san = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--sanitize=")), "")
+    print(build(force="--force" in sys.argv, sanitize=san))

@@ -117,9 +117,10 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   return cudaSuccess;
 }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// exact sizes (no rounding up): a sanitizer build then flags even a one-byte overrun of a "device" buffer
+inline cudaError_t cudaMalloc(void** p, size_t n) { return posix_memalign(p, 256, n ? n : 1) == 0 ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return posix_memalign(p, 256, n ? n : 1) == 0 ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memcpy(d, s, n); return cudaSuccess; }
