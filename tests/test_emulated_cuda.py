@@ -221,3 +221,94 @@ def test_emulated_multicast_replay_and_its_limits(emu_pipe):
     finally:
         emu_pipe.set_output_replicas([])
         emu_pipe.set_device_coefficients(None)
+
+
+@pytest.mark.timeout(900)
+def test_emulated_strided_outputs_and_accessors(emu_pipe):
+    """Row strides larger than a dense row (host: cudaMemcpy2D path of frame_finish / streamed output;
+    device: render_device into a padded buffer), the context-owned output + XYB accessors, profiling."""
+    from oracle import cpu
+    desc, coeffs = wl.synthetic_frame(203, 300, seed=31)        # 1 x 2 groups
+    want = oracle(desc, coeffs)
+    lib = pipeline.lib()
+    row = desc.out_row_bytes
+    stride = row + 40
+    # (a) frame_finish into a strided host buffer
+    buf = np.full((desc.ysize, stride), 0x5A, np.uint8)
+    emu_pipe.set_device_coefficients(None)
+    emu_pipe.frame_begin(desc)
+    for g in range(desc.num_groups):
+        emu_pipe.submit_group(g, [coeffs[c, g] for c in range(3)])
+    assert lib.jxlgpu_frame_finish(emu_pipe._h, buf.ctypes.data, stride) == 0
+    assert np.array_equal(buf[:, :row].copy().view(np.float32).reshape(want.shape), want)
+    assert (buf[:, row:] == 0x5A).all()
+    # (b) streamed output (frame_set_output) with the same stride
+    buf[:] = 0x5A
+    emu_pipe.frame_begin(desc)
+    assert lib.jxlgpu_frame_set_output(emu_pipe._h, buf.ctypes.data, stride) == 0
+    for g in reversed(range(desc.num_groups)):
+        emu_pipe.submit_group(g, [coeffs[c, g] for c in range(3)])
+    assert lib.jxlgpu_frame_finish(emu_pipe._h, buf.ctypes.data, stride) == 0
+    assert np.array_equal(buf[:, :row].copy().view(np.float32).reshape(want.shape), want)
+    assert (buf[:, row:] == 0x5A).all()
+    # (c) render_device into a padded "device" buffer, then the context-owned output and the XYB planes
+    dev = np.ascontiguousarray(coeffs)
+    emu_pipe.set_device_coefficients([dev[c].ctypes.data for c in range(3)])
+    emu_pipe.frame_begin(desc)
+    pad = np.full((desc.ysize, stride // 4 + 2), np.float32(-7), np.float32)
+    emu_pipe.set_profiling(True)
+    emu_pipe.render_device(pad.ctypes.data, pad.shape[1] * 4)
+    assert set(emu_pipe.kernel_times_ms()) == {"plan", "idct8", "idct_mid", "idct_large", "filter"}
+    emu_pipe.set_profiling(False)
+    assert np.array_equal(pad[:, :desc.xsize * 3].reshape(want.shape), want) and (pad[:, desc.xsize * 3:] == -7).all()
+    emu_pipe.render_device()                                     # into the context's own buffer
+    ptr, s = emu_pipe.device_output()
+    own = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(desc.ysize, s // 4))
+    assert s == row and np.array_equal(own.reshape(want.shape), want)
+    xyb_ptr, plane_stride, row_stride = emu_pipe.device_xyb()
+    planes = np.ctypeslib.as_array(C.cast(xyb_ptr, C.POINTER(C.c_float)), shape=(3, plane_stride // row_stride, row_stride))
+    desc.stage_mask, desc.out_format = abi.STAGE_EXPLICIT, abi.OUT_PLANAR_F32     # tap: after the inverse transforms
+    assert np.array_equal(planes[:, :desc.ysize, :desc.xsize], cpu.render_frame(desc, coeffs, rcp_mode=0))
+    emu_pipe.set_device_coefficients(None)
+
+
+@pytest.mark.timeout(900)
+def test_emulated_argument_validation(emu_pipe):
+    """Every documented rejection of frame_begin / submit / render, without side effects on the context."""
+    lib = pipeline.lib()
+    desc, coeffs = wl.synthetic_frame(300, 200, seed=3)
+
+    def begin_rc(mutate):
+        s = desc.to_struct()
+        mutate(s)
+        return lib.jxlgpu_frame_begin(emu_pipe._h, C.byref(s))
+
+    assert begin_rc(lambda s: None) == abi.OK
+    assert begin_rc(lambda s: setattr(s, "xsize", 0)) == abi.ERR_INVALID_ARGUMENT
+    assert begin_rc(lambda s: setattr(s, "xsize_blocks", s.xsize_blocks + 1)) == abi.ERR_INVALID_ARGUMENT
+    assert begin_rc(lambda s: setattr(s, "raw_quant", None)) == abi.ERR_INVALID_ARGUMENT
+    assert begin_rc(lambda s: setattr(s, "out_format", 6)) == abi.ERR_INVALID_ARGUMENT
+    assert begin_rc(lambda s: setattr(s, "ac_type", 2)) == abi.ERR_INVALID_ARGUMENT
+    assert begin_rc(lambda s: s.dequant_offsets.__setitem__(5, s.dequant_offsets[5] + 2)) == abi.ERR_INVALID_ARGUMENT
+    assert begin_rc(lambda s: s.dequant_offsets.__setitem__(5, s.dequant_table_floats)) == abi.ERR_INVALID_ARGUMENT
+    assert begin_rc(lambda s: (setattr(s, "band_y0_groups", 1), setattr(s, "band_ny_groups", 1))) == abi.ERR_INVALID_ARGUMENT
+    assert begin_rc(lambda s: setattr(s, "epf_sharpness", None)) == abi.ERR_INVALID_ARGUMENT   # epf_iters = 3
+    assert begin_rc(lambda s: s.dc.__setitem__(1, None)) == abi.ERR_INVALID_ARGUMENT
+    assert begin_rc(lambda s: None) == abi.OK
+    # submit: thread id beyond num_host_threads, null channel pointer, too many coefficients
+    ptrs = (C.c_void_p * 3)(*[coeffs[c, 0].ctypes.data for c in range(3)])
+    assert lib.jxlgpu_submit_group(emu_pipe._h, 0, 2, ptrs, 1000) == abi.ERR_INVALID_ARGUMENT
+    assert lib.jxlgpu_submit_group(emu_pipe._h, 0, 0, ptrs, 65537) == abi.ERR_INVALID_ARGUMENT
+    bad = (C.c_void_p * 3)(ptrs[0], None, ptrs[2])
+    assert lib.jxlgpu_submit_group(emu_pipe._h, 0, 0, bad, 1000) == abi.ERR_INVALID_ARGUMENT
+    # output stride smaller than a row, more replicas than the ABI carries
+    out = np.zeros((desc.ysize, desc.xsize, 3), np.float32)
+    assert lib.jxlgpu_frame_set_output(emu_pipe._h, out.ctypes.data, desc.out_row_bytes - 4) == abi.ERR_INVALID_ARGUMENT
+    assert lib.jxlgpu_set_output_replicas(emu_pipe._h, 9, (C.c_void_p * 9)(), None) == abi.ERR_INVALID_ARGUMENT
+    assert lib.jxlgpu_set_output_replicas(emu_pipe._h, 1, (C.c_void_p * 1)(out.ctypes.data + 4), None) == abi.ERR_INVALID_ARGUMENT
+    # the frame is still usable
+    got = emu_pipe.decode_frame(desc, coeffs)
+    assert same(got, oracle(desc, coeffs))
+    # calls outside a frame
+    assert lib.jxlgpu_frame_finish(emu_pipe._h, None, 0) == abi.ERR_STATE
+    assert lib.jxlgpu_submit_group(emu_pipe._h, 0, 0, ptrs, 1000) == abi.ERR_STATE
