@@ -1944,6 +1944,10 @@ __global__ void __launch_bounds__(kStripThreads, StripCfg<MASK>::E0 ? 2 : 4) fil
   else filter_strip_body<MASK, false, REPL, OUTK>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
 }
 
+}  // namespace jxlb
+#include "jxl_strip2.cuh"
+namespace jxlb {
+
 // Host launcher of one stage chain; each explicit specialisation lives in its own translation unit
 // (jxl_strip_inst.cu compiled with -DSTRIP_MASK=<mask>), so that the eight chains build in parallel.
 template <uint32_t MASK>

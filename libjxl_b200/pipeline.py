@@ -46,7 +46,7 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> Path:
     """Compile csrc/*.cu for sm_100a into libjxl_b200.so (in-tree): the main translation unit and one
     per filter stage chain, compiled in parallel, then linked."""
     from concurrent.futures import ThreadPoolExecutor
-    hdrs = [CSRC / "jxl_kernels.cuh", CSRC / "jxl_tables.h", PKG.parent / "include" / "jxl_b200.h"]
+    hdrs = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [PKG.parent / "include" / "jxl_b200.h"]
     units = [(CSRC / "jxl_b200.cu", OBJ / "jxl_b200.o", [])]
     units += [(CSRC / "jxl_strip_inst.cu", OBJ / f"jxl_strip_{m}.o", [f"-DSTRIP_MASK={m}"]) for m in STRIP_MASKS]
     newest_hdr = max(h.stat().st_mtime for h in hdrs)

@@ -1529,6 +1529,13 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
   int cn[7];
 #pragma unroll
   for (int d = -3; d <= 3; d++) cn[d + 3] = EDGE ? (mirror_i(x + d, W) - (x0 - H)) : (t + d);
+#ifdef JXLB_EMU_CLAMP_GARBAGE_LANES
+  // ThreadSanitizer build of tests/emu only: the outermost H lanes of a strip compute values nobody reads
+  // and, with cn = t + d, read a few floats of the neighbouring ring row while its owner writes them -- a
+  // deliberate, harmless overlap (the rings are padded for it) that would drown real reports.  Keeping
+  // those lanes inside their own row changes no lane whose result is used.
+  for (int k = 0; k < 7; k++) cn[k] = min(max(cn[k], 0), kStripThreads - 1);
+#endif
   auto mrow = [&](int r) { return r < 0 ? -r - 1 : (r >= HI ? 2 * HI - 1 - r : r); };
 
   float* ringG = smem + kStripPad;
@@ -1936,6 +1943,10 @@ __global__ void __launch_bounds__(kStripThreads, StripCfg<MASK>::E0 ? 2 : 4) fil
   if (edge) filter_strip_body<MASK, true, REPL, OUTK>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
   else filter_strip_body<MASK, false, REPL, OUTK>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
 }
+
+}  // namespace jxlb
+#include "jxl_strip2.cuh"
+namespace jxlb {
 
 // Host launcher of one stage chain; each explicit specialisation lives in its own translation unit
 // (jxl_strip_inst.cu compiled with -DSTRIP_MASK=<mask>), so that the eight chains build in parallel.
