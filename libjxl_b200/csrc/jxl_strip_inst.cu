@@ -3,6 +3,8 @@
 // PreparePipeline can build for a VarDCT XYB frame, lib/jxl/dec_cache.cc:151-170) and linked into
 // libjxl_b200.so; see libjxl_b200/pipeline.py:build().
 #define JXLB_STRIP_TU 1
+#include <cstdlib>
+
 #include "jxl_kernels.cuh"
 
 #ifndef STRIP_MASK
@@ -23,6 +25,7 @@ __attribute__((visibility("hidden"))) cudaError_t prepare_strip_mask<STRIP_MASK>
   set(filter_strip_kernel<MASK, false, 1>);
   set(filter_strip_kernel<MASK, true, 0>);
   set(filter_strip_kernel<MASK, true, 1>);
+  set(filter_strip_kernel<MASK, false, 2>);
   return e;
 }
 
@@ -53,6 +56,11 @@ cudaError_t launch_strip_mask<STRIP_MASK>(const FrameDev& P, char* dev_out, size
   const dim3 grid(strips, segs);
   const bool repl = P.mc || P.nrep;  // multi-GPU: the instantiation with the fused all-gather replay
   const bool plain = P.out_format == 0 && !(P.stage_mask & 32u);  // linear interleaved f32
+  static const bool special8 = [] { const char* e = getenv("JXLGPU_SRGB8_SPECIAL"); return e && e[0] == '1'; }();
+  if (special8 && !repl && P.out_format == 2 && (P.stage_mask & 32u)) {  // EXPERIMENT, see store_px<2>
+    filter_strip_kernel<MASK, false, 2><<<grid, kStripThreads, C::kSmemBytes, s>>>(P, dev_out, out_row_bytes, seg_rows);
+    return cudaGetLastError();
+  }
   if (repl) {
     if (plain) filter_strip_kernel<MASK, true, 0><<<grid, kStripThreads, C::kSmemBytes, s>>>(P, dev_out, out_row_bytes, seg_rows);
     else filter_strip_kernel<MASK, true, 1><<<grid, kStripThreads, C::kSmemBytes, s>>>(P, dev_out, out_row_bytes, seg_rows);
