@@ -1244,6 +1244,14 @@ __device__ __forceinline__ void store_px(const FrameDev& P, char* __restrict__ o
     o[0] = a; o[1] = b; o[2] = c3;
     return;
   }
+  if constexpr (OUTK == 2) {  // EXPERIMENT: sRGB transfer function + dithered 8-bit RGB, no run-time dispatch
+    const int y = yo + (int)P.out_y0;
+    uint8_t* o = reinterpret_cast<uint8_t*>(out + (size_t)yo * out_row_bytes) + (size_t)x * 3;
+    o[0] = (uint8_t)make_unsigned<8>(srgb_from_linear(a), x, y, 0);
+    o[1] = (uint8_t)make_unsigned<8>(srgb_from_linear(b), x, y, 1);
+    o[2] = (uint8_t)make_unsigned<8>(srgb_from_linear(c3), x, y, 2);
+    return;
+  }
   if (P.stage_mask & 32u) {
     a = srgb_from_linear(a);
     b = srgb_from_linear(b);

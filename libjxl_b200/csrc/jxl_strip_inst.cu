@@ -33,6 +33,7 @@ __attribute__((visibility("hidden"))) cudaError_t prepare_strip_mask<STRIP_MASK>
     set(filter_strip2_kernel<MASK, true, 0>);
     set(filter_strip2_kernel<MASK, true, 1>);
   }
+  set(filter_strip_kernel<MASK, false, 2>);
   return e;
 }
 
@@ -96,6 +97,11 @@ cudaError_t launch_strip_mask<STRIP_MASK>(const FrameDev& P, char* dev_out, size
   seg_rows = (seg_rows + 7) & ~7;
   segs = (band_h + seg_rows - 1) / seg_rows;
   const dim3 grid(strips, segs);
+  static const bool special8 = [] { const char* e = getenv("JXLGPU_SRGB8_SPECIAL"); return e && e[0] == '1'; }();
+  if (special8 && !repl && P.out_format == 2 && (P.stage_mask & 32u)) {  // EXPERIMENT, see store_px<2>
+    filter_strip_kernel<MASK, false, 2><<<grid, kStripThreads, C::kSmemBytes, s>>>(P, dev_out, out_row_bytes, seg_rows);
+    return cudaGetLastError();
+  }
   if (repl) {
     if (plain) filter_strip_kernel<MASK, true, 0><<<grid, kStripThreads, C::kSmemBytes, s>>>(P, dev_out, out_row_bytes, seg_rows);
     else filter_strip_kernel<MASK, true, 1><<<grid, kStripThreads, C::kSmemBytes, s>>>(P, dev_out, out_row_bytes, seg_rows);
