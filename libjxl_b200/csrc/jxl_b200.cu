@@ -193,7 +193,12 @@ int launch_idct(jxlgpu_ctx* ctx, uint32_t row0, uint32_t row1, uint32_t need_y0,
     CU(cudaStreamWaitEvent(sl, ctx->ev_fork, 0));
   }
   auto run8 = [&]() {
-    if (P.ac_is32) idct8_kernel<true><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
+    static const bool pipe = [] { const char* e = getenv("JXLGPU_IDCT8_PIPE"); return e && e[0] == '1'; }();
+    if (pipe) {  // EXPERIMENT: software-pipelined variant, 3 CTAs/SM
+      const int g = ctx->num_sms * 3;
+      if (P.ac_is32) idct8_kernel<true, true><<<g, kSmallWarpsPerCta * 32, 0, s>>>(P);
+      else idct8_kernel<false, true><<<g, kSmallWarpsPerCta * 32, 0, s>>>(P);
+    } else if (P.ac_is32) idct8_kernel<true><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
     else idct8_kernel<false><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
   };
   if (prof) {

@@ -439,6 +439,50 @@ __device__ __forceinline__ void load_row8(const void* plane, size_t elem, int* q
   }
 }
 
+// The same row, still packed as it came from memory (software-pipelined variant: the next item's rows
+// wait in registers while the current item is transformed).
+template <bool I32>
+struct RawRow8 {
+  int4 w[I32 ? 2 : 1];
+};
+template <bool I32>
+__device__ __forceinline__ void load_raw8(const void* plane, size_t elem, RawRow8<I32>& r) {
+  if constexpr (I32) {
+    const int4* p = reinterpret_cast<const int4*>(reinterpret_cast<const int32_t*>(plane) + elem);
+    r.w[0] = __ldg(p);
+    r.w[1] = __ldg(p + 1);
+  } else {
+    r.w[0] = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const int16_t*>(plane) + elem));
+  }
+}
+template <bool I32>
+__device__ __forceinline__ void unpack_raw8(const RawRow8<I32>& r, int* q) {
+  if constexpr (I32) {
+    q[0] = r.w[0].x; q[1] = r.w[0].y; q[2] = r.w[0].z; q[3] = r.w[0].w;
+    q[4] = r.w[1].x; q[5] = r.w[1].y; q[6] = r.w[1].z; q[7] = r.w[1].w;
+  } else {
+    const int w[4] = {r.w[0].x, r.w[0].y, r.w[0].z, r.w[0].w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      q[2 * i] = (int)(short)(w[i] & 0xffff);
+      q[2 * i + 1] = w[i] >> 16;
+    }
+  }
+}
+template <bool I32>
+struct RawBlock8 {
+  RawRow8<I32> ch[3];  // lane l's row of X, Y, B
+};
+template <bool I32>
+__device__ __forceinline__ void load_raw_block8(const FrameDev& P, uint4 entry, bool active, RawBlock8<I32>& r) {
+  if (active) {
+    const size_t e0 = (size_t)entry.y * 64u + (size_t)(threadIdx.x & 7) * 8;
+    load_raw8<I32>(P.coeff[1], e0, r.ch[1]);
+    load_raw8<I32>(P.coeff[0], e0, r.ch[0]);
+    load_raw8<I32>(P.coeff[2], e0, r.ch[2]);
+  }
+}
+
 __device__ __forceinline__ void load_row8f(const float* p, float* m) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
@@ -449,9 +493,11 @@ __device__ __forceinline__ void load_row8f(const float* p, float* m) {
 // Phase A: lane l loads row l (8 coefficients, 16/32 contiguous bytes) of all three channels with
 // vector loads and dequantises them in registers (CfL needs Y next to X and B anyway).
 // Phase B, per channel: rows go to shared memory, the strategy's transform runs on them.
-template <bool I32>
+// PIPE: the coefficient rows were loaded one item ahead (`raw`), see idct8_kernel<I32, true>.
+template <bool I32, bool PIPE = false>
 __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 entry, bool active,
-                                            uint4 entry_next, bool next_active, float* sm) {
+                                            uint4 entry_next, bool next_active, float* sm,
+                                            const RawBlock8<I32>* raw = nullptr) {
   const int lane = threadIdx.x & 31;
   const int slot = lane >> 3, l = lane & 7;
   // Inactive slots (tail of a list) run the same instruction stream on scratch data so that
@@ -466,9 +512,15 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 e
     int qx[8], qy[8], qb[8];
     float mx[8], my[8], mb[8];
     const size_t e0 = vb.cbase + (size_t)l * 8;
-    load_row8<I32>(P.coeff[1], e0, qy);
-    load_row8<I32>(P.coeff[0], e0, qx);
-    load_row8<I32>(P.coeff[2], e0, qb);
+    if constexpr (PIPE) {
+      unpack_raw8<I32>(raw->ch[1], qy);
+      unpack_raw8<I32>(raw->ch[0], qx);
+      unpack_raw8<I32>(raw->ch[2], qb);
+    } else {
+      load_row8<I32>(P.coeff[1], e0, qy);
+      load_row8<I32>(P.coeff[0], e0, qx);
+      load_row8<I32>(P.coeff[2], e0, qb);
+    }
     load_row8f(P.dq + P.dq_off[3 * kind + 1] + l * 8, my);
     load_row8f(P.dq + P.dq_off[3 * kind + 0] + l * 8, mx);
     load_row8f(P.dq + P.dq_off[3 * kind + 2] + l * 8, mb);
@@ -495,7 +547,7 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 e
   }
   // Pull the NEXT item's coefficient lines (streamed from HBM exactly once) into L2 while this
   // item is being transformed: no registers are held, the next item's loads become L2 hits.
-  if (next_active) {
+  if (!PIPE && next_active) {
     constexpr int kLines = I32 ? 2 : 1;  // a block-channel is 256 / 128 contiguous bytes
     if (l < 3 * kLines) {
       const int ch = l / kLines, half = l % kLines;
@@ -760,8 +812,8 @@ __device__ __forceinline__ int small_slots(int s) {
 }
 
 // 8x8-class strategies (DCT, IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4, AFV0-3).
-template <bool I32>
-__global__ void __launch_bounds__(kSmallWarpsPerCta * 32, 4) idct8_kernel(const __grid_constant__ FrameDev P) {
+template <bool I32, bool PIPE = false>
+__global__ void __launch_bounds__(kSmallWarpsPerCta * 32, PIPE ? 3 : 4) idct8_kernel(const __grid_constant__ FrameDev P) {
   __shared__ __align__(16) float smem[kSmallWarpsPerCta * 1056];
   float* sm = smem + (threadIdx.x >> 5) * 1056;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -779,14 +831,39 @@ __global__ void __launch_bounds__(kSmallWarpsPerCta * 32, 4) idct8_kernel(const 
     const uint4 zero = make_uint4(0, 0, 1, 0);
     bool act = it < items && it * 4 + slot < count;
     uint4 cur = act ? __ldg(list + it * 4 + slot) : zero;
+    if constexpr (PIPE) {
+      // EXPERIMENT (JXLGPU_IDCT8_PIPE=1): software pipelining over items -- the coefficient rows of the
+      // warp's next item are requested before the current item is transformed and wait in registers,
+      // and the record of the item after that is fetched as well
+      RawBlock8<I32> raw_cur;
+      load_raw_block8<I32>(P, cur, act, raw_cur);
+      const uint32_t nx0 = (it + nwarps) * 4 + slot;
+      bool nact = (it + nwarps) < items && nx0 < count;
+      uint4 next = nact ? __ldg(list + nx0) : zero;
 #pragma unroll 1
-    for (; it < items; it += nwarps) {
-      const uint32_t nx = (it + nwarps) * 4 + slot;  // the record of this warp's next item is fetched now
-      const bool nact = (it + nwarps) < items && nx < count;
-      const uint4 next = nact ? __ldg(list + nx) : zero;
-      block8_item<I32>(P, s, cur, act, next, nact, sm);
-      cur = next;
-      act = nact;
+      for (; it < items; it += nwarps) {
+        RawBlock8<I32> raw_next;
+        load_raw_block8<I32>(P, next, nact, raw_next);
+        const uint32_t nx2 = (it + 2 * nwarps) * 4 + slot;
+        const bool n2act = (it + 2 * nwarps) < items && nx2 < count;
+        const uint4 next2 = n2act ? __ldg(list + nx2) : zero;
+        block8_item<I32, true>(P, s, cur, act, next, nact, sm, &raw_cur);
+        cur = next;
+        act = nact;
+        raw_cur = raw_next;
+        next = next2;
+        nact = n2act;
+      }
+    } else {
+#pragma unroll 1
+      for (; it < items; it += nwarps) {
+        const uint32_t nx = (it + nwarps) * 4 + slot;  // the record of this warp's next item is fetched now
+        const bool nact = (it + nwarps) < items && nx < count;
+        const uint4 next = nact ? __ldg(list + nx) : zero;
+        block8_item<I32>(P, s, cur, act, next, nact, sm);
+        cur = next;
+        act = nact;
+      }
     }
     base += items;
   }
@@ -1165,6 +1242,14 @@ __device__ __forceinline__ void store_px(const FrameDev& P, char* __restrict__ o
   if constexpr (OUTK == 0) {
     float* o = reinterpret_cast<float*>(out + (size_t)yo * out_row_bytes) + (size_t)x * 3;
     o[0] = a; o[1] = b; o[2] = c3;
+    return;
+  }
+  if constexpr (OUTK == 2) {  // EXPERIMENT: sRGB transfer function + dithered 8-bit RGB, no run-time dispatch
+    const int y = yo + (int)P.out_y0;
+    uint8_t* o = reinterpret_cast<uint8_t*>(out + (size_t)yo * out_row_bytes) + (size_t)x * 3;
+    o[0] = (uint8_t)make_unsigned<8>(srgb_from_linear(a), x, y, 0);
+    o[1] = (uint8_t)make_unsigned<8>(srgb_from_linear(b), x, y, 1);
+    o[2] = (uint8_t)make_unsigned<8>(srgb_from_linear(c3), x, y, 2);
     return;
   }
   if (P.stage_mask & 32u) {
@@ -1943,6 +2028,10 @@ __global__ void __launch_bounds__(kStripThreads, StripCfg<MASK>::E0 ? 2 : 4) fil
   if (edge) filter_strip_body<MASK, true, REPL, OUTK>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
   else filter_strip_body<MASK, false, REPL, OUTK>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
 }
+
+}  // namespace jxlb
+#include "jxl_strip2.cuh"
+namespace jxlb {
 
 // Host launcher of one stage chain; each explicit specialisation lives in its own translation unit
 // (jxl_strip_inst.cu compiled with -DSTRIP_MASK=<mask>), so that the eight chains build in parallel.
