@@ -128,6 +128,82 @@ def prepare_frame(name: str, rank: int, world: int, barrier):
     return fr, source
 
 
+def host_cpu_info() -> dict:
+    """Cores this process may actually use: the scheduler affinity mask capped by the cgroup CPU quota
+    (os.cpu_count() reports the whole host, which a 1-GPU lease does not own)."""
+    import math
+    total = os.cpu_count() or 1
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except AttributeError:
+        aff = total
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:  # noqa: BLE001
+            continue
+    eff = aff if quota is None else max(1, min(aff, int(math.ceil(quota))))
+    return {"cores": eff, "affinity": aff, "cgroup_quota": quota, "os_cpu_count": total}
+
+
+def geomean_excluding_first(secs, px: int) -> float:
+    """Mpixel/s as tools/speed_stats.cc:37-57 reports it: geometric mean over the repetitions, the
+    first one excluded (when there is more than one)."""
+    v = [px / float(t) / 1e6 for t in secs]
+    if len(v) > 1:
+        v = v[1:]
+    return float(np.exp(np.mean(np.log(v))))
+
+
+def workload_text(name: str, desc, source: str, output: str) -> str:
+    """The one description of the workload both arms print (same frame, same hot path, same output)."""
+    w, h, dist, effort, _, _, _ = WORKLOADS[name]
+    es = "int16" if desc.ac_type == 0 else "int32"
+    return (f"{name}: {w}x{h} VarDCT d{dist} e{effort}, gab={desc.gab} epf_iters={desc.epf_iters}, {source}, "
+            f"coefficients {es} as the reference decoder chose, hot path = dequant+IDCT -> Gaborish/EPF -> XYB->RGB, "
+            f"output {OUTPUT_TEXT[output]}")
+
+
+def cpu_reference_numbers(fr, w: int, h: int, output: str, reps: int, threads_list) -> dict:
+    """The reference's own hot-path code (oracle/_ref) on `threads` host threads for each entry of
+    threads_list: {threads: {"f32": Mpx/s, "srgb8": Mpx/s}} + the whole decoder (entropy decode incl.)."""
+    from oracle import ref
+    out = {"hot": {}, "full": {}}
+    for nt in threads_list:
+        frame = ref.Frame(fr["jxl"], nt)
+        r = max(2, reps if nt > 1 else min(reps, 3))
+        by = {}
+        for kind in ("f32", "srgb8"):
+            if kind != output and nt == 1:
+                continue
+            if kind == "f32":
+                _, secs = frame.render(-1, reps=r + 1, want_output=False)
+            else:
+                _, secs = frame.render_out(-33, 2, reps=r + 1, want_output=False)
+            by[kind] = geomean_excluding_first(secs, w * h)
+        frame.close()
+        out["hot"][nt] = by
+        runner = ref.Runner(nt)
+        buf = np.empty((h, w, 3), np.float32)
+        ts = []
+        for _ in range(3 if nt > 1 else 2):
+            t0 = time.perf_counter()
+            ref.decode_linear_f32(fr["jxl"], nt, buf, runner)
+            ts.append(time.perf_counter() - t0)
+        runner.close()
+        out["full"][nt] = geomean_excluding_first(ts, w * h)
+    return out
+
+
 def algorithmic_bytes(desc, rows: int, out_px_bytes: int = 12) -> dict:
     """bytes one launch must move, per kernel, for `rows` pixel rows."""
     px = desc.xsize * rows
@@ -139,14 +215,16 @@ def algorithmic_bytes(desc, rows: int, out_px_bytes: int = 12) -> dict:
 
 def run_reference(args, rank: int) -> int:
     """--impl reference: the reference's own CPU implementation of the hot path (not the whole
-    decoder: entropy decoding is outside the path), all host threads, same frame."""
+    decoder: entropy decoding is outside the path) on every host core this process may use, same frame.
+    `steps` timed passes (+1 untimed first one, speed_stats.cc semantics)."""
     if rank != 0:
         return 0
     import jxl_workload as wl
     from oracle import ref
     name = args.workload
     w, h, dist, effort, gab, epf, kind = WORKLOADS[name]
-    cores = os.cpu_count() or 1
+    cpu = host_cpu_info()
+    cores = cpu["cores"]
     fr = wl.reference_frame(w, h, dist, effort, gab, epf, seed=1234, kind=kind, cache=True)
     frame = ref.Frame(fr["jxl"], cores)
 
@@ -157,36 +235,29 @@ def run_reference(args, rank: int) -> int:
         return frame.render_out(-33, 2, reps=reps, want_output=False)[1]
 
     hot(args.output, max(1, args.warmup))
-    secs = hot(args.output, args.steps)
+    secs = hot(args.output, args.steps + 1)
     other = "srgb8" if args.output == "f32" else "f32"
-    hot(other, 1)
-    other_secs = hot(other, max(3, min(args.steps, 8)))
+    other_secs = hot(other, max(3, min(args.steps, 8)) + 1)
     frame.close()
-    total = float(np.sum(secs))
-    mps = w * h * args.steps / total / 1e6
-    other_mps = w * h * len(other_secs) / float(np.sum(other_secs)) / 1e6
-    # whole decoder (entropy decode included) for context
-    runner = ref.Runner(cores)
-    out = np.empty((h, w, 3), np.float32)
-    ref.decode_linear_f32(fr["jxl"], cores, out, runner)
-    t0 = time.perf_counter()
-    reps = max(2, min(5, args.steps))
-    for _ in range(reps):
-        ref.decode_linear_f32(fr["jxl"], cores, out, runner)
-    full = w * h * reps / (time.perf_counter() - t0) / 1e6
-    runner.close()
+    mps = geomean_excluding_first(secs, w * h)
+    other_mps = geomean_excluding_first(other_secs, w * h)
+    one = cpu_reference_numbers(fr, w, h, args.output, 3, [1])
+    many_full = cpu_reference_numbers(fr, w, h, args.output, 2, [cores])["full"][cores] if cores > 1 else one["full"][1]
     line = {
         "impl": "reference", "metric": "decode_mpixels_per_s", "value": mps, "unit": "Mpixel/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "ms_per_step": 1e3 * w * h / (mps * 1e6), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}: {w}x{h} VarDCT d{dist} e{effort}, hot path only "
-                               "(DecodeGroupForRoundtrip + reference Gaborish/EPF/XYB stages) on host CPU, "
-                               f"output {OUTPUT_TEXT[args.output]}"},
+        "config": {"workload": workload_text(name, fr["desc"], "reference-encoded", args.output)},
         "variants": {other: {"value": other_mps, "unit": "Mpixel/s", "output": OUTPUT_TEXT[other]}},
         "cpu_baseline": {"value": mps, "unit": "Mpixel/s", "cores": cores, "kind": "reference",
-                         "sample": f"{args.steps} passes over the full {w}x{h} frame",
-                         "full_decode_mpixels_per_s": full},
+                         "host": cpu, "hwy_target": ref.hwy_target(),
+                         "sample": f"{args.steps} passes (+1 untimed first) of DecodeGroupForRoundtrip + the reference's "
+                                   f"Gaborish/EPF/XYB stages over the full {w}x{h} frame; geomean excluding the first "
+                                   "(tools/speed_stats.cc:37-57)",
+                         "one_thread_mpixels_per_s": one["hot"][1][args.output],
+                         "full_decode_mpixels_per_s": many_full,
+                         "full_decode_one_thread_mpixels_per_s": one["full"][1]},
         "e2e": {"value": mps, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,7 +266,6 @@ def run_reference(args, rank: int) -> int:
 
 
 def main() -> int:
-    os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (no NCCL version banner)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -206,10 +276,10 @@ def main() -> int:
                     help="pixel format the path ends in: linear f32 (the §8 scope, default) or sRGB 8-bit "
                          "(sRGB transfer function + WriteToOutput packing fused into the filter kernel's store); "
                          "the other one is measured too and reported under \"variants\"")
-    ap.add_argument("--submit", default="sparse", choices=["dense", "sparse"],
-                    help="e2e arm: the non-zero lists of jxlgpu_submit_groups_sparse (default), or dense "
-                         "[group][3][65536] coefficient blocks (libjxl's ACImage layout); the other one is measured "
-                         "too and reported under \"variants\"")
+    ap.add_argument("--submit", default="dense", choices=["dense", "sparse"],
+                    help="e2e arm: dense [group][3][65536] coefficient blocks (libjxl's ACImage layout, what the "
+                         "unmodified entropy decoder produces; default) or the non-zero lists of "
+                         "jxlgpu_submit_groups_sparse; the other one is measured too and reported under \"variants\"")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "p2p", "nccl"],
@@ -535,41 +605,27 @@ def main() -> int:
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1 and fr.get("jxl") is not None:
         from oracle import ref
-        cores = os.cpu_count() or 1
-        frame = ref.Frame(fr["jxl"], cores)
-        reps = 8
-        hot_by_kind = {}
-        for kind in ("f32", "srgb8"):
-            if kind == "f32":
-                frame.render(-1, reps=1, want_output=False)
-                _, secs = frame.render(-1, reps=reps, want_output=False)
-            else:
-                frame.render_out(-33, 2, reps=1, want_output=False)
-                _, secs = frame.render_out(-33, 2, reps=reps, want_output=False)
-            hot_by_kind[kind] = W * H * reps / float(np.sum(secs)) / 1e6
-        frame.close()
-        hot = hot_by_kind[args.output]
-        runner = ref.Runner(cores)
-        out = np.empty((H, W, 3), np.float32)
-        ref.decode_linear_f32(fr["jxl"], cores, out, runner)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            ref.decode_linear_f32(fr["jxl"], cores, out, runner)
-        full = W * H * 3 / (time.perf_counter() - t0) / 1e6
-        runner.close()
-        cpu_baseline = {"value": hot, "unit": "Mpixel/s", "cores": cores, "kind": "reference",
-                        "sample": f"{reps} passes of the reference's own hot-path code over the same {W}x{H} frame "
-                                  "(coefficients pre-decoded); full_decode = whole libjxl decoder incl. entropy decode, 3 passes",
-                        "full_decode_mpixels_per_s": full, "by_output": hot_by_kind}
+        cpu = host_cpu_info()
+        cores = cpu["cores"]
+        reps = 6
+        nums = cpu_reference_numbers(fr, W, H, args.output, reps, [cores] if cores == 1 else [cores, 1])
+        hot_by_kind = nums["hot"][cores]
+        cpu_baseline = {"value": hot_by_kind[args.output], "unit": "Mpixel/s", "cores": cores, "kind": "reference",
+                        "host": cpu, "hwy_target": ref.hwy_target(),
+                        "sample": f"{reps} passes (+1 untimed first) of the reference's own hot-path code over the same "
+                                  f"{W}x{H} frame (coefficients pre-decoded), geomean excluding the first "
+                                  "(tools/speed_stats.cc:37-57); one_thread = the same with 1 thread (3 passes); "
+                                  "full_decode = whole libjxl decoder incl. entropy decode",
+                        "one_thread_mpixels_per_s": nums["hot"][1][args.output],
+                        "full_decode_mpixels_per_s": nums["full"][cores],
+                        "full_decode_one_thread_mpixels_per_s": nums["full"][1], "by_output": hot_by_kind}
 
     w_, h_, dist_, effort_, _, _, _ = WORKLOADS[args.workload]
     line = {
         "metric": "decode_mpixels_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {W}x{H} VarDCT d{dist_} e{effort_}, gab={desc.gab} epf_iters={desc.epf_iters}, "
-                               f"{source}, coefficients {'int16' if es == 2 else 'int32'} as the reference decoder chose, "
-                               f"output {OUTPUT_TEXT[args.output]}",
+        "config": {"workload": workload_text(args.workload, desc, source, args.output),
                    "groups": desc.num_groups, "parallelism": f"band-sharded x{world}; all-gather: {gather_mode}" if world > 1 else "1 GPU",
                    "strategy_histogram": fr["hist"], "bpp": fr["bpp"],
                    "l2": "inputs larger than L2 (coefficients + XYB planes + output >> 126 MB per step)"},

@@ -360,7 +360,7 @@ int jxlgpu_create(jxlgpu_ctx** out, const jxlgpu_config* cfg) {
   ctx->num_threads = cfg->num_host_threads ? cfg->num_host_threads : 1;
   auto bail = [&](cudaError_t err, const char* what) {
     fprintf(stderr, "jxlgpu_create: %s: %s\n", what, cudaGetErrorString(err));
-    delete ctx;
+    jxlgpu_destroy(ctx);  // releases the streams / events / buffers created so far
     return JXLGPU_ERR_CUDA;
   };
   if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) return bail(e, "cudaSetDevice");
@@ -405,8 +405,10 @@ void jxlgpu_destroy(jxlgpu_ctx* ctx) {
                     &ctx->coeff, &ctx->coeff_off, &ctx->sigma,
                     &ctx->list, &ctx->counts, &ctx->xyb, &ctx->out, &ctx->sparse, &ctx->qdc, &ctx->dc_deq})
     b->release();
-  for (auto s : ctx->up_streams) cudaStreamDestroy(s);
-  for (auto ev : ctx->up_events) cudaEventDestroy(ev);
+  for (auto s : ctx->up_streams)
+    if (s) cudaStreamDestroy(s);
+  for (auto ev : ctx->up_events)
+    if (ev) cudaEventDestroy(ev);
   for (auto ev : ctx->row_events)
     if (ev) cudaEventDestroy(ev);
   for (auto ev : ctx->prof_ev)
@@ -431,6 +433,11 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
                    : (!f->dc[0] || !f->dc[1] || !f->dc[2]))
     return JXLGPU_ERR_INVALID_ARGUMENT;
   if (f->ac_type > JXLGPU_AC_INT32 || f->out_format > JXLGPU_OUT_RGB_F16) return JXLGPU_ERR_INVALID_ARGUMENT;
+  // plane strides (in elements) must cover a row: a short stride would make the uploads read out of bounds
+  if (f->ac_strategy_stride < f->xsize_blocks || f->raw_quant_stride < f->xsize_blocks ||
+      (f->epf_sharpness && f->epf_sharpness_stride < f->xsize_blocks) ||
+      (!dc_on_device && f->dc_stride < f->xsize_blocks) || f->cmap_stride < (f->xsize_blocks + 7) / 8)
+    return JXLGPU_ERR_INVALID_ARGUMENT;
   const uint32_t mask = effective_mask(*f);
   if ((mask & 14u) && !f->epf_sharpness) return JXLGPU_ERR_INVALID_ARGUMENT;
   for (int i = 0; i < 3 * kNumStrategies; i++) {
@@ -700,10 +707,10 @@ int jxlgpu_submit_groups_sparse(jxlgpu_ctx* ctx, size_t n, const jxlgpu_sparse_g
   const size_t es = ctx->elem_size, gelems = 3 * 65536, gbytes = gelems * es;
   // staging: worst case (every coefficient non-zero) is one word per coefficient + slack
   const size_t cap_words = (size_t)ctx->num_groups * (gelems + 8);
-  if (!ctx->sparse.p) {
-    e = ctx->sparse.ensure(cap_words * 4);
-    if (e != cudaSuccess) return fail_cuda(ctx, e, "alloc(sparse staging)");
-  }
+  // (DevBuf::ensure is a no-op when the capacity suffices; a context that decoded a small frame first
+  // must grow the staging buffer for a larger one)
+  e = ctx->sparse.ensure(cap_words * 4);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "alloc(sparse staging)");
   if (ctx->sparse_used + words > cap_words) {
     ctx->last_error = "sparse lists larger than the dense planes: submit dense groups instead";
     return JXLGPU_ERR_INVALID_ARGUMENT;

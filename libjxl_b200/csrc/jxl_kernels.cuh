@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(const __grid_constant__ Fram
   const size_t bi = (size_t)aby * P.xb + abx;
   const uint32_t raw = valid ? P.acs[bi] : 0u;
   const bool first = valid && (raw & 1u);
-  const int s = raw >> 1;
+  const int s = min((int)(raw >> 1), kNumStrategies - 1);  // (a corrupt strategy byte must not index past the tables)
   const uint32_t area = first ? (uint32_t)(covered_x(s) * covered_y(s)) : 0u;
   // exclusive scan of `area` in raster order (dec_group.cc:221,335-359: running offset)
   uint32_t incl = area;
@@ -1621,7 +1621,8 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
   // those lanes inside their own row changes no lane whose result is used.
   for (int k = 0; k < 7; k++) cn[k] = min(max(cn[k], 0), kStripThreads - 1);
 #endif
-  auto mrow = [&](int r) { return r < 0 ? -r - 1 : (r >= HI ? 2 * HI - 1 - r : r); };
+  // Mirror() (lib/jxl/image_ops.h:184-196) reflects repeatedly: images lower than a stage's border
+  auto mrow = [&](int r) { return mirror_i(r, HI); };
 
   float* ringG = smem + kStripPad;
   float* ring0 = ringG + C::NG * 3 * kStripThreads;

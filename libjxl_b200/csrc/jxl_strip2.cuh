@@ -43,7 +43,8 @@ __device__ __forceinline__ void filter_strip2_body(const FrameDev& P, char* __re
   int cn[6];
 #pragma unroll
   for (int k = 0; k < 6; k++) cn[k] = EDGE ? (mirror_i(x - 2 + k, W) - (x0 - Hp)) : (c0 - 2 + k);
-  auto mrow = [&](int r) { return r < 0 ? -r - 1 : (r >= HI ? 2 * HI - 1 - r : r); };
+  // Mirror() (lib/jxl/image_ops.h:184-196) reflects repeatedly: images lower than a stage's border
+  auto mrow = [&](int r) { return mirror_i(r, HI); };
 
   float* ringG = smem + kStripPad;
   float* ring1 = ringG + C::NG * 3 * RW;

@@ -97,6 +97,8 @@ def lib():
         L.ref_runner_create.argtypes = [C.c_int]
         L.ref_runner_destroy.argtypes = [C.c_void_p]
         L.ref_free.argtypes = [C.c_void_p]
+        if hasattr(L, "ref_hwy_target"):
+            L.ref_hwy_target.restype = C.c_char_p
         L.ref_transform_to_pixels.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.ref_transform_from_pixels.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.ref_llf_from_dc.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
@@ -334,3 +336,9 @@ def decode_native(data: bytes, shape, dtype, threads: int = 1) -> np.ndarray:
         raise RuntimeError(f"ref_decode_native rc={rc}")
     assert (h.value, w.value) == tuple(shape[:2]), (h.value, w.value, shape)
     return out
+
+
+def hwy_target() -> str:
+    """Highway target the reference's dynamic dispatch runs on this CPU (e.g. 'AVX2')."""
+    L = lib()
+    return L.ref_hwy_target().decode() if hasattr(L, "ref_hwy_target") else "unknown"

@@ -33,6 +33,8 @@
 #include <memory>
 #include <vector>
 
+#include "hwy/detect_targets.h"
+#include "hwy/targets.h"
 #include "lib/jxl/ac_strategy.h"
 #include "lib/jxl/base/data_parallel.h"
 #include "lib/jxl/base/span.h"
@@ -910,3 +912,11 @@ REF_API int ref_adaptive_dc_smoothing(const float* dc_factors, float* dc, size_t
 }
 
 REF_API const char* ref_version() { return "libjxl 0.13.0 (reference, oracle/_ref)"; }
+
+// The Highway target HWY_DYNAMIC_DISPATCH selects on this CPU: the best compiled-in target among the
+// supported ones (hwy/targets.h: lower bit = better target).  bench.py states it beside the CPU numbers.
+REF_API const char* ref_hwy_target() {
+  const int64_t usable = hwy::SupportedTargets() & HWY_TARGETS;
+  if (!usable) return "none";
+  return hwy::TargetName(usable & -usable);
+}

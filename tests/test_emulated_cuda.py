@@ -312,3 +312,37 @@ def test_emulated_argument_validation(emu_pipe):
     # calls outside a frame
     assert lib.jxlgpu_frame_finish(emu_pipe._h, None, 0) == abi.ERR_STATE
     assert lib.jxlgpu_submit_group(emu_pipe._h, 0, 0, ptrs, 1000) == abi.ERR_STATE
+
+
+def epf_engaged_frame(w, h, seed, gab=1, epf_iters=3):
+    """A synthetic frame whose EPF weights are non-zero (raw_quant 1, sharpness 7 puts sigma above
+    kMinSigma; smooth, small coefficients keep the SADs small).  synthetic_frame's random quantisers
+    make the EPF a pass-through, which hides filter bugs on tiny images."""
+    desc, coeffs = wl.synthetic_frame(w, h, seed=seed, gab=gab, epf_iters=epf_iters, density=0.05)
+    desc.raw_quant = np.where(desc.raw_quant > 0, 1, 0).astype(np.int32)
+    desc.epf_sharpness = np.full_like(desc.epf_sharpness, 7)
+    coeffs = np.clip(coeffs, -2, 2)
+    return desc, coeffs
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("w,h", [(40, 1), (40, 2), (300, 2), (1, 1), (9, 3), (270, 5)])
+@pytest.mark.parametrize("epf_iters", [1, 2, 3])
+def test_emulated_tiny_heights_with_epf_engaged(emu_pipe, w, h, epf_iters):
+    """Images lower than a stage's border: the vertical mirror must reflect repeatedly like
+    Mirror() (lib/jxl/image_ops.h:184-196)."""
+    desc, coeffs = epf_engaged_frame(w, h, seed=w * 7 + h, epf_iters=epf_iters)
+    want = oracle(desc, coeffs)
+    desc2, _ = epf_engaged_frame(w, h, seed=w * 7 + h, epf_iters=0)
+    if w * h > 1:   # the filters really change the picture (the test means something)
+        assert not np.array_equal(want, oracle(desc2, coeffs))
+    assert same(emu_pipe.decode_frame(desc, coeffs), want)
+
+
+@pytest.mark.timeout(900)
+def test_emulated_sparse_small_then_large_frame_on_one_context(emu_pipe):
+    """The sparse staging buffer must grow when a context is reused for a larger frame."""
+    small, cs = wl.synthetic_frame(64, 64, seed=5)
+    assert same(emu_pipe.decode_frame(small, cs, sparse=True), oracle(small, cs))
+    big, cb = wl.synthetic_frame(1024, 512, seed=6, density=0.9)
+    assert same(emu_pipe.decode_frame(big, cb, sparse=True), oracle(big, cb))
