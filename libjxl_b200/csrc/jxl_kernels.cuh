@@ -489,79 +489,96 @@ __device__ __forceinline__ void load_row8f(const float* p, float* m) {
   m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
 }
 
-// 8x8-class varblocks (DCT and the specials): 8 lanes per block, 4 blocks per warp.
-// Phase A: lane l loads row l (8 coefficients, 16/32 contiguous bytes) of all three channels with
-// vector loads and dequantises them in registers (CfL needs Y next to X and B anyway).
-// Phase B, per channel: rows go to shared memory, the strategy's transform runs on them.
-// PIPE: the coefficient rows were loaded one item ahead (`raw`), see idct8_kernel<I32, true>.
-template <bool I32, bool PIPE = false>
-__device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 entry, bool active,
-                                            uint4 entry_next, bool next_active, float* sm,
-                                            const RawBlock8<I32>* raw = nullptr) {
-  const int lane = threadIdx.x & 31;
-  const int slot = lane >> 3, l = lane & 7;
-  // Inactive slots (tail of a list) run the same instruction stream on scratch data so that
-  // every __syncwarp() is reached by all 32 lanes; only their loads and stores are masked.
-  float* co = sm + slot * 264;   // 264 = 96 + 96 + 64 + 8: slot bases 8 banks apart
-  float* tmp = co + 96;
-  float* px = co + 192;
-  VarblockCtx vb;
-  float val[3][8];
-  if (active) {
-    vb = make_ctx(P, entry);
-    int qx[8], qy[8], qb[8];
-    float mx[8], my[8], mb[8];
-    const size_t e0 = vb.cbase + (size_t)l * 8;
-    if constexpr (PIPE) {
-      unpack_raw8<I32>(raw->ch[1], qy);
-      unpack_raw8<I32>(raw->ch[0], qx);
-      unpack_raw8<I32>(raw->ch[2], qb);
-    } else {
-      load_row8<I32>(P.coeff[1], e0, qy);
-      load_row8<I32>(P.coeff[0], e0, qx);
-      load_row8<I32>(P.coeff[2], e0, qb);
-    }
-    load_row8f(P.dq + P.dq_off[3 * kind + 1] + l * 8, my);
-    load_row8f(P.dq + P.dq_off[3 * kind + 0] + l * 8, mx);
-    load_row8f(P.dq + P.dq_off[3 * kind + 2] + l * 8, mb);
-#pragma unroll
-    for (int e = 0; e < 8; e++) {
-      const float dy = adjust_quant_bias(qy[e], P.qbias[1], P.qbias[3]) * (my[e] * vb.sy);
-      const float dx = adjust_quant_bias(qx[e], P.qbias[0], P.qbias[3]) * (mx[e] * vb.sx);
-      const float db = adjust_quant_bias(qb[e], P.qbias[2], P.qbias[3]) * (mb[e] * vb.sb);
-      val[1][e] = dy;
-      val[0][e] = fmaf(vb.x_cc, dy, dx);
-      val[2][e] = fmaf(vb.b_cc, dy, db);
-    }
-    if (l == 0) {  // LowestFrequenciesFromDC for the 8x8 class: llf[0] = dc[0]
-      const size_t bi = (size_t)vb.aby * P.xb + vb.abx;
-#pragma unroll
-      for (int c = 0; c < 3; c++) val[c][0] = __ldg(P.dc + (size_t)c * P.yb * P.xb + bi);
-    }
+// One row (8 consecutive coefficients) of a block held in SHARED memory (the fused kernel's staging).
+template <bool I32>
+__device__ __forceinline__ void load_row8_smem(const void* block, int elem, int* q) {
+  if constexpr (I32) {
+    const int4* p = reinterpret_cast<const int4*>(reinterpret_cast<const int32_t*>(block) + elem);
+    const int4 a = p[0], b = p[1];
+    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
   } else {
-    vb = VarblockCtx{};
+    const int4 a = *reinterpret_cast<const int4*>(reinterpret_cast<const int16_t*>(block) + elem);
+    const int w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-    for (int c = 0; c < 3; c++)
-#pragma unroll
-      for (int e = 0; e < 8; e++) val[c][e] = 0.0f;
-  }
-  // Pull the NEXT item's coefficient lines (streamed from HBM exactly once) into L2 while this
-  // item is being transformed: no registers are held, the next item's loads become L2 hits.
-  if (!PIPE && next_active) {
-    constexpr int kLines = I32 ? 2 : 1;  // a block-channel is 256 / 128 contiguous bytes
-    if (l < 3 * kLines) {
-      const int ch = l / kLines, half = l % kLines;
-      const char* p = reinterpret_cast<const char*>(P.coeff[ch]) +
-                      ((size_t)entry_next.y * 64u) * (I32 ? 4 : 2) + half * 128;
-#if JXLB_PTX
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-      (void)p;
-#endif
+    for (int i = 0; i < 4; i++) {
+      q[2 * i] = (int)(short)(w[i] & 0xffff);
+      q[2 * i + 1] = w[i] >> 16;
     }
   }
+}
+
+// Dequantisation of row l of an 8x8-class block, all three channels (dec_group.cc:115-181): lane l owns
+// the 8 coefficients of row l.  qx/qy/qb: the integers; `dqkind` selects the dequant matrix rows.
+__device__ __forceinline__ void block8_dequant_row(const FrameDev& P, int dqkind, const VarblockCtx& vb, int l,
+                                                   const int* qx, const int* qy, const int* qb, float (&val)[3][8]) {
+  float mx[8], my[8], mb[8];
+  load_row8f(P.dq + P.dq_off[3 * dqkind + 1] + l * 8, my);
+  load_row8f(P.dq + P.dq_off[3 * dqkind + 0] + l * 8, mx);
+  load_row8f(P.dq + P.dq_off[3 * dqkind + 2] + l * 8, mb);
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    const float dy = adjust_quant_bias(qy[e], P.qbias[1], P.qbias[3]) * (my[e] * vb.sy);
+    const float dx = adjust_quant_bias(qx[e], P.qbias[0], P.qbias[3]) * (mx[e] * vb.sx);
+    const float db = adjust_quant_bias(qb[e], P.qbias[2], P.qbias[3]) * (mb[e] * vb.sb);
+    val[1][e] = dy;
+    val[0][e] = fmaf(vb.x_cc, dy, dx);
+    val[2][e] = fmaf(vb.b_cc, dy, db);
+  }
+  if (l == 0) {  // LowestFrequenciesFromDC for the 8x8 class: llf[0] = dc[0]
+    const size_t bi = (size_t)vb.aby * P.xb + vb.abx;
+#pragma unroll
+    for (int c = 0; c < 3; c++) val[c][0] = __ldg(P.dc + (size_t)c * P.yb * P.xb + bi);
+  }
+}
+
+// Where the pixels of an 8x8-class block go.
+//   Block8ToPlanes: the XYB planes in HBM (idct8_kernel).  The specials assemble the block in a 64-float
+//     scratch (row pitch 8) and lane l stores pixel row l with two 16-byte stores.
+//   (the fused kernel's policy, Block8ToRing in jxl_fused.cuh, writes straight into its shared-memory
+//     pixel ring: row pitch = one ring row.)
+// Interface: kPitch; px(c) = where pixel (y, x) of channel c is assembled (px(c)[y * kPitch + x]);
+// dct_col(c, l, u, active) = column l of a plain DCT8x8; finish(c, l, active) after the specials.
+struct Block8ToPlanes {
+  static constexpr int kPitch = 8;
+  static constexpr bool kGuardPx = false;  // inactive slots assemble garbage in their own scratch
+  float* scratch;
+  float* plane0;  // channel 0, pixel (0, 0) of the block
+  size_t plane_stride, row_stride;
+  __device__ __forceinline__ float* px(int) const { return scratch; }
+  __device__ __forceinline__ void dct_col(int c, int l, const float* u, bool active) const {
+    if (active) {
+      float* out = plane0 + (size_t)c * plane_stride + l;
+#pragma unroll
+      for (int y = 0; y < 8; y++) out[(size_t)y * row_stride] = u[y];
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void finish(int c, int l, bool active) const {
+    __syncwarp();
+    if (active) {  // lane l stores pixel row l (2 x 16 B)
+      float* out = plane0 + (size_t)c * plane_stride + (size_t)l * row_stride;
+      const float4 a = *reinterpret_cast<const float4*>(scratch + l * 8);
+      const float4 b = *reinterpret_cast<const float4*>(scratch + l * 8 + 4);
+      *reinterpret_cast<float4*>(out) = a;
+      *reinterpret_cast<float4*>(out + 4) = b;
+    }
+    __syncwarp();
+  }
+};
+
+// The 2-D inverse transform of one 8x8-class block per 8-lane slot (4 slots per warp), from the
+// dequantised rows val[c][e] (lane l = coefficient row l) to pixels, for strategy `kind` -- the same for
+// the whole warp; slots with active == false run the same instruction stream (every __syncwarp() is
+// reached by all 32 lanes) but store nothing outside their scratch.
+// co / tmp: 96 floats of per-slot scratch each.
+template <class Out>
+__device__ __forceinline__ void block8_transform(int kind, bool active, const float (&val)[3][8], int l,
+                                                 float* co, float* tmp, const Out& out) {
+  constexpr int PP = Out::kPitch;
+#define JXLB_PX_OK (!Out::kGuardPx || active)
 #pragma unroll
   for (int c = 0; c < 3; c++) {
+    float* px = out.px(c);
     if (kind == 0) {
       // ---- DCT 8x8: ComputeScaledIDCT<8,8> (dct-inl.h:376-397); rows at pitch 12 ----
       *reinterpret_cast<float4*>(co + l * 12) = make_float4(val[c][0], val[c][1], val[c][2], val[c][3]);
@@ -578,12 +595,7 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 e
 #pragma unroll
       for (int j = 0; j < 8; j++) u[j] = tmp[j * 12 + l];  // lane l = pixel column x
       idct1d<8>(u);
-      if (active) {
-        float* out = P.xyb + (size_t)c * P.plane_stride + (size_t)vb.aby * 8 * P.row_stride + vb.abx * 8 + l;
-#pragma unroll
-        for (int y = 0; y < 8; y++) out[(size_t)y * P.row_stride] = u[y];
-      }
-      __syncwarp();
+      out.dct_col(c, l, u, active);
       continue;
     }
     *reinterpret_cast<float4*>(co + l * 8) = make_float4(val[c][0], val[c][1], val[c][2], val[c][3]);
@@ -606,15 +618,17 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 e
                 residual_sum += co[(y + iy * 2) * 8 + x + ix * 2];
               }
             const float p11 = block_dc - residual_sum * (1.0f / 16);
+            if (JXLB_PX_OK) {
 #pragma unroll
-            for (int iy = 0; iy < 4; iy++)
+              for (int iy = 0; iy < 4; iy++)
 #pragma unroll
-              for (int ix = 0; ix < 4; ix++) {
-                if (ix == 1 && iy == 1) continue;
-                px[(y * 4 + iy) * 8 + x * 4 + ix] = co[(y + iy * 2) * 8 + x + ix * 2] + p11;
-              }
-            px[(4 * y + 1) * 8 + 4 * x + 1] = p11;
-            px[(y * 4) * 8 + x * 4] = co[(y + 2) * 8 + x + 2] + p11;
+                for (int ix = 0; ix < 4; ix++) {
+                  if (ix == 1 && iy == 1) continue;
+                  px[(y * 4 + iy) * PP + x * 4 + ix] = co[(y + iy * 2) * 8 + x + ix * 2] + p11;
+                }
+              px[(4 * y + 1) * PP + 4 * x + 1] = p11;
+              px[(y * 4) * PP + x * 4] = co[(y + 2) * 8 + x + 2] + p11;
+            }
           }
           break;
         }
@@ -637,16 +651,24 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 e
               }
             }
             __syncwarp();
-            float* dst = (S == 8) ? px : co;
 #pragma unroll
             for (int it = 0; it < 2; it++) {
               const int item = l + it * 8;
               if (item < n * n) {
                 const int y = item / n, x = item % n;
-                dst[(y * 2) * 8 + x * 2] = r[it][0];
-                dst[(y * 2) * 8 + x * 2 + 1] = r[it][1];
-                dst[(y * 2 + 1) * 8 + x * 2] = r[it][2];
-                dst[(y * 2 + 1) * 8 + x * 2 + 1] = r[it][3];
+                if (S == 8) {
+                  if (JXLB_PX_OK) {
+                    px[(y * 2) * PP + x * 2] = r[it][0];
+                    px[(y * 2) * PP + x * 2 + 1] = r[it][1];
+                    px[(y * 2 + 1) * PP + x * 2] = r[it][2];
+                    px[(y * 2 + 1) * PP + x * 2 + 1] = r[it][3];
+                  }
+                } else {
+                  co[(y * 2) * 8 + x * 2] = r[it][0];
+                  co[(y * 2) * 8 + x * 2 + 1] = r[it][1];
+                  co[(y * 2 + 1) * 8 + x * 2] = r[it][2];
+                  co[(y * 2 + 1) * 8 + x * 2 + 1] = r[it][3];
+                }
               }
             }
             __syncwarp();
@@ -677,8 +699,10 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 e
 #pragma unroll
             for (int j = 0; j < 4; j++) u[j] = tmp[sub * 16 + j * 4 + xx];
             idct1d<4>(u);
+            if (JXLB_PX_OK) {
 #pragma unroll
-            for (int yy = 0; yy < 4; yy++) px[(4 * y + yy) * 8 + 4 * x + xx] = u[yy];
+              for (int yy = 0; yy < 4; yy++) px[(4 * y + yy) * PP + 4 * x + xx] = u[yy];
+            }
           }
           break;
         }
@@ -701,8 +725,10 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 e
 #pragma unroll
             for (int j = 0; j < 4; j++) u[j] = tmp[half * 32 + j * 8 + l];
             idct1d<4>(u);
+            if (JXLB_PX_OK) {
 #pragma unroll
-            for (int yy = 0; yy < 4; yy++) px[(4 * half + yy) * 8 + l] = u[yy];
+              for (int yy = 0; yy < 4; yy++) px[(4 * half + yy) * PP + l] = u[yy];
+            }
           }
           break;
         }
@@ -725,8 +751,10 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 e
 #pragma unroll
             for (int j = 0; j < 8; j++) u[j] = tmp[half * 32 + j * 4 + xx];
             idct1d<8>(u);
+            if (JXLB_PX_OK) {
 #pragma unroll
-            for (int yy = 0; yy < 8; yy++) px[yy * 8 + half * 4 + xx] = u[yy];
+              for (int yy = 0; yy < 8; yy++) px[yy * PP + half * 4 + xx] = u[yy];
+            }
           }
           break;
         }
@@ -749,7 +777,7 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 e
             }
             const int r = i >> 2, cc = i & 3;
             const int iy = afv_y ? 3 - r : r, ix = afv_x ? 3 - cc : cc;
-            px[(iy + afv_y * 4) * 8 + afv_x * 4 + ix] = p;
+            if (JXLB_PX_OK) px[(iy + afv_y * 4) * PP + afv_x * 4 + ix] = p;
           }
           // (b) 4x4 IDCT of the (odd column) interleave, (c) 4x8 IDCT of the odd rows: pass 1
           if (l < 4) {
@@ -776,31 +804,81 @@ __device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 e
 #pragma unroll
             for (int j = 0; j < 4; j++) u[j] = tmp[j * 4 + l];
             idct1d<4>(u);
+            if (JXLB_PX_OK) {
 #pragma unroll
-            for (int yy = 0; yy < 4; yy++) px[(afv_y * 4 + yy) * 8 + (afv_x == 1 ? 0 : 4) + l] = u[yy];
+              for (int yy = 0; yy < 4; yy++) px[(afv_y * 4 + yy) * PP + (afv_x == 1 ? 0 : 4) + l] = u[yy];
+            }
           }
           {
             float u[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) u[j] = tmp[16 + j * 8 + l];
             idct1d<4>(u);
+            if (JXLB_PX_OK) {
 #pragma unroll
-            for (int yy = 0; yy < 4; yy++) px[((afv_y == 1 ? 0 : 4) + yy) * 8 + l] = u[yy];
+              for (int yy = 0; yy < 4; yy++) px[((afv_y == 1 ? 0 : 4) + yy) * PP + l] = u[yy];
+            }
           }
           break;
         }
       }
     }
-    __syncwarp();
-    if (active) {  // lane l stores pixel row l (2 x 16 B)
-      float* out = P.xyb + (size_t)c * P.plane_stride + ((size_t)vb.aby * 8 + l) * P.row_stride + vb.abx * 8;
-      const float4 a = *reinterpret_cast<const float4*>(px + l * 8);
-      const float4 b = *reinterpret_cast<const float4*>(px + l * 8 + 4);
-      *reinterpret_cast<float4*>(out) = a;
-      *reinterpret_cast<float4*>(out + 4) = b;
-    }
-    __syncwarp();
+    out.finish(c, l, active);
   }
+#undef JXLB_PX_OK
+}
+
+// 8x8-class varblocks (DCT and the specials): 8 lanes per block, 4 blocks per warp.
+// Phase A: lane l loads row l (8 coefficients, 16/32 contiguous bytes) of all three channels with
+// vector loads and dequantises them in registers (CfL needs Y next to X and B anyway).
+// Phase B, per channel: rows go to shared memory, the strategy's transform runs on them.
+template <bool I32>
+__device__ __forceinline__ void block8_item(const FrameDev& P, int kind, uint4 entry, bool active,
+                                            uint4 entry_next, bool next_active, float* sm) {
+  const int lane = threadIdx.x & 31;
+  const int slot = lane >> 3, l = lane & 7;
+  // Inactive slots (tail of a list) run the same instruction stream on scratch data so that
+  // every __syncwarp() is reached by all 32 lanes; only their loads and stores are masked.
+  float* co = sm + slot * 264;   // 264 = 96 + 96 + 64 + 8: slot bases 8 banks apart
+  float* tmp = co + 96;
+  VarblockCtx vb;
+  float val[3][8];
+  if (active) {
+    vb = make_ctx(P, entry);
+    int qx[8], qy[8], qb[8];
+    const size_t e0 = vb.cbase + (size_t)l * 8;
+    load_row8<I32>(P.coeff[1], e0, qy);
+    load_row8<I32>(P.coeff[0], e0, qx);
+    load_row8<I32>(P.coeff[2], e0, qb);
+    block8_dequant_row(P, kind, vb, l, qx, qy, qb, val);
+  } else {
+    vb = VarblockCtx{};
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int e = 0; e < 8; e++) val[c][e] = 0.0f;
+  }
+  // Pull the NEXT item's coefficient lines (streamed from HBM exactly once) into L2 while this
+  // item is being transformed: no registers are held, the next item's loads become L2 hits.
+  if (next_active) {
+    constexpr int kLines = I32 ? 2 : 1;  // a block-channel is 256 / 128 contiguous bytes
+    if (l < 3 * kLines) {
+      const int ch = l / kLines, half = l % kLines;
+      const char* p = reinterpret_cast<const char*>(P.coeff[ch]) +
+                      ((size_t)entry_next.y * 64u) * (I32 ? 4 : 2) + half * 128;
+#if JXLB_PTX
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+      (void)p;
+#endif
+    }
+  }
+  Block8ToPlanes out;
+  out.scratch = co + 192;
+  out.plane0 = P.xyb + (size_t)vb.aby * 8 * P.row_stride + vb.abx * 8;
+  out.plane_stride = P.plane_stride;
+  out.row_stride = P.row_stride;
+  block8_transform(kind, active, val, l, co, tmp, out);
 }
 
 constexpr int kSmallWarpsPerCta = 8;
