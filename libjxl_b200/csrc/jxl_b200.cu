@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "jxl_kernels.cuh"
+#include "jxl_fused.cuh"
 
 using namespace jxlb;
 
@@ -84,6 +85,8 @@ struct jxlgpu_ctx {
   size_t host_out_stride = 0;
   int stream_error = 0;
   DevBuf acs, quant, sharp, ytox, ytob, dc, dq, coeff, coeff_off, sigma, list, counts, xyb, out;
+  DevBuf bmap;                // fused path: one 16-byte record per 8x8 block (plan kernel)
+  bool allow_fused = true;    // JXLGPU_FUSED=0 forces the two-kernel path (A/B, debugging)
   DevBuf qdc, dc_deq;         // DC stage on the device: quantised planes (+ per-group mul), dequantised planes
   DevBuf sparse;              // staging for the non-zero lists of jxlgpu_submit_groups_sparse
   size_t sparse_used = 0;     // words handed out this frame (bump allocation, guarded by mu)
@@ -162,8 +165,38 @@ bool launch_strip(jxlgpu_ctx* ctx, const FrameDev& P, char* dev_out, size_t out_
   }
 }
 
+// The fused decode kernel (jxl_fused.cuh) exists for the chains below; it needs 16-byte aligned coefficient
+// planes (bulk copies) and no multicast replica.  (Gaborish + all three EPF passes does not fit its
+// shared-memory rings yet and stays on the two-kernel path.)
+bool fused_chain(uint32_t mask) {
+  switch (mask & 31u) {
+    case 16: case 17: case 20: case 21: case 28: case 29: case 30: return true;
+    default: return false;
+  }
+}
+bool use_fused(const jxlgpu_ctx* ctx) {
+  const FrameDev& P = ctx->P;
+  if (!ctx->allow_fused || ctx->force_generic_filter || !fused_chain(P.stage_mask) || P.mc) return false;
+  for (int c = 0; c < 3; c++)
+    if ((uintptr_t)P.coeff[c] % 16) return false;
+  return true;
+}
+
+cudaError_t launch_fused(jxlgpu_ctx* ctx, const FrameDev& P, char* dev_out, size_t out_row_stride, cudaStream_t s) {
+  switch (P.stage_mask & 31u) {
+    case 16: return launch_fused_mask<16>(P, dev_out, out_row_stride, ctx->num_sms, s);
+    case 17: return launch_fused_mask<17>(P, dev_out, out_row_stride, ctx->num_sms, s);
+    case 20: return launch_fused_mask<20>(P, dev_out, out_row_stride, ctx->num_sms, s);
+    case 21: return launch_fused_mask<21>(P, dev_out, out_row_stride, ctx->num_sms, s);
+    case 28: return launch_fused_mask<28>(P, dev_out, out_row_stride, ctx->num_sms, s);
+    case 29: return launch_fused_mask<29>(P, dev_out, out_row_stride, ctx->num_sms, s);
+    default: return launch_fused_mask<30>(P, dev_out, out_row_stride, ctx->num_sms, s);
+  }
+}
+
 // plan + inverse transforms of AC-group rows [row0, row1), restricted to the varblocks that
-// intersect pixel rows [need_y0, need_y1).
+// intersect pixel rows [need_y0, need_y1).  On the fused path only the varblocks larger than 8x8 are
+// transformed here (into the XYB planes); the 8x8 class is left to the fused kernel.
 int launch_idct(jxlgpu_ctx* ctx, uint32_t row0, uint32_t row1, uint32_t need_y0, uint32_t need_y1, cudaStream_t s) {
   FrameDev P = ctx->P;
   P.plan_g0 = row0 * P.xg;
@@ -172,6 +205,8 @@ int launch_idct(jxlgpu_ctx* ctx, uint32_t row0, uint32_t row1, uint32_t need_y0,
   const uint32_t plan_groups = (row1 - row0) * P.xg;
   if (!plan_groups) return JXLGPU_OK;
   const bool prof = ctx->profile;
+  const bool fused = use_fused(ctx);
+  P.fused = fused ? 1u : 0u;
   CU(cudaMemsetAsync(ctx->counts.p, 0, kNumStrategies * sizeof(uint32_t), s));
   const int want_sigma = (P.stage_mask & 14u) ? 1 : 0;
   if (prof) CU(cudaEventRecord(ctx->prof_ev[0], s));
@@ -193,12 +228,8 @@ int launch_idct(jxlgpu_ctx* ctx, uint32_t row0, uint32_t row1, uint32_t need_y0,
     CU(cudaStreamWaitEvent(sl, ctx->ev_fork, 0));
   }
   auto run8 = [&]() {
-    static const bool pipe = [] { const char* e = getenv("JXLGPU_IDCT8_PIPE"); return e && e[0] == '1'; }();
-    if (pipe) {  // EXPERIMENT: software-pipelined variant, 3 CTAs/SM
-      const int g = ctx->num_sms * 3;
-      if (P.ac_is32) idct8_kernel<true, true><<<g, kSmallWarpsPerCta * 32, 0, s>>>(P);
-      else idct8_kernel<false, true><<<g, kSmallWarpsPerCta * 32, 0, s>>>(P);
-    } else if (P.ac_is32) idct8_kernel<true><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
+    if (fused) return;  // (the fused kernel transforms the 8x8 class itself)
+    if (P.ac_is32) idct8_kernel<true><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
     else idct8_kernel<false><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
   };
   if (prof) {
@@ -218,7 +249,7 @@ int launch_idct(jxlgpu_ctx* ctx, uint32_t row0, uint32_t row1, uint32_t need_y0,
     CU(cudaStreamWaitEvent(s, ctx->ev_mid, 0));
     CU(cudaStreamWaitEvent(s, ctx->ev_large, 0));
   }
-  ctx->launches += 4;
+  ctx->launches += fused ? 3 : 4;
   CU(cudaGetLastError());
   return JXLGPU_OK;
 }
@@ -233,7 +264,14 @@ int launch_filter(jxlgpu_ctx* ctx, uint32_t y0, uint32_t y1, uint32_t out_y0, ui
   P.out_y0 = out_y0;
   P.out_h = out_h;
   cudaError_t strip_err = cudaSuccess;
-  if (!launch_strip(ctx, P, dev_out, out_row_stride, s, &strip_err)) {
+  if (use_fused(ctx)) {
+    // coefficients -> pixels in one kernel; finished rows leave through the TMA unit when every row
+    // segment is 16-byte aligned (the kernel checks the per-strip size)
+    bool aligned = (uintptr_t)dev_out % 16 == 0 && out_row_stride % 16 == 0;
+    for (uint32_t q = 0; q < P.nrep; q++) aligned = aligned && (uintptr_t)P.rep[q] % 16 == 0;
+    P.fused = 1u | (aligned ? 2u : 0u);
+    strip_err = launch_fused(ctx, P, dev_out, out_row_stride, s);
+  } else if (!launch_strip(ctx, P, dev_out, out_row_stride, s, &strip_err)) {
     // stage chains outside the production set (test taps): generic tile kernel
     dim3 grid((P.xsize + kTW - 1) / kTW, (y1 - y0 + kTH - 1) / kTH);
     filter_kernel<<<grid, kFilterThreads, kFilterSmemFloats * sizeof(float), s>>>(P, dev_out, out_row_stride);
@@ -384,6 +422,11 @@ int jxlgpu_create(jxlgpu_ctx** out, const jxlgpu_config* cfg) {
                          prepare_strip_mask<21>(), prepare_strip_mask<28>(), prepare_strip_mask<29>(),
                          prepare_strip_mask<30>(), prepare_strip_mask<31>()})
     if (ea != cudaSuccess) return bail(ea, "cudaFuncSetAttribute(filter_strip_kernel)");
+  for (cudaError_t ea : {prepare_fused_mask<16>(), prepare_fused_mask<17>(), prepare_fused_mask<20>(),
+                         prepare_fused_mask<21>(), prepare_fused_mask<28>(), prepare_fused_mask<29>(),
+                         prepare_fused_mask<30>()})
+    if (ea != cudaSuccess) return bail(ea, "cudaFuncSetAttribute(fused_tile_kernel)");
+  if (const char* fe = getenv("JXLGPU_FUSED")) ctx->allow_fused = fe[0] != '0';
   {
     const char* env = getenv("JXLGPU_FORCE_GENERIC_FILTER");
     ctx->force_generic_filter = env && env[0] == '1';
@@ -403,7 +446,7 @@ void jxlgpu_destroy(jxlgpu_ctx* ctx) {
   cudaDeviceSynchronize();
   for (DevBuf* b : {&ctx->acs, &ctx->quant, &ctx->sharp, &ctx->ytox, &ctx->ytob, &ctx->dc, &ctx->dq,
                     &ctx->coeff, &ctx->coeff_off, &ctx->sigma,
-                    &ctx->list, &ctx->counts, &ctx->xyb, &ctx->out, &ctx->sparse, &ctx->qdc, &ctx->dc_deq})
+                    &ctx->list, &ctx->counts, &ctx->xyb, &ctx->out, &ctx->sparse, &ctx->qdc, &ctx->dc_deq, &ctx->bmap})
     b->release();
   for (auto s : ctx->up_streams)
     if (s) cudaStreamDestroy(s);
@@ -488,6 +531,7 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   CU(ctx->dq.ensure(f->dequant_table_floats * 4));
   CU(ctx->coeff_off.ensure(nblocks * 2));
   CU(ctx->sigma.ensure(nblocks * 4));
+  CU(ctx->bmap.ensure(nblocks * sizeof(uint4)));
   // per-strategy work lists, capacity = max number of varblocks of that size
   size_t total = 0;
   for (int s = 0; s < kNumStrategies; s++) {
@@ -554,6 +598,8 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   }
   P.coeff_off = (uint16_t*)ctx->coeff_off.p;
   P.sigma = (float*)ctx->sigma.p;
+  P.bmap = (uint4*)ctx->bmap.p;
+  P.fused = 0;
   P.list = (uint4*)ctx->list.p;
   P.counts = (uint32_t*)ctx->counts.p;
   P.xyb = (float*)ctx->xyb.p;

@@ -61,6 +61,11 @@ __host__ __device__ constexpr int covered_y(int s) {
   return k[s];
 }
 
+constexpr uint32_t kBmapCopy = 255u;  // bmap kind: pixels come from the XYB planes (varblock not of the 8x8 class)
+constexpr uint32_t kBmapSkip = 254u;  // (fused kernel internal: block outside the image)
+// strategies whose varblock is one 8x8 block: DCT, IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4, AFV0..3
+__host__ __device__ constexpr bool is_block8_class(int s) { return s <= 3 || (s >= 12 && s <= 17); }
+
 struct FrameDev {
   uint32_t xsize, ysize, xb, yb, xg, yg;
   uint32_t ac_is32;
@@ -93,6 +98,11 @@ struct FrameDev {
   uint4* list;               // work lists: {(aby<<16)|abx, coefficient base / 64, raw quant, ytox | ytob<<8}
   uint32_t* counts;          // [27]
   uint32_t list_base[kNumStrategies];
+  // fused path (jxl_fused.cuh): one 16-byte record per 8x8 block, [yb][xb]:
+  //   {kind (strategy 0..17 of an 8x8-class varblock | kBmapCopy), coefficient base / 64, raw quant, ytox | ytob<<8}
+  // and no work lists for the 8x8 class (the fused kernel transforms those itself).
+  uint4* bmap;
+  uint32_t fused;
   // planes
   float* xyb;                // 3 planes [yb*8][xb*8]
   size_t plane_stride, row_stride;
@@ -274,19 +284,34 @@ __global__ void __launch_bounds__(1024) plan_kernel(const __grid_constant__ Fram
   const uint32_t off = incl - area + ((t >> 5) ? warp_sums[(t >> 5) - 1] : 0u);
   uint32_t rank = 0;
   // band sharding: only varblocks that intersect the rows this band's filters read are listed
-  const bool wanted = first && (aby * 8u < P.need_y1) && ((aby + (uint32_t)covered_y(s)) * 8u > P.need_y0);
+  bool wanted = first && (aby * 8u < P.need_y1) && ((aby + (uint32_t)covered_y(s)) * 8u > P.need_y0);
   if (first) P.coeff_off[bi] = (uint16_t)off;
-  if (wanted) rank = atomicAdd(&local_count[s], 1u);
+  const bool inline8 = P.fused && is_block8_class(s);
+  if (P.fused && valid) {
+    // fused path: the 8x8 class is transformed by the fused kernel straight from this record; every other
+    // block is fetched from the XYB planes the mid / large kernels fill (kBmapCopy)
+    uint4 rec = make_uint4(kBmapCopy, 0u, 1u, 0u);
+    if (first && inline8) {
+      const size_t ti = (size_t)(aby >> 3) * P.cmap_stride + (abx >> 3);
+      rec = make_uint4((uint32_t)s, (uint32_t)((size_t)g * (P.coeff_gstride >> 6) + off), (uint32_t)P.quant[bi],
+                       (uint32_t)(uint8_t)P.ytox[ti] | ((uint32_t)(uint8_t)P.ytob[ti] << 8));
+    }
+    P.bmap[bi] = rec;
+  }
+  const bool listed = wanted && !inline8;
+  if (listed) rank = atomicAdd(&local_count[s], 1u);
   __syncthreads();
   if (t < kNumStrategies && local_count[t]) local_base[t] = atomicAdd(&P.counts[t], local_count[t]);
   __syncthreads();
   if (wanted) {
     // everything an IDCT warp needs about the varblock in one 16-byte record (one load instead of
     // a dependent chain list -> coeff_off / quant / cmap)
-    const size_t ti = (size_t)(aby >> 3) * P.cmap_stride + (abx >> 3);
-    const uint32_t cfl = (uint32_t)(uint8_t)P.ytox[ti] | ((uint32_t)(uint8_t)P.ytob[ti] << 8);
-    P.list[P.list_base[s] + local_base[s] + rank] =
-        make_uint4((aby << 16) | abx, (uint32_t)((size_t)g * (P.coeff_gstride >> 6) + off), (uint32_t)P.quant[bi], cfl);
+    if (listed) {
+      const size_t ti = (size_t)(aby >> 3) * P.cmap_stride + (abx >> 3);
+      const uint32_t cfl = (uint32_t)(uint8_t)P.ytox[ti] | ((uint32_t)(uint8_t)P.ytob[ti] << 8);
+      P.list[P.list_base[s] + local_base[s] + rank] =
+          make_uint4((aby << 16) | abx, (uint32_t)((size_t)g * (P.coeff_gstride >> 6) + off), (uint32_t)P.quant[bi], cfl);
+    }
     if (want_sigma) {
       // ComputeSigma (epf.cc:39-133)
       const float kInvSigmaNum = -1.1715728752538099024f;
@@ -436,50 +461,6 @@ __device__ __forceinline__ void load_row8(const void* plane, size_t elem, int* q
       q[2 * i] = (int)(short)(w[i] & 0xffff);
       q[2 * i + 1] = w[i] >> 16;
     }
-  }
-}
-
-// The same row, still packed as it came from memory (software-pipelined variant: the next item's rows
-// wait in registers while the current item is transformed).
-template <bool I32>
-struct RawRow8 {
-  int4 w[I32 ? 2 : 1];
-};
-template <bool I32>
-__device__ __forceinline__ void load_raw8(const void* plane, size_t elem, RawRow8<I32>& r) {
-  if constexpr (I32) {
-    const int4* p = reinterpret_cast<const int4*>(reinterpret_cast<const int32_t*>(plane) + elem);
-    r.w[0] = __ldg(p);
-    r.w[1] = __ldg(p + 1);
-  } else {
-    r.w[0] = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const int16_t*>(plane) + elem));
-  }
-}
-template <bool I32>
-__device__ __forceinline__ void unpack_raw8(const RawRow8<I32>& r, int* q) {
-  if constexpr (I32) {
-    q[0] = r.w[0].x; q[1] = r.w[0].y; q[2] = r.w[0].z; q[3] = r.w[0].w;
-    q[4] = r.w[1].x; q[5] = r.w[1].y; q[6] = r.w[1].z; q[7] = r.w[1].w;
-  } else {
-    const int w[4] = {r.w[0].x, r.w[0].y, r.w[0].z, r.w[0].w};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      q[2 * i] = (int)(short)(w[i] & 0xffff);
-      q[2 * i + 1] = w[i] >> 16;
-    }
-  }
-}
-template <bool I32>
-struct RawBlock8 {
-  RawRow8<I32> ch[3];  // lane l's row of X, Y, B
-};
-template <bool I32>
-__device__ __forceinline__ void load_raw_block8(const FrameDev& P, uint4 entry, bool active, RawBlock8<I32>& r) {
-  if (active) {
-    const size_t e0 = (size_t)entry.y * 64u + (size_t)(threadIdx.x & 7) * 8;
-    load_raw8<I32>(P.coeff[1], e0, r.ch[1]);
-    load_raw8<I32>(P.coeff[0], e0, r.ch[0]);
-    load_raw8<I32>(P.coeff[2], e0, r.ch[2]);
   }
 }
 
@@ -890,8 +871,8 @@ __device__ __forceinline__ int small_slots(int s) {
 }
 
 // 8x8-class strategies (DCT, IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4, AFV0-3).
-template <bool I32, bool PIPE = false>
-__global__ void __launch_bounds__(kSmallWarpsPerCta * 32, PIPE ? 3 : 4) idct8_kernel(const __grid_constant__ FrameDev P) {
+template <bool I32>
+__global__ void __launch_bounds__(kSmallWarpsPerCta * 32, 4) idct8_kernel(const __grid_constant__ FrameDev P) {
   __shared__ __align__(16) float smem[kSmallWarpsPerCta * 1056];
   float* sm = smem + (threadIdx.x >> 5) * 1056;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -909,30 +890,7 @@ __global__ void __launch_bounds__(kSmallWarpsPerCta * 32, PIPE ? 3 : 4) idct8_ke
     const uint4 zero = make_uint4(0, 0, 1, 0);
     bool act = it < items && it * 4 + slot < count;
     uint4 cur = act ? __ldg(list + it * 4 + slot) : zero;
-    if constexpr (PIPE) {
-      // EXPERIMENT (JXLGPU_IDCT8_PIPE=1): software pipelining over items -- the coefficient rows of the
-      // warp's next item are requested before the current item is transformed and wait in registers,
-      // and the record of the item after that is fetched as well
-      RawBlock8<I32> raw_cur;
-      load_raw_block8<I32>(P, cur, act, raw_cur);
-      const uint32_t nx0 = (it + nwarps) * 4 + slot;
-      bool nact = (it + nwarps) < items && nx0 < count;
-      uint4 next = nact ? __ldg(list + nx0) : zero;
-#pragma unroll 1
-      for (; it < items; it += nwarps) {
-        RawBlock8<I32> raw_next;
-        load_raw_block8<I32>(P, next, nact, raw_next);
-        const uint32_t nx2 = (it + 2 * nwarps) * 4 + slot;
-        const bool n2act = (it + 2 * nwarps) < items && nx2 < count;
-        const uint4 next2 = n2act ? __ldg(list + nx2) : zero;
-        block8_item<I32, true>(P, s, cur, act, next, nact, sm, &raw_cur);
-        cur = next;
-        act = nact;
-        raw_cur = raw_next;
-        next = next2;
-        nact = n2act;
-      }
-    } else {
+    {
 #pragma unroll 1
       for (; it < items; it += nwarps) {
         const uint32_t nx = (it + nwarps) * 4 + slot;  // the record of this warp's next item is fetched now
@@ -2127,5 +2085,19 @@ __attribute__((visibility("hidden"))) cudaError_t prepare_strip_mask();
 JXLB_DECLARE_STRIP(16) JXLB_DECLARE_STRIP(17) JXLB_DECLARE_STRIP(20) JXLB_DECLARE_STRIP(21)
 JXLB_DECLARE_STRIP(28) JXLB_DECLARE_STRIP(29) JXLB_DECLARE_STRIP(30) JXLB_DECLARE_STRIP(31)
 #undef JXLB_DECLARE_STRIP
+
+// The fused decode kernel (jxl_fused.cuh), one translation unit per stage chain (jxl_fused_inst.cu).
+template <uint32_t MASK>
+cudaError_t launch_fused_mask(const FrameDev& P, char* dev_out, size_t out_row_bytes, int num_sms, cudaStream_t s);
+template <uint32_t MASK>
+__attribute__((visibility("hidden"))) cudaError_t prepare_fused_mask();
+#define JXLB_DECLARE_FUSED(M)                                                            \
+  template <>                                                                            \
+  cudaError_t launch_fused_mask<M>(const FrameDev&, char*, size_t, int, cudaStream_t);   \
+  template <>                                                                            \
+  __attribute__((visibility("hidden"))) cudaError_t prepare_fused_mask<M>();
+JXLB_DECLARE_FUSED(16) JXLB_DECLARE_FUSED(17) JXLB_DECLARE_FUSED(20) JXLB_DECLARE_FUSED(21)
+JXLB_DECLARE_FUSED(28) JXLB_DECLARE_FUSED(29) JXLB_DECLARE_FUSED(30)
+#undef JXLB_DECLARE_FUSED
 
 }  // namespace jxlb

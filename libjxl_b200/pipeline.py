@@ -27,6 +27,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 OBJ = PKG / "build"
 # the stage chains with their own row-streaming filter instantiation (one translation unit each)
 STRIP_MASKS = (16, 17, 20, 21, 28, 29, 30, 31)
+# the stage chains of the fused decode kernel (csrc/jxl_fused.cuh), one translation unit each
+FUSED_MASKS = (16, 17, 20, 21, 28, 29, 30)
 
 EXPORTS = ["jxlgpu_abi_version", "jxlgpu_error_string", "jxlgpu_last_error", "jxlgpu_create",
            "jxlgpu_destroy", "jxlgpu_frame_begin", "jxlgpu_frame_set_output", "jxlgpu_submit_group",
@@ -49,6 +51,7 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> Path:
     hdrs = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [PKG.parent / "include" / "jxl_b200.h"]
     units = [(CSRC / "jxl_b200.cu", OBJ / "jxl_b200.o", [])]
     units += [(CSRC / "jxl_strip_inst.cu", OBJ / f"jxl_strip_{m}.o", [f"-DSTRIP_MASK={m}"]) for m in STRIP_MASKS]
+    units += [(CSRC / "jxl_fused_inst.cu", OBJ / f"jxl_fused_{m}.o", [f"-DFUSED_MASK={m}"]) for m in FUSED_MASKS]
     newest_hdr = max(h.stat().st_mtime for h in hdrs)
     newest_src = max(newest_hdr, *(u[0].stat().st_mtime for u in units))
     if not force and SO.exists() and SO.stat().st_mtime >= newest_src:

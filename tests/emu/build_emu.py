@@ -22,6 +22,7 @@ CSRC = ROOT / "libjxl_b200" / "csrc"
 OUT = HERE / "_build"
 SO = OUT / "libjxl_b200_emu.so"
 MASKS = (16, 17, 20, 21, 28, 29, 30, 31)
+FUSED_MASKS = (16, 17, 20, 21, 28, 29, 30)
 LAUNCH = re.compile(r"(\b\w+(?:<[^<>;]*>)?)<<<(.+?)>>>\((.*)\);")
 
 
@@ -57,6 +58,7 @@ def build(force: bool = False, sanitize: str = "") -> Path:
         flags += ["-DJXLB_EMU_CLAMP_GARBAGE_LANES=1"]   # see filter_strip_body in jxl_kernels.cuh
     units = [(gen / "jxl_b200.cc", OUT / "jxl_b200.o", [])]
     units += [(gen / "jxl_strip_inst.cc", OUT / f"strip_{m}.o", [f"-DSTRIP_MASK={m}"]) for m in MASKS]
+    units += [(gen / "jxl_fused_inst.cc", OUT / f"fused_{m}.o", [f"-DFUSED_MASK={m}"]) for m in FUSED_MASKS]
 
     def cc(u):
         src, obj, defs = u

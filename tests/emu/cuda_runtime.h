@@ -60,7 +60,8 @@ namespace emu {
 struct Warp {
   std::barrier<> bar;
   uint64_t scratch[32];
-  explicit Warp(int n) : bar(n) {}
+  unsigned size;
+  explicit Warp(int n) : bar(n), size((unsigned)n) {}
 };
 struct Block {
   std::barrier<> bar;
@@ -89,6 +90,27 @@ inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
   emu::t_warp->bar.arrive_and_wait();
   return r;
 }
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "");
+  uint64_t bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  emu::t_warp->scratch[emu::t_lane] = bits;
+  emu::t_warp->bar.arrive_and_wait();
+  T r;
+  memcpy(&r, &emu::t_warp->scratch[src_lane & 31], sizeof(T));
+  emu::t_warp->bar.arrive_and_wait();
+  return r;
+}
+inline unsigned __ballot_sync(unsigned, bool pred) {
+  emu::t_warp->scratch[emu::t_lane] = pred ? 1 : 0;
+  emu::t_warp->bar.arrive_and_wait();
+  unsigned m = 0;
+  for (unsigned i = 0; i < emu::t_warp->size; i++) m |= (unsigned)emu::t_warp->scratch[i] << i;
+  emu::t_warp->bar.arrive_and_wait();
+  return m;
+}
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 template <typename T>

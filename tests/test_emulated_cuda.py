@@ -346,3 +346,31 @@ def test_emulated_sparse_small_then_large_frame_on_one_context(emu_pipe):
     assert same(emu_pipe.decode_frame(small, cs, sparse=True), oracle(small, cs))
     big, cb = wl.synthetic_frame(1024, 512, seed=6, density=0.9)
     assert same(emu_pipe.decode_frame(big, cb, sparse=True), oracle(big, cb))
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("segs", ["2", "5"])
+def test_emulated_fused_kernel_row_segments(emu_pipe, segs, monkeypatch):
+    """The fused kernel cuts a strip into row segments (work units); each segment re-transforms the block
+    rows of its halo.  Segment boundaries must not show in the pixels."""
+    monkeypatch.setenv("JXLGPU_FUSED_SEGS", segs)
+    for gab, epf_iters in [(1, 1), (1, 2), (0, 3)]:
+        desc, coeffs = epf_engaged_frame(270, 330, seed=31 + epf_iters, gab=gab, epf_iters=epf_iters)
+        assert same(emu_pipe.decode_frame(desc, coeffs), oracle(desc, coeffs))
+
+
+@pytest.mark.timeout(900)
+def test_emulated_fused_equals_two_kernel_path(emu_pipe, monkeypatch):
+    """JXLGPU_FUSED=0 (read at context creation) selects the two-kernel path: both give the oracle's pixels,
+    in every output format the fused kernel stages through shared memory."""
+    from tests.emu import build_emu
+    desc, coeffs = wl.synthetic_frame(500, 90, seed=3, gab=1, epf_iters=1, ac_type=abi.AC_INT32)
+    monkeypatch.setenv("JXLGPU_FUSED", "0")
+    two = pipeline.TransformPipeline(device=0, num_host_threads=1)
+    try:
+        for fmt in (abi.OUT_RGB_F32, abi.OUT_PLANAR_F32, abi.OUT_RGB_U8, abi.OUT_RGBA_U8, abi.OUT_RGB_U16, abi.OUT_RGB_F16):
+            desc.out_format, desc.stage_mask = fmt, abi.STAGE_SRGB if fmt != abi.OUT_RGB_F32 else 0
+            a, b = emu_pipe.decode_frame(desc, coeffs), two.decode_frame(desc, coeffs)
+            assert same(a, b) and same(a, oracle(desc, coeffs))
+    finally:
+        two.close()
