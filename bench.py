@@ -620,6 +620,44 @@ def main() -> int:
                         "full_decode_mpixels_per_s": nums["full"][cores],
                         "full_decode_one_thread_mpixels_per_s": nums["full"][1], "by_output": hot_by_kind}
 
+    # ---------------- T_e2e: .jxl bytes -> pixels through the public JxlDecoder API ----------------
+    # the reference with the jxl_b200 backend compiled in (oracle/build_ref.py "gpu" variant: build-time patched
+    # dec_frame.cc / dec_group.cc + integration/libjxl_gpu_backend.h) against the stock decoder; the host
+    # still does header parsing + ANS entropy decoding, the GPU does the transform path (SURVEY §8d scope 3)
+    t_e2e = None
+    if not args.no_cpu_baseline and world == 1 and fr.get("jxl") is not None:
+        from oracle import ref
+        if ref.available("gpu"):
+            cpu = host_cpu_info()
+            cores = cpu["cores"]
+            try:
+                ref.use_variant("gpu")
+                runner = ref.Runner(cores)
+                out_px = pipeline.pinned_array((H, W, 3), np.float32)   # the application's buffer (page-locked)
+                before = ref.gpu_frames_taken()
+                ts = []
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    ref.decode_linear_f32(fr["jxl"], cores, out_px, runner)
+                    ts.append(time.perf_counter() - t0)
+                taken = ref.gpu_frames_taken() - before
+                runner.close()
+                err = None
+                if fr.get("decoded") is not None:
+                    err = float(np.abs(out_px - fr["decoded"]).max())
+                t_e2e = {"value": geomean_excluding_first(ts, W * H), "unit": "Mpixel/s", "threads": cores,
+                         "frames_on_gpu": int(taken), "reps": len(ts) - 1,
+                         "peak_abs_err_vs_stock_decoder": err,
+                         "what": ".jxl codestream -> linear RGB f32 in a page-locked application buffer, public JxlDecoder "
+                                 "API + JxlThreadParallelRunner; patched FrameDecoder hands entropy-decoded AC-group rows to "
+                                 "libjxl_b200.so (dense ACImage hand-off)",
+                         "stock_decoder_mpixels_per_s": (cpu_baseline or {}).get("full_decode_mpixels_per_s"),
+                         "stock_decoder_one_thread_mpixels_per_s": (cpu_baseline or {}).get("full_decode_one_thread_mpixels_per_s")}
+            except Exception as e:  # noqa: BLE001
+                t_e2e = {"error": repr(e)}
+            finally:
+                ref.use_variant("default")
+
     w_, h_, dist_, effort_, _, _, _ = WORKLOADS[args.workload]
     line = {
         "metric": "decode_mpixels_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
@@ -640,6 +678,8 @@ def main() -> int:
     }
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
+    if t_e2e:
+        line["t_e2e_decoder"] = t_e2e
     if variant is not None:
         # the same frame with the other output kind (same kernels; only the fused store differs)
         line["variants"] = {other_kind: {"output": OUTPUT_TEXT[other_kind], "value": variant["value"],

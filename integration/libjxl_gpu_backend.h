@@ -1,0 +1,246 @@
+// libjxl_gpu_backend.h -- the libjxl-side half of the drop-in: what FrameDecoder calls at the three sites
+// INTEGRATION.md §2 names.  This header is OURS (it only includes reference headers and include/jxl_b200.h);
+// integration/patch_libjxl.py inserts the one-line calls into a BUILD-TIME COPY of lib/jxl/dec_frame.cc and
+// lib/jxl/dec_group.cc (never committed; oracle/_ref/patched/), and oracle/build_ref.py links that variant
+// ("gpu") against libjxl_b200.so.  The public JxlDecoder API and the JxlParallelRunner stay untouched: an
+// application keeps calling JxlDecoderSetParallelRunner / JxlDecoderSetImageOutBuffer / JxlDecoderProcessInput.
+//
+//   site 1  FrameDecoder::ProcessACGlobal (lib/jxl/dec_frame.cc:417-434)   -> WantFrame(): accumulate-mode
+//           coefficient storage in page-locked, group-major memory (pinned_ac_image.h)
+//   site 2  FrameDecoder::ProcessSections, after ProcessACGlobal (:693-696) -> BeginFrame(): jxlgpu_frame_begin
+//           with pointers into the decoder's own images (gpu_frame_binding.h) + jxlgpu_frame_set_output
+//   site 3  FrameDecoder::ProcessACGroup (:483-560): DecodeGroup runs with draw == kDontDraw
+//           (lib/jxl/dec_group.cc:357-363,724-727 -> DontDraw()), then GroupDecoded(): the thread that
+//           completes a row of AC groups hands the whole row to jxlgpu_submit_groups (one DMA)
+//   site 4  FrameDecoder::FinalizeFrame (:860-882)                          -> FinishFrame(): jxlgpu_frame_finish
+//
+// A frame that is not eligible, a process without a CUDA device, or JXLB_GPU_BACKEND=0 keeps libjxl's CPU
+// path: every hook then returns "not mine".  Errors after a frame was taken are decode errors (jxl::Status).
+#ifndef JXL_B200_INTEGRATION_LIBJXL_GPU_BACKEND_H_
+#define JXL_B200_INTEGRATION_LIBJXL_GPU_BACKEND_H_
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "gpu_frame_binding.h"
+#include "jxl_b200.h"
+#include "lib/jxl/base/status.h"
+#include "lib/jxl/blending.h"
+#include "lib/jxl/dec_cache.h"
+#include "lib/jxl/frame_header.h"
+#include "lib/jxl/image_bundle.h"
+#include "lib/jxl/render_pipeline/stage_tone_mapping.h"
+#include "pinned_ac_image.h"
+
+namespace jxlb_integration {
+
+// dec_group.cc asks this for every group (defined in the dec_frame.cc translation unit)
+bool DontDraw(const jxl::PassesDecoderState* dec_state);
+
+#ifdef JXLB_GPU_BACKEND_IMPLEMENTATION
+
+struct GpuFrame {
+  GpuFrameBinding binding;
+  std::vector<std::atomic<uint32_t>> row_count;  // decoded groups per AC-group row
+  uint32_t xg = 0, yg = 0;
+  bool is16 = false;
+  bool begun = false;
+  std::atomic<int> error{0};
+};
+
+struct GpuBackend {
+  std::mutex mu;
+  jxlgpu_ctx* ctx = nullptr;
+  bool tried = false;
+  std::unordered_map<const void*, std::unique_ptr<GpuFrame>> frames;  // key: PassesDecoderState*
+  uint64_t frames_taken = 0;
+
+  static GpuBackend& Get() {
+    static GpuBackend b;
+    return b;
+  }
+  // one context per process, created on the first eligible frame; any failure = CPU path for good
+  jxlgpu_ctx* Context() {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!tried) {
+      tried = true;
+      const char* e = getenv("JXLB_GPU_BACKEND");
+      if (!(e && e[0] == '0')) {
+        jxlgpu_config cfg = {JXLGPU_ABI_VERSION, 0, 1, 0};
+        if (const char* d = getenv("JXLB_GPU_DEVICE")) cfg.device = atoi(d);
+        if (jxlgpu_create(&ctx, &cfg) != JXLGPU_OK) ctx = nullptr;
+      }
+    }
+    return ctx;
+  }
+  GpuFrame* Find(const void* dec_state) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = frames.find(dec_state);
+    return it == frames.end() ? nullptr : it->second.get();
+  }
+};
+
+inline uint64_t FramesTaken() { return GpuBackend::Get().frames_taken; }
+
+// JxlPixelFormat of the application's buffer -> JXLGPU_OUT_* (INTEGRATION.md §1); false: CPU path
+inline bool MapOutput(const jxl::PassesDecoderState& ds, bool has_alpha, uint32_t* out_format) {
+  const jxl::ImageOutput& o = ds.main_output;
+  if (!o.buffer || o.callback.IsPresent() || ds.undo_orientation != jxl::Orientation::kIdentity || ds.unpremul_alpha ||
+      ds.fast_xyb_srgb8_conversion || has_alpha)
+    return false;
+  const uint16_t one = 1;
+  const bool little = *reinterpret_cast<const uint8_t*>(&one) == 1;
+  const bool native = o.format.endianness == JXL_NATIVE_ENDIAN ||
+                      o.format.endianness == (little ? JXL_LITTLE_ENDIAN : JXL_BIG_ENDIAN);
+  switch (o.format.data_type) {
+    case JXL_TYPE_FLOAT:
+      if (o.format.num_channels != 3 || !native) return false;
+      *out_format = JXLGPU_OUT_RGB_F32;
+      return true;
+    case JXL_TYPE_UINT8:
+      if (o.bits_per_sample != 8) return false;
+      if (o.format.num_channels == 3) *out_format = JXLGPU_OUT_RGB_U8;
+      else if (o.format.num_channels == 4) *out_format = JXLGPU_OUT_RGBA_U8;
+      else return false;
+      return true;
+    case JXL_TYPE_UINT16:
+      if (o.format.num_channels != 3 || !native || o.bits_per_sample != 16) return false;
+      *out_format = JXLGPU_OUT_RGB_U16;
+      return true;
+    case JXL_TYPE_FLOAT16:
+      if (o.format.num_channels != 3 || !native) return false;
+      *out_format = JXLGPU_OUT_RGB_F16;
+      return true;
+    default:
+      return false;
+  }
+}
+
+// The frames whose render pipeline is exactly [Gaborish] [EPF..] XYB [FromLinear(sRGB)] WriteToOutput
+// (PassesDecoderState::PreparePipeline, lib/jxl/dec_cache.cc:117-345) into a caller-owned buffer.
+inline bool FrameIsOurs(const jxl::FrameHeader& fh, const jxl::PassesDecoderState& ds, const jxl::ImageBundle* decoded,
+                        uint32_t* out_format, uint32_t* stage_mask) {
+  const jxl::CodecMetadata& md = *fh.nonserialized_metadata;
+  if (!IsEligible(fh, md) || decoded->IsJPEG()) return false;
+  if (fh.frame_type != jxl::FrameType::kRegularFrame || fh.dc_level != 0 || fh.CanBeReferenced() ||
+      jxl::NeedsBlending(fh) || fh.custom_size_or_origin || fh.nonserialized_is_preview)
+    return false;
+  const auto& oei = ds.output_encoding_info;
+  const auto& ce = oei.color_encoding;
+  if (ce.GetColorSpace() != jxl::ColorSpace::kRGB) return false;
+  if (!(oei.color_encoding_is_original || !oei.cms_set)) return false;   // a CMS stage would follow
+  if (jxl::GetToneMappingStage(oei)) return false;
+  if (ce.Tf().IsLinear()) *stage_mask = 0;
+  else if (ce.Tf().IsSRGB()) *stage_mask = JXLGPU_STAGE_SRGB;
+  else return false;
+  if (ds.width != ds.shared->frame_dim.xsize || ds.height != ds.shared->frame_dim.ysize) return false;
+  return MapOutput(ds, /*has_alpha=*/false, out_format);
+}
+
+// ---- site 1: coefficient storage (ProcessACGlobal).  `use_16_bit` as the reference computed it. ----
+// Returns true and installs pinned group-major accumulate-mode storage when the frame will go to the GPU.
+inline bool WantFrame(const jxl::FrameHeader& fh, jxl::PassesDecoderState* ds, const jxl::ImageBundle* decoded,
+                      bool use_16_bit, size_t num_groups) {
+  uint32_t fmt = 0, mask = 0;
+  if (!FrameIsOurs(fh, *ds, decoded, &fmt, &mask)) return false;
+  GpuBackend& be = GpuBackend::Get();
+  if (!be.Context()) return false;
+  std::unique_ptr<jxl::ACImage> store;
+  if (use_16_bit) store = GroupMajorACImage<int16_t>::Make(num_groups, jxlgpu_alloc_pinned, jxlgpu_free_pinned);
+  else store = GroupMajorACImage<int32_t>::Make(num_groups, jxlgpu_alloc_pinned, jxlgpu_free_pinned);
+  if (!store) return false;
+  store->ZeroFill();
+  ds->coefficients = std::move(store);
+  auto fr = std::make_unique<GpuFrame>();
+  fr->is16 = use_16_bit;
+  fr->binding.frame.out_format = fmt;
+  fr->binding.frame.stage_mask = mask;
+  std::lock_guard<std::mutex> lk(be.mu);
+  be.frames[ds] = std::move(fr);
+  return true;
+}
+
+// ---- site 2: after ProcessACGlobal, DC finalised, output buffer known ----
+inline jxl::Status BeginFrame(const jxl::FrameHeader& fh, jxl::PassesDecoderState* ds) {
+  GpuBackend& be = GpuBackend::Get();
+  GpuFrame* fr = be.Find(ds);
+  if (!fr || fr->begun) return true;
+  const uint32_t fmt = fr->binding.frame.out_format, mask = fr->binding.frame.stage_mask;
+  if (!BindGpuFrame(*ds, fh, fmt, mask, &fr->binding)) return JXL_FAILURE("gpu backend: frame binding failed");
+  const jxl::FrameDimensions& d = ds->shared->frame_dim;
+  fr->xg = static_cast<uint32_t>(d.xsize_groups);
+  fr->yg = static_cast<uint32_t>(d.ysize_groups);
+  fr->row_count = std::vector<std::atomic<uint32_t>>(fr->yg);
+  for (auto& c : fr->row_count) c.store(0);
+  if (jxlgpu_frame_begin(be.ctx, &fr->binding.frame) != JXLGPU_OK)
+    return JXL_FAILURE("gpu backend: frame_begin: %s", jxlgpu_last_error(be.ctx));
+  if (jxlgpu_frame_set_output(be.ctx, ds->main_output.buffer, ds->main_output.stride) != JXLGPU_OK)
+    return JXL_FAILURE("gpu backend: frame_set_output");
+  fr->begun = true;
+  return true;
+}
+
+// ---- site 3: one AC group has been entropy-decoded into the pinned storage ----
+inline bool FrameActive(const jxl::PassesDecoderState* ds) {
+  GpuFrame* fr = GpuBackend::Get().Find(ds);
+  return fr != nullptr;
+}
+inline jxl::Status GroupDecoded(jxl::PassesDecoderState* ds, size_t group) {
+  GpuBackend& be = GpuBackend::Get();
+  GpuFrame* fr = be.Find(ds);
+  if (!fr || !fr->begun) return JXL_FAILURE("gpu backend: group before frame_begin");
+  const uint32_t row = static_cast<uint32_t>(group / fr->xg);
+  if (fr->row_count[row].fetch_add(1) + 1 != fr->xg) return true;
+  // this thread completed the row: hand the whole row over (adjacent [3][65536] blocks -> one DMA)
+  const jxl::FrameDimensions& d = ds->shared->frame_dim;
+  std::vector<uint32_t> idx(fr->xg);
+  std::vector<const void*> co(3 * fr->xg);
+  std::vector<size_t> nco(fr->xg);
+  for (uint32_t gx = 0; gx < fr->xg; gx++) {
+    const size_t g = static_cast<size_t>(row) * fr->xg + gx;
+    idx[gx] = static_cast<uint32_t>(g);
+    const jxl::Rect br = d.BlockGroupRect(g);
+    nco[gx] = 64 * br.xsize() * br.ysize();
+    for (size_t c = 0; c < 3; c++) {
+      jxl::ACPtr p = ds->coefficients->PlaneRow(c, g, 0);
+      co[3 * gx + c] = fr->is16 ? static_cast<const void*>(p.ptr16) : static_cast<const void*>(p.ptr32);
+    }
+  }
+  if (jxlgpu_submit_groups(be.ctx, fr->xg, idx.data(), 0, co.data(), nco.data()) != JXLGPU_OK) {
+    fr->error.store(1);
+    return JXL_FAILURE("gpu backend: submit_groups: %s", jxlgpu_last_error(be.ctx));
+  }
+  return true;
+}
+
+// ---- site 4: FinalizeFrame ----
+inline jxl::Status FinishFrame(jxl::PassesDecoderState* ds) {
+  GpuBackend& be = GpuBackend::Get();
+  GpuFrame* fr = be.Find(ds);
+  if (!fr) return true;
+  jxl::Status st = true;
+  if (fr->begun) {
+    if (jxlgpu_frame_finish(be.ctx, ds->main_output.buffer, ds->main_output.stride) != JXLGPU_OK)
+      st = JXL_FAILURE("gpu backend: frame_finish: %s", jxlgpu_last_error(be.ctx));
+    else be.frames_taken++;
+  }
+  std::lock_guard<std::mutex> lk(be.mu);
+  be.frames.erase(ds);
+  return st;
+}
+
+bool DontDraw(const jxl::PassesDecoderState* dec_state) { return FrameActive(dec_state); }
+
+#endif  // JXLB_GPU_BACKEND_IMPLEMENTATION
+
+}  // namespace jxlb_integration
+
+// exported by the patched library so that a test / bench can see that frames really took the GPU path
+extern "C" __attribute__((visibility("default"))) unsigned long long jxlb_gpu_backend_frames_taken(void);
+
+#endif  // JXL_B200_INTEGRATION_LIBJXL_GPU_BACKEND_H_

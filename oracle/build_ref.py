@@ -128,6 +128,14 @@ def compile_one(src: Path, extra: list[str], variant: str) -> Path:
 VARIANTS = {"default": ("libjxl_ref_harness.so", []),
             "strict": ("libjxl_ref_harness_strict.so", ["-ffp-contract=off"])}
 
+# A third library, "gpu": the reference with the jxl_b200 backend compiled in -- the
+# same objects as "default" except lib/jxl/dec_frame.cc and lib/jxl/dec_group.cc, which are built from the
+# patched copies integration/patch_libjxl.py writes to oracle/_ref/patched/ (hooks into OUR
+# integration/libjxl_gpu_backend.h), linked against libjxl_b200/libjxl_b200.so.  It is what measures
+# T_e2e (.jxl bytes -> pixels through the public JxlDecoder API with the GPU doing the transform path).
+GPU_SO = "libjxl_ref_harness_gpu.so"
+PATCHED = ("lib/jxl/dec_frame.cc", "lib/jxl/dec_group.cc")
+
 
 def main() -> int:
     if not REF.exists():
@@ -138,12 +146,54 @@ def main() -> int:
         rc = build_variant(variant)
         if rc:
             return rc
+    return build_gpu_variant()
+
+
+def build_gpu_variant() -> int:
+    product = HERE.parent / "libjxl_b200" / "libjxl_b200.so"
+    if not product.exists():
+        print("[build_ref] [gpu] libjxl_b200.so not built yet: skipping the integrated variant")
+        return 0
+    repo = HERE.parent
+    patched_dir = OUT / "patched"
+    subprocess.check_call([sys.executable, str(repo / "integration" / "patch_libjxl.py"), str(REF), str(patched_dir)])
+    (OBJ / "gpu").mkdir(parents=True, exist_ok=True)
+    extra = [f"-I{repo / 'integration'}", f"-I{repo / 'include'}"]
+    hdrs = [repo / "integration" / n for n in ("libjxl_gpu_backend.h", "gpu_frame_binding.h", "pinned_ac_image.h")]
+    hdrs.append(repo / "include" / "jxl_b200.h")
+    new_objs = {}
+    for rel in PATCHED:
+        src = patched_dir / Path(rel).name
+        o = OBJ / "gpu" / (Path(rel).stem + ".o")
+        if not (o.exists() and o.stat().st_mtime >= max([src.stat().st_mtime] + [h.stat().st_mtime for h in hdrs])):
+            cmd = ["g++", *CXXFLAGS, *COMMON_DEFS, *includes(), *extra, "-c", str(src), "-o", str(o)]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"compile failed: {' '.join(cmd)}\n{r.stderr[-6000:]}")
+        new_objs[str(REF / rel)] = o
+    # every other object is the default variant's
+    objs = []
+    for s_, _ in source_list([]):
+        objs.append(new_objs.get(str(s_), obj_path(s_, "default")))
+    lib = OUT / "libjxl_ref_gpu.a"
+    if lib.exists():
+        lib.unlink()
+    subprocess.check_call(["ar", "rcs", str(lib), *map(str, objs)])
+    so = OUT / GPU_SO
+    cmd = ["g++", *CXXFLAGS, *COMMON_DEFS, "-DJXLB_REF_HARNESS_GPU=1", *includes(), f"-I{repo / 'include'}", *extra,
+           "-shared", str(HERE / "ref_harness.cc"),
+           "-Wl,--whole-archive", str(lib), "-Wl,--no-whole-archive", "-Wl,--exclude-libs,ALL",
+           f"-L{product.parent}", "-l:libjxl_b200.so", "-Wl,-rpath,$ORIGIN/../../libjxl_b200",
+           "-lpthread", "-lm", "-o", str(so)]
+    cmd.remove("-w")
+    cmd.append("-Wno-attributes")
+    subprocess.check_call(cmd)
+    print(f"[build_ref] built {so}")
     return 0
 
 
-def build_variant(variant: str) -> int:
-    so_name, vflags = VARIANTS[variant]
-    (OBJ / variant).mkdir(parents=True, exist_ok=True)
+def source_list(vflags: list[str]) -> list[tuple[Path, list[str]]]:
+    """Every reference / vendored source of the library with its extra flags, de-duplicated."""
     lists = parse_lists()
     srcs: list[tuple[Path, list[str]]] = []
     for key in ("JPEGXL_INTERNAL_BASE_SOURCES", "JPEGXL_INTERNAL_DEC_SOURCES",
@@ -174,6 +224,13 @@ def build_variant(variant: str) -> int:
         if s not in seen:
             seen.add(s)
             uniq.append((s, e))
+    return uniq
+
+
+def build_variant(variant: str) -> int:
+    so_name, vflags = VARIANTS[variant]
+    (OBJ / variant).mkdir(parents=True, exist_ok=True)
+    uniq = source_list(vflags)
     jobs = int(os.environ.get("JOBS", os.cpu_count() or 4))
     print(f"[build_ref] [{variant}] compiling {len(uniq)} reference sources with {jobs} jobs")
     objs = []

@@ -17,6 +17,10 @@ SO = HERE / "_ref" / "libjxl_ref_harness.so"
 # Same sources built with -ffp-contract=off (FMA only where the source says MulAdd):
 # the bit-exact pin for oracle/jxl_oracle.c.  Select with use_variant("strict").
 SO_STRICT = HERE / "_ref" / "libjxl_ref_harness_strict.so"
+# The reference with the jxl_b200 backend compiled in (build-time patched copies of dec_frame.cc /
+# dec_group.cc + integration/libjxl_gpu_backend.h, linked against libjxl_b200.so): use_variant("gpu").
+SO_GPU = HERE / "_ref" / "libjxl_ref_harness_gpu.so"
+_SO = {"default": SO, "strict": SO_STRICT, "gpu": SO_GPU}
 
 
 class RefFrameInfo(C.Structure):
@@ -54,19 +58,19 @@ _variant = "default"
 
 
 def available(variant: str = "default") -> bool:
-    return (SO if variant == "default" else SO_STRICT).exists()
+    return _SO[variant].exists()
 
 
 def use_variant(variant: str) -> None:
     """'default' = the reference's own build flags; 'strict' = + -ffp-contract=off."""
     global _variant
-    assert variant in ("default", "strict")
+    assert variant in _SO
     _variant = variant
 
 
 def lib():
     if _variant not in _libs:
-        so = SO if _variant == "default" else SO_STRICT
+        so = _SO[_variant]
         if not so.exists():
             raise RuntimeError(f"{so} missing: run `python oracle/build_ref.py` where /root/reference exists")
         L = C.CDLL(str(so))
@@ -97,6 +101,8 @@ def lib():
         L.ref_runner_create.argtypes = [C.c_int]
         L.ref_runner_destroy.argtypes = [C.c_void_p]
         L.ref_free.argtypes = [C.c_void_p]
+        if hasattr(L, "ref_gpu_frames_taken"):
+            L.ref_gpu_frames_taken.restype = C.c_ulonglong
         if hasattr(L, "ref_hwy_target"):
             L.ref_hwy_target.restype = C.c_char_p
         L.ref_transform_to_pixels.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
@@ -342,3 +348,9 @@ def hwy_target() -> str:
     """Highway target the reference's dynamic dispatch runs on this CPU (e.g. 'AVX2')."""
     L = lib()
     return L.ref_hwy_target().decode() if hasattr(L, "ref_hwy_target") else "unknown"
+
+
+def gpu_frames_taken() -> int:
+    """'gpu' variant: frames the compiled-in jxl_b200 backend has rendered in this process."""
+    L = lib()
+    return int(L.ref_gpu_frames_taken()) if hasattr(L, "ref_gpu_frames_taken") else 0

@@ -911,6 +911,12 @@ REF_API int ref_adaptive_dc_smoothing(const float* dc_factors, float* dc, size_t
   return 0;
 }
 
+#ifdef JXLB_REF_HARNESS_GPU
+// "gpu" variant only (oracle/build_ref.py): how many frames the compiled-in jxl_b200 backend rendered
+extern "C" unsigned long long jxlb_gpu_backend_frames_taken(void);
+REF_API unsigned long long ref_gpu_frames_taken() { return jxlb_gpu_backend_frames_taken(); }
+#endif
+
 REF_API const char* ref_version() { return "libjxl 0.13.0 (reference, oracle/_ref)"; }
 
 // The Highway target HWY_DYNAMIC_DISPATCH selects on this CPU: the best compiled-in target among the

@@ -1,0 +1,131 @@
+"""The libjxl-side integration, compiled: oracle/build_ref.py builds a third variant of the reference ("gpu")
+from build-time patched copies of lib/jxl/dec_frame.cc / dec_group.cc (integration/patch_libjxl.py) whose hooks
+call integration/libjxl_gpu_backend.h -> include/jxl_b200.h.  These tests drive it through the PUBLIC
+JxlDecoder API (JxlDecoderSetParallelRunner + JxlDecoderSetImageOutBuffer, oracle/ref_harness.cc:
+ref_decode_linear_f32 / ref_decode_native), i.e. exactly what djxl does.
+
+  * without a CUDA device the patched decoder must behave like the stock one (CPU path, same bytes);
+  * with the SIMT-emulated product library preloaded (tests/emu) the whole hand-off runs on the CPU:
+    eligibility, pinned group-major storage, kDontDraw entropy decode, row-wise submit, frame_finish;
+  * on a GPU (-m gpu) the same through the real library, pixels within the conformance tolerance.
+"""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import jxl_workload as wl
+
+ROOT = Path(__file__).resolve().parents[1]
+REF_ROOT = Path(os.environ.get("JXL_REFERENCE_ROOT", "/root/reference"))
+
+# peak error of linear RGB in [0,1] against the stock CPU decoder (ISO 18181-3 tooling default is 1e-3,
+# tools/conformance/tooling_test.sh:49-50; the reference's fast-vs-simple pipeline bound is 2e-4)
+TOL_PEAK = 2e-5
+
+
+def need_gpu_variant():
+    from oracle import ref
+    if not ref.available("gpu"):
+        if REF_ROOT.exists():
+            pytest.fail("oracle/_ref/libjxl_ref_harness_gpu.so missing although the reference is present: "
+                        "run `python oracle/build_ref.py` (after building libjxl_b200.so)")
+        pytest.skip("integrated reference variant not built (no /root/reference on this box)")
+    return ref
+
+
+CHILD = r"""
+import ctypes, os, sys, json
+import numpy as np
+sys.path.insert(0, {root!r})
+mode = sys.argv[1]
+if mode == "emu":
+    from tests.emu import build_emu
+    ctypes.CDLL(str(build_emu.build()), mode=ctypes.RTLD_GLOBAL)   # jxlgpu_* resolve to the emulated library
+import jxl_workload as wl
+from oracle import ref
+res = {{}}
+for (w, h, dist, epf, fmt) in {cases!r}:
+    img = wl.synth_image(w, h, seed=w + h)
+    data = ref.encode_rgb8(img, dist, 7, -1, epf, 4)
+    ref.use_variant("default")
+    dec = (lambda: ref.decode_linear_f32(data, 4)) if fmt == "f32" else (lambda: ref.decode_native(data, (h, w, 3), np.uint8, 4))
+    want = dec()
+    ref.use_variant("gpu")
+    before = ref.gpu_frames_taken()
+    got = dec()
+    taken = ref.gpu_frames_taken() - before
+    d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    res[f"{{w}}x{{h}}-d{{dist}}-epf{{epf}}-{{fmt}}"] = dict(taken=int(taken), peak=float(d.max()), differing=float((d != 0).mean()))
+print("RESULT " + json.dumps(res))
+"""
+
+
+def run_child(mode, cases):
+    code = CHILD.format(root=str(ROOT), cases=cases)
+    r = subprocess.run([sys.executable, "-c", code, mode], capture_output=True, text=True, timeout=1500, cwd=str(ROOT))
+    assert r.returncode == 0, r.stderr[-4000:]
+    import json
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    return json.loads(line[7:])
+
+
+def test_patch_anchors_match_the_reference(tmp_path):
+    """integration/patch_libjxl.py applies cleanly (every anchor exactly once) to the reference as it is."""
+    if not REF_ROOT.exists():
+        pytest.skip("no reference tree on this box")
+    subprocess.check_call([sys.executable, str(ROOT / "integration" / "patch_libjxl.py"), str(REF_ROOT), str(tmp_path)])
+    for name in ("dec_frame.cc", "dec_group.cc"):
+        assert "jxlb_integration::" in (tmp_path / name).read_text()
+
+
+def test_patched_decoder_without_device_is_the_stock_decoder():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present: covered by the gpu test")
+    ref = need_gpu_variant()
+    img = wl.synth_image(520, 300, seed=9)
+    data = ref.encode_rgb8(img, 1.0, 7, -1, -1, 4)
+    try:
+        ref.use_variant("default")
+        want = ref.decode_linear_f32(data, 4)
+        ref.use_variant("gpu")
+        got = ref.decode_linear_f32(data, 4)
+        assert ref.gpu_frames_taken() == 0          # no device: the hooks said "not mine"
+    finally:
+        ref.use_variant("default")
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.timeout(1800)
+def test_patched_decoder_through_the_emulated_library():
+    """.jxl bytes -> public JxlDecoder API -> patched FrameDecoder -> C ABI -> (emulated) kernels -> the
+    application's buffer; compared with the stock decoder's pixels."""
+    need_gpu_variant()
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present: covered by the gpu test")
+    res = run_child("emu", [(300, 200, 1.0, -1, "f32"), (520, 264, 2.0, 2, "f32"), (300, 200, 1.0, -1, "u8")])
+    for k, v in res.items():
+        assert v["taken"] == 1, (k, v)               # the frame really went through the backend
+        if k.endswith("u8"):                         # the application's default: 8-bit sRGB, dithered
+            assert v["peak"] <= 1 and v["differing"] < 1e-3, (k, v)
+        else:
+            assert v["peak"] <= TOL_PEAK, (k, v)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(1800)
+def test_patched_decoder_on_the_gpu():
+    need_gpu_variant()
+    res = run_child("gpu", [(1000, 700, 1.0, -1, "f32"), (2048, 1100, 2.0, 2, "f32"), (777, 333, 0.5, 0, "f32"),
+                            (1500, 900, 4.0, 3, "f32"), (1000, 700, 1.0, -1, "u8")])
+    for k, v in res.items():
+        assert v["taken"] == 1, (k, v)
+        if k.endswith("u8"):
+            assert v["peak"] <= 1 and v["differing"] < 1e-3, (k, v)
+        else:
+            assert v["peak"] <= TOL_PEAK, (k, v)
