@@ -42,7 +42,15 @@ WORKLOADS = {
     "4k-d1": (4096, 4096, 1.0, 7, -1, -1, "photo"),          # BASELINE config 2
     "1080p-d1": (1920, 1080, 1.0, 7, -1, -1, "photo"),
     "512-d1": (512, 512, 1.0, 7, -1, -1, "photo"),
+    # BASELINE config 4: 16384^2 uniform-noise image, d2.0, EPF iters 3 (gab on at d2) -- sharded over 8 GPUs
+    "16k-d2-epf3": (16384, 16384, 2.0, 7, -1, 3, "noise"),
+    # BASELINE config 2, second half: synthetic frame whose AcStrategy map cycles through all 27 transforms
+    # (cjxl never emits > 64x64, SURVEY.md §8c caveat); coefficients int16 Laplace, gab + 3 EPF passes
+    "4k-all27": (4096, 4096, None, None, 1, 3, "synthetic-all-strategies"),
+    # BASELINE config 5: 64 independent 1920x1080 frames, frame-per-GPU replicas (no collective): --workload 64x1080p
+    "64x1080p": (1920, 1080, 1.0, 7, -1, -1, "photo"),
 }
+BIG = {"16k-d2-epf3"}   # no cached copy of the reference decoder's pixels (3.2 GB): parity vs the reference hot path
 
 
 OUTPUT_TEXT = {"f32": "interleaved linear RGB f32 (12 B/px)",
@@ -112,6 +120,10 @@ def prepare_frame(name: str, rank: int, world: int, barrier):
     from oracle import ref
     w, h, dist, effort, gab, epf, kind = WORKLOADS[name]
     source = "reference-encoded"
+    if kind == "synthetic-all-strategies":
+        desc, coeffs = wl.synthetic_frame(w, h, seed=1234, gab=gab, epf_iters=epf)
+        return dict(desc=desc, coeffs=coeffs, jxl=None, hist=wl.strategy_histogram(desc.ac_strategy), bpp=None,
+                    decoded=None), "synthetic coefficients, every AcStrategy"
     if not ref.available():
         log("oracle/_ref missing: falling back to a synthetic all-strategy frame")
         desc, coeffs = wl.synthetic_frame(w, h, seed=1234)
@@ -119,12 +131,14 @@ def prepare_frame(name: str, rank: int, world: int, barrier):
                     decoded=None), "synthetic-coefficients"
     if rank == 0:
         t = time.time()
-        fr = wl.reference_frame(w, h, dist, effort, gab, epf, seed=1234, kind=kind, cache=True)
+        fr = wl.reference_frame(w, h, dist, effort, gab, epf, seed=1234, kind=kind, cache=True,
+                                want_decoded=name not in BIG)
         log(f"frame ready in {time.time() - t:.1f}s: {w}x{h} d{dist} e{effort} gab={fr['desc'].gab} "
             f"epf={fr['desc'].epf_iters} bpp={fr['bpp']:.2f} ac_type={'int16' if fr['desc'].ac_type == 0 else 'int32'}")
     barrier()
     if rank != 0:
-        fr = wl.reference_frame(w, h, dist, effort, gab, epf, seed=1234, kind=kind, cache=True)
+        fr = wl.reference_frame(w, h, dist, effort, gab, epf, seed=1234, kind=kind, cache=True,
+                                want_decoded=name not in BIG)
     return fr, source
 
 
@@ -168,7 +182,8 @@ def workload_text(name: str, desc, source: str, output: str) -> str:
     """The one description of the workload both arms print (same frame, same hot path, same output)."""
     w, h, dist, effort, _, _, _ = WORKLOADS[name]
     es = "int16" if desc.ac_type == 0 else "int32"
-    return (f"{name}: {w}x{h} VarDCT d{dist} e{effort}, gab={desc.gab} epf_iters={desc.epf_iters}, {source}, "
+    enc = f"VarDCT d{dist} e{effort}" if dist is not None else "VarDCT"
+    return (f"{name}: {w}x{h} {enc}, gab={desc.gab} epf_iters={desc.epf_iters}, {source}, "
             f"coefficients {es} as the reference decoder chose, hot path = dequant+IDCT -> Gaborish/EPF -> XYB->RGB, "
             f"output {OUTPUT_TEXT[output]}")
 
@@ -265,6 +280,151 @@ def run_reference(args, rank: int) -> int:
     return 0
 
 
+def run_replicas(args, rank: int, local_rank: int, world: int) -> int:
+    """BASELINE config 5: a batch of 64 independent 1920x1080 frames, frame-per-GPU (round-robin over the
+    ranks, no collective -- SURVEY.md §8e "replicas only").  value = whole-batch Mpixel/s with the coefficients
+    resident in HBM (every frame still does its own frame_begin: side-info upload + plan); e2e = host
+    coefficient blocks -> host pixels through the C ABI; latency = per-frame wall time of the e2e call
+    sequence (frame_begin .. frame_finish) on an otherwise idle GPU, p50 over the rank's frames."""
+    import torch
+    import torch.distributed as dist
+
+    import jxl_workload as wl
+    from libjxl_b200 import abi, pipeline
+    from oracle import ref
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    w, h, dist_, effort, gab, epf, kind = WORKLOADS["64x1080p"]
+    NF = 64
+    mine = list(range(rank, NF, world))
+    t0 = time.time()
+    if rank == 0:   # build the cache files once
+        for i in range(NF):
+            wl.reference_frame(w, h, dist_, effort, gab, epf, seed=i, kind=kind, cache=True, threads=host_cpu_info()["cores"])
+    barrier()
+    frames = [wl.reference_frame(w, h, dist_, effort, gab, epf, seed=i, kind=kind, cache=True) for i in mine]
+    log(f"rank {rank}: {len(frames)} frames ready in {time.time() - t0:.1f}s")
+    pipe = pipeline.TransformPipeline(device=local_rank, num_host_threads=1)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    descs = [pipeline.pin_side_info(f["desc"]) for f in frames]
+    dev = [torch.from_numpy(f["coeffs"]).cuda() for f in frames]
+    ptrs = [[d[c].data_ptr() for c in range(3)] for d in dev]
+    outs = [torch.empty((h, w, 3), dtype=torch.float32, device="cuda") for _ in frames]
+    row_bytes = w * 12
+
+    def batch_device():
+        for i, d in enumerate(descs):
+            pipe.set_device_coefficients(ptrs[i])
+            pipe.frame_begin(d)
+            pipe.render_device(outs[i].data_ptr(), row_bytes, stream.cuda_stream)
+
+    for _ in range(max(3, args.warmup)):
+        batch_device()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = pipe.launch_count()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        batch_device()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    launches = pipe.launch_count() - launches0
+    t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = NF * w * h / (ms_step * 1e-3) / 1e6
+    # parity of every frame of this rank against the reference decoder's pixels
+    peak = 0.0
+    for i, f in enumerate(frames):
+        peak = max(peak, float(np.abs(outs[i].cpu().numpy() - f["decoded"]).max()))
+
+    # ---- end to end: host coefficient blocks -> host pixels, frame by frame ----
+    pipe.set_device_coefficients(None)
+    host = []
+    h2d = d2h = 0
+    for f, d in zip(frames, descs):
+        blk = pipeline.pinned_array((d.num_groups, 3, abi.GROUP_COEFFS), f["coeffs"].dtype)
+        groups = {}
+        for g in range(d.num_groups):
+            n = d.group_ncoeff(g)
+            blk[g] = f["coeffs"][:, g]
+            groups[g] = [blk[g, c, :n] for c in range(3)]
+            h2d += (2 * abi.GROUP_COEFFS + n) * f["coeffs"].dtype.itemsize
+        yb, xb = d.ysize_blocks, d.xsize_blocks
+        h2d += yb * xb * (1 + 4 + 1 + 12) + d.dequant.nbytes + 2 * d.ytox.size
+        out = pipeline.pinned_array((h, w, 3), np.float32)
+        d2h += out.nbytes
+        host.append((pipe.make_batch(list(range(d.num_groups)), groups), out, blk))
+
+    def one_frame(i):
+        pipe.frame_begin(descs[i])
+        pipe.frame_set_output(host[i][1])
+        pipe.submit_batch(host[i][0], 0)
+        pipe.frame_finish(host[i][1])
+
+    for i in range(len(frames)):
+        one_frame(i)
+    barrier()
+    lat = []
+    n_e2e = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        for i in range(len(frames)):
+            a = time.perf_counter()
+            one_frame(i)
+            lat.append(time.perf_counter() - a)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    te = torch.tensor([e2e_s], device="cuda")
+    lat_t = torch.tensor([float(np.median(lat)), float(np.percentile(lat, 95))], device="cuda")
+    by = torch.tensor([float(h2d), float(d2h), peak], device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lat_t, op=dist.ReduceOp.MAX)
+        by2 = by.clone()
+        dist.all_reduce(by2)
+        dist.all_reduce(by, op=dist.ReduceOp.MAX)
+        by[0], by[1] = by2[0], by2[1]
+    clocks = sampler.stop() if rank == 0 else None
+    pipe.close()
+    if rank == 0:
+        line = {
+            "metric": "decode_mpixels_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"64x1080p: batch of {NF} independent {w}x{h} VarDCT d{dist_} e{effort} frames (seeds 0..{NF - 1}), "
+                                   "frame-per-GPU replicas round-robin over the ranks, no collective; one step = the whole batch; "
+                                   "output interleaved linear RGB f32",
+                       "parallelism": f"{world} x replicas", "frames_per_rank": len(mine),
+                       "l2": f"batch working set per rank {len(mine) * (3 * frames[0]['coeffs'][0].nbytes + 2 * w * h * 12) / 1e6:.0f} MB"},
+            "e2e": {"value": NF * w * h / float(te.item()) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": int(by[0].item()),
+                    "d2h_bytes_per_step": int(by[1].item()), "steps": n_e2e, "submit": "dense",
+                    "how": "per frame: frame_begin + frame_set_output + submit_groups (all groups, pinned host blocks) + frame_finish"},
+            "latency_ms": {"p50": 1e3 * float(lat_t[0].item()), "p95": 1e3 * float(lat_t[1].item()),
+                           "what": "host coefficients -> host pixels of one 1080p frame (max over ranks of the per-rank percentiles)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "parity": {"peak_abs_err_vs_reference": float(by[2].item()), "frames_checked": NF},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -293,6 +453,8 @@ def main() -> int:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         return run_reference(args, rank)
+    if args.workload == "64x1080p":
+        return run_replicas(args, rank, local_rank, world)
 
     import torch
     import torch.distributed as dist
@@ -315,6 +477,9 @@ def main() -> int:
     desc, coeffs = fr["desc"], fr["coeffs"]
     W, H = desc.xsize, desc.ysize
     es = 2 if desc.ac_type == abi.AC_INT16 else 4
+    if world > desc.ysize_groups:
+        print(json.dumps({"error": f"{world} ranks but only {desc.ysize_groups} rows of AC groups to shard"}))
+        return 2
     bands = sharding.band_partition(desc.ysize_groups, world)
     y0g, nyg = bands[rank]
     if world > 1:
@@ -440,6 +605,39 @@ def main() -> int:
 
         # correctness spot check of the timed output against the reference decoder's pixels
         parity = None
+        if fr.get("decoded") is None and rank == 0 and full and kind == "f32":
+            # no cached pixels of the reference decoder: compare with the reference's own hot path (big frames)
+            # or, for synthetic coefficient frames, with the C oracle on the first 512 rows
+            if world == 1:
+                got = gathered.cpu().numpy()
+            else:
+                got = np.concatenate([gathered[r, :sharding.band_pixel_rows(desc, *bands[r])[1]].cpu().numpy()
+                                      for r in range(world)])
+            from oracle import ref
+            if fr.get("jxl") is not None and ref.available():
+                frame = ref.Frame(fr["jxl"], host_cpu_info()["cores"])
+                planar, _ = frame.render(-1)
+                frame.close()
+                want = np.moveaxis(planar, 0, 2)
+                d = np.abs(got - want[:got.shape[0]])
+                parity = {"peak_abs_err_vs_reference_hot_path": float(d.max()), "rows_checked": int(got.shape[0])}
+                del planar, want, d
+            else:
+                from oracle import cpu as ocpu
+                import copy
+                sub = copy.copy(desc)
+                rows = min(512, H)
+                sub.ysize = rows
+                for name_ in ("ac_strategy", "raw_quant", "epf_sharpness"):
+                    setattr(sub, name_, getattr(desc, name_)[:rows // 8])
+                sub.dc = desc.dc[:, :rows // 8]
+                sub.ytox, sub.ytob = desc.ytox[:(rows // 8 + 7) // 8], desc.ytob[:(rows // 8 + 7) // 8]
+                sub.band_y0_groups = sub.band_ny_groups = 0
+                ng = sub.num_groups
+                want = ocpu.render_frame(sub, coeffs[:, :ng], rcp_mode=0)
+                halo = 8   # rows next to the cut see different neighbours
+                parity = {"bit_exact_vs_oracle": bool(np.array_equal(got[:rows - halo], want[:rows - halo])),
+                          "rows_checked": int(rows - halo)}
         if fr.get("decoded") is not None and rank == 0 and full:
             if world == 1:
                 got = gathered.cpu().numpy()

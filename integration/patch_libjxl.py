@@ -31,6 +31,10 @@ DEC_FRAME = [
      '    JXL_RETURN_IF_ERROR(ProcessACGlobal(sections[ac_global_sec].br));\n'
      '    section_status[ac_global_sec] = SectionStatus::kDone;\n'
      '    JXL_RETURN_IF_ERROR(jxlb_integration::BeginFrame(frame_header_, dec_state_));\n'),
+    # site 3a (dec_frame.cc:503-505): zero-fill this group's pinned blocks / arm the thread's sparse sink
+    ('    JXL_RETURN_IF_ERROR(DecodeGroup(\n        frame_header_, br.data(), num_passes, ac_group_id, dec_state_,\n',
+     '    jxlb_integration::PrepareGroup(dec_state_, ac_group_id);\n'
+     '    JXL_RETURN_IF_ERROR(DecodeGroup(\n        frame_header_, br.data(), num_passes, ac_group_id, dec_state_,\n'),
     # site 3 (dec_frame.cc:506-516): the group was entropy-decoded only (DecodeGroup saw kDontDraw) -> submit
     ('        force_draw, dc_only, &should_run_pipeline));\n  }\n',
      '        force_draw, dc_only, &should_run_pipeline));\n'
@@ -45,6 +49,20 @@ DEC_FRAME = [
 
 DEC_GROUP = [
     ('#include "lib/jxl/dec_group.h"\n', '#include "lib/jxl/dec_group.h"\n\n' + HOOK_INCLUDE),
+    # lib/jxl/dec_group.cc:335-338: the varblock's offset inside the group, for the sparse sink
+    ('            qblock[c] = dec_state->coefficients->PlaneRow(c, group_idx, offset);\n          }\n',
+     '            qblock[c] = dec_state->coefficients->PlaneRow(c, group_idx, offset);\n          }\n'
+     '          if (jxlb_integration::SparseSink* jxlb_s = jxlb_integration::CurrentSink()) {\n'
+     '            jxlb_s->offset = static_cast<uint32_t>(offset);\n          }\n'),
+    # lib/jxl/dec_group.cc:483-485 + 527-531: append non-zeros to the sink instead of adding into a zero-filled block
+    ('  int32_t predicted_nzeros =\n      PredictFromTopAndLeft(row_nzeros_top, row_nzeros, bx, 32);\n',
+     '  jxlb_integration::SparseSink* const jxlb_sink = jxlb_integration::CurrentSink();\n'
+     '  int32_t predicted_nzeros =\n      PredictFromTopAndLeft(row_nzeros_top, row_nzeros, bx, 32);\n'),
+    ('    if (ac_type == ACType::k16) {\n      block.ptr16[order[k]] += coeff;\n    } else {\n'
+     '      block.ptr32[order[k]] += coeff;\n    }\n',
+     '    if (jxlb_sink) {\n      if (u_coeff != 0) jxlb_sink->Append(c, order[k], coeff);\n'
+     '    } else if (ac_type == ACType::k16) {\n      block.ptr16[order[k]] += coeff;\n    } else {\n'
+     '      block.ptr32[order[k]] += coeff;\n    }\n'),
     # lib/jxl/dec_group.cc:724-727: a GPU frame's groups are entropy-decoded only
     ('          ? kDraw\n          : kDontDraw;\n',
      '          ? kDraw\n          : kDontDraw;\n  if (jxlb_integration::DontDraw(dec_state)) draw = kDontDraw;\n'),
@@ -62,10 +80,13 @@ def apply(text: str, edits, name: str) -> str:
 
 def main() -> int:
     ref, out = Path(sys.argv[1]), Path(sys.argv[2])
-    out.mkdir(parents=True, exist_ok=True)
+    # The copies keep their path below the output directory: lib/jxl/dec_group.cc re-includes ITSELF once per
+    # Highway target (HWY_TARGET_INCLUDE + hwy/foreach_target.h), so the output directory must come first on
+    # the include path -- otherwise every target but the static one would be compiled from the unpatched file.
     for rel, edits in (("lib/jxl/dec_frame.cc", DEC_FRAME), ("lib/jxl/dec_group.cc", DEC_GROUP)):
         src = (ref / rel).read_text()
-        dst = out / Path(rel).name
+        dst = out / rel
+        dst.parent.mkdir(parents=True, exist_ok=True)
         new = apply(src, edits, rel)
         if not dst.exists() or dst.read_text() != new:
             dst.write_text(new)

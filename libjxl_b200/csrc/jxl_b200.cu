@@ -86,7 +86,9 @@ struct jxlgpu_ctx {
   int stream_error = 0;
   DevBuf acs, quant, sharp, ytox, ytob, dc, dq, coeff, coeff_off, sigma, list, counts, xyb, out;
   DevBuf bmap;                // fused path: one 16-byte record per 8x8 block (plan kernel)
-  bool allow_fused = true;    // JXLGPU_FUSED=0 forces the two-kernel path (A/B, debugging)
+  // JXLGPU_FUSED=1 selects the fused decode kernel (jxl_fused.cuh).  Opt-in: on B200 it moves 2x fewer DRAM
+  // bytes than the two-kernel path but is slower (1.33 ms vs 0.66 ms at 8K d1.0, profiles/r02_*fused*).
+  bool allow_fused = false;
   DevBuf qdc, dc_deq;         // DC stage on the device: quantised planes (+ per-group mul), dequantised planes
   DevBuf sparse;              // staging for the non-zero lists of jxlgpu_submit_groups_sparse
   size_t sparse_used = 0;     // words handed out this frame (bump allocation, guarded by mu)
@@ -426,7 +428,7 @@ int jxlgpu_create(jxlgpu_ctx** out, const jxlgpu_config* cfg) {
                          prepare_fused_mask<21>(), prepare_fused_mask<28>(), prepare_fused_mask<29>(),
                          prepare_fused_mask<30>()})
     if (ea != cudaSuccess) return bail(ea, "cudaFuncSetAttribute(fused_tile_kernel)");
-  if (const char* fe = getenv("JXLGPU_FUSED")) ctx->allow_fused = fe[0] != '0';
+  if (const char* fe = getenv("JXLGPU_FUSED")) ctx->allow_fused = fe[0] == '1';
   {
     const char* env = getenv("JXLGPU_FORCE_GENERIC_FILTER");
     ctx->force_generic_filter = env && env[0] == '1';

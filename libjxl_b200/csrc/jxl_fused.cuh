@@ -283,29 +283,30 @@ template <bool EDGE, int BORDER>
 struct TileRows {
   // rowp[k]: pointer to (row 4g + ly - BORDER + k, channel 0, strip column of the lane) for k = 0 .. 2*BORDER
   const float* rowp[2 * BORDER + 1];
-  int cn[2 * BORDER + 1];  // EDGE: strip-relative column offsets of x - BORDER .. x + BORDER (mirrored), relative to the lane's column
+  int cn[2 * BORDER + 1];  // EDGE: column offsets of x - BORDER .. x + BORDER (mirrored), relative to the lane's column
   __device__ __forceinline__ float at(int k, int c, int d) const {  // row offset k - BORDER, channel c, column offset d - BORDER
     if constexpr (EDGE) return rowp[k][c * kTPitch + cn[d]];
     else return rowp[k][c * kTPitch + (d - BORDER)];
   }
 };
 
-template <bool EDGE, int BORDER>
-__device__ __forceinline__ void tile_rows_init(TileRows<EDGE, BORDER>& R, const TileUnit& U, const float* ring, int nin,
+// fast path: `off[k]` = float offset of (ring row of image row 4g + ly - BORDER + k, column lx), computed once per
+// step; the tile only adds its first column
+template <int BORDER>
+__device__ __forceinline__ void tile_rows_fast(TileRows<false, BORDER>& R, const float* ring_col, const int* off) {
+#pragma unroll
+  for (int k = 0; k <= 2 * BORDER; k++) R.rowp[k] = ring_col + off[k];
+}
+// image border: rows and columns mirrored about the true image size (Mirror(), lib/jxl/image_ops.h:184-196)
+template <int BORDER>
+__device__ __forceinline__ void tile_rows_edge(TileRows<true, BORDER>& R, const TileUnit& U, const float* ring, int nin,
                                                int g, int col, int ly) {
   const int x = U.xs0 + col;
-  if constexpr (!EDGE) {
-    const int s0 = mod_n(4 * g - BORDER, nin) + ly;  // < nin + 3
+  const int r = 4 * g + ly;
 #pragma unroll
-    for (int k = 0; k <= 2 * BORDER; k++) R.rowp[k] = ring + wrap_n(s0 + k, nin) * kTRow + col;
-  } else {
-    const int r = 4 * g + ly;
+  for (int k = 0; k <= 2 * BORDER; k++) R.rowp[k] = ring + mod_n(mirror_i(r - BORDER + k, U.HI), nin) * kTRow + col;
 #pragma unroll
-    for (int k = 0; k <= 2 * BORDER; k++)
-      R.rowp[k] = ring + mod_n(mirror_i(r - BORDER + k, U.HI), nin) * kTRow + col;
-#pragma unroll
-    for (int d = 0; d <= 2 * BORDER; d++) R.cn[d] = mirror_i(x - BORDER + d, U.W) - x;
-  }
+  for (int d = 0; d <= 2 * BORDER; d++) R.cn[d] = mirror_i(x - BORDER + d, U.W) - x;
 }
 
 // Gaborish (stage_gaborish.cc:56-100)
@@ -454,6 +455,20 @@ __device__ __forceinline__ void tile_epf2(const FrameDev& P, const TileRows<EDGE
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
+// shared-space atomic (a generic-address atomicAdd costs ~40 instructions of address-space dispatch)
+__device__ __forceinline__ int smem_fetch_add(int* p, int v) {
+#if JXLB_PTX
+  int old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_addr(p)), "r"(v) : "memory");
+  return old;
+#else
+  return atomicAdd(p, v);
+#endif
+}
+
+constexpr int kTChunk = 2;                       // tiles per filter item
+constexpr int kTChunks = kTBlocks / kTChunk;     // filter items per stage and step
+
 template <uint32_t MASK, bool I32, int OUTK>
 __global__ void __launch_bounds__(kTThreads, 1)
 fused_tile_kernel(const __grid_constant__ FrameDev P, char* __restrict__ out, size_t out_row_stride, int seg_rows,
@@ -468,13 +483,14 @@ fused_tile_kernel(const __grid_constant__ FrameDev P, char* __restrict__ out, si
   int* ctr = reinterpret_cast<int*>(smem + C::off_ctr);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + C::off_bar);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int lx = lane & 7, ly = lane >> 3;
   const float kMinSigma = -3.90524291751269967465540850526868f;
   const int pxb = out_pixel_bytes(P.out_format);
   const int band_h = (int)P.out_h;
   constexpr int H = C::H;
   constexpr int NST = C::nst;
+  const bool lxborder = lx == 0 || lx == 7;
 
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -483,6 +499,33 @@ fused_tile_kernel(const __grid_constant__ FrameDev P, char* __restrict__ out, si
   fence_async_smem();
   __syncthreads();
   uint32_t tma_phase = 0;  // parity of the coefficient barrier's next completion (uniform)
+
+  // the rows a finished step left in the staging buffer `sb` (group g) leave through the TMA unit (thread 0)
+  auto store_rows = [&](const TileUnit& U, int g, const char* sb) {
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+      const int y = 4 * g + r;
+      if (y < U.y_begin || y >= U.y_end) continue;
+      const size_t yo = (size_t)(y - (int)P.out_y0);
+      if (P.out_format == 1) {
+#pragma unroll 1
+        for (int c = 0; c < 3; c++) {
+          const size_t off = ((size_t)c * band_h + yo) * out_row_stride + (size_t)U.x0 * 4;
+          const char* src = sb + (size_t)r * kTStageRow + (size_t)c * kTOut * 4;
+          bulk_s2g(out + off, src, (uint32_t)(U.ncols * 4));
+#pragma unroll 1
+          for (uint32_t q = 0; q < P.nrep; q++) bulk_s2g(P.rep[q] + off, src, (uint32_t)(U.ncols * 4));
+        }
+      } else {
+        const size_t off = yo * out_row_stride + (size_t)U.x0 * pxb;
+        const char* src = sb + (size_t)r * kTStageRow;
+        bulk_s2g(out + off, src, (uint32_t)(U.ncols * pxb));
+#pragma unroll 1
+        for (uint32_t q = 0; q < P.nrep; q++) bulk_s2g(P.rep[q] + off, src, (uint32_t)(U.ncols * pxb));
+      }
+    }
+    bulk_commit();
+  };
 
 #pragma unroll 1
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
@@ -499,12 +542,17 @@ fused_tile_kernel(const __grid_constant__ FrameDev P, char* __restrict__ out, si
     U.tma_out = ((U.ncols * (P.out_format == 1 ? 4 : pxb)) & 15) == 0 && (P.fused & 2u);
     const int bx0 = U.xs0 >> 3;  // block column of strip column 0 (-1 for the first strip)
 
-    // rows each stage must produce: stage i output feeds rem(i) rows of halo
-    int lo[NST], hi[NST];
+    // rows each stage must produce (stage i's output feeds rem(i) rows of halo) and the tiles of a stage that
+    // need the slow path because of the left / right image border
+    int lo[NST], hi[NST], t_lo[NST], t_hi[NST];
 #pragma unroll
     for (int i = 0; i < NST; i++) {
       lo[i] = max(0, U.y_begin - C::rem(i));
       hi[i] = min(U.HI, U.y_end + C::rem(i));
+      // fast iff xs0 + 8t - b >= 0 and xs0 + 8t + 7 + b < W
+      t_lo[i] = U.xs0 < 0 ? 2 : 0;  // (xs0 = -8: tile 0 is outside, tile 1 touches column 0)
+      t_hi[i] = (U.W - 8 - C::border(i) - U.xs0) >> 3;  // last fast tile (may be negative or >= kTBlocks)
+      if (U.W - 8 - C::border(i) - U.xs0 < 0) t_hi[i] = -1;
     }
     const int lo_p = max(0, U.y_begin - H), hi_p = min(U.HI, U.y_end + H);
     const int B0 = lo_p >> 3, B1 = (hi_p - 1) >> 3;
@@ -517,250 +565,265 @@ fused_tile_kernel(const __grid_constant__ FrameDev P, char* __restrict__ out, si
 #pragma unroll 1
     for (int k = k_first; k <= k_last; k++) {
       // ---- finished rows of the previous step leave through the TMA unit ----
-      if (tid == 0 && U.tma_out && staged_k == k - 1) {
-        const int g = (k - 1) - 2 * NST;
-        const char* sb = stage + (size_t)((k - 1) & 1) * 4 * kTStageRow;
-#pragma unroll 1
-        for (int r = 0; r < 4; r++) {
-          const int y = 4 * g + r;
-          if (y < U.y_begin || y >= U.y_end) continue;
-          const size_t yo = (size_t)(y - (int)P.out_y0);
-          if (P.out_format == 1) {
-            for (int c = 0; c < 3; c++) {
-              const size_t off = ((size_t)c * band_h + yo) * out_row_stride + (size_t)U.x0 * 4;
-              const char* src = sb + (size_t)r * kTStageRow + (size_t)c * kTOut * 4;
-              bulk_s2g(out + off, src, (uint32_t)(U.ncols * 4));
-              for (uint32_t q = 0; q < P.nrep; q++) bulk_s2g(P.rep[q] + off, src, (uint32_t)(U.ncols * 4));
-            }
-          } else {
-            const size_t off = yo * out_row_stride + (size_t)U.x0 * pxb;
-            const char* src = sb + (size_t)r * kTStageRow;
-            bulk_s2g(out + off, src, (uint32_t)(U.ncols * pxb));
-            for (uint32_t q = 0; q < P.nrep; q++) bulk_s2g(P.rep[q] + off, src, (uint32_t)(U.ncols * pxb));
-          }
-        }
-        bulk_commit();
-      }
-      // ---- the items of this step ----
+      if (tid == 0 && U.tma_out && staged_k == k - 1) store_rows(U, (k - 1) - 2 * NST, stage + (size_t)((k - 1) & 1) * 4 * kTStageRow);
+
+      // ---- per-step state, hoisted out of the items ----
       const bool prep_on = (k & 1) && ((k + 1) >> 1) >= B0 && ((k + 1) >> 1) <= B1;
       const bool idct_on = !(k & 1) && (k >> 1) >= B0 && (k >> 1) <= B1;
-      int n_items = (idct_on ? kTBlocks / 4 : 0) + (prep_on ? 1 : 0);
-      const int base_filter = n_items;
-      bool st_on[NST];
+      const int base_filter = (idct_on ? kTBlocks / 4 : 0) + (prep_on ? 1 : 0);
+      int n_items = base_filter;
+      uint32_t amap = 0;                 // active filter stages, last first, 4 bits each
+      bool edge_y[NST];
+      int in_off[NST][7];                // per lane: ring offsets of the stage's input rows (fast path)
+      int out_off[NST];                  // per lane: ring offset of the row the lane writes
+      const float* sig_row[NST];
+      float vsm[NST];
+      {
+        int slot = 0;
 #pragma unroll
-      for (int i = 0; i < NST; i++) {
-        const int g = k - 2 * (i + 1);
-        st_on[i] = g >= 0 && 4 * g + 3 >= lo[i] && 4 * g < hi[i];
-        if (st_on[i]) n_items += kTBlocks;
+        for (int i = NST - 1; i >= 0; i--) {
+          const int g = k - 2 * (i + 1);
+          const bool on = g >= 0 && 4 * g + 3 >= lo[i] && 4 * g < hi[i];
+          if (on) {
+            amap |= (uint32_t)i << (4 * slot);
+            slot++;
+            n_items += kTChunks;
+          }
+          constexpr int b = 0;
+          (void)b;
+          const int B = C::border(i);
+          const int NIN = C::in_rows(i);
+          edge_y[i] = (4 * g - B < 0) || (4 * g + 3 + B >= U.HI);
+          const int s0 = mod_n(4 * g - B, NIN) + ly;
+#pragma unroll
+          for (int q = 0; q < 7; q++)
+            if (q <= 2 * B) in_off[i][q] = wrap_n(s0 + q, NIN) * kTRow + lx;
+          if (i + 1 < NST) {
+            const int NOUT = C::in_rows(i + 1 < NST ? i + 1 : i);
+            out_off[i] = wrap_n(mod_n(4 * g, NOUT) + ly, NOUT) * kTRow + lx;
+          } else {
+            out_off[i] = 0;
+          }
+          const int KIND = C::kind(i);
+          if (KIND == kStE0 || KIND == kStE1 || KIND == kStE2) {
+            const int r = min(max(4 * g, 0), U.HI - 1);
+            sig_row[i] = P.sigma + (size_t)(r >> 3) * P.xb + bx0;
+            const int iy = (4 * g + ly) & 7;
+            const float sm_ = P.epf_sm[KIND - kStE0];
+            vsm[i] = (iy == 0 || iy == 7 || lxborder) ? sm_ * P.epf_border_mul : sm_;
+          } else {
+            sig_row[i] = nullptr;
+            vsm[i] = 0.0f;
+          }
+        }
       }
-      if (st_on[NST - 1] && tid == 0) staged_k = k;
+      const bool emit_on = (amap & 15u) == (uint32_t)(NST - 1) && n_items > base_filter;
+      if (emit_on && tid == 0) staged_k = k;
+      char* stg_lane = stage + ((size_t)(k & 1) * 4 + ly) * kTStageRow;
+
+      // ---- one filter tile ----
+      auto tile = [&](auto itag, int t) {
+        constexpr int I = decltype(itag)::value;
+        constexpr int KIND = C::kind(I);
+        constexpr int BORDER = C::border(I);
+        constexpr int NIN = C::in_rows(I);
+        constexpr bool LAST = I == NST - 1;
+        const int g = k - 2 * (I + 1);
+        const int r = 4 * g + ly;
+        const int col = 8 * t + lx;
+        const int x = U.xs0 + col;
+        const float* in_ring = rings + C::ring_off(I);
+        const bool edge = edge_y[I] || t < t_lo[I] || t > t_hi[I];
+        float v[3];
+        bool ok = true;  // the lane produces a pixel
+        auto run = [&](auto edge_tag) {
+          constexpr bool EDGE = decltype(edge_tag)::value;
+          if constexpr (EDGE) ok = x >= 0 && x < U.W && r < U.HI;
+          if (!ok) return;
+          float s = 0.0f, inv_sigma = 0.0f;
+          if constexpr (KIND == kStE0 || KIND == kStE1 || KIND == kStE2) {
+            if constexpr (EDGE) {
+              const int bxs = min(max(bx0 + t, 0), (int)P.xb - 1);
+              s = __ldg(P.sigma + (size_t)(min(r, U.HI - 1) >> 3) * P.xb + bxs);
+            } else {
+              s = __ldg(sig_row[I] + t);
+            }
+            inv_sigma = s * vsm[I];
+          }
+          TileRows<EDGE, BORDER> R;
+          if constexpr (KIND != kStX) {
+            if constexpr (EDGE) tile_rows_edge(R, U, in_ring, NIN, g, col, ly);
+            else tile_rows_fast(R, in_ring + 8 * t, in_off[I]);
+          }
+          if constexpr (KIND == kStG) {
+            tile_gab(P, R, v);
+          } else if constexpr (KIND == kStE0) {
+            if (s < kMinSigma) { v[0] = R.at(3, 0, 3); v[1] = R.at(3, 1, 3); v[2] = R.at(3, 2, 3); }
+            else tile_epf0(P, R, inv_sigma, v);
+          } else if constexpr (KIND == kStE1) {
+            if (s < kMinSigma) { v[0] = R.at(2, 0, 2); v[1] = R.at(2, 1, 2); v[2] = R.at(2, 2, 2); }
+            else tile_epf1(P, R, inv_sigma, v);
+          } else if constexpr (KIND == kStE2) {
+            if (s < kMinSigma) { v[0] = R.at(1, 0, 1); v[1] = R.at(1, 1, 1); v[2] = R.at(1, 2, 1); }
+            else tile_epf2(P, R, inv_sigma, v);
+          } else {
+            const float* p = in_ring + in_off[I][0] + 8 * t;
+            v[0] = p[0]; v[1] = p[kTPitch]; v[2] = p[2 * kTPitch];
+          }
+        };
+        if (edge) run(std::true_type());
+        else run(std::false_type());
+        if (!ok) return;
+        if constexpr (!LAST) {
+          float* o = rings + C::ring_off(I + 1) + out_off[I] + 8 * t;
+          o[0] = v[0];
+          o[kTPitch] = v[1];
+          o[2 * kTPitch] = v[2];
+        } else {
+          if (r < U.y_begin || r >= U.y_end || x >= U.W) return;
+          float a = v[0], b = v[1], c3 = v[2];
+          if constexpr (C::XYB) xyb_to_rgb(P, a, b, c3);
+          if (U.tma_out) {
+            store_px_at<OUTK>(P, stg_lane, (size_t)kTOut * 4, col - kTLead, x, r, a, b, c3);
+          } else {
+            const size_t yo = (size_t)(r - (int)P.out_y0);
+            if (P.out_format == 1)
+              store_px_at<OUTK>(P, out + yo * out_row_stride + (size_t)U.x0 * 4, (size_t)band_h * out_row_stride,
+                                col - kTLead, x, r, a, b, c3);
+            else
+              store_px_at<OUTK>(P, out + yo * out_row_stride + (size_t)U.x0 * pxb, 0, col - kTLead, x, r, a, b, c3);
+          }
+        }
+      };
+      auto chunk = [&](auto itag, int c) {
+        constexpr int I = decltype(itag)::value;
+        constexpr bool LAST = I == NST - 1;
+#pragma unroll 1
+        for (int q = 0; q < kTChunk; q++) {
+          const int t = kTChunk * c + q;
+          if (LAST && (t == 0 || t == kTBlocks - 1)) continue;  // halo block columns produce no output
+          tile(itag, t);
+        }
+      };
 
 #pragma unroll 1
       while (true) {
         int item = 0;
-        if (lane == 0) item = atomicAdd(&ctr[k & 1], 1);
+        if (lane == 0) item = smem_fetch_add(&ctr[k & 1], 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
-        if (item < base_filter) {
-          if (idct_on && item < kTBlocks / 4) {
-            // =================== IDCT item: ranks 4*item .. 4*item+3 of block row B ===================
-            const int B = k >> 1;
-            const int slot = lane >> 3, l = lane & 7;
-            const int rank = 4 * item + slot;
-            mbar_wait(bar, tma_phase);
-            const uint4 rec = recs[rank];
-            const int kind = (int)(rec.x & 0xffu), bxl = (int)((rec.x >> 8) & 0xffu);
-            uint32_t* stg = scratch + rank * kTScratchWords;
-            float* co = reinterpret_cast<float*>(stg);
-            float* tmp = co + 96;
-            Block8ToRing ro;
-            ro.base = rings + (size_t)((B % 3) * 8) * kTRow + bxl * 8;
-            float val[3][8];
-            const bool inl = kind < (int)kBmapSkip;
-            if (inl) {
-              VarblockCtx vb;
-              vb.abx = (uint32_t)(bx0 + bxl);
-              vb.aby = (uint32_t)B;
-              vb.cbase = 0;
-              const float s = P.inv_global_scale / (float)(int)rec.z;
-              vb.sx = s * P.x_dm;
-              vb.sy = s;
-              vb.sb = s * P.b_dm;
-              vb.x_cc = P.cfl_base_x + (float)(int)(int8_t)(rec.w & 0xffu) * P.cfl_scale;
-              vb.b_cc = P.cfl_base_b + (float)(int)(int8_t)((rec.w >> 8) & 0xffu) * P.cfl_scale;
-              int qx[8], qy[8], qb[8];
-              constexpr int kChWords = I32 ? 64 : 32;
-              load_row8_smem<I32>(stg + kChWords, l * 8, qy);
-              load_row8_smem<I32>(stg, l * 8, qx);
-              load_row8_smem<I32>(stg + 2 * kChWords, l * 8, qb);
-              block8_dequant_row(P, kind, vb, l, qx, qy, qb, val);
-            } else {
-#pragma unroll
-              for (int c = 0; c < 3; c++)
-#pragma unroll
-                for (int e = 0; e < 8; e++) val[c][e] = 0.0f;
-            }
-            __syncwarp();  // every lane holds its row: the staging words become the transform's scratch
-            // the (at most four) distinct kinds of the warp's slots, one after the other
-            uint32_t done = 0;
-#pragma unroll 1
-            for (int sidx = 0; sidx < 4; sidx++) {
-              if ((done >> sidx) & 1u) continue;
-              const int kc = __shfl_sync(0xffffffffu, kind, 8 * sidx);
-              const bool act = kind == kc;
-              const uint32_t m = __ballot_sync(0xffffffffu, act);
-              done |= (m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u);
-              if (kc == (int)kBmapSkip) continue;
-              if (kc == (int)kBmapCopy) {
-                if (act) {  // lane l copies pixel row l of the block from the XYB planes
-                  const float* src = P.xyb + ((size_t)B * 8 + l) * P.row_stride + (size_t)(bx0 + bxl) * 8;
-#pragma unroll
-                  for (int c = 0; c < 3; c++) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * P.plane_stride));
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * P.plane_stride) + 1);
-                    float* d = ro.base + (size_t)l * kTRow + c * kTPitch;
-                    *reinterpret_cast<float4*>(d) = a;
-                    *reinterpret_cast<float4*>(d + 4) = b;
-                  }
-                }
-                continue;
-              }
-              block8_transform(kc, act, val, l, co, tmp, ro);
-            }
-            fence_async_smem();  // the scratch is the TMA destination of the next block row
-          } else {
-            // =================== PREP item: block row B's records, sorted by kind; its coefficients ===================
-            const int B = (k + 1) >> 1;
-            const int abx = bx0 + lane;
-            uint4 rec = make_uint4(kBmapSkip, 0u, 1u, 0u);
-            if (abx >= 0 && abx < (int)P.xb && B < (int)P.yb) rec = __ldg(P.bmap + (size_t)B * P.xb + abx);
-            const int kind = (int)(rec.x & 0xffu);
-            // sort key: the kinds in the order of idct8_kernel's lists, then copies, then nothing
-            const int cls = kind == 0 ? 0 : kind == 2 ? 1 : kind == 12 ? 2 : kind == 13 ? 3 : kind == 1 ? 4 : kind == 3 ? 5
-                          : (kind >= 14 && kind <= 17) ? kind - 8 : kind == (int)kBmapCopy ? 10 : 11;
-            int below = 0, within = 0;
-#pragma unroll
-            for (int q = 0; q < 12; q++) {
-              const uint32_t m = __ballot_sync(0xffffffffu, cls == q);
-              if (q < cls) below += __popc(m);
-              if (q == cls) within = __popc(m & ((1u << lane) - 1u));
-            }
-            const int rank = below + within;
-            rec.x = (uint32_t)kind | ((uint32_t)lane << 8);
-            recs[rank] = rec;
-            const bool inl = kind < (int)kBmapSkip;
-            const uint32_t ninl = __popc(__ballot_sync(0xffffffffu, inl));
-            constexpr uint32_t kChBytes = I32 ? 256 : 128;
-            if (lane == 0) mbar_arrive_expect_tx(bar, ninl * 3 * kChBytes);
-            __syncwarp();
-            if (inl) {
-              char* dst = reinterpret_cast<char*>(scratch + rank * kTScratchWords);
-              const size_t e0 = (size_t)rec.y * 64u * (I32 ? 4 : 2);
-#pragma unroll
-              for (int c = 0; c < 3; c++)
-                bulk_g2s(dst + c * kChBytes, reinterpret_cast<const char*>(P.coeff[c]) + e0, kChBytes, bar);
-            }
-          }
+        if (item >= base_filter) {
+          const int fi = item - base_filter;
+          const int si = (int)((amap >> (4 * (fi / kTChunks))) & 15u);
+          const int c = fi % kTChunks;
+          if (si == 0) chunk(IC<0>(), c);
+          if constexpr (NST > 1) { if (si == 1) chunk(IC<1>(), c); }
+          if constexpr (NST > 2) { if (si == 2) chunk(IC<2>(), c); }
+          if constexpr (NST > 3) { if (si == 3) chunk(IC<3>(), c); }
           continue;
         }
-        // =================== filter items: stage i, tile t ===================
-        int fi = item - base_filter;
-        int si = -1;
+        if (idct_on) {
+          // =================== IDCT item: ranks 4*item .. 4*item+3 of block row B ===================
+          const int B = k >> 1;
+          const int slot = lane >> 3, l = lane & 7;
+          const int rank = 4 * item + slot;
+          mbar_wait(bar, tma_phase);
+          const uint4 rec = recs[rank];
+          const int kind = (int)(rec.x & 0xffu), bxl = (int)((rec.x >> 8) & 0xffu);
+          uint32_t* stg = scratch + rank * kTScratchWords;
+          float* co = reinterpret_cast<float*>(stg);
+          float* tmp = co + 96;
+          Block8ToRing ro;
+          ro.base = rings + (size_t)((B % 3) * 8) * kTRow + bxl * 8;
+          float val[3][8];
+          const bool inl = kind < (int)kBmapSkip;
+          if (inl) {
+            VarblockCtx vb;
+            vb.abx = (uint32_t)(bx0 + bxl);
+            vb.aby = (uint32_t)B;
+            vb.cbase = 0;
+            const float s = P.inv_global_scale / (float)(int)rec.z;
+            vb.sx = s * P.x_dm;
+            vb.sy = s;
+            vb.sb = s * P.b_dm;
+            vb.x_cc = P.cfl_base_x + (float)(int)(int8_t)(rec.w & 0xffu) * P.cfl_scale;
+            vb.b_cc = P.cfl_base_b + (float)(int)(int8_t)((rec.w >> 8) & 0xffu) * P.cfl_scale;
+            int qx[8], qy[8], qb[8];
+            constexpr int kChWords = I32 ? 64 : 32;
+            load_row8_smem<I32>(stg + kChWords, l * 8, qy);
+            load_row8_smem<I32>(stg, l * 8, qx);
+            load_row8_smem<I32>(stg + 2 * kChWords, l * 8, qb);
+            block8_dequant_row(P, kind, vb, l, qx, qy, qb, val);
+          } else {
 #pragma unroll
-        for (int i = NST - 1; i >= 0; i--) {  // later (heavier) stages first
-          if (si < 0 && st_on[i]) {
-            if (fi < kTBlocks) si = i;
-            else fi -= kTBlocks;
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+              for (int e = 0; e < 8; e++) val[c][e] = 0.0f;
+          }
+          __syncwarp();  // every lane holds its row: the staging words become the transform's scratch
+          // the (at most four) distinct kinds of the warp's slots, one after the other
+          uint32_t done = 0;
+#pragma unroll 1
+          for (int sidx = 0; sidx < 4; sidx++) {
+            if ((done >> sidx) & 1u) continue;
+            const int kc = __shfl_sync(0xffffffffu, kind, 8 * sidx);
+            const bool act = kind == kc;
+            const uint32_t m = __ballot_sync(0xffffffffu, act);
+            done |= (m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u);
+            if (kc == (int)kBmapSkip) continue;
+            if (kc == (int)kBmapCopy) {
+              if (act) {  // lane l copies pixel row l of the block from the XYB planes
+                const float* src = P.xyb + ((size_t)B * 8 + l) * P.row_stride + (size_t)(bx0 + bxl) * 8;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                  const float4 a = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * P.plane_stride));
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * P.plane_stride) + 1);
+                  float* d = ro.base + (size_t)l * kTRow + c * kTPitch;
+                  *reinterpret_cast<float4*>(d) = a;
+                  *reinterpret_cast<float4*>(d + 4) = b;
+                }
+              }
+              continue;
+            }
+            block8_transform(kc, act, val, l, co, tmp, ro);
+          }
+          fence_async_smem();  // the scratch is the TMA destination of the next block row
+        } else {
+          // =================== PREP item: block row B's records, sorted by kind; its coefficients ===================
+          const int B = (k + 1) >> 1;
+          const int abx = bx0 + lane;
+          uint4 rec = make_uint4(kBmapSkip, 0u, 1u, 0u);
+          if (abx >= 0 && abx < (int)P.xb && B < (int)P.yb) rec = __ldg(P.bmap + (size_t)B * P.xb + abx);
+          const int kind = (int)(rec.x & 0xffu);
+          // sort key: the kinds in the order of idct8_kernel's lists, then copies, then nothing
+          const int cls = kind == 0 ? 0 : kind == 2 ? 1 : kind == 12 ? 2 : kind == 13 ? 3 : kind == 1 ? 4 : kind == 3 ? 5
+                        : (kind >= 14 && kind <= 17) ? kind - 8 : kind == (int)kBmapCopy ? 10 : 11;
+          int below = 0, within = 0;
+#pragma unroll
+          for (int q = 0; q < 12; q++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, cls == q);
+            if (q < cls) below += __popc(m);
+            if (q == cls) within = __popc(m & ((1u << lane) - 1u));
+          }
+          const int rank = below + within;
+          rec.x = (uint32_t)kind | ((uint32_t)lane << 8);
+          recs[rank] = rec;
+          const bool inl = kind < (int)kBmapSkip;
+          const uint32_t ninl = __popc(__ballot_sync(0xffffffffu, inl));
+          constexpr uint32_t kChBytes = I32 ? 256 : 128;
+          if (lane == 0) mbar_arrive_expect_tx(bar, ninl * 3 * kChBytes);
+          __syncwarp();
+          if (inl) {
+            char* dst = reinterpret_cast<char*>(scratch + rank * kTScratchWords);
+            const size_t e0 = (size_t)rec.y * 64u * (I32 ? 4 : 2);
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+              bulk_g2s(dst + c * kChBytes, reinterpret_cast<const char*>(P.coeff[c]) + e0, kChBytes, bar);
           }
         }
-        const int t = fi;
-        const int col = 8 * t + lx;
-        const int x = U.xs0 + col;
-        auto stage_item = [&](auto itag) {
-          constexpr int I = decltype(itag)::value;
-          constexpr int KIND = C::kind(I);
-          constexpr int BORDER = C::border(I);
-          constexpr int NIN = C::in_rows(I);
-          constexpr bool LAST = I == NST - 1;
-          const int g = k - 2 * (I + 1);
-          const int r = 4 * g + ly;
-          const float* in_ring = rings + C::ring_off(I);
-          if (LAST && (t == 0 || t == kTBlocks - 1)) return;  // halo block columns produce no output
-          // does the tile touch the image border (mirroring, partial rows / columns)?
-          const bool edge = (4 * g - BORDER < 0) || (4 * g + 3 + BORDER >= U.HI) || (U.xs0 + 8 * t - BORDER < 0) ||
-                            (U.xs0 + 8 * t + 7 + BORDER >= U.W);
-          float v[3];
-          bool ok = true;  // the lane produces a pixel
-          auto run = [&](auto edge_tag) {
-            constexpr bool EDGE = decltype(edge_tag)::value;
-            if constexpr (EDGE) ok = x >= 0 && x < U.W && r < U.HI;
-            if (!ok) return;
-            float s = 0.0f, inv_sigma = 0.0f;
-            if constexpr (KIND == kStE0 || KIND == kStE1 || KIND == kStE2) {
-              const int bxs = min(max(bx0 + t, 0), (int)P.xb - 1);
-              s = __ldg(P.sigma + (size_t)(min(r, U.HI - 1) >> 3) * P.xb + bxs);
-              const int iy = r & 7;
-              const float sm_ = P.epf_sm[KIND - kStE0];
-              const float vsm = (iy == 0 || iy == 7 || lx == 0 || lx == 7) ? sm_ * P.epf_border_mul : sm_;
-              inv_sigma = s * vsm;
-            }
-            if constexpr (KIND == kStG) {
-              TileRows<EDGE, 1> R;
-              tile_rows_init(R, U, in_ring, NIN, g, col, ly);
-              tile_gab(P, R, v);
-            } else if constexpr (KIND == kStE0) {
-              TileRows<EDGE, 3> R;
-              tile_rows_init(R, U, in_ring, NIN, g, col, ly);
-              if (s < kMinSigma) { v[0] = R.at(3, 0, 3); v[1] = R.at(3, 1, 3); v[2] = R.at(3, 2, 3); }
-              else tile_epf0(P, R, inv_sigma, v);
-            } else if constexpr (KIND == kStE1) {
-              TileRows<EDGE, 2> R;
-              tile_rows_init(R, U, in_ring, NIN, g, col, ly);
-              if (s < kMinSigma) { v[0] = R.at(2, 0, 2); v[1] = R.at(2, 1, 2); v[2] = R.at(2, 2, 2); }
-              else tile_epf1(P, R, inv_sigma, v);
-            } else if constexpr (KIND == kStE2) {
-              TileRows<EDGE, 1> R;
-              tile_rows_init(R, U, in_ring, NIN, g, col, ly);
-              if (s < kMinSigma) { v[0] = R.at(1, 0, 1); v[1] = R.at(1, 1, 1); v[2] = R.at(1, 2, 1); }
-              else tile_epf2(P, R, inv_sigma, v);
-            } else {
-              const float* p = in_ring + wrap_n(mod_n(4 * g, NIN) + ly, NIN) * kTRow + col;
-              v[0] = p[0]; v[1] = p[kTPitch]; v[2] = p[2 * kTPitch];
-            }
-          };
-          if (edge) run(std::true_type());
-          else run(std::false_type());
-          if (!ok) return;
-          if constexpr (!LAST) {
-            constexpr int NOUT = C::in_rows(I + 1);
-            float* o = rings + C::ring_off(I + 1) + wrap_n(mod_n(4 * g, NOUT) + ly, NOUT) * kTRow + col;
-            o[0] = v[0];
-            o[kTPitch] = v[1];
-            o[2 * kTPitch] = v[2];
-          } else {
-            if (r < U.y_begin || r >= U.y_end || x >= U.W) return;
-            float a = v[0], b = v[1], c3 = v[2];
-            if constexpr (C::XYB) xyb_to_rgb(P, a, b, c3);
-            if (U.tma_out) {
-              char* row0 = stage + ((size_t)(k & 1) * 4 + ly) * kTStageRow;
-              store_px_at<OUTK>(P, row0, (size_t)kTOut * 4, col - kTLead, x, r, a, b, c3);
-            } else {
-              const size_t yo = (size_t)(r - (int)P.out_y0);
-              if (P.out_format == 1)
-                store_px_at<OUTK>(P, out + yo * out_row_stride + (size_t)U.x0 * 4, (size_t)band_h * out_row_stride,
-                                  col - kTLead, x, r, a, b, c3);
-              else
-                store_px_at<OUTK>(P, out + yo * out_row_stride + (size_t)U.x0 * pxb, 0, col - kTLead, x, r, a, b, c3);
-            }
-          }
-        };
-        if (si == 0) stage_item(IC<0>());
-        if constexpr (NST > 1) { if (si == 1) stage_item(IC<1>()); }
-        if constexpr (NST > 2) { if (si == 2) stage_item(IC<2>()); }
-        if constexpr (NST > 3) { if (si == 3) stage_item(IC<3>()); }
       }
       // ---- end of step ----
-      if (st_on[NST - 1] && U.tma_out) fence_async_smem();  // staged rows -> visible to the TMA unit
+      if (emit_on && U.tma_out) fence_async_smem();  // staged rows -> visible to the TMA unit
       if (tid == 0) {
         ctr[(k + 1) & 1] = 0;
         bulk_wait_read_all();  // the rows staged two steps ago have left: their buffer is written next step
@@ -770,28 +833,7 @@ fused_tile_kernel(const __grid_constant__ FrameDev P, char* __restrict__ out, si
     }
     // the last step's rows
     if (tid == 0 && U.tma_out && staged_k == k_last) {
-      const int g = k_last - 2 * NST;
-      const char* sb = stage + (size_t)(k_last & 1) * 4 * kTStageRow;
-#pragma unroll 1
-      for (int r = 0; r < 4; r++) {
-        const int y = 4 * g + r;
-        if (y < U.y_begin || y >= U.y_end) continue;
-        const size_t yo = (size_t)(y - (int)P.out_y0);
-        if (P.out_format == 1) {
-          for (int c = 0; c < 3; c++) {
-            const size_t off = ((size_t)c * band_h + yo) * out_row_stride + (size_t)U.x0 * 4;
-            const char* src = sb + (size_t)r * kTStageRow + (size_t)c * kTOut * 4;
-            bulk_s2g(out + off, src, (uint32_t)(U.ncols * 4));
-            for (uint32_t q = 0; q < P.nrep; q++) bulk_s2g(P.rep[q] + off, src, (uint32_t)(U.ncols * 4));
-          }
-        } else {
-          const size_t off = yo * out_row_stride + (size_t)U.x0 * pxb;
-          const char* src = sb + (size_t)r * kTStageRow;
-          bulk_s2g(out + off, src, (uint32_t)(U.ncols * pxb));
-          for (uint32_t q = 0; q < P.nrep; q++) bulk_s2g(P.rep[q] + off, src, (uint32_t)(U.ncols * pxb));
-        }
-      }
-      bulk_commit();
+      store_rows(U, k_last - 2 * NST, stage + (size_t)(k_last & 1) * 4 * kTStageRow);
       bulk_wait_read_all();
     }
     __syncthreads();

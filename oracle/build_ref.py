@@ -163,10 +163,11 @@ def build_gpu_variant() -> int:
     hdrs.append(repo / "include" / "jxl_b200.h")
     new_objs = {}
     for rel in PATCHED:
-        src = patched_dir / Path(rel).name
+        src = patched_dir / rel
         o = OBJ / "gpu" / (Path(rel).stem + ".o")
         if not (o.exists() and o.stat().st_mtime >= max([src.stat().st_mtime] + [h.stat().st_mtime for h in hdrs])):
-            cmd = ["g++", *CXXFLAGS, *COMMON_DEFS, *includes(), *extra, "-c", str(src), "-o", str(o)]
+            # the patched tree first: dec_group.cc re-includes itself per Highway target (see patch_libjxl.py)
+            cmd = ["g++", *CXXFLAGS, *COMMON_DEFS, f"-I{patched_dir}", *includes(), *extra, "-c", str(src), "-o", str(o)]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError(f"compile failed: {' '.join(cmd)}\n{r.stderr[-6000:]}")

@@ -13,18 +13,27 @@ from libjxl_b200 import abi, pipeline
 from tests import support
 
 
-@pytest.fixture(scope="module")
-def emu_pipe():
+@pytest.fixture(scope="module", params=["two-kernel", "fused"])
+def emu_pipe(request):
+    """Every test of this file runs twice: through the two-kernel path (plan -> IDCT kernels -> strip filter,
+    the default) and through the fused decode kernel (JXLGPU_FUSED=1, read when the context is created)."""
+    import os
     from tests.emu import build_emu
     so = build_emu.build()
     saved = pipeline._lib
     pipeline._lib = pipeline.bind(C.CDLL(str(so)))      # the emulated library instead of libjxl_b200.so
+    old = os.environ.get("JXLGPU_FUSED")
+    os.environ["JXLGPU_FUSED"] = "1" if request.param == "fused" else "0"
     try:
         p = pipeline.TransformPipeline(device=0, num_host_threads=2)
         yield p
         p.close()
     finally:
         pipeline._lib = saved
+        if old is None:
+            os.environ.pop("JXLGPU_FUSED", None)
+        else:
+            os.environ["JXLGPU_FUSED"] = old
 
 
 def oracle(desc, coeffs):
@@ -365,7 +374,7 @@ def test_emulated_fused_equals_two_kernel_path(emu_pipe, monkeypatch):
     in every output format the fused kernel stages through shared memory."""
     from tests.emu import build_emu
     desc, coeffs = wl.synthetic_frame(500, 90, seed=3, gab=1, epf_iters=1, ac_type=abi.AC_INT32)
-    monkeypatch.setenv("JXLGPU_FUSED", "0")
+    monkeypatch.setenv("JXLGPU_FUSED", "1")    # (the fixture's context is one of the two; this one is the fused kernel)
     two = pipeline.TransformPipeline(device=0, num_host_threads=1)
     try:
         for fmt in (abi.OUT_RGB_F32, abi.OUT_PLANAR_F32, abi.OUT_RGB_U8, abi.OUT_RGBA_U8, abi.OUT_RGB_U16, abi.OUT_RGB_F16):

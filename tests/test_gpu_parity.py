@@ -12,11 +12,22 @@ from tests import support
 pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("built")]
 
 
-@pytest.fixture(scope="module")
-def pipe():
-    p = pipeline.TransformPipeline(device=0, num_host_threads=4)
-    yield p
-    p.close()
+@pytest.fixture(scope="module", params=["two-kernel", "fused"])
+def pipe(request):
+    """Both device paths: plan -> IDCT kernels -> strip filter (default) and the fused decode kernel
+    (JXLGPU_FUSED=1, read when the context is created)."""
+    import os
+    old = os.environ.get("JXLGPU_FUSED")
+    os.environ["JXLGPU_FUSED"] = "1" if request.param == "fused" else "0"
+    try:
+        p = pipeline.TransformPipeline(device=0, num_host_threads=4)
+        yield p
+        p.close()
+    finally:
+        if old is None:
+            os.environ.pop("JXLGPU_FUSED", None)
+        else:
+            os.environ["JXLGPU_FUSED"] = old
 
 
 def oracle(desc, coeffs):

@@ -64,9 +64,11 @@ print("RESULT " + json.dumps(res))
 """
 
 
-def run_child(mode, cases):
+def run_child(mode, cases, sparse=True):
     code = CHILD.format(root=str(ROOT), cases=cases)
-    r = subprocess.run([sys.executable, "-c", code, mode], capture_output=True, text=True, timeout=1500, cwd=str(ROOT))
+    env = dict(os.environ, JXLB_GPU_SPARSE="1" if sparse else "0")
+    r = subprocess.run([sys.executable, "-c", code, mode], capture_output=True, text=True, timeout=1500, cwd=str(ROOT),
+                       env=env)
     assert r.returncode == 0, r.stderr[-4000:]
     import json
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
@@ -79,7 +81,7 @@ def test_patch_anchors_match_the_reference(tmp_path):
         pytest.skip("no reference tree on this box")
     subprocess.check_call([sys.executable, str(ROOT / "integration" / "patch_libjxl.py"), str(REF_ROOT), str(tmp_path)])
     for name in ("dec_frame.cc", "dec_group.cc"):
-        assert "jxlb_integration::" in (tmp_path / name).read_text()
+        assert "jxlb_integration::" in (tmp_path / "lib" / "jxl" / name).read_text()
 
 
 def test_patched_decoder_without_device_is_the_stock_decoder():
@@ -101,14 +103,15 @@ def test_patched_decoder_without_device_is_the_stock_decoder():
 
 
 @pytest.mark.timeout(1800)
-def test_patched_decoder_through_the_emulated_library():
+@pytest.mark.parametrize("sparse", [True, False], ids=["sparse-lists", "dense-blocks"])
+def test_patched_decoder_through_the_emulated_library(sparse):
     """.jxl bytes -> public JxlDecoder API -> patched FrameDecoder -> C ABI -> (emulated) kernels -> the
     application's buffer; compared with the stock decoder's pixels."""
     need_gpu_variant()
     import torch
     if torch.cuda.is_available():
         pytest.skip("a device is present: covered by the gpu test")
-    res = run_child("emu", [(300, 200, 1.0, -1, "f32"), (520, 264, 2.0, 2, "f32"), (300, 200, 1.0, -1, "u8")])
+    res = run_child("emu", [(300, 200, 1.0, -1, "f32"), (520, 264, 2.0, 2, "f32"), (300, 200, 1.0, -1, "u8")], sparse)
     for k, v in res.items():
         assert v["taken"] == 1, (k, v)               # the frame really went through the backend
         if k.endswith("u8"):                         # the application's default: 8-bit sRGB, dithered
@@ -119,10 +122,13 @@ def test_patched_decoder_through_the_emulated_library():
 
 @pytest.mark.gpu
 @pytest.mark.timeout(1800)
-def test_patched_decoder_on_the_gpu():
+@pytest.mark.parametrize("sparse", [True, False], ids=["sparse-lists", "dense-blocks"])
+def test_patched_decoder_on_the_gpu(sparse):
+    """sparse: the patched entropy decoder (lib/jxl/dec_group.cc:515-534) appends non-zero coefficients to
+    per-thread lists that go to jxlgpu_submit_groups_sparse; dense: pinned [group][3][65536] blocks."""
     need_gpu_variant()
     res = run_child("gpu", [(1000, 700, 1.0, -1, "f32"), (2048, 1100, 2.0, 2, "f32"), (777, 333, 0.5, 0, "f32"),
-                            (1500, 900, 4.0, 3, "f32"), (1000, 700, 1.0, -1, "u8")])
+                            (1500, 900, 4.0, 3, "f32"), (1000, 700, 1.0, -1, "u8")], sparse)
     for k, v in res.items():
         assert v["taken"] == 1, (k, v)
         if k.endswith("u8"):
