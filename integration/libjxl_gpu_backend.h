@@ -117,7 +117,6 @@ struct GpuBackend {
         if (const char* d = getenv("JXLB_GPU_DEVICE")) cfg.device = atoi(d);
         if (jxlgpu_create(&ctx, &cfg) != JXLGPU_OK) ctx = nullptr;
       }
-      if (const char* sp = getenv("JXLB_GPU_SPARSE")) want_sparse = sp[0] != '0';
     }
     return ctx;
   }
@@ -255,7 +254,9 @@ inline bool WantFrame(const jxl::FrameHeader& fh, jxl::PassesDecoderState* ds, c
   // lists, bump-allocated (a group never needs more words than its dense block: larger lists are handed
   // over dense, see GroupDecoded)
   std::unique_ptr<jxl::ACImage> store;
-  const bool sparse = be.want_sparse;
+  // JXLB_GPU_SPARSE=0: dense [group][3][65536] blocks instead of non-zero lists (read per frame)
+  const char* sp = getenv("JXLB_GPU_SPARSE");
+  const bool sparse = sp ? sp[0] != '0' : be.want_sparse;
   if (sparse) {
     if (!ArenaAlloc(num_groups * 3 * 65536 * sizeof(uint32_t))) return false;
     store.reset(new SinkACImage(use_16_bit));

@@ -85,6 +85,11 @@ struct jxlgpu_ctx {
   size_t host_out_stride = 0;
   int stream_error = 0;
   DevBuf acs, quant, sharp, ytox, ytob, dc, dq, coeff, coeff_off, sigma, list, counts, xyb, out;
+  // multi-GPU gather through the copy engines: finished row chunks are copied to the peers' frame buffers on
+  // side streams while the next chunk is filtered (JXLGPU_GATHER=kernel keeps the in-kernel replay)
+  cudaStream_t rep_streams[8] = {};
+  cudaEvent_t ev_chunk[8] = {}, ev_rep[8] = {};
+  bool gather_in_kernel = false;
   DevBuf bmap;                // fused path: one 16-byte record per 8x8 block (plan kernel)
   // JXLGPU_FUSED=1 selects the fused decode kernel (jxl_fused.cuh).  Opt-in: on B200 it moves 2x fewer DRAM
   // bytes than the two-kernel path but is slower (1.33 ms vs 0.66 ms at 8K d1.0, profiles/r02_*fused*).
@@ -429,6 +434,7 @@ int jxlgpu_create(jxlgpu_ctx** out, const jxlgpu_config* cfg) {
                          prepare_fused_mask<30>()})
     if (ea != cudaSuccess) return bail(ea, "cudaFuncSetAttribute(fused_tile_kernel)");
   if (const char* fe = getenv("JXLGPU_FUSED")) ctx->allow_fused = fe[0] == '1';
+  if (const char* ge = getenv("JXLGPU_GATHER")) ctx->gather_in_kernel = ge[0] == 'k';
   {
     const char* env = getenv("JXLGPU_FORCE_GENERIC_FILTER");
     ctx->force_generic_filter = env && env[0] == '1';
@@ -462,6 +468,11 @@ void jxlgpu_destroy(jxlgpu_ctx* ctx) {
     if (ev) cudaEventDestroy(ev);
   for (cudaStream_t s : {ctx->stream, ctx->s_mid, ctx->s_large, ctx->s_down})
     if (s) cudaStreamDestroy(s);
+  for (int i = 0; i < 8; i++) {
+    if (ctx->rep_streams[i]) cudaStreamDestroy(ctx->rep_streams[i]);
+    if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+    if (ctx->ev_rep[i]) cudaEventDestroy(ctx->ev_rep[i]);
+  }
   delete ctx;
 }
 
@@ -892,7 +903,47 @@ int jxlgpu_render_device(jxlgpu_ctx* ctx, void* dev_out, size_t out_stride_bytes
   }
   int rc = launch_idct(ctx, ctx->need_row0, ctx->need_row1, P.need_y0, P.need_y1, s);
   if (rc) return rc;
-  return launch_filter(ctx, P.band_y0, P.band_y1, P.band_y0, band_h, o, stride, s);
+  if (!P.nrep || P.mc || ctx->gather_in_kernel || use_fused(ctx))
+    return launch_filter(ctx, P.band_y0, P.band_y1, P.band_y0, band_h, o, stride, s);
+  // Gather through the copy engines: the band is filtered in row chunks; as soon as a chunk is finished its
+  // rows travel to every peer's frame buffer (peer-mapped addresses, NVLink) on side streams while the SMs
+  // filter the next chunk.  The kernels run without the replay instantiation.
+  const uint32_t nrep = P.nrep;
+  for (uint32_t q = 0; q < nrep; q++) {
+    if (!ctx->rep_streams[q]) CU(cudaStreamCreateWithFlags(&ctx->rep_streams[q], cudaStreamNonBlocking));
+    if (!ctx->ev_rep[q]) CU(cudaEventCreateWithFlags(&ctx->ev_rep[q], cudaEventDisableTiming));
+  }
+  for (int i = 0; i < 8; i++)
+    if (!ctx->ev_chunk[i]) CU(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+  uint32_t chunk_rows = (band_h / 4 + 7) & ~7u;
+  if (chunk_rows < 256) chunk_rows = 256;
+  char* rep[8];
+  for (uint32_t q = 0; q < nrep; q++) rep[q] = P.rep[q];
+  ctx->P.nrep = 0;  // (the kernels of this call do not replicate)
+  const size_t planes = out_planes(P.out_format);
+  int chunk = 0;
+  for (uint32_t y0 = P.band_y0; y0 < P.band_y1 && !rc; y0 += chunk_rows, chunk++) {
+    const uint32_t y1 = y0 + chunk_rows < P.band_y1 ? y0 + chunk_rows : P.band_y1;
+    rc = launch_filter(ctx, y0, y1, P.band_y0, band_h, o, stride, s);
+    if (rc) break;
+    cudaEvent_t ev = ctx->ev_chunk[chunk & 7];
+    CU(cudaEventRecord(ev, s));
+    for (uint32_t q = 0; q < nrep; q++) {
+      const uint32_t peer = (q + (uint32_t)chunk) % nrep;  // (start every chunk at a different peer)
+      CU(cudaStreamWaitEvent(ctx->rep_streams[peer], ev, 0));
+      for (size_t pl = 0; pl < planes; pl++) {
+        const size_t off = (pl * band_h + (y0 - P.band_y0)) * stride;
+        CU(cudaMemcpyAsync(rep[peer] + off, o + off, (size_t)(y1 - y0) * stride, cudaMemcpyDeviceToDevice,
+                           ctx->rep_streams[peer]));
+      }
+    }
+  }
+  ctx->P.nrep = nrep;
+  for (uint32_t q = 0; q < nrep && !rc; q++) {  // the caller's stream continues when every copy has landed
+    CU(cudaEventRecord(ctx->ev_rep[q], ctx->rep_streams[q]));
+    CU(cudaStreamWaitEvent(s, ctx->ev_rep[q], 0));
+  }
+  return rc;
 }
 
 int jxlgpu_frame_finish(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes) {
