@@ -313,6 +313,13 @@ def run_replicas(args, rank: int, local_rank: int, world: int) -> int:
     pipe = pipeline.TransformPipeline(device=local_rank, num_host_threads=1)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
+    # a 1080p frame fills about a quarter of the SMs: NPIPE contexts on their own streams keep several
+    # frames in flight (device-resident throughput number); the e2e / latency loop below uses one context
+    NPIPE = 4
+    pipes = [pipe] + [pipeline.TransformPipeline(device=local_rank, num_host_threads=1) for _ in range(NPIPE - 1)]
+    side = [torch.cuda.Stream() for _ in range(NPIPE)]
+    ev_start = torch.cuda.Event()
+    ev_side = [torch.cuda.Event() for _ in range(NPIPE)]
     descs = [pipeline.pin_side_info(f["desc"]) for f in frames]
     dev = [torch.from_numpy(f["coeffs"]).cuda() for f in frames]
     ptrs = [[d[c].data_ptr() for c in range(3)] for d in dev]
@@ -320,10 +327,17 @@ def run_replicas(args, rank: int, local_rank: int, world: int) -> int:
     row_bytes = w * 12
 
     def batch_device():
+        ev_start.record(stream)
+        for q in range(NPIPE):
+            side[q].wait_event(ev_start)
         for i, d in enumerate(descs):
-            pipe.set_device_coefficients(ptrs[i])
-            pipe.frame_begin(d)
-            pipe.render_device(outs[i].data_ptr(), row_bytes, stream.cuda_stream)
+            q = i % NPIPE
+            pipes[q].set_device_coefficients(ptrs[i])
+            pipes[q].frame_begin(d)
+            pipes[q].render_device(outs[i].data_ptr(), row_bytes, side[q].cuda_stream)
+        for q in range(NPIPE):   # join: the timing events live on `stream`
+            ev_side[q].record(side[q])
+            stream.wait_event(ev_side[q])
 
     for _ in range(max(3, args.warmup)):
         batch_device()
@@ -334,14 +348,14 @@ def run_replicas(args, rank: int, local_rank: int, world: int) -> int:
     barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = pipe.launch_count()
+    launches0 = sum(p_.launch_count() for p_ in pipes)
     ev0.record(stream)
     for _ in range(args.steps):
         batch_device()
     ev1.record(stream)
     torch.cuda.synchronize()
     barrier()
-    launches = pipe.launch_count() - launches0
+    launches = sum(p_.launch_count() for p_ in pipes) - launches0
     t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -353,6 +367,8 @@ def run_replicas(args, rank: int, local_rank: int, world: int) -> int:
         peak = max(peak, float(np.abs(outs[i].cpu().numpy() - f["decoded"]).max()))
 
     # ---- end to end: host coefficient blocks -> host pixels, frame by frame ----
+    for p_ in pipes[1:]:
+        p_.close()
     pipe.set_device_coefficients(None)
     host = []
     h2d = d2h = 0
@@ -409,7 +425,7 @@ def run_replicas(args, rank: int, local_rank: int, world: int) -> int:
             "config": {"workload": f"64x1080p: batch of {NF} independent {w}x{h} VarDCT d{dist_} e{effort} frames (seeds 0..{NF - 1}), "
                                    "frame-per-GPU replicas round-robin over the ranks, no collective; one step = the whole batch; "
                                    "output interleaved linear RGB f32",
-                       "parallelism": f"{world} x replicas", "frames_per_rank": len(mine),
+                       "parallelism": f"{world} x replicas", "frames_per_rank": len(mine), "contexts_per_rank": NPIPE,
                        "l2": f"batch working set per rank {len(mine) * (3 * frames[0]['coeffs'][0].nbytes + 2 * w * h * 12) / 1e6:.0f} MB"},
             "e2e": {"value": NF * w * h / float(te.item()) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": int(by[0].item()),
                     "d2h_bytes_per_step": int(by[1].item()), "steps": n_e2e, "submit": "dense",

@@ -58,6 +58,8 @@ struct jxlgpu_ctx {
   cudaStream_t stream = nullptr;                 // compute (and side-info upload) stream
   cudaStream_t s_mid = nullptr, s_large = nullptr, s_down = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_mid = nullptr, ev_large = nullptr, ev_filter = nullptr, ev_ext = nullptr;
+  cudaEvent_t ev_ext_done = nullptr;  // last render_device on a caller's stream: the next frame_begin's uploads wait for it
+  bool ext_pending = false;
   std::vector<cudaStream_t> up_streams;
   std::vector<cudaEvent_t> up_events;
   // row_events[r]: recorded on the upload stream after the latest copy of AC-group row r, so that
@@ -225,7 +227,7 @@ int launch_idct(jxlgpu_ctx* ctx, uint32_t row0, uint32_t row1, uint32_t need_y0,
   if ((uint32_t)grid8 > px_blocks / 32u + 1u) grid8 = (int)(px_blocks / 32u + 1u);
   int grid_mid = ctx->num_sms * 2, grid_large = ctx->num_sms * 2;
   if ((uint32_t)grid_mid > px_blocks / 32u + 1u) grid_mid = (int)(px_blocks / 32u + 1u);
-  if ((uint32_t)grid_large > px_blocks / 64u + 1u) grid_large = (int)(px_blocks / 64u + 1u);
+  if ((uint32_t)grid_large > px_blocks / 16u + 1u) grid_large = (int)(px_blocks / 16u + 1u);
   // The mid/large kernels usually have little work: run them beside the 8x8 kernel (fork/join)
   // unless per-kernel times are being measured.
   cudaStream_t sm = prof ? s : ctx->s_mid, sl = prof ? s : ctx->s_large;
@@ -246,8 +248,15 @@ int launch_idct(jxlgpu_ctx* ctx, uint32_t row0, uint32_t row1, uint32_t need_y0,
   if (P.ac_is32) idct_mid_kernel<true><<<grid_mid, kSmallWarpsPerCta * 32, 0, sm>>>(P);
   else idct_mid_kernel<false><<<grid_mid, kSmallWarpsPerCta * 32, 0, sm>>>(P);
   if (prof) CU(cudaEventRecord(ctx->prof_ev[3], s));
-  if (P.ac_is32) idct_large_kernel<true><<<grid_large, 256, 0, sl>>>(P);
-  else idct_large_kernel<false><<<grid_large, 256, 0, sl>>>(P);
+  // two launches: row slabs, then column slabs (jxl_kernels.cuh: large_item)
+  constexpr size_t kLargeSmem = kLargeSmemFloats * sizeof(float);
+  if (P.ac_is32) {
+    idct_large_kernel<true, 0><<<grid_large, kLargeWarps * 32, kLargeSmem, sl>>>(P);
+    idct_large_kernel<true, 1><<<grid_large, kLargeWarps * 32, kLargeSmem, sl>>>(P);
+  } else {
+    idct_large_kernel<false, 0><<<grid_large, kLargeWarps * 32, kLargeSmem, sl>>>(P);
+    idct_large_kernel<false, 1><<<grid_large, kLargeWarps * 32, kLargeSmem, sl>>>(P);
+  }
   if (prof) CU(cudaEventRecord(ctx->prof_ev[4], s));
   if (!prof) run8();  // after the (usually tiny) side kernels grabbed their few SM slots
   if (!prof) {
@@ -256,7 +265,7 @@ int launch_idct(jxlgpu_ctx* ctx, uint32_t row0, uint32_t row1, uint32_t need_y0,
     CU(cudaStreamWaitEvent(s, ctx->ev_mid, 0));
     CU(cudaStreamWaitEvent(s, ctx->ev_large, 0));
   }
-  ctx->launches += fused ? 3 : 4;
+  ctx->launches += fused ? 4 : 5;
   CU(cudaGetLastError());
   return JXLGPU_OK;
 }
@@ -414,7 +423,7 @@ int jxlgpu_create(jxlgpu_ctx** out, const jxlgpu_config* cfg) {
   ctx->num_sms = prop.multiProcessorCount;
   for (cudaStream_t* sp : {&ctx->stream, &ctx->s_mid, &ctx->s_large, &ctx->s_down})
     if ((e = cudaStreamCreateWithFlags(sp, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
-  for (cudaEvent_t* ep : {&ctx->ev_fork, &ctx->ev_mid, &ctx->ev_large, &ctx->ev_filter, &ctx->ev_ext})
+  for (cudaEvent_t* ep : {&ctx->ev_fork, &ctx->ev_mid, &ctx->ev_large, &ctx->ev_filter, &ctx->ev_ext, &ctx->ev_ext_done})
     if ((e = cudaEventCreateWithFlags(ep, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
   ctx->up_streams.resize(ctx->num_threads);
   ctx->up_events.resize(ctx->num_threads);
@@ -425,6 +434,11 @@ int jxlgpu_create(jxlgpu_ctx** out, const jxlgpu_config* cfg) {
   if ((e = cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(kFilterSmemFloats * sizeof(float)))) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(filter_kernel)");
+  for (cudaError_t ea : {cudaFuncSetAttribute(idct_large_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLargeSmemFloats * sizeof(float))),
+                         cudaFuncSetAttribute(idct_large_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLargeSmemFloats * sizeof(float))),
+                         cudaFuncSetAttribute(idct_large_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLargeSmemFloats * sizeof(float))),
+                         cudaFuncSetAttribute(idct_large_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLargeSmemFloats * sizeof(float)))})
+    if (ea != cudaSuccess) return bail(ea, "cudaFuncSetAttribute(idct_large_kernel)");
   for (cudaError_t ea : {prepare_strip_mask<16>(), prepare_strip_mask<17>(), prepare_strip_mask<20>(),
                          prepare_strip_mask<21>(), prepare_strip_mask<28>(), prepare_strip_mask<29>(),
                          prepare_strip_mask<30>(), prepare_strip_mask<31>()})
@@ -464,7 +478,7 @@ void jxlgpu_destroy(jxlgpu_ctx* ctx) {
     if (ev) cudaEventDestroy(ev);
   for (auto ev : ctx->prof_ev)
     if (ev) cudaEventDestroy(ev);
-  for (cudaEvent_t ev : {ctx->ev_fork, ctx->ev_mid, ctx->ev_large, ctx->ev_filter, ctx->ev_ext})
+  for (cudaEvent_t ev : {ctx->ev_fork, ctx->ev_mid, ctx->ev_large, ctx->ev_filter, ctx->ev_ext, ctx->ev_ext_done})
     if (ev) cudaEventDestroy(ev);
   for (cudaStream_t s : {ctx->stream, ctx->s_mid, ctx->s_large, ctx->s_down})
     if (s) cudaStreamDestroy(s);
@@ -558,6 +572,10 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   // host-fed coefficients live group-major on the device: [group][channel][65536]
   if (!ctx->coeff_external) CU(ctx->coeff.ensure((size_t)ctx->num_groups * 3 * 65536 * ctx->elem_size));
   cudaStream_t s = ctx->stream;
+  if (ctx->ext_pending) {  // kernels of the previous frame may still read the side information on the caller's stream
+    CU(cudaStreamWaitEvent(s, ctx->ev_ext_done, 0));
+    ctx->ext_pending = false;
+  }
   CU(upload_plane<uint8_t>(ctx->acs.p, f->ac_strategy, f->ac_strategy_stride, xb, yb, s));
   CU(upload_plane<int32_t>(ctx->quant.p, f->raw_quant, f->raw_quant_stride, xb, yb, s));
   if (f->epf_sharpness) CU(upload_plane<uint8_t>(ctx->sharp.p, f->epf_sharpness, f->epf_sharpness_stride, xb, yb, s));
@@ -872,6 +890,8 @@ int jxlgpu_set_device_coefficients(jxlgpu_ctx* ctx, const void* const dev_coeff[
   return JXLGPU_OK;
 }
 
+static int render_device_on(jxlgpu_ctx* ctx, void* dev_out, size_t out_stride_bytes, cudaStream_t s);
+
 int jxlgpu_render_device(jxlgpu_ctx* ctx, void* dev_out, size_t out_stride_bytes, void* cuda_stream) {
   if (!ctx) return JXLGPU_ERR_INVALID_ARGUMENT;
   if (!ctx->in_frame) return JXLGPU_ERR_STATE;
@@ -882,6 +902,17 @@ int jxlgpu_render_device(jxlgpu_ctx* ctx, void* dev_out, size_t out_stride_bytes
     CU(cudaEventRecord(ctx->ev_ext, ctx->stream));
     CU(cudaStreamWaitEvent(s, ctx->ev_ext, 0));
   }
+  const int rc = render_device_on(ctx, dev_out, out_stride_bytes, s);
+  if (cuda_stream && rc == JXLGPU_OK) {
+    // the context's buffers (side information, work lists, XYB planes) are busy until this render has run:
+    // the next frame_begin / render on another stream is ordered behind it
+    CU(cudaEventRecord(ctx->ev_ext_done, s));
+    ctx->ext_pending = true;
+  }
+  return rc;
+}
+
+static int render_device_on(jxlgpu_ctx* ctx, void* dev_out, size_t out_stride_bytes, cudaStream_t s) {
   const FrameDev& P = ctx->P;
   const uint32_t band_h = P.band_y1 - P.band_y0;
   char* o = (char*)dev_out;

@@ -945,10 +945,12 @@ __global__ void __launch_bounds__(kSmallWarpsPerCta * 32) idct_mid_kernel(const 
 // Pass 1 writes the horizontally transformed rows into the varblock's own region of
 // the output plane; pass 2 transforms the columns in place.
 // ---------------------------------------------------------------------------
-// Warp-cooperative N-point IDCT (N = 128, 256) on a vector in shared memory:
-// recursion levels down to 32-point leaves done by all lanes, leaves in registers.
-template <int N>
-__device__ __forceinline__ void idct1d_warp(float* v /*N*/, float* w /*N scratch*/) {
+// Warp-cooperative N-point IDCTs (N = 128, 256) on TOT / N vectors stored back to back in shared memory
+// (a segment of the recursion never straddles two vectors, so the batch is just a longer index range):
+// recursion levels down to 32-point leaves done by all lanes, leaves in registers, one leaf per lane --
+// with TOT = 1024 every lane has a leaf.
+template <int N, int TOT>
+__device__ __forceinline__ void idct1d_warp(float* v /*TOT*/, float* w /*TOT scratch*/) {
   const int lane = threadIdx.x & 31;
   // top-down: even/odd split + BTranspose of the odd half, sizes N, N/2, ..., 64
   float* src = v;
@@ -956,7 +958,7 @@ __device__ __forceinline__ void idct1d_warp(float* v /*N*/, float* w /*N scratch
 #pragma unroll
   for (int n = N; n > 32; n >>= 1) {
     const int h = n >> 1;
-    for (int i = lane; i < N; i += 32) {
+    for (int i = lane; i < TOT; i += 32) {
       const int seg = i / n, r = i % n;  // element r of segment seg
       const float* s = src + seg * n;
       float val;
@@ -971,8 +973,8 @@ __device__ __forceinline__ void idct1d_warp(float* v /*N*/, float* w /*N scratch
     __syncwarp();
     float* t = src; src = dst; dst = t;
   }
-  // leaves: N/32 independent 32-point IDCTs
-  if (lane < N / 32) {
+  // leaves: TOT/32 independent 32-point IDCTs
+  if (lane < TOT / 32) {
     float r[32];
 #pragma unroll
     for (int i = 0; i < 32; i++) r[i] = src[lane * 32 + i];
@@ -985,7 +987,7 @@ __device__ __forceinline__ void idct1d_warp(float* v /*N*/, float* w /*N scratch
 #pragma unroll
   for (int n = 64; n <= N; n <<= 1) {
     const int h = n >> 1;
-    for (int i = lane; i < N / 2; i += 32) {
+    for (int i = lane; i < TOT / 2; i += 32) {
       const int seg = i / h, r = i % h;
       const float* s = src + seg * n;
       const float wv = JXT_WC[h - 2 + r];
@@ -997,115 +999,158 @@ __device__ __forceinline__ void idct1d_warp(float* v /*N*/, float* w /*N scratch
     float* t = src; src = dst; dst = t;
   }
   if (src != v) {
-    for (int i = lane; i < N; i += 32) v[i] = src[i];
+    for (int i = lane; i < TOT; i += 32) v[i] = src[i];
     __syncwarp();
   }
 }
 
-template <int N>
-__device__ __forceinline__ constexpr bool in_regs() { return N <= 64; }
+// Work items of the two passes.  A 256x256 varblock is 196 K coefficients: one CTA per varblock (round 1)
+// left the handful of largest varblocks of a frame running alone for milliseconds, so each pass is cut into
+// slabs -- pass 0: rows of one channel, pass 1: columns of one channel -- that spread over the grid, and the
+// two passes are two launches (the only dependency between them is per varblock).
+constexpr int kLargeWarps = 8;
+template <int R, int C>
+__host__ __device__ constexpr int large_rows_per_item() { return C <= 64 ? 256 : kLargeWarps * (1024 / C); }
+template <int R, int C>
+__host__ __device__ constexpr int large_slabs(int pass) {
+  return pass == 0 ? (3 * R + large_rows_per_item<R, C>() - 1) / large_rows_per_item<R, C>()
+                   : (R <= 64 ? (3 * C + 255) / 256 : 3 * C / 32);
+}
+// shared memory (floats): llf 1024 | llf_tmp 1024 | per-warp transform buffers 8 x 2048 | (pass 1) a
+// [R][33] tile of 32 columns, aliasing the LLF area and growing past the buffers
+constexpr int kLargeCoopOff = 2048;
+constexpr int kLargeTileOff = kLargeCoopOff + kLargeWarps * 2048;
+constexpr int kLargeSmemFloats = kLargeTileOff + 256 * 33;
 
-template <int R, int C, bool I32>
-__device__ __forceinline__ void large_item(const FrameDev& P, int kind, uint4 entry, float* sm) {
+template <int R, int C, bool I32, int PASS>
+__device__ __forceinline__ void large_item(const FrameDev& P, int kind, uint4 entry, int slab, float* sm) {
   constexpr int CY = R / 8, CX = C / 8;
   const int tid = threadIdx.x;
-  float* llf = sm;                 // 3 * CY*CX
-  float* llf_tmp = sm + 3 * 1024;  // CY*CX
-  float* coop = sm + 4 * 1024;     // 8 warps * 2 * 256
+  const int warp = tid >> 5, lane = tid & 31;
+  float* llf = sm;                   // <= 1024 floats
+  float* llf_tmp = sm + 1024;        // CY*CX
+  float* coop = sm + kLargeCoopOff;  // 8 warps * 2 * 1024
   const VarblockCtx vb = make_ctx(P, entry);
-  for (int c = 0; c < 3; c++)
-    llf_from_dc<CY, CX>(P.dc + (size_t)c * P.yb * P.xb + (size_t)vb.aby * P.xb + vb.abx, P.xb, tid,
-                        llf_tmp, llf + c * CY * CX, BlockSync());
-  // ---- pass 1: rows (c, j): IDCT over horizontal frequency ----
-  if constexpr (C <= 64) {
-    for (int r = tid; r < 3 * R; r += blockDim.x) {
-      const int c = r / R, j = r % R;
-      float v[C];
+  if constexpr (PASS == 0) {
+    // ---- pass 0: rows (c, j): IDCT over horizontal frequency, into the varblock's region of the planes ----
+    if constexpr (C <= 64) {
+      for (int c = 0; c < 3; c++)  // (tiny: at most 16 x 8 values per channel)
+        llf_from_dc<CY, CX>(P.dc + (size_t)c * P.yb * P.xb + (size_t)vb.aby * P.xb + vb.abx, P.xb, tid,
+                            llf_tmp, llf + c * CY * CX, BlockSync());
+      const int r = slab * 256 + tid;
+      if (r < 3 * R) {
+        const int c = r / R, j = r % R;
+        float v[C];
 #pragma unroll
-      for (int k = 0; k < C; k++) {
-        const uint32_t i = (R >= C) ? (uint32_t)(k * R + j) : (uint32_t)(j * C + k);
-        v[k] = dequant<I32>(P, vb, kind, c, i);
+        for (int k = 0; k < C; k++) {
+          const uint32_t i = (R >= C) ? (uint32_t)(k * R + j) : (uint32_t)(j * C + k);
+          v[k] = dequant<I32>(P, vb, kind, c, i);
+        }
+        if (j < CY) {
+#pragma unroll
+          for (int k = 0; k < CX; k++) v[k] = llf[c * CY * CX + j * CX + k];
+        }
+        idct1d<C>(v);
+        float* out = P.xyb + (size_t)c * P.plane_stride + ((size_t)vb.aby * 8 + j) * P.row_stride + vb.abx * 8;
+#pragma unroll
+        for (int x = 0; x < C; x += 4)
+          *reinterpret_cast<float4*>(out + x) = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
       }
-      if (j < CY) {
-#pragma unroll
-        for (int k = 0; k < CX; k++) v[k] = llf[c * CY * CX + j * CX + k];
-      }
-      idct1d<C>(v);
-      float* out = P.xyb + (size_t)c * P.plane_stride + ((size_t)vb.aby * 8 + j) * P.row_stride + vb.abx * 8;
-#pragma unroll
-      for (int x = 0; x < C; x += 4)
-        *reinterpret_cast<float4*>(out + x) = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
-    }
-  } else {
-    const int warp = tid >> 5, lane = tid & 31;
-    float* buf = coop + warp * 512;
-    for (int r = warp; r < 3 * R; r += blockDim.x >> 5) {
-      const int c = r / R, j = r % R;
-      for (int k = lane; k < C; k += 32) {
+    } else {
+      constexpr int NB = 1024 / C;                 // rows per warp
+      constexpr int RPI = kLargeWarps * NB;        // rows per item, all of one channel (R % RPI == 0)
+      static_assert(R % RPI == 0, "a slab stays inside one channel");
+      const int c = (slab * RPI) / R, j0 = (slab * RPI) % R;
+      if (j0 == 0)  // the slab holds the rows with the lowest vertical frequencies
+        llf_from_dc<CY, CX>(P.dc + (size_t)c * P.yb * P.xb + (size_t)vb.aby * P.xb + vb.abx, P.xb, tid,
+                            llf_tmp, llf, BlockSync());
+      float* buf = coop + warp * 2048;
+      const int jw = j0 + warp * NB;
+      for (int e = lane; e < NB * C; e += 32) {
+        const int b = e / C, k = e % C, j = jw + b;
         const uint32_t i = (R >= C) ? (uint32_t)(k * R + j) : (uint32_t)(j * C + k);
         float val = dequant<I32>(P, vb, kind, c, i);
-        if (j < CY && k < CX) val = llf[c * CY * CX + j * CX + k];
-        buf[k] = val;
+        if (j < CY && k < CX) val = llf[j * CX + k];
+        buf[e] = val;
       }
       __syncwarp();
-      idct1d_warp<C>(buf, buf + 256);
-      float* out = P.xyb + (size_t)c * P.plane_stride + ((size_t)vb.aby * 8 + j) * P.row_stride + vb.abx * 8;
-      for (int x = lane; x < C; x += 32) out[x] = buf[x];
+      idct1d_warp<C, 1024>(buf, buf + 1024);
+      for (int b = 0; b < NB; b++) {
+        float* out = P.xyb + (size_t)c * P.plane_stride + ((size_t)vb.aby * 8 + jw + b) * P.row_stride + vb.abx * 8;
+        for (int x = lane; x < C; x += 32) out[x] = buf[b * C + x];
+      }
       __syncwarp();
-    }
-  }
-  __syncthreads();
-  // ---- pass 2: columns (c, x): IDCT over vertical frequency, in place ----
-  if constexpr (R <= 64) {
-    for (int r = tid; r < 3 * C; r += blockDim.x) {
-      const int c = r / C, x = r % C;
-      float* col = P.xyb + (size_t)c * P.plane_stride + (size_t)vb.aby * 8 * P.row_stride + vb.abx * 8 + x;
-      float u[R];
-#pragma unroll
-      for (int j = 0; j < R; j++) u[j] = col[(size_t)j * P.row_stride];
-      idct1d<R>(u);
-#pragma unroll
-      for (int y = 0; y < R; y++) col[(size_t)y * P.row_stride] = u[y];
     }
   } else {
-    const int warp = tid >> 5, lane = tid & 31;
-    float* buf = coop + warp * 512;
-    for (int r = warp; r < 3 * C; r += blockDim.x >> 5) {
-      const int c = r / C, x = r % C;
-      float* col = P.xyb + (size_t)c * P.plane_stride + (size_t)vb.aby * 8 * P.row_stride + vb.abx * 8 + x;
-      for (int j = lane; j < R; j += 32) buf[j] = col[(size_t)j * P.row_stride];
+    // ---- pass 1: columns (c, x): IDCT over vertical frequency, in place ----
+    if constexpr (R <= 64) {
+      const int r = slab * 256 + tid;
+      if (r < 3 * C) {
+        const int c = r / C, x = r % C;
+        float* col = P.xyb + (size_t)c * P.plane_stride + (size_t)vb.aby * 8 * P.row_stride + vb.abx * 8 + x;
+        float u[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) u[j] = col[(size_t)j * P.row_stride];
+        idct1d<R>(u);
+#pragma unroll
+        for (int y = 0; y < R; y++) col[(size_t)y * P.row_stride] = u[y];
+      }
+    } else {
+      // 32 columns of one channel: the [R][32] tile travels between the plane and shared memory in
+      // full 128-byte rows; each warp transforms 4 of its columns at a time
+      constexpr int XS = C / 32;  // column slabs per channel
+      const int c = slab / XS, x0 = (slab % XS) * 32;
+      float* tile = sm + kLargeTileOff;  // [R][33]
+      float* base = P.xyb + (size_t)c * P.plane_stride + (size_t)vb.aby * 8 * P.row_stride + vb.abx * 8 + x0;
+      for (int j = warp; j < R; j += kLargeWarps) tile[j * 33 + lane] = base[(size_t)j * P.row_stride + lane];
+      __syncthreads();
+      float* buf = coop + warp * 2048;
+      for (int e = lane; e < 4 * R; e += 32) buf[e] = tile[(e % R) * 33 + 4 * warp + e / R];
       __syncwarp();
-      idct1d_warp<R>(buf, buf + 256);
-      for (int y = lane; y < R; y += 32) col[(size_t)y * P.row_stride] = buf[y];
-      __syncwarp();
+      idct1d_warp<R, 4 * R>(buf, buf + 1024);
+      for (int e = lane; e < 4 * R; e += 32) tile[(e % R) * 33 + 4 * warp + e / R] = buf[e];
+      __syncthreads();
+      for (int j = warp; j < R; j += kLargeWarps) base[(size_t)j * P.row_stride + lane] = tile[j * 33 + lane];
     }
   }
   __syncthreads();
 }
 
-constexpr int kLargeSmemFloats = 4 * 1024 + 8 * 512;
-
-template <bool I32>
-__global__ void __launch_bounds__(256) idct_large_kernel(const __grid_constant__ FrameDev P) {
-  __shared__ __align__(16) float sm[kLargeSmemFloats];
+template <bool I32, int PASS>
+__global__ void __launch_bounds__(kLargeWarps * 32) idct_large_kernel(const __grid_constant__ FrameDev P) {
+  extern __shared__ __align__(16) float fsm[];
+  float* sm = fsm;
   uint32_t base = 0;
 #pragma unroll 1
   for (int s = kNumStrategies - 1; s >= kFirstLarge; s--) {
-    const uint32_t count = P.counts[s];
+    int slabs;
+    switch (s) {
+      case 18: slabs = large_slabs<64, 64>(PASS); break;
+      case 19: slabs = large_slabs<64, 32>(PASS); break;
+      case 20: slabs = large_slabs<32, 64>(PASS); break;
+      case 21: slabs = large_slabs<128, 128>(PASS); break;
+      case 22: slabs = large_slabs<128, 64>(PASS); break;
+      case 23: slabs = large_slabs<64, 128>(PASS); break;
+      case 24: slabs = large_slabs<256, 256>(PASS); break;
+      case 25: slabs = large_slabs<256, 128>(PASS); break;
+      default: slabs = large_slabs<128, 256>(PASS); break;
+    }
+    const uint32_t count = P.counts[s] * (uint32_t)slabs;
     uint32_t it = (blockIdx.x + gridDim.x - (base % gridDim.x)) % gridDim.x;
 #pragma unroll 1
     for (; it < count; it += gridDim.x) {
-      const uint4 entry = __ldg(P.list + P.list_base[s] + it);
+      const uint4 entry = __ldg(P.list + P.list_base[s] + it / (uint32_t)slabs);
+      const int slab = (int)(it % (uint32_t)slabs);
       switch (s) {
-        case 18: large_item<64, 64, I32>(P, s, entry, sm); break;
-        case 19: large_item<64, 32, I32>(P, s, entry, sm); break;
-        case 20: large_item<32, 64, I32>(P, s, entry, sm); break;
-        case 21: large_item<128, 128, I32>(P, s, entry, sm); break;
-        case 22: large_item<128, 64, I32>(P, s, entry, sm); break;
-        case 23: large_item<64, 128, I32>(P, s, entry, sm); break;
-        case 24: large_item<256, 256, I32>(P, s, entry, sm); break;
-        case 25: large_item<256, 128, I32>(P, s, entry, sm); break;
-        default: large_item<128, 256, I32>(P, s, entry, sm); break;
+        case 18: large_item<64, 64, I32, PASS>(P, s, entry, slab, sm); break;
+        case 19: large_item<64, 32, I32, PASS>(P, s, entry, slab, sm); break;
+        case 20: large_item<32, 64, I32, PASS>(P, s, entry, slab, sm); break;
+        case 21: large_item<128, 128, I32, PASS>(P, s, entry, slab, sm); break;
+        case 22: large_item<128, 64, I32, PASS>(P, s, entry, slab, sm); break;
+        case 23: large_item<64, 128, I32, PASS>(P, s, entry, slab, sm); break;
+        case 24: large_item<256, 256, I32, PASS>(P, s, entry, slab, sm); break;
+        case 25: large_item<256, 128, I32, PASS>(P, s, entry, slab, sm); break;
+        default: large_item<128, 256, I32, PASS>(P, s, entry, slab, sm); break;
       }
     }
     base += count;
@@ -1627,8 +1672,14 @@ struct StripCfg {
   // ring sizes (rows, power of two >= 2*border+2) of each stage's input; 0 when absent
   static constexpr int NG = G ? 4 : 0, N0 = E0 ? 8 : 0, N1 = E1 ? 8 : 0, N2 = E2 ? 4 : 0;
   static constexpr int kRows = NG + N0 + N1 + N2;
-  static constexpr size_t kSmemBytes = ((size_t)(kRows ? kRows : 1) * 3 * kStripThreads + 2 * kStripPad) * sizeof(float);
-  static constexpr int kOutCols = kStripThreads - 2 * H;
+  // Chains with an EPF pass run those passes on a PERMUTATION of the strip's 32 block columns, the blocks whose
+  // sigma engages the filter first (see filter_strip_body): the strip then starts on a block boundary.
+  static constexpr bool kCompact = E0 || E1 || E2;
+  static constexpr int LEAD = kCompact ? 8 : H;  // strip column of the first output column
+  static constexpr size_t kListBytes = kCompact ? 4 * 32 * 8 : 0;  // [4 block rows][32] permutation + sigma
+  static constexpr size_t kSmemBytes =
+      ((size_t)(kRows ? kRows : 1) * 3 * kStripThreads + 2 * kStripPad) * sizeof(float) + kListBytes;
+  static constexpr int kOutCols = kStripThreads - 2 * LEAD;
 };
 
 __device__ __forceinline__ float* ring_row(float* ring, int n, int r, int c) {
@@ -1643,13 +1694,15 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
   constexpr int H = C::H;
   const int t = threadIdx.x;
   const int W = (int)P.xsize, HI = (int)P.ysize;
-  const int x = x0 - H + t;  // image column of this thread
+  constexpr int LEAD = C::LEAD;
+  const int xs0 = x0 - LEAD;  // image column of strip column 0 (a multiple of 8 when the chain has an EPF pass)
+  const int x = xs0 + t;      // image column of this thread
   const bool xin = x >= 0 && x < W;
   const int xs = min(max(x, 0), W - 1) >> 3;  // sigma column (clamped: garbage lanes stay in bounds)
   // strip-relative indices of the horizontal neighbours x-3 .. x+3 (mirrored at the image edge)
   int cn[7];
 #pragma unroll
-  for (int d = -3; d <= 3; d++) cn[d + 3] = EDGE ? (mirror_i(x + d, W) - (x0 - H)) : (t + d);
+  for (int d = -3; d <= 3; d++) cn[d + 3] = EDGE ? (mirror_i(x + d, W) - xs0) : (t + d);
 #ifdef JXLB_EMU_CLAMP_GARBAGE_LANES
   // ThreadSanitizer build of tests/emu only: the outermost H lanes of a strip compute values nobody reads
   // and, with cn = t + d, read a few floats of the neighbouring ring row while its owner writes them -- a
@@ -1664,6 +1717,10 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
   float* ring0 = ringG + C::NG * 3 * kStripThreads;
   float* ring1 = ring0 + C::N0 * 3 * kStripThreads;
   float* ring2 = ring1 + C::N1 * 3 * kStripThreads;
+  // EPF block permutation: for each of the (up to four) block rows in flight, the strip's 32 block columns
+  // ordered "sigma engages the filter" first, and the blocks' inverse sigmas
+  int* permv = reinterpret_cast<int*>(ring2 + C::N2 * 3 * kStripThreads + kStripPad);
+  float* sigv = reinterpret_cast<float*>(permv + 4 * 32);
 
   // halo consumed after each stage: that stage computes lanes [h, 256 - h)
   constexpr int hG = C::G ? 1 : 0;
@@ -1675,14 +1732,13 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
   auto lo = [&](int rem) { return max(0, y_begin - rem); };
   auto hi = [&](int rem) { return min(HI, y_end + rem); };
 
-  const float kMinSigma = -3.90524291751269967465540850526868f;
-  const bool xborder = ((x & 7) == 0 || (x & 7) == 7);
+  const bool xborder = ((x & 7) == 0 || (x & 7) == 7);  // (compact chains: the same for every column a lane is given)
   const int band_h = (int)P.out_h;
-  const bool emit_lane = xin && t >= H && t < kStripThreads - H;
 
   // Final step of the chain: XYB -> linear RGB (dec_xyb-inl.h:38-86) and the global store.
-  auto emit = [&](int r, float a, float b, float c3) {
-    if (!emit_lane) return;
+  auto emit = [&](int r, int col, float a, float b, float c3) {
+    const int xe = xs0 + col;
+    if (!(col >= LEAD && col < kStripThreads - LEAD && xe < W)) return;
     if constexpr (C::XYB) {
       float gr = b + a, gg = b - a, gb = c3;
       gr = gr - P.opsin_cbrt[0];
@@ -1697,7 +1753,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
       lr = fmaf(P.opsin_m[2], mb, lr); lg = fmaf(P.opsin_m[5], mb, lg); lb = fmaf(P.opsin_m[8], mb, lb);
       a = lr; b = lg; c3 = lb;
     }
-    store_px<OUTK>(P, out, out_row_stride, r - (int)P.out_y0, x, band_h, a, b, c3);
+    store_px<OUTK>(P, out, out_row_stride, r - (int)P.out_y0, xe, band_h, a, b, c3);
   };
   // cumulative delays (steps between loading row r and the stage producing row r)
   constexpr int dG = C::G ? 2 : 0;
@@ -1706,6 +1762,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
   constexpr int d2 = d1 + (C::E2 ? 2 : 0);
   const int r_in_lo = lo(H), r_in_hi = hi(H);
   const int r_end = hi(0) + d2;  // after this many input-row steps the last output row is out
+  const float kMinSigma = -3.90524291751269967465540850526868f;
 
   // row r_in_lo is fetched up front, every later row one step ahead of its use
   float pre_a = 0.0f, pre_b = 0.0f, pre_c = 0.0f;
@@ -1718,10 +1775,59 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
 
   // inverse sigma of each EPF stage's next row, fetched one step ahead as well.  A stage's first
   // produced row is max(0, y_begin - rem) (its `lo`), reached at step lo + delay.
-  float sg0 = 0.0f, sg1 = 0.0f, sg2 = 0.0f;
-  if (C::E0) sg0 = __ldg(P.sigma + (size_t)(lo(H - h0) >> 3) * P.xb + xs);
-  if (C::E1) sg1 = __ldg(P.sigma + (size_t)(lo(H - h1) >> 3) * P.xb + xs);
-  if (C::E2) sg2 = __ldg(P.sigma + (size_t)(lo(0) >> 3) * P.xb + xs);
+  // ---- EPF block permutation ----
+  // The filter is skipped where a block's sigma is below kMinSigma (stage_epf.cc:121-128) -- on typical frames
+  // most blocks.  With one column per lane a warp spans four blocks and runs the EPF arithmetic as soon as one
+  // of them is engaged, three quarters of its lanes masked off.  Instead every EPF pass works on a permutation
+  // of the strip's 32 block columns, engaged blocks first: lane t handles column 8 * perm[t / 8] + t % 8, so
+  // the engaged blocks fill whole warps and the remaining warps only copy their pixels through.  The
+  // permutation of a block row is built by warp 0 when the loader reaches the row above it.
+  auto build_lists = [&](int row) {
+    if constexpr (C::kCompact) {
+      if (t < 32) {
+        const int br = row >> 3;
+        const int bx = (xs0 >> 3) + t;
+        float sv = -1e30f;  // outside the image: never engaged
+        if (bx >= 0 && bx < (int)P.xb) sv = __ldg(P.sigma + (size_t)br * P.xb + bx);
+        const bool act = !(sv < kMinSigma);
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        const unsigned lt = (1u << t) - 1u;
+        const int pos = act ? __popc(m & lt) : __popc(m) + __popc(~m & lt);
+        permv[(br & 3) * 32 + pos] = t;
+        sigv[(br & 3) * 32 + t] = sv;
+      }
+    }
+  };
+  // per EPF pass: the column this lane handles in the pass's current block row, that block's inverse sigma,
+  // and (edge strips) the mirrored strip columns col-3 .. col+3
+  int colE0 = t, colE1 = t, colE2 = t;
+  float sgE0 = 0.0f, sgE1 = 0.0f, sgE2 = 0.0f;
+  int cnE0[7], cnE1[7], cnE2[7];
+#pragma unroll
+  for (int k = 0; k < 7; k++) cnE0[k] = cnE1[k] = cnE2[k] = cn[k];
+  auto load_sel = [&](int r, int& col, float& sg, int* cnk) {
+    const int slot = (r >> 3) & 3;
+    const int b = permv[slot * 32 + (t >> 3)];
+    col = 8 * b + (t & 7);
+    sg = sigv[slot * 32 + b];
+    if constexpr (EDGE) {
+#pragma unroll
+      for (int d = -3; d <= 3; d++) cnk[d + 3] = mirror_i(xs0 + col + d, W) - xs0;
+    }
+#ifdef JXLB_EMU_CLAMP_GARBAGE_LANES
+    for (int k = 0; k < 7; k++) cnk[k] = min(max(EDGE ? cnk[k] : col + k - 3, 0), kStripThreads - 1);
+#endif
+  };
+  // does the lane produce column `col` of a pass whose cumulative halo is `h`?
+  auto lane_run = [&](auto steady_tag, int col, int h) {
+    constexpr bool ST = decltype(steady_tag)::value;
+    if constexpr (ST && !EDGE) return true;
+    const int xc = xs0 + col;
+    bool ok = xc >= 0 && xc < W;
+    if constexpr (!ST) ok = ok && col >= h && col < kStripThreads - h;
+    return ok;
+  };
+  if (r_in_lo < r_in_hi) build_lists(r_in_lo);
 
   // One pipeline step.
   //   ST (steady): every stage has an in-range, unmirrored row; lanes are not range-checked (only
@@ -1742,7 +1848,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
     };
     // Hand a stage's result (row rin - D) to the next stage's ring, or emit it after the last stage.
     // `which`: 0 = loader output, 1 = Gaborish, 2 = EPF0, 3 = EPF1, 4 = EPF2.
-    auto deliver = [&](auto which_tag, int r, float X, float Y, float B) {
+    auto deliver = [&](auto which_tag, int r, int col, float X, float Y, float B) {
       constexpr int which = decltype(which_tag)::value;
       constexpr int D = which == 0 ? 0 : (which == 1 ? dG : (which == 2 ? d0 : (which == 3 ? d1 : d2)));
       constexpr bool toG = which < 1 && C::G;
@@ -1755,17 +1861,20 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
       else if constexpr (to1) dst = RP(ring1, IC<C::N1 ? C::N1 : 1>(), IC<-D>(), r);
       else if constexpr (to2) dst = RP(ring2, IC<C::N2 ? C::N2 : 1>(), IC<-D>(), r);
       if constexpr (toG || to0 || to1 || to2) {
-        dst[t] = X;
-        dst[kStripThreads + t] = Y;
-        dst[2 * kStripThreads + t] = B;
+        dst[col] = X;
+        dst[kStripThreads + col] = Y;
+        dst[2 * kStripThreads + col] = B;
       } else {
-        emit(r, X, Y, B);
+        emit(r, col, X, Y, B);
       }
     };
     const bool lane_ok = (ST && !EDGE) ? true : xin;
     // ---- loader: XYB row rin was fetched during the previous step (its latency hid behind that
     // step's arithmetic); hand it on and start fetching row rin + 1 ----
-    if ((ST || rin < r_in_hi) && xin) deliver(IC<0>(), rin, pre_a, pre_b, pre_c);
+    if ((ST || rin < r_in_hi) && xin) deliver(IC<0>(), rin, t, pre_a, pre_b, pre_c);
+    if constexpr (C::kCompact) {  // the block row that starts with the next input row
+      if ((J >= 0 ? J == 7 : ((rin + 1) & 7) == 0) && rin + 1 < r_in_hi) build_lists(rin + 1);
+    }
     if (rin + 1 < r_in_hi && xin) {
       const size_t off = (size_t)(rin + 1) * P.row_stride + x;
       pre_a = __ldg(P.xyb + off);
@@ -1789,15 +1898,18 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
           const float sum2 = (pT[cn[2]] + pT[cn[4]]) + (pB[cn[2]] + pB[cn[4]]);
           v[c] = fmaf(sum2, P.gab_w[3 * c + 2], fmaf(sum1, P.gab_w[3 * c + 1], pM[t] * P.gab_w[3 * c]));
         }
-        deliver(IC<1>(), r, v[0], v[1], v[2]);
+        deliver(IC<1>(), r, t, v[0], v[1], v[2]);
       }
     }
     // ---- EPF0 (stage_epf.cc:54-193) ----
     if constexpr (C::E0) {
       const int r = rin - d0;
-      if ((ST || (r >= lo(H - h0) && r < hi(H - h0) && t >= h0 && t < kStripThreads - h0)) && lane_ok) {
-        const float s = sg0;
-        sg0 = __ldg(P.sigma + (size_t)(min(max(r + 1, 0), HI - 1) >> 3) * P.xb + xs);
+      const bool row_on = ST || (r >= lo(H - h0) && r < hi(H - h0));
+      if (row_on && !(J >= 0 && ((J - d0) & 7) != 0)) load_sel(r, colE0, sgE0, cnE0);
+      const int col = colE0;
+      const int* cnk = cnE0;
+      if (row_on && lane_run(steady_tag, col, h0)) {
+        const float s = sgE0;
         const float* rows[7];
         rows[0] = RP(ring0, IC<C::N0>(), IC<-d0 - 3>(), mr(r - 3));
         rows[1] = RP(ring0, IC<C::N0>(), IC<-d0 - 2>(), mr(r - 2));
@@ -1806,9 +1918,9 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
         rows[4] = RP(ring0, IC<C::N0>(), IC<-d0 + 1>(), mr(r + 1));
         rows[5] = RP(ring0, IC<C::N0>(), IC<-d0 + 2>(), mr(r + 2));
         rows[6] = RP(ring0, IC<C::N0>(), IC<-d0 + 3>(), mr(r + 3));
-        float X = rows[3][t];
-        float Y = rows[3][kStripThreads + t];
-        float B = rows[3][2 * kStripThreads + t];
+        float X = rows[3][col];
+        float Y = rows[3][kStripThreads + col];
+        float B = rows[3][2 * kStripThreads + col];
         if (!(s < kMinSigma)) {
           const int iy = r & 7;
           const float sm_ = P.epf_sm[0];
@@ -1831,7 +1943,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
 #pragma unroll
               for (int b = 0; b < 7; b++)
                 if ((a > 3 ? a - 3 : 3 - a) + (b > 3 ? b - 3 : 3 - b) <= 3)
-                  v[a][b] = rows[a][c * kStripThreads + cn[b]];
+                  v[a][b] = rows[a][c * kStripThreads + (EDGE ? cnk[b] : col + b - 3)];
             const float scale = P.epf_scale[c];
 #pragma unroll
             for (int k = 0; k < 12; k++) {
@@ -1863,19 +1975,23 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
           const float inv_w = 1.0f / w;
           X = X * inv_w; Y = Y * inv_w; B = B * inv_w;
         }
-        deliver(IC<2>(), r, X, Y, B);
+        deliver(IC<2>(), r, col, X, Y, B);
       }
     }
     // ---- EPF1 (stage_epf.cc:197-379) ----
     if constexpr (C::E1) {
       const int r = rin - d1;
-      if ((ST || (r >= lo(H - h1) && r < hi(H - h1) && t >= h1 && t < kStripThreads - h1)) && lane_ok) {
-        const float s = sg1;
-        sg1 = __ldg(P.sigma + (size_t)(min(max(r + 1, 0), HI - 1) >> 3) * P.xb + xs);
+      const bool row_on = ST || (r >= lo(H - h1) && r < hi(H - h1));
+      if (row_on && !(J >= 0 && ((J - d1) & 7) != 0)) load_sel(r, colE1, sgE1, cnE1);
+      const int col = colE1;
+      const int* cnk = cnE1;
+      auto CC = [&](int d) { return EDGE ? cnk[d + 3] : col + d; };
+      if (row_on && lane_run(steady_tag, col, h1)) {
+        const float s = sgE1;
         const float* q2x = RP(ring1, IC<C::N1>(), IC<-d1>(), r);
-        float X = q2x[t];
-        float Y = q2x[kStripThreads + t];
-        float B = q2x[2 * kStripThreads + t];
+        float X = q2x[col];
+        float Y = q2x[kStripThreads + col];
+        float B = q2x[2 * kStripThreads + col];
         if (!(s < kMinSigma)) {
           const int iy = r & 7;
           const float sm_ = P.epf_sm[1];
@@ -1894,9 +2010,9 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
             const float* q2 = q2x + c * kStripThreads;
             const float* q3 = q3x + c * kStripThreads;
             const float* q4 = q4x + c * kStripThreads;
-            const float p20 = q0[t], p11 = q1[cn[2]], p21 = q1[t], p31 = q1[cn[4]];
-            const float p02 = q2[cn[1]], p12 = q2[cn[2]], p22 = q2[t], p32 = q2[cn[4]], p42 = q2[cn[5]];
-            const float p13 = q3[cn[2]], p23 = q3[t], p33 = q3[cn[4]], p24 = q4[t];
+            const float p20 = q0[col], p11 = q1[CC(-1)], p21 = q1[col], p31 = q1[CC(1)];
+            const float p02 = q2[CC(-2)], p12 = q2[CC(-1)], p22 = q2[col], p32 = q2[CC(1)], p42 = q2[CC(2)];
+            const float p13 = q3[CC(-1)], p23 = q3[col], p33 = q3[CC(1)], p24 = q4[col];
             nb[c][0] = p21; nb[c][1] = p12; nb[c][2] = p32; nb[c][3] = p23;
             float tt;
             float sad0c = fabsf(p20 - p21);
@@ -1942,19 +2058,22 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
           const float inv_w = 1.0f / w;
           X = X * inv_w; Y = Y * inv_w; B = B * inv_w;
         }
-        deliver(IC<3>(), r, X, Y, B);
+        deliver(IC<3>(), r, col, X, Y, B);
       }
     }
     // ---- EPF2 (stage_epf.cc:383-506) ----
     if constexpr (C::E2) {
       const int r = rin - d2;
-      if ((ST || (r >= lo(0) && r < hi(0) && t >= h2 && t < kStripThreads - h2)) && lane_ok) {
-        const float s = sg2;
-        sg2 = __ldg(P.sigma + (size_t)(min(max(r + 1, 0), HI - 1) >> 3) * P.xb + xs);
+      const bool row_on = ST || (r >= lo(0) && r < hi(0));
+      if (row_on && !(J >= 0 && ((J - d2) & 7) != 0)) load_sel(r, colE2, sgE2, cnE2);
+      const int col = colE2;
+      const int* cnk = cnE2;
+      if (row_on && lane_run(steady_tag, col, h2)) {
+        const float s = sgE2;
         const float* pM = RP(ring2, IC<C::N2>(), IC<-d2>(), r);
-        float X = pM[t];
-        float Y = pM[kStripThreads + t];
-        float B = pM[2 * kStripThreads + t];
+        float X = pM[col];
+        float Y = pM[kStripThreads + col];
+        float B = pM[2 * kStripThreads + col];
         if (!(s < kMinSigma)) {
           const int iy = r & 7;
           const float sm_ = P.epf_sm[2];
@@ -1963,7 +2082,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
           const float* pT = RP(ring2, IC<C::N2>(), IC<-d2 - 1>(), mr(r - 1));
           const float* pB = RP(ring2, IC<C::N2>(), IC<-d2 + 1>(), mr(r + 1));
           const float* nr[4] = {pT, pM, pM, pB};
-          const int nc[4] = {t, cn[2], cn[4], t};
+          const int nc[4] = {col, EDGE ? cnk[2] : col - 1, EDGE ? cnk[4] : col + 1, col};
           const float rx = X, ry = Y, rb = B;
           float w = 1.0f;
 #pragma unroll
@@ -1983,7 +2102,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
           const float inv_w = 1.0f / w;
           X = X * inv_w; Y = Y * inv_w; B = B * inv_w;
         }
-        deliver(IC<4>(), r, X, Y, B);
+        deliver(IC<4>(), r, col, X, Y, B);
       }
     }
     if constexpr (H > 0) __syncthreads();
@@ -2028,6 +2147,10 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
   for (; rin < s_begin; rin++) step(F(), IC<-1>(), rin);
   if constexpr (H > 0 && !C::E0) {
     // 8x unrolled steady loop with compile-time ring slots (EPF0 chains are too large to replicate)
+    if (C::kCompact && rin < s_end) {  // (an unaligned step loads every pass's block selection: the aligned
+      step(T(), IC<-1>(), rin);        //  steps below reload it only where a block row begins)
+      rin++;
+    }
     for (; rin < s_end && (rin & 7); rin++) step(T(), IC<-1>(), rin);
     for (; rin + 8 <= s_end; rin += 8) {
       step(T(), IC<0>(), rin);
@@ -2061,14 +2184,11 @@ __global__ void __launch_bounds__(kStripThreads, StripCfg<MASK>::E0 ? 2 : 4) fil
   const int y_begin = (int)P.band_y0 + blockIdx.y * seg_rows;
   const int y_end = min((int)P.band_y1, y_begin + seg_rows);
   if (y_begin >= y_end) return;
-  const bool edge = (x0 - C::H < 0) || (x0 - C::H + kStripThreads > (int)P.xsize);
+  const bool edge = (x0 - C::LEAD < 0) || (x0 - C::LEAD + kStripThreads > (int)P.xsize);
   if (edge) filter_strip_body<MASK, true, REPL, OUTK>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
   else filter_strip_body<MASK, false, REPL, OUTK>(P, out, out_row_stride, x0, y_begin, y_end, fsm);
 }
 
-}  // namespace jxlb
-#include "jxl_strip2.cuh"
-namespace jxlb {
 
 // Host launcher of one stage chain; each explicit specialisation lives in its own translation unit
 // (jxl_strip_inst.cu compiled with -DSTRIP_MASK=<mask>), so that the eight chains build in parallel.

@@ -27,12 +27,6 @@ __attribute__((visibility("hidden"))) cudaError_t prepare_strip_mask<STRIP_MASK>
   set(filter_strip_kernel<MASK, false, 1>);
   set(filter_strip_kernel<MASK, true, 0>);
   set(filter_strip_kernel<MASK, true, 1>);
-  if constexpr (!StripCfg<MASK>::E0) {
-    set(filter_strip2_kernel<MASK, false, 0>);
-    set(filter_strip2_kernel<MASK, false, 1>);
-    set(filter_strip2_kernel<MASK, true, 0>);
-    set(filter_strip2_kernel<MASK, true, 1>);
-  }
   set(filter_strip_kernel<MASK, false, 2>);
   return e;
 }
@@ -44,39 +38,6 @@ cudaError_t launch_strip_mask<STRIP_MASK>(const FrameDev& P, char* dev_out, size
   using C = StripCfg<MASK>;
   const bool repl = P.mc || P.nrep;  // multi-GPU: the instantiation with the fused all-gather replay
   const bool plain = P.out_format == 0 && !(P.stage_mask & 32u);  // linear interleaved f32
-  if constexpr (!C::E0) {
-    // EXPERIMENT (JXLGPU_STRIP2=1): two columns per thread, see jxl_strip2.cuh
-    static const bool use2 = [] { const char* e = getenv("JXLGPU_STRIP2"); return e && e[0] == '1'; }();
-    if (use2) {
-      using C2 = Strip2Cfg<MASK>;
-      static const bool traced = [] { if (getenv("JXLGPU_TRACE")) fprintf(stderr, "[jxl_b200] filter chain %u: two-column strip kernel\n", (unsigned)MASK); return true; }();
-      (void)traced;
-      static int bps2 = 0;
-      if (!bps2) {
-        int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, filter_strip2_kernel<MASK, false, 0>,
-                                                                      kStrip2Threads, C::kSmemBytes);
-        if (e != cudaSuccess) return e;
-        bps2 = n < 1 ? 1 : n;
-      }
-      const int band_h = (int)(P.band_y1 - P.band_y0);
-      const int strips = ((int)P.xsize + C2::kOutCols - 1) / C2::kOutCols;
-      int segs = std::max(1, num_sms * bps2 / strips);
-      int seg_rows = (band_h + segs - 1) / segs;
-      if (seg_rows < 64) seg_rows = 64;
-      seg_rows = (seg_rows + 7) & ~7;
-      segs = (band_h + seg_rows - 1) / seg_rows;
-      const dim3 grid(strips, segs);
-      if (repl) {
-        if (plain) filter_strip2_kernel<MASK, true, 0><<<grid, kStrip2Threads, C::kSmemBytes, s>>>(P, dev_out, out_row_bytes, seg_rows);
-        else filter_strip2_kernel<MASK, true, 1><<<grid, kStrip2Threads, C::kSmemBytes, s>>>(P, dev_out, out_row_bytes, seg_rows);
-      } else {
-        if (plain) filter_strip2_kernel<MASK, false, 0><<<grid, kStrip2Threads, C::kSmemBytes, s>>>(P, dev_out, out_row_bytes, seg_rows);
-        else filter_strip2_kernel<MASK, false, 1><<<grid, kStrip2Threads, C::kSmemBytes, s>>>(P, dev_out, out_row_bytes, seg_rows);
-      }
-      return cudaGetLastError();
-    }
-  }
   static int blocks_per_sm = 0;  // occupancy of this chain (all four instantiations share the bounds)
   if (!blocks_per_sm) {
     int n = 0;

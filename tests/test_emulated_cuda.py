@@ -55,7 +55,8 @@ def test_emulated_golden_frame(emu_pipe):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("w,h,ac_type", [(520, 264, abi.AC_INT16), (300, 200, abi.AC_INT32)])
+@pytest.mark.parametrize("w,h,ac_type", [(520, 264, abi.AC_INT16), (300, 200, abi.AC_INT32),
+                                         (1024, 520, abi.AC_INT16)])   # the last: all nine 64..256 transforms (sliced passes)
 def test_emulated_all_strategy_frame(emu_pipe, w, h, ac_type):
     desc, coeffs = wl.synthetic_frame(w, h, seed=w + h, ac_type=ac_type)
     assert same(emu_pipe.decode_frame(desc, coeffs), oracle(desc, coeffs))
@@ -345,6 +346,28 @@ def test_emulated_tiny_heights_with_epf_engaged(emu_pipe, w, h, epf_iters):
     desc2, _ = epf_engaged_frame(w, h, seed=w * 7 + h, epf_iters=0)
     if w * h > 1:   # the filters really change the picture (the test means something)
         assert not np.array_equal(want, oracle(desc2, coeffs))
+    assert same(emu_pipe.decode_frame(desc, coeffs), want)
+
+
+def epf_mixed_frame(w, h, seed, gab=1, epf_iters=3, engaged=0.3):
+    """EPF engaged on a random subset of the blocks (sharpness 7 there, 0 elsewhere -- what the reference
+    encoder's sharpness map looks like): the strip kernel runs its EPF passes on a block permutation,
+    engaged blocks first, and this frame mixes both kinds inside every strip and block row."""
+    desc, coeffs = epf_engaged_frame(w, h, seed, gab=gab, epf_iters=epf_iters)
+    rng = np.random.default_rng(seed + 99)
+    desc.epf_sharpness = np.where(rng.random(desc.epf_sharpness.shape) < engaged, 7, 0).astype(np.uint8)
+    return desc, coeffs
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("gab", [0, 1])
+@pytest.mark.parametrize("epf_iters", [1, 2, 3])
+@pytest.mark.parametrize("w,h,engaged", [(523, 90, 0.3), (250, 41, 0.7), (8, 200, 0.5)])
+def test_emulated_epf_block_permutation(emu_pipe, w, h, engaged, gab, epf_iters):
+    desc, coeffs = epf_mixed_frame(w, h, seed=w + 3 * h + gab, gab=gab, epf_iters=epf_iters, engaged=engaged)
+    want = oracle(desc, coeffs)
+    desc0, _ = epf_mixed_frame(w, h, seed=w + 3 * h + gab, gab=gab, epf_iters=0, engaged=engaged)
+    assert not np.array_equal(want, oracle(desc0, coeffs))
     assert same(emu_pipe.decode_frame(desc, coeffs), want)
 
 
