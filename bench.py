@@ -452,10 +452,12 @@ def main() -> int:
                     help="pixel format the path ends in: linear f32 (the §8 scope, default) or sRGB 8-bit "
                          "(sRGB transfer function + WriteToOutput packing fused into the filter kernel's store); "
                          "the other one is measured too and reported under \"variants\"")
-    ap.add_argument("--submit", default="dense", choices=["dense", "sparse"],
-                    help="e2e arm: dense [group][3][65536] coefficient blocks (libjxl's ACImage layout, what the "
-                         "unmodified entropy decoder produces; default) or the non-zero lists of "
-                         "jxlgpu_submit_groups_sparse; the other one is measured too and reported under \"variants\"")
+    ap.add_argument("--submit", default="sparse", choices=["dense", "sparse"],
+                    help="e2e arm: sparse = the non-zero lists of jxlgpu_submit_groups_sparse, which the compiled "
+                         "libjxl integration (integration/patch_libjxl.py: the patched DecodeACVarBlock appends them "
+                         "while it entropy-decodes; tests/test_integration_libjxl.py) hands over -- default; dense = "
+                         "[group][3][65536] coefficient blocks in libjxl's ACImage layout.  The other one is measured "
+                         "too and reported under \"variants\"")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="auto", choices=["auto", "ce", "multicast", "p2p", "nccl"],

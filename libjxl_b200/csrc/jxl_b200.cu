@@ -96,6 +96,7 @@ struct jxlgpu_ctx {
   // JXLGPU_FUSED=1 selects the fused decode kernel (jxl_fused.cuh).  Opt-in: on B200 it moves 2x fewer DRAM
   // bytes than the two-kernel path but is slower (1.33 ms vs 0.66 ms at 8K d1.0, profiles/r02_*fused*).
   bool allow_fused = false;
+  bool idct8_tma = true;      // JXLGPU_IDCT8_TMA=0: the round-1 idct8_kernel (ordinary loads) for A/B runs
   DevBuf qdc, dc_deq;         // DC stage on the device: quantised planes (+ per-group mul), dequantised planes
   DevBuf sparse;              // staging for the non-zero lists of jxlgpu_submit_groups_sparse
   size_t sparse_used = 0;     // words handed out this frame (bump allocation, guarded by mu)
@@ -238,6 +239,15 @@ int launch_idct(jxlgpu_ctx* ctx, uint32_t row0, uint32_t row1, uint32_t need_y0,
   }
   auto run8 = [&]() {
     if (fused) return;  // (the fused kernel transforms the 8x8 class itself)
+    bool tma = ctx->idct8_tma;
+    for (int c = 0; c < 3; c++) tma = tma && (uintptr_t)P.coeff[c] % 16 == 0;
+    if (tma) {  // coefficients staged by the bulk-copy unit one item ahead (3 CTAs per SM)
+      int grid = ctx->num_sms * 3;
+      if (grid > grid8) grid = grid8;
+      if (P.ac_is32) idct8_tma_kernel<true><<<grid, kSmallWarpsPerCta * 32, kTma8SmemBytes, s>>>(P);
+      else idct8_tma_kernel<false><<<grid, kSmallWarpsPerCta * 32, kTma8SmemBytes, s>>>(P);
+      return;
+    }
     if (P.ac_is32) idct8_kernel<true><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
     else idct8_kernel<false><<<grid8, kSmallWarpsPerCta * 32, 0, s>>>(P);
   };
@@ -434,6 +444,9 @@ int jxlgpu_create(jxlgpu_ctx** out, const jxlgpu_config* cfg) {
   if ((e = cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(kFilterSmemFloats * sizeof(float)))) != cudaSuccess)
     return bail(e, "cudaFuncSetAttribute(filter_kernel)");
+  for (cudaError_t ea : {cudaFuncSetAttribute(idct8_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTma8SmemBytes),
+                         cudaFuncSetAttribute(idct8_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTma8SmemBytes)})
+    if (ea != cudaSuccess) return bail(ea, "cudaFuncSetAttribute(idct8_tma_kernel)");
   for (cudaError_t ea : {cudaFuncSetAttribute(idct_large_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLargeSmemFloats * sizeof(float))),
                          cudaFuncSetAttribute(idct_large_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLargeSmemFloats * sizeof(float))),
                          cudaFuncSetAttribute(idct_large_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLargeSmemFloats * sizeof(float))),
@@ -448,6 +461,7 @@ int jxlgpu_create(jxlgpu_ctx** out, const jxlgpu_config* cfg) {
                          prepare_fused_mask<30>()})
     if (ea != cudaSuccess) return bail(ea, "cudaFuncSetAttribute(fused_tile_kernel)");
   if (const char* fe = getenv("JXLGPU_FUSED")) ctx->allow_fused = fe[0] == '1';
+  if (const char* te = getenv("JXLGPU_IDCT8_TMA")) ctx->idct8_tma = te[0] != '0';
   if (const char* ge = getenv("JXLGPU_GATHER")) ctx->gather_in_kernel = ge[0] == 'k';
   {
     const char* env = getenv("JXLGPU_FORCE_GENERIC_FILTER");

@@ -33,86 +33,7 @@
 
 namespace jxlb {
 
-// ---------------------------------------------------------------------------
-// mbarrier + bulk async copy (TMA) primitives.  Host emulation (tests/emu): copies are synchronous, the
-// barriers around them are the kernel's own __syncthreads().
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) {
-#if JXLB_PTX
-  return (uint32_t)__cvta_generic_to_shared(p);
-#else
-  return 0;
-#endif
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-#if JXLB_PTX
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#else
-  *bar = count;
-#endif
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-#if JXLB_PTX
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-#else
-  (void)bar; (void)bytes;
-#endif
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#if JXLB_PTX
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
-#else
-  (void)bar; (void)parity;
-#endif
-}
-// global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-#if JXLB_PTX
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_addr(dst_smem)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-#else
-  memcpy(dst_smem, src, bytes);
-  (void)bar;
-#endif
-}
-// shared -> global (bulk group of the issuing thread)
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
-#if JXLB_PTX
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
-#else
-  memcpy(dst, src_smem, bytes);
-#endif
-}
-__device__ __forceinline__ void bulk_commit() {
-#if JXLB_PTX
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void bulk_wait_read_all() {  // the sources of all committed groups have been read
-#if JXLB_PTX
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void bulk_wait_all() {
-#if JXLB_PTX
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-#endif
-}
-// generic-proxy writes to shared memory -> visible to the async proxy (the TMA unit)
-__device__ __forceinline__ void fence_async_smem() {
-#if JXLB_PTX
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-}
+// (mbarrier + bulk-copy primitives: jxl_kernels.cuh)
 
 // ---------------------------------------------------------------------------
 // geometry

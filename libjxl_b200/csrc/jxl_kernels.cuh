@@ -118,6 +118,88 @@ struct FrameDev {
 };
 
 // ---------------------------------------------------------------------------
+// mbarrier + bulk async copy (TMA) primitives.  Host emulation (tests/emu): copies are synchronous, the
+// barriers around them are the kernel's own __syncthreads().
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+#if JXLB_PTX
+  return (uint32_t)__cvta_generic_to_shared(p);
+#else
+  return 0;
+#endif
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+#if JXLB_PTX
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+  *bar = count;
+#endif
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+#if JXLB_PTX
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+#else
+  (void)bar; (void)bytes;
+#endif
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if JXLB_PTX
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+#else
+  (void)bar; (void)parity;
+  __syncwarp();  // (emulation: the copies were made synchronously by other lanes of this warp, or before a barrier)
+#endif
+}
+// global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+#if JXLB_PTX
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst_smem)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+#else
+  memcpy(dst_smem, src, bytes);
+  (void)bar;
+#endif
+}
+// shared -> global (bulk group of the issuing thread)
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+#if JXLB_PTX
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+#else
+  memcpy(dst, src_smem, bytes);
+#endif
+}
+__device__ __forceinline__ void bulk_commit() {
+#if JXLB_PTX
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_wait_read_all() {  // the sources of all committed groups have been read
+#if JXLB_PTX
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_wait_all() {
+#if JXLB_PTX
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (the TMA unit)
+__device__ __forceinline__ void fence_async_smem() {
+#if JXLB_PTX
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+
+// ---------------------------------------------------------------------------
 // 1-D transforms in registers
 // ---------------------------------------------------------------------------
 // IDCT1DImpl<N> (dct-inl.h:191-232): even/odd split, BTranspose, butterflies.
@@ -251,6 +333,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(const __grid_constant__ Fram
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t local_count[kNumStrategies];
   __shared__ uint32_t local_base[kNumStrategies];
+  __shared__ uint16_t owner[1024];
   const uint32_t t = threadIdx.x;
   const uint32_t g = blockIdx.x + P.plan_g0;
   const uint32_t gx = g % P.xg, gy = g / P.xg;
@@ -312,17 +395,28 @@ __global__ void __launch_bounds__(1024) plan_kernel(const __grid_constant__ Fram
       P.list[P.list_base[s] + local_base[s] + rank] =
           make_uint4((aby << 16) | abx, (uint32_t)((size_t)g * (P.coeff_gstride >> 6) + off), (uint32_t)P.quant[bi], cfl);
     }
-    if (want_sigma) {
-      // ComputeSigma (epf.cc:39-133)
+  }
+  if (want_sigma) {
+    // ComputeSigma (epf.cc:39-133): every block of a varblock takes the quantiser of the varblock's first
+    // block and its own sharpness.  The first block's thread only marks the blocks it covers (shared-memory
+    // stores); the divisions and global accesses are then done by all 1024 threads, one block each -- a
+    // 256x256 varblock used to leave one thread looping over 1024 blocks.
+    owner[t] = (uint16_t)t;
+    __syncthreads();
+    if (first) {
+      const int ny = min(covered_y(s), 32 - (int)(t >> 5)), nx = min(covered_x(s), 32 - (int)(t & 31));  // (never past the group)
+      for (int iy = 0; iy < ny; iy++)
+        for (int ix = 0; ix < nx; ix++) owner[t + iy * 32 + ix] = (uint16_t)t;
+    }
+    __syncthreads();
+    if (valid) {
+      const uint32_t o = owner[t];
+      const size_t bo = (size_t)(gy * 32 + (o >> 5)) * P.xb + gx * 32 + (o & 31);
       const float kInvSigmaNum = -1.1715728752538099024f;
-      const float sigma_quant = P.epf_quant_mul / (P.quant_scale * (float)P.quant[bi] * kInvSigmaNum);
-      for (int iy = 0; iy < covered_y(s); iy++)
-        for (int ix = 0; ix < covered_x(s); ix++) {
-          const size_t bj = (size_t)(aby + iy) * P.xb + abx + ix;
-          float sg = sigma_quant * P.epf_sharp_lut[P.sharp[bj]];
-          sg = fminf(-1e-4f, sg);
-          P.sigma[bj] = 1.0f / sg;
-        }
+      const float sigma_quant = P.epf_quant_mul / (P.quant_scale * (float)P.quant[bo] * kInvSigmaNum);
+      float sg = sigma_quant * P.epf_sharp_lut[P.sharp[bi]];
+      sg = fminf(-1e-4f, sg);
+      P.sigma[bi] = 1.0f / sg;
     }
   }
 }
@@ -469,13 +563,25 @@ __device__ __forceinline__ void load_row8f(const float* p, float* m) {
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
 }
+// row l of an 8x8 float matrix in SHARED memory (same bank-conflict-free half order as load_row8_smem)
+__device__ __forceinline__ void load_row8f_smem(const float* mat, int l, float* m) {
+  const float4* p = reinterpret_cast<const float4*>(mat + l * 8);
+  const int sw = (l >> 2) & 1;
+  const float4 u = p[sw], v = p[sw ^ 1];
+  const float4 a = sw ? v : u, b = sw ? u : v;
+  m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+}
 
 // One row (8 consecutive coefficients) of a block held in SHARED memory (the fused kernel's staging).
 template <bool I32>
 __device__ __forceinline__ void load_row8_smem(const void* block, int elem, int* q) {
   if constexpr (I32) {
+    // eight lanes read eight 32-byte rows with two 16-byte loads each: rows 4..7 take their second half first,
+    // so that the eight lanes of a load phase touch all 32 banks once instead of 16 banks twice
     const int4* p = reinterpret_cast<const int4*>(reinterpret_cast<const int32_t*>(block) + elem);
-    const int4 a = p[0], b = p[1];
+    const int sw = (elem >> 5) & 1;
+    const int4 u = p[sw], v = p[sw ^ 1];
+    const int4 a = sw ? v : u, b = sw ? u : v;
     q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
   } else {
     const int4 a = *reinterpret_cast<const int4*>(reinterpret_cast<const int16_t*>(block) + elem);
@@ -490,12 +596,21 @@ __device__ __forceinline__ void load_row8_smem(const void* block, int elem, int*
 
 // Dequantisation of row l of an 8x8-class block, all three channels (dec_group.cc:115-181): lane l owns
 // the 8 coefficients of row l.  qx/qy/qb: the integers; `dqkind` selects the dequant matrix rows.
-__device__ __forceinline__ void block8_dequant_row(const FrameDev& P, int dqkind, const VarblockCtx& vb, int l,
-                                                   const int* qx, const int* qy, const int* qb, float (&val)[3][8]) {
+//   dqx/dqy/dqb: the strategy's 8x8 dequant matrices (global memory, or a shared-memory copy)
+template <bool SMEM>
+__device__ __forceinline__ void block8_dequant_row_m(const FrameDev& P, const float* dqx, const float* dqy,
+                                                     const float* dqb, const VarblockCtx& vb, int l, const int* qx,
+                                                     const int* qy, const int* qb, float (&val)[3][8]) {
   float mx[8], my[8], mb[8];
-  load_row8f(P.dq + P.dq_off[3 * dqkind + 1] + l * 8, my);
-  load_row8f(P.dq + P.dq_off[3 * dqkind + 0] + l * 8, mx);
-  load_row8f(P.dq + P.dq_off[3 * dqkind + 2] + l * 8, mb);
+  if constexpr (SMEM) {
+    load_row8f_smem(dqy, l, my);
+    load_row8f_smem(dqx, l, mx);
+    load_row8f_smem(dqb, l, mb);
+  } else {
+    load_row8f(dqy + l * 8, my);
+    load_row8f(dqx + l * 8, mx);
+    load_row8f(dqb + l * 8, mb);
+  }
 #pragma unroll
   for (int e = 0; e < 8; e++) {
     const float dy = adjust_quant_bias(qy[e], P.qbias[1], P.qbias[3]) * (my[e] * vb.sy);
@@ -510,6 +625,12 @@ __device__ __forceinline__ void block8_dequant_row(const FrameDev& P, int dqkind
 #pragma unroll
     for (int c = 0; c < 3; c++) val[c][0] = __ldg(P.dc + (size_t)c * P.yb * P.xb + bi);
   }
+}
+
+__device__ __forceinline__ void block8_dequant_row(const FrameDev& P, int dqkind, const VarblockCtx& vb, int l,
+                                                   const int* qx, const int* qy, const int* qb, float (&val)[3][8]) {
+  block8_dequant_row_m<false>(P, P.dq + P.dq_off[3 * dqkind + 0], P.dq + P.dq_off[3 * dqkind + 1],
+                       P.dq + P.dq_off[3 * dqkind + 2], vb, l, qx, qy, qb, val);
 }
 
 // Where the pixels of an 8x8-class block go.
@@ -906,6 +1027,154 @@ __global__ void __launch_bounds__(kSmallWarpsPerCta * 32, 4) idct8_kernel(const 
 }
 
 // multi-block DCTs with sides <= 32 (DCT16X16 .. DCT16X32).
+// ---------------------------------------------------------------------------
+// idct8_tma_kernel: the same items as idct8_kernel, with the coefficients staged by the bulk-copy (TMA)
+// unit.  idct8_kernel is latency bound (ncu: 8 long-scoreboard stall cycles per issue, 57 % of the HBM
+// peak): a warp loads the 3 x 256 bytes of each of its four blocks with ordinary loads and waits for them.
+// Here every warp owns two staging buffers of 4 blocks x 192 words in shared memory and an mbarrier each;
+// while item i is transformed, the 12 block-channels of item i+1 (the warp's next item, possibly of the next
+// strategy list) are already in flight as cp.async.bulk copies (global -> shared, complete_tx on the
+// barrier), issued by 12 lanes as soon as buffer (i+1)&1 is free.  After dequantisation (all of a block's
+// coefficients sit in registers) the staging words serve as the transform's scratch, like in the fused
+// kernel.  3 CTAs x 8 warps per SM keep ~70 KB of coefficient reads in flight per SM.
+// Needs 16-byte aligned coefficient planes (jxlgpu_set_device_coefficients may bring others: idct8_kernel).
+// ---------------------------------------------------------------------------
+constexpr int kTma8BlockWords = 192;                                    // 3 channels x 64 int32 (int16: half used)
+constexpr int kTma8StageWords = 4 * kTma8BlockWords;
+constexpr int kTma8WarpWords = 2 * kTma8StageWords + 4 * 64 + 4;        // 2 stages | 4 pixel scratches | 2 mbarriers
+constexpr size_t kTma8SmemBytes = (size_t)kSmallWarpsPerCta * kTma8WarpWords * 4;
+
+template <bool I32>
+__global__ void __launch_bounds__(kSmallWarpsPerCta * 32, 3) idct8_tma_kernel(const __grid_constant__ FrameDev P) {
+  extern __shared__ __align__(16) float fsm[];
+  uint32_t* wsm = reinterpret_cast<uint32_t*>(fsm) + (threadIdx.x >> 5) * kTma8WarpWords;
+  float* pxs = reinterpret_cast<float*>(wsm + 2 * kTma8StageWords);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + 2 * kTma8StageWords + 4 * 64);
+  const int lane = threadIdx.x & 31, slot = lane >> 3, l = lane & 7;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  constexpr uint32_t kChBytes = I32 ? 256 : 128;
+  constexpr int kChWords = I32 ? 64 : 32;
+  // the ten 8x8-class work lists as one index space: items [pre[i], pre[i+1]) belong to strategy skind[i];
+  // the ten strategies' dequant matrices (3 x 64 floats each) are copied to shared memory once per CTA
+  __shared__ uint32_t pre[11];
+  __shared__ int skind[10];
+  __shared__ __align__(16) float sdq[10 * 192];
+  {
+    const int order[10] = {0, 2, 12, 13, 1, 3, 14, 15, 16, 17};
+    if (threadIdx.x == 0) {
+      uint32_t acc = 0;
+      for (int i = 0; i < 10; i++) {
+        pre[i] = acc;
+        skind[i] = order[i];
+        acc += (P.counts[order[i]] + 3) / 4;
+      }
+      pre[10] = acc;
+    }
+    for (int e = threadIdx.x; e < 10 * 192; e += blockDim.x) {
+      const int i = e / 192, c = (e % 192) / 64, k = e % 64;
+      int s_ = 0;
+#pragma unroll
+      for (int q = 0; q < 10; q++) s_ = (q == i) ? order[q] : s_;
+      sdq[e] = __ldg(P.dq + P.dq_off[3 * s_ + c] + k);
+    }
+  }
+  if (lane == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+  }
+  fence_async_smem();
+  __syncthreads();
+  const uint32_t total = pre[10];
+
+  // item v (warp-uniform): list index `oi` and the slot's record (zero record for the inactive slots at a
+  // list's tail and past the end) -- loaded two items before it is needed for the copies
+  const uint4 zero = make_uint4(0, 0, 1, 0);
+  auto fetch_rec = [&](uint32_t v, uint4& rec, int& oi) {
+    rec = zero;
+    oi = -1;
+    if (v >= total) return;
+    oi = 0;
+    while (v >= pre[oi + 1]) oi++;
+    const int kind = skind[oi];
+    const uint32_t e = (v - pre[oi]) * 4 + slot;
+    if (e < P.counts[kind]) rec = __ldg(P.list + P.list_base[kind] + e);
+  };
+  // (a record's third word is the raw quantiser: 0 never occurs, so zero.z == 1 with y == 0 marks "inactive"
+  //  only through the explicit flag below)
+  auto issue = [&](int st, const uint4& rec, bool act) {
+    const uint32_t nact = __popc(__ballot_sync(0xffffffffu, act && l == 0));
+    if (nact == 0) return;
+    if (lane == 0) mbar_arrive_expect_tx(&bars[st], nact * 3 * kChBytes);
+    __syncwarp();
+    if (act && l < 3) {
+      char* dst = reinterpret_cast<char*>(wsm + st * kTma8StageWords + slot * kTma8BlockWords) + l * kChBytes;
+      const char* src = reinterpret_cast<const char*>(P.coeff[l]) + (size_t)rec.y * 64u * (I32 ? 4 : 2);
+      bulk_g2s(dst, src, kChBytes, &bars[st]);
+    }
+  };
+  auto is_act = [&](uint32_t v, int oi) {
+    if (oi < 0) return false;
+    return (v - pre[oi]) * 4 + slot < P.counts[skind[oi]];
+  };
+
+  uint32_t v = warp;
+  uint4 rec_cur, rec_next, rec_nn;
+  int oi_cur, oi_next, oi_nn;
+  fetch_rec(v, rec_cur, oi_cur);
+  fetch_rec(v + nwarps, rec_next, oi_next);
+  fetch_rec(v + 2 * nwarps, rec_nn, oi_nn);
+  issue(0, rec_cur, is_act(v, oi_cur));
+  issue(1, rec_next, is_act(v + nwarps, oi_next));
+  uint32_t phase = 0;  // bit st: parity of buffer st's next completion
+  int st = 0;
+#pragma unroll 1
+  for (; v < total; v += nwarps) {
+    // the record of the item three ahead starts its trip now; it is used (for the copies) next iteration
+    uint4 rec_3;
+    int oi_3;
+    fetch_rec(v + 3 * nwarps, rec_3, oi_3);
+    const bool act_cur = is_act(v, oi_cur);
+    const int kind = skind[oi_cur];
+    mbar_wait(&bars[st], (phase >> st) & 1u);
+    phase ^= 1u << st;
+    uint32_t* stg = wsm + st * kTma8StageWords + slot * kTma8BlockWords;
+    float* co = reinterpret_cast<float*>(stg);
+    VarblockCtx vb;
+    float val[3][8];
+    if (act_cur) {
+      vb = make_ctx(P, rec_cur);
+      int qx[8], qy[8], qb[8];
+      load_row8_smem<I32>(stg + kChWords, l * 8, qy);
+      load_row8_smem<I32>(stg, l * 8, qx);
+      load_row8_smem<I32>(stg + 2 * kChWords, l * 8, qb);
+      const float* dqm = sdq + oi_cur * 192;
+      block8_dequant_row_m<true>(P, dqm, dqm + 64, dqm + 128, vb, l, qx, qy, qb, val);
+    } else {
+      vb = VarblockCtx{};
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) val[c][e] = 0.0f;
+    }
+    __syncwarp();  // every lane holds its row: the staging words become the transform's scratch
+    Block8ToPlanes out;
+    out.scratch = pxs + slot * 64;
+    out.plane0 = P.xyb + (size_t)vb.aby * 8 * P.row_stride + vb.abx * 8;
+    out.plane_stride = P.plane_stride;
+    out.row_stride = P.row_stride;
+    block8_transform(kind, act_cur, val, l, co, co + 96, out);
+    // buffer `st` is free: the item after next goes there
+    fence_async_smem();
+    __syncwarp();
+    issue(st, rec_nn, is_act(v + 2 * nwarps, oi_nn));
+    rec_cur = rec_next; oi_cur = oi_next;
+    rec_next = rec_nn; oi_next = oi_nn;
+    rec_nn = rec_3; oi_nn = oi_3;
+    st ^= 1;
+  }
+}
+
 template <bool I32>
 __global__ void __launch_bounds__(kSmallWarpsPerCta * 32) idct_mid_kernel(const __grid_constant__ FrameDev P) {
   __shared__ __align__(16) float smem[kSmallWarpsPerCta * kSmallWarpFloats];
@@ -1793,7 +2062,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
         const unsigned m = __ballot_sync(0xffffffffu, act);
         const unsigned lt = (1u << t) - 1u;
         const int pos = act ? __popc(m & lt) : __popc(m) + __popc(~m & lt);
-        permv[(br & 3) * 32 + pos] = t;
+        permv[(br & 3) * 32 + pos] = t;  // (rotating the first engaged warp per CTA / block row measured 4 % slower)
         sigv[(br & 3) * 32 + t] = sv;
       }
     }
