@@ -44,7 +44,7 @@ extern "C" {
 #define JXLGPU_API
 #endif
 
-#define JXLGPU_ABI_VERSION 3
+#define JXLGPU_ABI_VERSION 4
 
 enum {
   JXLGPU_OK = 0,
@@ -167,7 +167,17 @@ typedef struct jxlgpu_frame {
   const float* dc_group_mul;    /* per DC group (2048x2048 px, raster order) 1 / (1 << extra_precision)
                                    (dec_modular.cc:443-444); NULL = 1 everywhere */
   uint32_t dc_smoothing;        /* 0 when kSkipAdaptiveDCSmoothing or kUseDcFrame is set */
-  uint32_t reserved0;
+
+  /* Upsampling (UpsamplingStage, lib/jxl/render_pipeline/stage_upsampling.cc:51-271,
+   * placed after the filters and before XYB->RGB by PreparePipeline, dec_cache.cc:216-227).
+   * upsampling: frame_header.upsampling = 1 (or 0: none), 2, 4 or 8.  Everything above (xsize, blocks,
+   * filters) is at the coded resolution; the output buffer is xsize_upsampled x ysize_upsampled
+   * (FrameDimensions::{x,y}size_upsampled, <= upsampling * size; 0 = upsampling * size).
+   * upsampling_weights: CustomTransformData::upsampling{2,4,8}_weights of that factor (15 / 55 / 210 floats,
+   * image_metadata.h:193-196), read by frame_begin.  Whole-frame contexts only (band_ny_groups == 0). */
+  uint32_t upsampling;
+  uint32_t xsize_upsampled, ysize_upsampled;
+  const float* upsampling_weights;
 } jxlgpu_frame;
 
 JXLGPU_API uint32_t jxlgpu_abi_version(void);

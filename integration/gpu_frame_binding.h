@@ -27,7 +27,8 @@ namespace jxlb_integration {
 inline bool IsEligible(const jxl::FrameHeader& fh, const jxl::CodecMetadata& metadata) {
   using jxl::FrameHeader;
   return fh.encoding == jxl::FrameEncoding::kVarDCT && metadata.m.xyb_encoded &&
-         fh.color_transform == jxl::ColorTransform::kXYB && fh.chroma_subsampling.Is444() && fh.upsampling == 1 &&
+         fh.color_transform == jxl::ColorTransform::kXYB && fh.chroma_subsampling.Is444() &&
+         (fh.upsampling == 1 || fh.upsampling == 2 || fh.upsampling == 4 || fh.upsampling == 8) &&
          !(fh.flags & (FrameHeader::kPatches | FrameHeader::kSplines | FrameHeader::kNoise)) &&
          fh.passes.num_passes == 1 && metadata.m.num_extra_channels == 0;
 }
@@ -118,6 +119,14 @@ inline bool BindGpuFrame(const jxl::PassesDecoderState& ds, const jxl::FrameHead
   }
   f.out_format = out_format;
   f.stage_mask = stage_mask;
+  if (fh.upsampling != 1) {  // UpsamplingStage of the colour channels (dec_cache.cc:216-227)
+    const jxl::CustomTransformData& td = fh.nonserialized_metadata->transform_data;
+    f.upsampling = fh.upsampling;
+    f.xsize_upsampled = static_cast<uint32_t>(d.xsize_upsampled);
+    f.ysize_upsampled = static_cast<uint32_t>(d.ysize_upsampled);
+    f.upsampling_weights = fh.upsampling == 2 ? td.upsampling2_weights
+                           : fh.upsampling == 4 ? td.upsampling4_weights : td.upsampling8_weights;
+  }
   return true;
 }
 

@@ -238,7 +238,7 @@ inline bool FrameIsOurs(const jxl::FrameHeader& fh, const jxl::PassesDecoderStat
   if (ce.Tf().IsLinear()) *stage_mask = 0;
   else if (ce.Tf().IsSRGB()) *stage_mask = JXLGPU_STAGE_SRGB;
   else return false;
-  if (ds.width != ds.shared->frame_dim.xsize || ds.height != ds.shared->frame_dim.ysize) return false;
+  if (ds.width != ds.shared->frame_dim.xsize_upsampled || ds.height != ds.shared->frame_dim.ysize_upsampled) return false;
   return MapOutput(ds, /*has_alpha=*/false, out_format);
 }
 

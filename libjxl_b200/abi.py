@@ -12,7 +12,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 NUM_STRATEGIES = 27
 GROUP_DIM = 256
 GROUP_COEFFS = 65536
@@ -67,7 +67,9 @@ class JxlGpuFrame(C.Structure):
         ("out_format", C.c_uint32), ("stage_mask", C.c_uint32),
         ("quant_dc", C.c_void_p * 3), ("quant_dc_stride", C.c_size_t),
         ("dc_factors", C.c_float * 3), ("dc_cfl_factors", C.c_float * 3),
-        ("dc_group_mul", C.c_void_p), ("dc_smoothing", C.c_uint32), ("reserved0", C.c_uint32),
+        ("dc_group_mul", C.c_void_p), ("dc_smoothing", C.c_uint32),
+        ("upsampling", C.c_uint32), ("xsize_upsampled", C.c_uint32), ("ysize_upsampled", C.c_uint32),
+        ("upsampling_weights", C.c_void_p),
     ]
 
 
@@ -141,6 +143,12 @@ class FrameDesc:
     dc_cfl_factors: tuple = (0.0, 0.0, 1.0)
     dc_group_mul: np.ndarray | None = None    # f32 (ceil(yb/256), ceil(xb/256)) or None
     dc_smoothing: int = 1
+    # upsampling after the filters (frame_header.upsampling): 1, 2, 4, 8; weights = the 15 / 55 / 210 floats of
+    # CustomTransformData; the output has xsize_upsampled x ysize_upsampled pixels (0 = upsampling * size)
+    upsampling: int = 1
+    upsampling_weights: np.ndarray | None = None
+    xsize_upsampled: int = 0
+    ysize_upsampled: int = 0
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -163,13 +171,27 @@ class FrameDesc:
     def num_groups(self) -> int:
         return self.xsize_groups * self.ysize_groups
 
+    @property
+    def out_xsize(self) -> int:
+        if self.upsampling <= 1:
+            return self.xsize
+        return self.xsize_upsampled or self.upsampling * self.xsize
+
+    @property
+    def out_ysize(self) -> int:
+        if self.upsampling <= 1:
+            return self.ysize
+        return self.ysize_upsampled or self.upsampling * self.ysize
+
     def out_shape(self, rows: int | None = None) -> tuple:
         """Shape of the (dense) output array for `rows` pixel rows (default: this band's rows)."""
         if rows is None:
             rows = self.band_rows()[1]
+        if self.upsampling > 1 and rows == self.ysize:
+            rows = self.out_ysize
         if self.out_format == OUT_PLANAR_F32:
-            return (3, rows, self.xsize)
-        return (rows, self.xsize, OUT_LAYOUT[self.out_format][1])
+            return (3, rows, self.out_xsize)
+        return (rows, self.out_xsize, OUT_LAYOUT[self.out_format][1])
 
     @property
     def out_dtype(self):
@@ -178,7 +200,7 @@ class FrameDesc:
     @property
     def out_row_bytes(self) -> int:
         dt, ch = OUT_LAYOUT[self.out_format]
-        return self.xsize * ch * np.dtype(dt).itemsize
+        return self.out_xsize * ch * np.dtype(dt).itemsize
 
     def band_rows(self) -> tuple[int, int]:
         """(first pixel row, number of pixel rows) this band renders."""
@@ -240,6 +262,11 @@ class FrameDesc:
                 keep.append(gm)
                 s.dc_group_mul = gm.ctypes.data
             s.dc_smoothing = int(self.dc_smoothing)
+        if self.upsampling > 1:
+            nw = {2: 15, 4: 55, 8: 210}[int(self.upsampling)]
+            s.upsampling = int(self.upsampling)
+            s.xsize_upsampled, s.ysize_upsampled = self.out_xsize, self.out_ysize
+            s.upsampling_weights = pin(np.asarray(self.upsampling_weights, np.float32).ravel()[:nw], np.float32, (nw,))
         s.dequant_table = pin(self.dequant, np.float32)
         s.dequant_table_floats = int(np.asarray(self.dequant).size)
         offs = np.asarray(self.dequant_offsets, np.uint32).reshape(NUM_STRATEGIES * 3)

@@ -97,6 +97,7 @@ struct jxlgpu_ctx {
   // bytes than the two-kernel path but is slower (1.33 ms vs 0.66 ms at 8K d1.0, profiles/r02_*fused*).
   bool allow_fused = false;
   bool idct8_tma = true;      // JXLGPU_IDCT8_TMA=0: the round-1 idct8_kernel (ordinary loads) for A/B runs
+  DevBuf ups_in, ups_kern;    // upsampling: filtered XYB planes at the coded size, the N*N x 25 tap table
   DevBuf qdc, dc_deq;         // DC stage on the device: quantised planes (+ per-group mul), dequantised planes
   DevBuf sparse;              // staging for the non-zero lists of jxlgpu_submit_groups_sparse
   size_t sparse_used = 0;     // words handed out this frame (bump allocation, guarded by mu)
@@ -186,7 +187,7 @@ bool fused_chain(uint32_t mask) {
 }
 bool use_fused(const jxlgpu_ctx* ctx) {
   const FrameDev& P = ctx->P;
-  if (!ctx->allow_fused || ctx->force_generic_filter || !fused_chain(P.stage_mask) || P.mc) return false;
+  if (!ctx->allow_fused || ctx->force_generic_filter || !fused_chain(P.stage_mask) || P.mc || P.ups) return false;
   for (int c = 0; c < 3; c++)
     if ((uintptr_t)P.coeff[c] % 16) return false;
   return true;
@@ -289,8 +290,20 @@ int launch_filter(jxlgpu_ctx* ctx, uint32_t y0, uint32_t y1, uint32_t out_y0, ui
   P.band_y1 = y1;
   P.out_y0 = out_y0;
   P.out_h = out_h;
+  if (P.ups) {
+    // the filters run at the coded size into planar XYB; upsample_kernel (launch_upsample) carries the
+    // stages behind the upsampling: XYB -> RGB, transfer function, packing
+    P.stage_mask &= 15u;
+    P.out_format = 1;
+    P.out_y0 = 0;
+    P.out_h = P.ysize;
+    P.nrep = 0;
+    P.mc = nullptr;
+    dev_out = (char*)ctx->ups_in.p;
+    out_row_stride = (size_t)P.xsize * 4;
+  }
   cudaError_t strip_err = cudaSuccess;
-  if (use_fused(ctx)) {
+  if (!P.ups && use_fused(ctx)) {
     // coefficients -> pixels in one kernel; finished rows leave through the TMA unit when every row
     // segment is 16-byte aligned (the kernel checks the per-strip size)
     bool aligned = (uintptr_t)dev_out % 16 == 0 && out_row_stride % 16 == 0;
@@ -309,8 +322,20 @@ int launch_filter(jxlgpu_ctx* ctx, uint32_t y0, uint32_t y1, uint32_t out_y0, ui
   return JXLGPU_OK;
 }
 
+// the whole frame: filtered planes (ups_in) -> upsampled, colour-converted, packed pixels
+int launch_upsample(jxlgpu_ctx* ctx, char* dev_out, size_t out_row_stride, cudaStream_t s) {
+  FrameDev P = ctx->P;
+  P.out_y0 = 0;
+  P.out_h = P.out_hh;
+  const dim3 grid((P.out_w + 31) / 32, (P.out_hh + 7) / 8);
+  upsample_kernel<<<grid, 256, 0, s>>>(P, (const float*)ctx->ups_in.p, dev_out, out_row_stride);
+  ctx->launches += 1;
+  CU(cudaGetLastError());
+  return JXLGPU_OK;
+}
+
 int ensure_out(jxlgpu_ctx* ctx) {
-  const uint32_t band_h = ctx->P.band_y1 - ctx->P.band_y0;
+  const uint32_t band_h = ctx->P.ups ? ctx->P.out_hh : ctx->P.band_y1 - ctx->P.band_y0;
   CU(ctx->out.ensure(out_planes(ctx->P.out_format) * band_h * ctx->out_row_bytes));
   return JXLGPU_OK;
 }
@@ -376,7 +401,7 @@ int pump(jxlgpu_ctx* ctx, bool force) {
     rc = launch_filter(ctx, y0, y1, P.band_y0, band_h, (char*)ctx->out.p, ctx->out_row_bytes, s);
     if (rc) return rc;
     for (uint32_t r = g; r < h; r++) ctx->row_filtered[r] = 1;
-    if (ctx->host_out && y1 > y0) {  // copy the finished rows back while later rows still arrive
+    if (ctx->host_out && y1 > y0 && !P.ups) {  // copy the finished rows back while later rows still arrive
       CU(cudaEventRecord(ctx->ev_filter, s));
       CU(cudaStreamWaitEvent(ctx->s_down, ctx->ev_filter, 0));
       const size_t row_bytes = ctx->out_row_bytes;
@@ -517,6 +542,17 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
                    : (!f->dc[0] || !f->dc[1] || !f->dc[2]))
     return JXLGPU_ERR_INVALID_ARGUMENT;
   if (f->ac_type > JXLGPU_AC_INT32 || f->out_format > JXLGPU_OUT_RGB_F16) return JXLGPU_ERR_INVALID_ARGUMENT;
+  const uint32_t ups = f->upsampling <= 1 ? 0 : f->upsampling;
+  uint32_t out_w = f->xsize, out_hh = f->ysize;
+  if (ups) {
+    if (ups != 2 && ups != 4 && ups != 8) return JXLGPU_ERR_INVALID_ARGUMENT;
+    if (!f->upsampling_weights) return JXLGPU_ERR_INVALID_ARGUMENT;
+    if (f->band_ny_groups) return JXLGPU_ERR_UNSUPPORTED;  // whole-frame contexts only
+    out_w = f->xsize_upsampled ? f->xsize_upsampled : ups * f->xsize;
+    out_hh = f->ysize_upsampled ? f->ysize_upsampled : ups * f->ysize;
+    // FrameDimensions: size = DivCeil(size_upsampled, upsampling)
+    if ((out_w + ups - 1) / ups != f->xsize || (out_hh + ups - 1) / ups != f->ysize) return JXLGPU_ERR_INVALID_ARGUMENT;
+  }
   // plane strides (in elements) must cover a row: a short stride would make the uploads read out of bounds
   if (f->ac_strategy_stride < f->xsize_blocks || f->raw_quant_stride < f->xsize_blocks ||
       (f->epf_sharpness && f->epf_sharpness_stride < f->xsize_blocks) ||
@@ -670,7 +706,37 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   memcpy(P.opsin_m, f->inverse_opsin_matrix, sizeof(P.opsin_m));
   memcpy(P.opsin_bias, f->opsin_biases, sizeof(P.opsin_bias));
   memcpy(P.opsin_cbrt, f->opsin_biases_cbrt, sizeof(P.opsin_cbrt));
-  ctx->out_row_bytes = out_bytes_per_row(*f);
+  ctx->out_row_bytes = (size_t)out_w * out_pixel_bytes(f->out_format);
+  P.ups = ups;
+  P.out_w = out_w;
+  P.out_hh = out_hh;
+  P.ups_kernel = nullptr;
+  if (ups) {
+    // the stage's constructor (stage_upsampling.cc:61-86): N/2 x N/2 x 25 symmetric weights -> N*N kernels of 25 taps
+    const uint32_t N = ups, H = N / 2;
+    std::vector<float> kern((size_t)N * N * 25);
+    const float* w = f->upsampling_weights;
+    for (uint32_t ky = 0; ky < H; ky++)
+      for (uint32_t kx = 0; kx < H; kx++) {
+        const size_t o0 = (ky * N + kx) * 25, o1 = (ky * N + (N - 1 - kx)) * 25;
+        const size_t o2 = ((N - 1 - ky) * N + kx) * 25, o3 = ((N - 1 - ky) * N + (N - 1 - kx)) * 25;
+        for (uint32_t py = 0; py < 5; py++)
+          for (uint32_t px = 0; px < 5; px++) {
+            const uint32_t j = 5 * ky + py, i = 5 * kx + px;
+            const uint32_t my = i < j ? i : j, mx = i < j ? j : i;
+            const float v = w[5 * H * my - my * (my - 1) / 2 + mx - my];
+            kern[o0 + py * 5 + px] = v;
+            kern[o1 + py * 5 + (4 - px)] = v;
+            kern[o2 + (4 - py) * 5 + px] = v;
+            kern[o3 + (4 - py) * 5 + (4 - px)] = v;
+          }
+      }
+    CU(ctx->ups_kern.ensure(kern.size() * 4));
+    CU(cudaMemcpyAsync(ctx->ups_kern.p, kern.data(), kern.size() * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));  // (`kern` is pageable and about to go out of scope)
+    CU(ctx->ups_in.ensure((size_t)3 * f->xsize * f->ysize * 4));
+    P.ups_kernel = (const float*)ctx->ups_kern.p;
+  }
   ctx->sparse_used = 0;
   ctx->submitted.assign(ctx->num_groups, ctx->coeff_external ? 1 : 0);
   ctx->row_count.assign(P.yg, ctx->coeff_external ? P.xg : 0);
@@ -948,6 +1014,10 @@ static int render_device_on(jxlgpu_ctx* ctx, void* dev_out, size_t out_stride_by
   }
   int rc = launch_idct(ctx, ctx->need_row0, ctx->need_row1, P.need_y0, P.need_y1, s);
   if (rc) return rc;
+  if (P.ups) {
+    rc = launch_filter(ctx, P.band_y0, P.band_y1, P.band_y0, band_h, o, stride, s);
+    return rc ? rc : launch_upsample(ctx, o, stride, s);
+  }
   if (!P.nrep || P.mc || ctx->gather_in_kernel || use_fused(ctx))
     return launch_filter(ctx, P.band_y0, P.band_y1, P.band_y0, band_h, o, stride, s);
   // Gather through the copy engines: the band is filtered in row chunks; as soon as a chunk is finished its
@@ -1012,8 +1082,17 @@ int jxlgpu_frame_finish(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes) {
         return JXLGPU_ERR_STATE;
       }
   }
+  if (ctx->P.ups) {  // every row is filtered: upsample the frame, then the whole output travels
+    int rc = launch_upsample(ctx, (char*)ctx->out.p, ctx->out_row_bytes, ctx->stream);
+    if (rc) return rc;
+    if (!out && ctx->host_out) {
+      out = ctx->host_out;
+      out_stride_bytes = ctx->host_out_stride;
+    }
+    ctx->host_out = nullptr;
+  }
   if (out && out != ctx->host_out) {
-    const uint32_t band_h = ctx->P.band_y1 - ctx->P.band_y0;
+    const uint32_t band_h = ctx->P.ups ? ctx->P.out_hh : ctx->P.band_y1 - ctx->P.band_y0;
     const size_t row_bytes = ctx->out_row_bytes;
     if (out_stride_bytes < row_bytes) return JXLGPU_ERR_INVALID_ARGUMENT;
     const size_t planes = out_planes(ctx->P.out_format);

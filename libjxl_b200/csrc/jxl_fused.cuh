@@ -47,7 +47,7 @@ constexpr int kTRow = 3 * kTPitch;        // floats per ring row (X, Y, B)
 constexpr int kTWarps = 16;
 constexpr int kTThreads = 32 * kTWarps;
 constexpr int kTPRows = 24;               // pixel ring: three block rows
-constexpr int kTScratchWords = 192;       // per block: raw coefficients (3 x 64 int32 at most), then co/tmp of the transform
+constexpr int kTScratchWords = 200;       // per block: raw coefficients (3 x 64 int32 at most), then co/tmp of the transform
 constexpr int kTStageRow = kTOut * 12;    // bytes of one staged output row (RGB f32 at most)
 constexpr int kTPad = 8;                  // floats in front of the rings (tile 0 reads up to 3 columns to the left)
 

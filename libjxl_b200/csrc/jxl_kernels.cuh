@@ -115,6 +115,9 @@ struct FrameDev {
   float epf_scale[3];
   float epf_quant_mul, epf_sm[3], epf_border_mul;  // epf_sm[pass]: sigma multiplier of pass 0/1/2
   float opsin_m[9], opsin_bias[3], opsin_cbrt[3];
+  // upsampling after the filters (stage_upsampling.cc): factor (0/1 = none), output size, the N*N x 25 tap table
+  uint32_t ups, out_w, out_hh;
+  const float* ups_kernel;
 };
 
 // ---------------------------------------------------------------------------
@@ -1039,7 +1042,7 @@ __global__ void __launch_bounds__(kSmallWarpsPerCta * 32, 4) idct8_kernel(const 
 // kernel.  3 CTAs x 8 warps per SM keep ~70 KB of coefficient reads in flight per SM.
 // Needs 16-byte aligned coefficient planes (jxlgpu_set_device_coefficients may bring others: idct8_kernel).
 // ---------------------------------------------------------------------------
-constexpr int kTma8BlockWords = 192;                                    // 3 channels x 64 int32 (int16: half used)
+constexpr int kTma8BlockWords = 200;  // 3 channels x 64 int32 (int16: half used) + 8: the four blocks of a warp start 8 banks apart
 constexpr int kTma8StageWords = 4 * kTma8BlockWords;
 constexpr int kTma8WarpWords = 2 * kTma8StageWords + 4 * 64 + 4;        // 2 stages | 4 pixel scratches | 2 mbarriers
 constexpr size_t kTma8SmemBytes = (size_t)kSmallWarpsPerCta * kTma8WarpWords * 4;
@@ -1679,6 +1682,76 @@ __device__ __forceinline__ float epf_weight(float sad, float inv_sigma) {
 }
 
 #ifndef JXLB_STRIP_TU
+// ---------------------------------------------------------------------------
+// UpsamplingStage (lib/jxl/render_pipeline/stage_upsampling.cc:51-271) fused with the
+// stages PreparePipeline puts behind it (dec_cache.cc:216-330): XYB -> linear RGB [-> sRGB] -> output packing.
+// `in`: the filtered XYB planes at the coded size ([3][ysize][xsize] f32, written by the filter chain run
+// without its XYB stage).  One thread per OUTPUT pixel (X, Y): sub-pixel k = N*(Y%N) + X%N of input pixel
+// (X/N, Y/N); 25 taps of the 5x5 window (mirrored about the coded size) in three accumulators in the
+// reference's order (:246-262), clamped to the window's minimum / maximum (:152-206).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample_kernel(const __grid_constant__ FrameDev P, const float* __restrict__ in,
+                                                       char* __restrict__ out, size_t out_row_stride) {
+  const int X = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (X >= (int)P.out_w || Y >= (int)P.out_hh) return;
+  const int N = (int)P.ups, W = (int)P.xsize, H = (int)P.ysize;
+  const int x = X / N, y = Y / N;
+  const float* k = P.ups_kernel + (N * (Y - y * N) + (X - x * N)) * 25;
+  int cx[5], ry[5];
+#pragma unroll
+  for (int d = 0; d < 5; d++) {
+    cx[d] = mirror_i(x + d - 2, W);
+    ry[d] = mirror_i(y + d - 2, H) * W;
+  }
+  float kw[25];
+#pragma unroll
+  for (int i = 0; i < 25; i++) kw[i] = __ldg(k + i);
+  float res[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const float* p = in + (size_t)c * W * H;
+    float v[25];
+#pragma unroll
+    for (int iy = 0; iy < 5; iy++)
+#pragma unroll
+      for (int ix = 0; ix < 5; ix++) v[5 * iy + ix] = __ldg(p + ry[iy] + cx[ix]);
+    float mn = v[0], mx = v[0];
+#pragma unroll
+    for (int i = 1; i < 25; i++) {
+      mn = fminf(mn, v[i]);
+      mx = fmaxf(mx, v[i]);
+    }
+    float a0 = v[0] * kw[0], a1 = v[1] * kw[1], a2 = v[2] * kw[2];
+#pragma unroll
+    for (int i = 3; i < 24; i += 3) {
+      a0 = fmaf(v[i], kw[i], a0);
+      a1 = fmaf(v[i + 1], kw[i + 1], a1);
+      a2 = fmaf(v[i + 2], kw[i + 2], a2);
+    }
+    a0 = fmaf(v[24], kw[24], a0);
+    float r = (a1 + a2) + a0;
+    r = r < mn ? mn : r;
+    r = r > mx ? mx : r;
+    res[c] = r;
+  }
+  float a = res[0], b = res[1], c3 = res[2];
+  if (P.stage_mask & 16u) {  // XYB -> linear RGB (dec_xyb-inl.h:38-86)
+    float gr = b + a, gg = b - a, gb = c3;
+    gr = gr - P.opsin_cbrt[0];
+    gg = gg - P.opsin_cbrt[1];
+    gb = gb - P.opsin_cbrt[2];
+    const float r2 = gr * gr, g2 = gg * gg, b2 = gb * gb;
+    const float mr = fmaf(r2, gr, P.opsin_bias[0]);
+    const float mg = fmaf(g2, gg, P.opsin_bias[1]);
+    const float mb = fmaf(b2, gb, P.opsin_bias[2]);
+    float lr = P.opsin_m[0] * mr, lg = P.opsin_m[3] * mr, lb = P.opsin_m[6] * mr;
+    lr = fmaf(P.opsin_m[1], mg, lr); lg = fmaf(P.opsin_m[4], mg, lg); lb = fmaf(P.opsin_m[7], mg, lb);
+    lr = fmaf(P.opsin_m[2], mb, lr); lg = fmaf(P.opsin_m[5], mb, lg); lb = fmaf(P.opsin_m[8], mb, lb);
+    a = lr; b = lg; c3 = lb;
+  }
+  store_px<1>(P, out, out_row_stride, Y, X, (int)P.out_hh, a, b, c3);
+}
+
 __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_constant__ FrameDev P,
                                                                char* __restrict__ out,
                                                                size_t out_row_stride /*bytes*/) {

@@ -94,7 +94,7 @@ def render_frame(desc: abi.FrameDesc, coeffs: np.ndarray, rcp_mode: int = 0) -> 
     assert co.shape == (3, desc.num_groups, abi.GROUP_COEFFS), co.shape
     s = desc.to_struct()
     ptrs = (C.c_void_p * 3)(*[co.ctypes.data + c * co[0].nbytes for c in range(3)])
-    out = np.zeros(desc.out_shape(desc.ysize), desc.out_dtype)
+    out = np.zeros(desc.out_shape(desc.ysize), desc.out_dtype)   # (upsampled frames: out_ysize rows)
     rc = lib().jxo_render_frame(C.byref(s), ptrs, rcp_mode, out.ctypes.data)
     if rc:
         raise RuntimeError(f"jxo_render_frame rc={rc}")
@@ -161,6 +161,10 @@ def desc_from_dump(d, **overrides) -> abi.FrameDesc:
         opsin_biases=tuple(i.opsin_biases)[:3], opsin_biases_cbrt=tuple(i.opsin_biases_cbrt)[:3],
         ac_type=abi.AC_INT16 if i.ac_is16 else abi.AC_INT32,
     )
+    if getattr(i, "upsampling", 1) > 1:
+        desc.upsampling = int(i.upsampling)
+        desc.upsampling_weights = np.array(list(i.upsampling_weights), np.float32)
+        desc.xsize_upsampled, desc.ysize_upsampled = int(i.xsize_upsampled), int(i.ysize_upsampled)
     for k, v in overrides.items():
         setattr(desc, k, v)
     return desc

@@ -861,6 +861,71 @@ size_t jxo_out_bytes(const jxlgpu_frame* f) {
   }
 }
 
+/* ---- UpsamplingStage (lib/jxl/render_pipeline/stage_upsampling.cc:51-271), SURVEY.md §8f rank 4 ----
+ * N = 2, 4, 8.  kernel[k][i], k = N*oy + ox, i = 5*(iy+2) + (ix+2): the 25 taps of output sub-pixel (ox, oy),
+ * expanded from the N/2 x N/2 x 25 symmetric weights exactly as the stage's constructor does (:61-86).
+ * Per input pixel and sub-pixel (:246-262): three accumulators over taps i, i+1, i+2 (Mul for the first three
+ * taps, MulAdd afterwards), acc0 takes tap 24, result = (acc1 + acc2) + acc0, clamped to the minimum / maximum of
+ * the 5x5 input window (:152-206).  Input mirrored about the coded frame size. */
+void jxo_upsampling_kernel(int N, const float* weights, float* kernel /* N*N*25 */) {
+  const int H = N / 2;
+  for (int ky = 0; ky < H; ky++)
+    for (int kx = 0; kx < H; kx++) {
+      const int o0 = (ky * N + kx) * 25, o1 = (ky * N + (N - 1 - kx)) * 25;
+      const int o2 = ((N - 1 - ky) * N + kx) * 25, o3 = ((N - 1 - ky) * N + (N - 1 - kx)) * 25;
+      for (int py = 0; py < 5; py++)
+        for (int px = 0; px < 5; px++) {
+          const int j = 5 * ky + py, i = 5 * kx + px;
+          const int my = i < j ? i : j, mx = i < j ? j : i;
+          const float w = weights[5 * H * my - my * (my - 1) / 2 + mx - my];
+          kernel[o0 + py * 5 + px] = w;
+          kernel[o1 + py * 5 + (4 - px)] = w;
+          kernel[o2 + (4 - py) * 5 + px] = w;
+          kernel[o3 + (4 - py) * 5 + (4 - px)] = w;
+        }
+    }
+}
+
+static size_t mirror_sz(int64_t x, int64_t size) {
+  while (x < 0 || x >= size) x = x < 0 ? -x - 1 : 2 * size - 1 - x;
+  return (size_t)x;
+}
+
+/* in: w x h (row stride ps_in); out: ow x oh (ow <= N*w, oh <= N*h; row stride ps_out) */
+void jxo_upsample_plane(int N, const float* kernel, const float* in, size_t w, size_t h, size_t ps_in, float* out,
+                        size_t ow, size_t oh, size_t ps_out) {
+#pragma omp parallel for schedule(static)
+  for (int64_t y = 0; y < (int64_t)h; y++)
+    for (size_t x = 0; x < w; x++) {
+      float v[25];
+      float mn = 0, mx = 0;
+      for (int iy = -2; iy <= 2; iy++)
+        for (int ix = -2; ix <= 2; ix++) {
+          const float p = in[mirror_sz(y + iy, (int64_t)h) * ps_in + mirror_sz((int64_t)x + ix, (int64_t)w)];
+          v[5 * (iy + 2) + ix + 2] = p;
+          if (iy == -2 && ix == -2) { mn = mx = p; }
+          else { mn = p < mn ? p : mn; mx = p > mx ? p : mx; }
+        }
+      for (int oy = 0; oy < N; oy++)
+        for (int ox = 0; ox < N; ox++) {
+          const size_t X = x * (size_t)N + ox, Y = (size_t)y * N + oy;
+          if (X >= ow || Y >= oh) continue;
+          const float* k = kernel + (N * oy + ox) * 25;
+          float a0 = v[0] * k[0], a1 = v[1] * k[1], a2 = v[2] * k[2];
+          for (int i = 3; i < 24; i += 3) {
+            a0 = fmaf(v[i], k[i], a0);
+            a1 = fmaf(v[i + 1], k[i + 1], a1);
+            a2 = fmaf(v[i + 2], k[i + 2], a2);
+          }
+          a0 = fmaf(v[24], k[24], a0);
+          float r = (a1 + a2) + a0;
+          r = r < mn ? mn : r;  /* Clamp(v, lo, hi) = Min(Max(lo, v), hi) */
+          r = r > mx ? mx : r;
+          out[Y * ps_out + X] = r;
+        }
+    }
+}
+
 int jxo_render_frame(const jxlgpu_frame* f_in, const void* const coeff[3], int rcp_mode, void* out_v) {
   float* out = (float*)out_v;
   /* optional DC stage (quant_dc given): DequantDC per DC group + AdaptiveDCSmoothing, then as usual */
@@ -888,7 +953,8 @@ int jxo_render_frame(const jxlgpu_frame* f_in, const void* const coeff[3], int r
     f_local.dc_stride = xbb;
   }
   const size_t xb = f->xsize_blocks, yb = f->ysize_blocks;
-  const size_t ps = xb * 8, plane = ps * yb * 8;
+  size_t ps = xb * 8;
+  const size_t plane = ps * yb * 8;
   const size_t xg = (xb + 31) / 32, yg = (yb + 31) / 32;
   float* a = (float*)calloc(3 * plane, sizeof(float));
   float* b = (float*)calloc(3 * plane, sizeof(float));
@@ -919,10 +985,34 @@ int jxo_render_frame(const jxlgpu_frame* f_in, const void* const coeff[3], int r
   if (mask & JXLGPU_STAGE_EPF0) { epf(f, 0, sigma, cur, nxt, ps); SWAP(); }
   if (mask & JXLGPU_STAGE_EPF1) { epf(f, 1, sigma, cur, nxt, ps); SWAP(); }
   if (mask & JXLGPU_STAGE_EPF2) { epf(f, 2, sigma, cur, nxt, ps); SWAP(); }
-  if (mask & JXLGPU_STAGE_XYB) xyb_to_linear(f, cur, ps);
-  if (mask & JXLGPU_STAGE_SRGB) srgb_from_linear(f, cur, ps);
+  float* up = NULL;
+  float* U[3];
+  size_t ps_out = ps;
+  jxlgpu_frame f_up = *f;  /* the stages after the upsampling work at the upsampled size */
+  const jxlgpu_frame* fo = f;
+  if (f->upsampling > 1) {
+    const int N = (int)f->upsampling;
+    const size_t ow = f->xsize_upsampled ? f->xsize_upsampled : (size_t)N * f->xsize;
+    const size_t oh = f->ysize_upsampled ? f->ysize_upsampled : (size_t)N * f->ysize;
+    float kernel[64 * 25];
+    jxo_upsampling_kernel(N, f->upsampling_weights, kernel);
+    up = (float*)malloc(3 * ow * oh * sizeof(float));
+    if (!up) { free(a); free(b); free(sigma); free(dc_own); return 2; }
+    for (int c = 0; c < 3; c++) {
+      U[c] = up + (size_t)c * ow * oh;
+      jxo_upsample_plane(N, kernel, cur[c], f->xsize, f->ysize, ps, U[c], ow, oh, ow);
+    }
+    cur = U;
+    ps_out = ow;
+    f_up.xsize = (uint32_t)ow;
+    f_up.ysize = (uint32_t)oh;
+    fo = &f_up;
+  }
+  if (mask & JXLGPU_STAGE_XYB) xyb_to_linear(fo, cur, ps_out);
+  if (mask & JXLGPU_STAGE_SRGB) srgb_from_linear(fo, cur, ps_out);
 #undef SWAP
-  const size_t W = f->xsize, H = f->ysize;
+  const size_t W = fo->xsize, H = fo->ysize;
+  ps = ps_out;
   if (f->out_format >= JXLGPU_OUT_RGB_U8 && f->out_format <= JXLGPU_OUT_RGB_F16) {
     /* WriteToOutputStage (stage_write.cc:455-640): interleave + convert; opaque alpha = all ones */
     uint8_t* o8 = (uint8_t*)out_v;
@@ -949,6 +1039,6 @@ int jxo_render_frame(const jxlgpu_frame* f_in, const void* const coeff[3], int r
       for (size_t x = 0; x < W; x++)
         for (int c = 0; c < 3; c++) out[(y * W + x) * 3 + c] = cur[c][y * ps + x];
   }
-  free(a); free(b); free(sigma); free(dc_own);
+  free(a); free(b); free(sigma); free(dc_own); free(up);
   return 0;
 }

@@ -38,6 +38,10 @@ size_t jxo_out_bytes(const jxlgpu_frame* f);
 /* Whole frame: coeff[c] = [num_groups][65536] host planes of f->ac_type.
  * out: jxo_out_bytes(f) bytes, dense rows, in f->out_format. Returns 0 on success. */
 int jxo_render_frame(const jxlgpu_frame* f, const void* const coeff[3], int rcp_mode, void* out);
+/* UpsamplingStage (stage_upsampling.cc:51-271): weights -> N*N*25 kernel; one plane w x h -> ow x oh */
+void jxo_upsampling_kernel(int N, const float* weights, float* kernel);
+void jxo_upsample_plane(int N, const float* kernel, const float* in, size_t w, size_t h, size_t ps_in, float* out,
+                        size_t ow, size_t oh, size_t ps_out);
 #ifdef __cplusplus
 }
 #endif

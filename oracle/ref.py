@@ -45,6 +45,8 @@ class RefFrameInfo(C.Structure):
         ("opsin_biases_cbrt", C.c_float * 4),
         ("dequant_table_floats", C.c_int32),
         ("dequant_offsets", C.c_int32 * 81),
+        ("upsampling", C.c_int32), ("xsize_upsampled", C.c_int32), ("ysize_upsampled", C.c_int32),
+        ("upsampling_weights", C.c_float * 210),
     ]
 
 
@@ -52,6 +54,7 @@ PLANE_AC_STRATEGY, PLANE_RAW_QUANT, PLANE_SHARPNESS, PLANE_YTOX, PLANE_YTOB = 0,
 PLANE_DC, PLANE_SIGMA, PLANE_DEQUANT, PLANE_COEFFS, PLANE_DECODED = 5, 6, 7, 8, 9
 
 STAGE_GAB, STAGE_EPF0, STAGE_EPF1, STAGE_EPF2, STAGE_XYB = 1, 2, 4, 8, 16
+STAGE_UPSAMPLING = 64   # ref_frame_render: the frame's own UpsamplingStage (before XYB)
 
 _libs: dict = {}
 _variant = "default"
@@ -92,9 +95,9 @@ def lib():
         L.ref_adaptive_dc_smoothing.argtypes = [C.c_float * 3, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
         L.ref_frame_render_out.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                            C.POINTER(C.c_double)]
-        L.ref_encode_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
-                                      C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_uint8)),
-                                      C.POINTER(C.c_size_t)]
+        L.ref_encode_rgb8_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_uint8)),
+                                         C.POINTER(C.c_size_t)]
         L.ref_decode_linear_f32.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
                                             C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ref_runner_create.restype = C.c_void_p
@@ -113,15 +116,15 @@ def lib():
 
 
 def encode_rgb8(img: np.ndarray, distance: float = 1.0, effort: int = 7, gaborish: int = -1,
-                epf: int = -1, threads: int | None = None) -> bytes:
+                epf: int = -1, threads: int | None = None, resampling: int = -1) -> bytes:
     """cjxl-equivalent through the public JxlEncoder API; returns a bare codestream."""
     img = np.ascontiguousarray(img, dtype=np.uint8)
     h, w, c = img.shape
     assert c == 3
     out = C.POINTER(C.c_uint8)()
     n = C.c_size_t()
-    rc = lib().ref_encode_rgb8(img.ctypes.data, w, h, distance, effort, gaborish, epf,
-                               threads or os.cpu_count() or 1, C.byref(out), C.byref(n))
+    rc = lib().ref_encode_rgb8_ex(img.ctypes.data, w, h, distance, effort, gaborish, epf, resampling,
+                                  threads or os.cpu_count() or 1, C.byref(out), C.byref(n))
     if rc:
         raise RuntimeError(f"ref_encode_rgb8 failed rc={rc}")
     data = C.string_at(out, n.value)
@@ -243,14 +246,16 @@ class Frame:
             dequant_offsets=np.array(list(i.dequant_offsets), np.int32).reshape(27, 3),
             coeffs=self._plane(PLANE_COEFFS, (3, i.num_groups, 65536),
                                np.int16 if i.ac_is16 else np.int32),
-            decoded=self._plane(PLANE_DECODED, (i.ysize, i.xsize, 3), np.float32),
+            decoded=self._plane(PLANE_DECODED, (i.ysize_upsampled, i.xsize_upsampled, 3), np.float32),
         )
 
     def render(self, stage_mask: int = -1, reps: int = 1, want_output: bool = True):
         """Hot path only (reference code) from the retained coefficients.
         Returns (planar f32 (3,H,W) or None, [seconds per rep])."""
         i = self.info
-        out = np.empty((3, i.ysize, i.xsize), np.float32) if want_output else None
+        ups = stage_mask >= 0 and (stage_mask & STAGE_UPSAMPLING) and i.upsampling > 1
+        shape = (3, i.ysize_upsampled, i.xsize_upsampled) if ups else (3, i.ysize, i.xsize)
+        out = np.empty(shape, np.float32) if want_output else None
         secs = (C.c_double * max(reps, 1))()
         rc = lib().ref_frame_render(self.h, stage_mask, out.ctypes.data if want_output else None,
                                     reps, secs)

@@ -67,6 +67,7 @@
 #include "lib/jxl/render_pipeline/stage_epf.h"
 #include "lib/jxl/render_pipeline/stage_from_linear.h"
 #include "lib/jxl/render_pipeline/stage_gaborish.h"
+#include "lib/jxl/render_pipeline/stage_upsampling.h"
 #include "lib/jxl/render_pipeline/stage_write.h"
 #include "lib/jxl/render_pipeline/stage_xyb.h"
 
@@ -96,9 +97,16 @@ REF_API void ref_free(void* p) { free(p); }
 
 // gaborish / epf: -1 keeps the encoder default for the distance
 // (lib/jxl/enc_frame.cc:316-341).  Output: bare codestream, malloc'd.
+REF_API int ref_encode_rgb8_ex(const uint8_t* rgb, int w, int h, float distance, int effort, int gaborish, int epf,
+                               int resampling, int threads, uint8_t** out, size_t* out_size);
 REF_API int ref_encode_rgb8(const uint8_t* rgb, int w, int h, float distance,
                             int effort, int gaborish, int epf, int threads,
                             uint8_t** out, size_t* out_size) {
+  return ref_encode_rgb8_ex(rgb, w, h, distance, effort, gaborish, epf, -1, threads, out, out_size);
+}
+// resampling: -1 = encoder default, 1/2/4/8 = JXL_ENC_FRAME_SETTING_RESAMPLING (frame_header.upsampling)
+REF_API int ref_encode_rgb8_ex(const uint8_t* rgb, int w, int h, float distance, int effort, int gaborish, int epf,
+                               int resampling, int threads, uint8_t** out, size_t* out_size) {
   Runner runner(threads);
   JxlEncoder* enc = JxlEncoderCreate(nullptr);
   if (!enc) return 1;
@@ -129,6 +137,8 @@ REF_API int ref_encode_rgb8(const uint8_t* rgb, int w, int h, float distance,
       JxlEncoderFrameSettingsSetOption(fs, JXL_ENC_FRAME_SETTING_GABORISH, gaborish);
     if (epf >= 0)
       JxlEncoderFrameSettingsSetOption(fs, JXL_ENC_FRAME_SETTING_EPF, epf);
+    if (resampling > 0)
+      JxlEncoderFrameSettingsSetOption(fs, JXL_ENC_FRAME_SETTING_RESAMPLING, resampling);
     JxlPixelFormat pf = {3, JXL_TYPE_UINT8, JXL_NATIVE_ENDIAN, 0};
     if (JxlEncoderAddImageFrame(fs, &pf, rgb, static_cast<size_t>(w) * h * 3) !=
         JXL_ENC_SUCCESS) { rc = 5; break; }
@@ -323,7 +333,7 @@ Status OpenImpl(RefFrame* f, const uint8_t* data, size_t n) {
   const FrameHeader& fh = *f->frame_header;
   if (fh.encoding != FrameEncoding::kVarDCT) return JXL_FAILURE("not VarDCT");
   if (!fh.chroma_subsampling.Is444()) return JXL_FAILURE("not 444");
-  if (fh.upsampling != 1) return JXL_FAILURE("upsampling");
+  // (fh.upsampling != 1 is fine: UpsamplingStage, SURVEY.md §8f rank 4, follows the filters)
   if (fh.flags & (FrameHeader::kPatches | FrameHeader::kSplines | FrameHeader::kNoise))
     return JXL_FAILURE("image features present");
   if (fh.passes.num_passes != 1) return JXL_FAILURE("multi-pass");
@@ -432,6 +442,9 @@ struct RefFrameInfo {
   float opsin_biases_cbrt[4];
   int32_t dequant_table_floats;             // 2056*64*3
   int32_t dequant_offsets[27 * 3];          // float offset of Matrix(kind,c)
+  int32_t upsampling;                       // frame_header.upsampling (1, 2, 4, 8)
+  int32_t xsize_upsampled, ysize_upsampled; // FrameDimensions (frame_dimensions.h:34-60)
+  float upsampling_weights[210];            // CustomTransformData::upsampling{2,4,8}_weights of that factor (15 / 55 / 210 used)
 };
 
 REF_API void* ref_frame_open_storage(const uint8_t* jxl, size_t n, int threads, int storage);
@@ -517,6 +530,15 @@ REF_API int ref_frame_info(void* h, RefFrameInfo* o) {
       const float* p = sh.matrices.Matrix(static_cast<AcStrategyType>(k), c);
       if (p < base) base = p;
     }
+  o->upsampling = static_cast<int32_t>(f->frame_header->upsampling);
+  o->xsize_upsampled = d.xsize_upsampled;
+  o->ysize_upsampled = d.ysize_upsampled;
+  {
+    const CustomTransformData& td = f->frame_header->nonserialized_metadata->transform_data;
+    const float* w = o->upsampling == 2 ? td.upsampling2_weights : o->upsampling == 4 ? td.upsampling4_weights : td.upsampling8_weights;
+    const size_t n = o->upsampling == 2 ? 15 : o->upsampling == 4 ? 55 : 210;
+    memcpy(o->upsampling_weights, w, n * sizeof(float));
+  }
   o->dequant_table_floats = DequantMatrices::kSumRequiredXy * kDCTBlockSize * 3;
   for (int k = 0; k < 27; k++)
     for (int c = 0; c < 3; c++)
@@ -615,13 +637,14 @@ REF_API int ref_frame_get_plane(void* h, int which, void* out, size_t out_bytes)
       return 0;
     }
     case REF_PLANE_DECODED: {
-      if (!need(static_cast<size_t>(d.xsize) * d.ysize * 3 * 4)) return 2;
+      const size_t dx = d.xsize_upsampled, dy = d.ysize_upsampled;  // (== xsize, ysize without upsampling)
+      if (!need(dx * dy * 3 * 4)) return 2;
       const Image3F& img = *f->decoded->color();
       float* o = static_cast<float*>(out);
-      for (size_t y = 0; y < d.ysize; y++)
+      for (size_t y = 0; y < dy; y++)
         for (size_t c = 0; c < 3; c++) {
           const float* r = img.ConstPlaneRow(c, y);
-          for (size_t x = 0; x < d.xsize; x++) o[(y * d.xsize + x) * 3 + c] = r[x];
+          for (size_t x = 0; x < dx; x++) o[(y * dx + x) * 3 + c] = r[x];
         }
       return 0;
     }
@@ -682,6 +705,11 @@ REF_API int ref_frame_render(void* h, int stage_mask, float* out, int reps, doub
       JXL_RETURN_IF_ERROR(builder.AddStage(GetEPFStage(lf, ds->sigma, EpfStage::One)));
     if (stage_mask & 8)
       JXL_RETURN_IF_ERROR(builder.AddStage(GetEPFStage(lf, ds->sigma, EpfStage::Two)));
+    if ((stage_mask & 64) && fh.upsampling != 1) {  // UpsamplingStage per colour channel, where PreparePipeline puts it (dec_cache.cc:216-227)
+      for (size_t c = 0; c < 3; c++)
+        JXL_RETURN_IF_ERROR(builder.AddStage(GetUpsamplingStage(&f->mm, fh.nonserialized_metadata->transform_data, c,
+                                                                CeilLog2Nonzero(fh.upsampling))));
+    }
     if (stage_mask & 16)
       JXL_RETURN_IF_ERROR(builder.AddStage(GetXYBStage(ds->output_encoding_info)));
     JXL_RETURN_IF_ERROR(builder.AddStage(GetWriteToImage3FStage(&f->mm, &result)));
@@ -691,11 +719,13 @@ REF_API int ref_frame_render(void* h, int stage_mask, float* out, int reps, doub
     return true;
   }();
   if (!st) return 1;
+  const bool ups = (stage_mask & 64) && fh.upsampling != 1;
+  const size_t ox = ups ? d.xsize_upsampled : d.xsize, oy = ups ? d.ysize_upsampled : d.ysize;
   if (out) {
-    if (result.xsize() != d.xsize || result.ysize() != d.ysize) return 5;
+    if (result.xsize() != ox || result.ysize() != oy) return 5;
     for (size_t c = 0; c < 3; c++)
-      for (size_t y = 0; y < d.ysize; y++)
-        memcpy(out + (c * d.ysize + y) * d.xsize, result.ConstPlaneRow(c, y), d.xsize * sizeof(float));
+      for (size_t y = 0; y < oy; y++)
+        memcpy(out + (c * oy + y) * ox, result.ConstPlaneRow(c, y), ox * sizeof(float));
   }
   for (int rep = 0; rep < reps; rep++) {
     for (size_t g = 0; g < d.num_groups; g++) ds->render_pipeline->ClearDone(g);
@@ -707,8 +737,8 @@ REF_API int ref_frame_render(void* h, int stage_mask, float* out, int reps, doub
   }
   if (out && getenv("REF_CHECK_RERUN")) {  // the re-armed passes produce the same pixels
     for (size_t c = 0; c < 3; c++)
-      for (size_t y = 0; y < d.ysize; y++)
-        if (memcmp(out + (c * d.ysize + y) * d.xsize, result.ConstPlaneRow(c, y), d.xsize * sizeof(float)))
+      for (size_t y = 0; y < oy; y++)
+        if (memcmp(out + (c * oy + y) * ox, result.ConstPlaneRow(c, y), ox * sizeof(float)))
           return 9;
   }
   return 0;

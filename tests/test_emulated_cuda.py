@@ -406,3 +406,30 @@ def test_emulated_fused_equals_two_kernel_path(emu_pipe, monkeypatch):
             assert same(a, b) and same(a, oracle(desc, coeffs))
     finally:
         two.close()
+
+
+def upsampled_frame(n, w, h, seed, fmt=abi.OUT_RGB_F32, srgb=0, ragged=True):
+    """A synthetic frame whose frame header asks for N-times upsampling (default weights of the codestream,
+    tests/golden/upsampling_weights.npz); the image size is not a multiple of N when `ragged`."""
+    from pathlib import Path
+    wts = np.load(Path(__file__).parent / "golden" / "upsampling_weights.npz")
+    desc, coeffs = wl.synthetic_frame(w, h, seed=seed, epf_iters=1)
+    desc.upsampling, desc.upsampling_weights = n, wts[f"weights{n}"]
+    desc.xsize_upsampled, desc.ysize_upsampled = (n * w - (n - 1), n * h - 1) if ragged else (n * w, n * h)
+    desc.out_format, desc.stage_mask = fmt, srgb
+    return desc, coeffs
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("n,w,h", [(2, 201, 131), (4, 100, 70), (8, 40, 30)])
+@pytest.mark.parametrize("fmt,srgb", [(abi.OUT_RGB_F32, 0), (abi.OUT_RGB_U8, abi.STAGE_SRGB), (abi.OUT_PLANAR_F32, 0)])
+def test_emulated_upsampling(emu_pipe, n, w, h, fmt, srgb):
+    """UpsamplingStage 2x / 4x / 8x after the filters, fused with XYB -> RGB and the
+    output packing (upsample_kernel), host-fed and device-resident entry points."""
+    desc, coeffs = upsampled_frame(n, w, h, seed=5 + n, fmt=fmt, srgb=srgb)
+    want = oracle(desc, coeffs)
+    assert want.shape == desc.out_shape(desc.ysize)
+    assert same(emu_pipe.decode_frame(desc, coeffs), want)
+    desc.band_y0_groups, desc.band_ny_groups = 0, 1       # bands and upsampling do not combine (yet)
+    with pytest.raises(pipeline.JxlGpuError):
+        emu_pipe.frame_begin(desc)

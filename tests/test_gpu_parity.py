@@ -335,3 +335,34 @@ def test_submit_errors(pipe):
         pipe.submit_group(99, [coeffs[c, 0] for c in range(3)])
     with pytest.raises(pipeline.JxlGpuError):      # finishing with missing groups
         pipe.frame_finish()
+
+
+@pytest.mark.parametrize("n,w,h", [(2, 1201, 531), (4, 600, 270), (8, 300, 130)])
+@pytest.mark.parametrize("fmt,srgb", [(abi.OUT_RGB_F32, 0), (abi.OUT_RGB_U8, abi.STAGE_SRGB)])
+def test_upsampling_bit_exact(pipe, n, w, h, fmt, srgb):
+    """UpsamplingStage (stage_upsampling.cc:51-271) 2x / 4x / 8x after the filters, fused with
+    XYB -> RGB, transfer function and packing; the restatement it is compared with is pinned bit-exactly against
+    the reference's own stage (tests/test_oracle_vs_reference.py::test_upsampling_stage_bit_exact)."""
+    from tests.test_emulated_cuda import upsampled_frame
+    desc, coeffs = upsampled_frame(n, w, h, seed=11 + n, fmt=fmt, srgb=srgb)
+    assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), f"upsampling {n}x")
+
+
+@pytest.mark.parametrize("rs", [2, 4, 8])
+def test_upsampled_reference_frames(pipe, rs):
+    """Codestreams the reference encoder made with resampling 2 / 4 / 8 (tests/golden/upsampling_weights.npz):
+    entropy-decoded by the reference, rendered here, compared with the reference decoder's own pixels."""
+    from pathlib import Path
+    from oracle import cpu, ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    data = bytes(np.load(Path(__file__).parent / "golden" / "upsampling_weights.npz")[f"jxl{rs}"])
+    fr = ref.Frame(data, 2)
+    d = fr.dump()
+    fr.close()
+    desc = cpu.desc_from_dump(d)
+    assert desc.upsampling == rs
+    got = pipe.decode_frame(desc, d.coeffs)
+    assert got.shape == d.decoded.shape
+    assert_same(got, oracle(desc, d.coeffs), f"resampling {rs} vs oracle")
+    assert np.abs(got - d.decoded).max() <= 2e-5       # vs the reference decoder (rcpps in AdjustQuantBias)

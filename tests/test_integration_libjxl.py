@@ -48,9 +48,11 @@ if mode == "emu":
 import jxl_workload as wl
 from oracle import ref
 res = {{}}
-for (w, h, dist, epf, fmt) in {cases!r}:
+for case in {cases!r}:
+    w, h, dist, epf, fmt = case[:5]
+    rs = case[5] if len(case) > 5 else -1          # frame_header.upsampling (JXL_ENC_FRAME_SETTING_RESAMPLING)
     img = wl.synth_image(w, h, seed=w + h)
-    data = ref.encode_rgb8(img, dist, 7, -1, epf, 4)
+    data = ref.encode_rgb8(img, dist, 7, -1, epf, 4, resampling=rs)
     ref.use_variant("default")
     dec = (lambda: ref.decode_linear_f32(data, 4)) if fmt == "f32" else (lambda: ref.decode_native(data, (h, w, 3), np.uint8, 4))
     want = dec()
@@ -59,7 +61,7 @@ for (w, h, dist, epf, fmt) in {cases!r}:
     got = dec()
     taken = ref.gpu_frames_taken() - before
     d = np.abs(got.astype(np.float64) - want.astype(np.float64))
-    res[f"{{w}}x{{h}}-d{{dist}}-epf{{epf}}-{{fmt}}"] = dict(taken=int(taken), peak=float(d.max()), differing=float((d != 0).mean()))
+    res[f"{{w}}x{{h}}-d{{dist}}-epf{{epf}}-{{fmt}}" + (f"-rs{{rs}}" if rs > 0 else "")] = dict(taken=int(taken), peak=float(d.max()), differing=float((d != 0).mean()))
 print("RESULT " + json.dumps(res))
 """
 
@@ -111,7 +113,8 @@ def test_patched_decoder_through_the_emulated_library(sparse):
     import torch
     if torch.cuda.is_available():
         pytest.skip("a device is present: covered by the gpu test")
-    res = run_child("emu", [(300, 200, 1.0, -1, "f32"), (520, 264, 2.0, 2, "f32"), (300, 200, 1.0, -1, "u8")], sparse)
+    res = run_child("emu", [(300, 200, 1.0, -1, "f32"), (520, 264, 2.0, 2, "f32"), (300, 200, 1.0, -1, "u8"),
+                             (600, 300, 1.0, -1, "f32", 2)], sparse)   # the last: an upsampled frame (resampling 2)
     for k, v in res.items():
         assert v["taken"] == 1, (k, v)               # the frame really went through the backend
         if k.endswith("u8"):                         # the application's default: 8-bit sRGB, dithered
@@ -128,7 +131,8 @@ def test_patched_decoder_on_the_gpu(sparse):
     per-thread lists that go to jxlgpu_submit_groups_sparse; dense: pinned [group][3][65536] blocks."""
     need_gpu_variant()
     res = run_child("gpu", [(1000, 700, 1.0, -1, "f32"), (2048, 1100, 2.0, 2, "f32"), (777, 333, 0.5, 0, "f32"),
-                            (1500, 900, 4.0, 3, "f32"), (1000, 700, 1.0, -1, "u8")], sparse)
+                            (1500, 900, 4.0, 3, "f32"), (1000, 700, 1.0, -1, "u8"),
+                            (1400, 900, 1.0, -1, "f32", 2), (2200, 1100, 1.0, -1, "u8", 4)], sparse)   # upsampled frames
     for k, v in res.items():
         assert v["taken"] == 1, (k, v)
         if k.endswith("u8"):

@@ -14,7 +14,11 @@ pytestmark = pytest.mark.usefixtures("built")
 @pytest.fixture(scope="module")
 def refmod(ref_available):
     if not ref_available:
-        pytest.skip("oracle/_ref not built")
+        import os
+        if os.path.isdir(os.environ.get("JXL_REFERENCE_ROOT", "/root/reference")):
+            pytest.fail("oracle/_ref is not built although the reference is present: the oracle (and the tables it "
+                        "shares with the product, csrc/jxl_tables.h) would go unpinned -- run `python oracle/build_ref.py`")
+        pytest.skip("oracle/_ref not built (no reference on this box)")
     from oracle import ref
     ref.use_variant("strict")
     yield ref
@@ -211,3 +215,31 @@ def test_gpu_frame_binding_from_decoder_state(cfg, refmod):
     want, _ = fr.render(-1)
     assert np.array_equal(out, want.transpose(1, 2, 0))
     fr.close()
+
+
+@pytest.mark.parametrize("rs,w,h", [(2, 600, 300), (4, 1100, 210), (8, 2100, 160)])
+def test_upsampling_stage_bit_exact(rs, w, h, refmod):
+    """SURVEY.md §8f rank 4, UpsamplingStage (stage_upsampling.cc:51-271): frames encoded with resampling 2/4/8.
+    The restatement (jxo_upsample_plane, after the filters and before XYB like PreparePipeline orders them) is
+    bit-exact against the reference's own stage, and the reference's hot path + stage equals its public decode."""
+    from oracle import cpu
+    img = wl.synth_image(w, h, seed=rs)
+    data = refmod.encode_rgb8(img, 1.0, 7, -1, -1, 4, resampling=rs)
+    fr = refmod.Frame(data, 2)
+    i = fr.info
+    assert i.upsampling == rs and (i.xsize_upsampled, i.ysize_upsampled) == (w, h)
+    d = fr.dump()
+    desc = cpu.desc_from_dump(d)
+    assert desc.upsampling == rs and desc.out_xsize == w and desc.out_ysize == h
+    desc.out_format = abi.OUT_PLANAR_F32
+    chain = (1 if i.gab else 0) | (2 if i.epf_iters >= 3 else 0) | (4 if i.epf_iters >= 1 else 0) | (8 if i.epf_iters >= 2 else 0)
+    want, _ = fr.render(chain | refmod.STAGE_XYB | refmod.STAGE_UPSAMPLING)
+    assert want.shape == (3, h, w)
+    got = cpu.render_frame(desc, d.coeffs, rcp_mode=1)
+    assert np.array_equal(got, want)
+    desc.stage_mask = abi.STAGE_EXPLICIT | chain          # the upsampled XYB planes themselves
+    want_xyb, _ = fr.render(chain | refmod.STAGE_UPSAMPLING)
+    assert np.array_equal(cpu.render_frame(desc, d.coeffs, rcp_mode=1), want_xyb)
+    fr.close()
+    full = refmod.decode_linear_f32(data, 2)              # the decoder's real pipeline
+    assert np.array_equal(np.moveaxis(want, 0, 2), full)
