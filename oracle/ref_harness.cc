@@ -104,7 +104,8 @@ REF_API int ref_encode_rgb8(const uint8_t* rgb, int w, int h, float distance,
                             uint8_t** out, size_t* out_size) {
   return ref_encode_rgb8_ex(rgb, w, h, distance, effort, gaborish, epf, -1, threads, out, out_size);
 }
-// resampling: -1 = encoder default, 1/2/4/8 = JXL_ENC_FRAME_SETTING_RESAMPLING (frame_header.upsampling)
+// resampling: -1 = encoder default, 1/2/4/8 = JXL_ENC_FRAME_SETTING_RESAMPLING (frame_header.upsampling);
+// + 256: JXL_ENC_FRAME_SETTING_PROGRESSIVE_AC (multi-pass frame)
 REF_API int ref_encode_rgb8_ex(const uint8_t* rgb, int w, int h, float distance, int effort, int gaborish, int epf,
                                int resampling, int threads, uint8_t** out, size_t* out_size) {
   Runner runner(threads);
@@ -138,7 +139,9 @@ REF_API int ref_encode_rgb8_ex(const uint8_t* rgb, int w, int h, float distance,
     if (epf >= 0)
       JxlEncoderFrameSettingsSetOption(fs, JXL_ENC_FRAME_SETTING_EPF, epf);
     if (resampling > 0)
-      JxlEncoderFrameSettingsSetOption(fs, JXL_ENC_FRAME_SETTING_RESAMPLING, resampling);
+      JxlEncoderFrameSettingsSetOption(fs, JXL_ENC_FRAME_SETTING_RESAMPLING, resampling & 15);
+    if (resampling > 0 && (resampling & 256))  // bit 8: progressive AC (several passes per group)
+      JxlEncoderFrameSettingsSetOption(fs, JXL_ENC_FRAME_SETTING_PROGRESSIVE_AC, 1);
     JxlPixelFormat pf = {3, JXL_TYPE_UINT8, JXL_NATIVE_ENDIAN, 0};
     if (JxlEncoderAddImageFrame(fs, &pf, rgb, static_cast<size_t>(w) * h * 3) !=
         JXL_ENC_SUCCESS) { rc = 5; break; }

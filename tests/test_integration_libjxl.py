@@ -123,6 +123,18 @@ def test_patched_decoder_through_the_emulated_library(sparse):
             assert v["peak"] <= TOL_PEAK, (k, v)
 
 
+@pytest.mark.timeout(1800)
+def test_progressive_frames_stay_on_the_cpu_path():
+    """A frame with several AC passes (JXL_ENC_FRAME_SETTING_PROGRESSIVE_AC) is not handed to the backend
+    (integration/gpu_frame_binding.h: IsEligible wants num_passes == 1): the patched decoder renders it with
+    libjxl's own pipeline, byte-identical to the stock decoder."""
+    need_gpu_variant()
+    import torch
+    res = run_child("gpu" if torch.cuda.is_available() else "emu", [(300, 200, 1.0, -1, "f32", 1 + 256)])
+    (k, v), = res.items()
+    assert v["taken"] == 0 and v["peak"] == 0.0, (k, v)
+
+
 @pytest.mark.gpu
 @pytest.mark.timeout(1800)
 @pytest.mark.parametrize("sparse", [True, False], ids=["sparse-lists", "dense-blocks"])
