@@ -685,6 +685,13 @@ def main() -> int:
                               "fraction_differing": float((d != 0).mean()), "rows_checked": int(got.shape[0])}
         res["parity"] = parity
         del gathered, my_out
+        if world > 1 and os.environ.get("BENCH_KEEP_SYMM") != "1":
+            # the host-fed arm has no gather: release the symmetric-memory frame buffers (and their peer mappings)
+            import gc
+            flat = None   # noqa: F841
+            hdl = None
+            gc.collect()
+            torch.cuda.empty_cache()
 
         # ---------------- end-to-end arm: host buffers through the C ABI ----------------
         pipe.set_device_coefficients(None)

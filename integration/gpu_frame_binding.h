@@ -30,7 +30,7 @@ inline bool IsEligible(const jxl::FrameHeader& fh, const jxl::CodecMetadata& met
          fh.color_transform == jxl::ColorTransform::kXYB && fh.chroma_subsampling.Is444() &&
          (fh.upsampling == 1 || fh.upsampling == 2 || fh.upsampling == 4 || fh.upsampling == 8) &&
          !(fh.flags & (FrameHeader::kPatches | FrameHeader::kSplines | FrameHeader::kNoise)) &&
-         fh.passes.num_passes == 1 && metadata.m.num_extra_channels == 0;
+         metadata.m.num_extra_channels == 0;   // (several passes: accumulated in the dense pinned storage)
 }
 
 struct GpuFrameBinding {

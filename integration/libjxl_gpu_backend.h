@@ -256,7 +256,8 @@ inline bool WantFrame(const jxl::FrameHeader& fh, jxl::PassesDecoderState* ds, c
   std::unique_ptr<jxl::ACImage> store;
   // JXLB_GPU_SPARSE=0: dense [group][3][65536] blocks instead of non-zero lists (read per frame)
   const char* sp = getenv("JXLB_GPU_SPARSE");
-  const bool sparse = sp ? sp[0] != '0' : be.want_sparse;
+  // a multi-pass (progressive) frame accumulates its passes in the dense blocks; the lists hold each position once
+  const bool sparse = (sp ? sp[0] != '0' : be.want_sparse) && fh.passes.num_passes == 1;
   if (sparse) {
     if (!ArenaAlloc(num_groups * 3 * 65536 * sizeof(uint32_t))) return false;
     store.reset(new SinkACImage(use_16_bit));
@@ -304,13 +305,14 @@ inline bool FrameActive(const jxl::PassesDecoderState* ds) {
 }
 // before DecodeGroup: dense -> zero-fill this group's blocks (accumulate mode adds into them,
 // lib/jxl/dec_group.cc:527-531); sparse -> arm the calling thread's sink
-inline void PrepareGroup(jxl::PassesDecoderState* ds, size_t group) {
+inline void PrepareGroup(jxl::PassesDecoderState* ds, size_t group, size_t passes_done) {
   GpuFrame* fr = GpuBackend::Get().Find(ds);
   if (!fr) return;
   if (fr->sparse) {
     TlsSink().Arm();
     return;
   }
+  if (passes_done != 0) return;  // later passes add to what the earlier ones left (dec_group.cc:527-531)
   const jxl::Rect br = ds->shared->frame_dim.BlockGroupRect(group);
   const size_t n = 64 * br.xsize() * br.ysize();
   for (size_t c = 0; c < 3; c++) {

@@ -33,12 +33,13 @@ DEC_FRAME = [
      '    JXL_RETURN_IF_ERROR(jxlb_integration::BeginFrame(frame_header_, dec_state_));\n'),
     # site 3a (dec_frame.cc:503-505): zero-fill this group's pinned blocks / arm the thread's sparse sink
     ('    JXL_RETURN_IF_ERROR(DecodeGroup(\n        frame_header_, br.data(), num_passes, ac_group_id, dec_state_,\n',
-     '    jxlb_integration::PrepareGroup(dec_state_, ac_group_id);\n'
+     '    jxlb_integration::PrepareGroup(dec_state_, ac_group_id, decoded_passes_per_ac_group_[ac_group_id]);\n'
      '    JXL_RETURN_IF_ERROR(DecodeGroup(\n        frame_header_, br.data(), num_passes, ac_group_id, dec_state_,\n'),
     # site 3 (dec_frame.cc:506-516): the group was entropy-decoded only (DecodeGroup saw kDontDraw) -> submit
     ('        force_draw, dc_only, &should_run_pipeline));\n  }\n',
      '        force_draw, dc_only, &should_run_pipeline));\n'
-     '    if (num_passes > 0 && jxlb_integration::DontDraw(dec_state_)) {\n'
+     '    if (num_passes > 0 && jxlb_integration::DontDraw(dec_state_) &&\n'
+     '        decoded_passes_per_ac_group_[ac_group_id] + num_passes >= frame_header_.passes.num_passes) {\n'
      '      JXL_RETURN_IF_ERROR(jxlb_integration::GroupDecoded(dec_state_, ac_group_id));\n'
      '    }\n  }\n'),
     # site 4 (dec_frame.cc:860-882): wait for the GPU, pixels are in the application's buffer

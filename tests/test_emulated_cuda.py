@@ -36,6 +36,22 @@ def emu_pipe(request):
             os.environ["JXLGPU_FUSED"] = old
 
 
+# The fused decode kernel shares its arithmetic (block8_item, the stage bodies) with the two-kernel path; it is run
+# on the tests that exercise what is its own -- tiling, rings, scheduling, bulk copies, output staging -- and skipped
+# on the rest (every test twice cost the CPU suite ten minutes of SIMT emulation).
+FUSED_TESTS = {"test_emulated_golden_frame", "test_emulated_production_chains", "test_emulated_output_stages",
+               "test_emulated_ragged_sizes", "test_emulated_fused_all_gather_replay", "test_emulated_fused_kernel_row_segments",
+               "test_emulated_fused_equals_two_kernel_path", "test_emulated_tiny_heights_with_epf_engaged",
+               "test_emulated_sparse_hand_off"}
+
+
+@pytest.fixture(autouse=True)
+def _fused_subset(request):
+    cs = getattr(request.node, "callspec", None)
+    if cs is not None and cs.params.get("emu_pipe") == "fused" and request.node.originalname not in FUSED_TESTS:
+        pytest.skip("fused kernel: covered by the tests of FUSED_TESTS")
+
+
 def oracle(desc, coeffs):
     from oracle import cpu
     return cpu.render_frame(desc, coeffs, rcp_mode=0)

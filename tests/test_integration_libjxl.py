@@ -124,15 +124,18 @@ def test_patched_decoder_through_the_emulated_library(sparse):
 
 
 @pytest.mark.timeout(1800)
-def test_progressive_frames_stay_on_the_cpu_path():
-    """A frame with several AC passes (JXL_ENC_FRAME_SETTING_PROGRESSIVE_AC) is not handed to the backend
-    (integration/gpu_frame_binding.h: IsEligible wants num_passes == 1): the patched decoder renders it with
-    libjxl's own pipeline, byte-identical to the stock decoder."""
+def test_progressive_frames_accumulate_in_the_dense_blocks():
+    """A frame with several AC passes (JXL_ENC_FRAME_SETTING_PROGRESSIVE_AC; lib/jxl/dec_group.cc:219,335-338 adds
+    every pass into the stored coefficients) goes to the backend too: the passes accumulate in the pinned dense
+    blocks (zero-filled before a group's first pass only), the group is handed over after its last pass; the
+    sparse lists (each position once) are not used for such frames."""
     need_gpu_variant()
     import torch
-    res = run_child("gpu" if torch.cuda.is_available() else "emu", [(300, 200, 1.0, -1, "f32", 1 + 256)])
-    (k, v), = res.items()
-    assert v["taken"] == 0 and v["peak"] == 0.0, (k, v)
+    mode = "gpu" if torch.cuda.is_available() else "emu"
+    for sparse in (True, False):       # JXLB_GPU_SPARSE=1 must fall back to dense for this frame by itself
+        res = run_child(mode, [(300, 200, 1.0, -1, "f32", 1 + 256), (520, 264, 2.0, 2, "f32", 1 + 256)], sparse)
+        for k, v in res.items():
+            assert v["taken"] == 1 and v["peak"] <= TOL_PEAK, (k, v)
 
 
 @pytest.mark.gpu

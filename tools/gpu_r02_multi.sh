@@ -21,14 +21,16 @@ PY
 }
 run() {  # name, args...
   name=$1; shift
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+  timeout ${STEP_TIMEOUT:-900} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
       bench.py --gpus $N --no-cpu-baseline "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err
   show $name
 }
 echo "=== 8k-d1, gather = copy engines (default) ==="
 run mg${N}_8k-d1_ce --workload 8k-d1
+if [ "$N" != "8" ]; then
 echo "=== 8k-d1, gather = p2p stores fused in the kernel ==="
 run mg${N}_8k-d1_p2p --workload 8k-d1 --gather p2p --no-variants
+fi
 echo "=== 8k-d1, gather = nccl ==="
 run mg${N}_8k-d1_nccl --workload 8k-d1 --gather nccl --no-variants
 echo "=== 8k-d0.5-full ==="
@@ -37,5 +39,5 @@ echo "=== 64x1080p replicas ==="
 run mg${N}_1080p --workload 64x1080p --steps 10
 if [ "$N" = "8" ]; then
 echo "=== 16k-d2-epf3 ==="
-run mg${N}_16k --workload 16k-d2-epf3 --steps 10 --no-variants
+STEP_TIMEOUT=300 run mg${N}_16k --workload 16k-d2-epf3 --steps 10 --no-variants
 fi
