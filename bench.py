@@ -142,6 +142,32 @@ def prepare_frame(name: str, rank: int, world: int, barrier):
     return fr, source
 
 
+def bind_near_gpu(index: int) -> str:
+    """Pin this process (and so its page-locked buffers, first touch) to the CPUs of the GPU's NUMA node -- what
+    `numactl` does for a production decoder.  A host buffer on the far socket halves the PCIe rates of the e2e
+    arm (seen as 2x run-to-run differences on the same box before this was here).  Returns a note for the log."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(index)
+        try:   # the physical device behind this CUDA index (CUDA_VISIBLE_DEVICES may renumber)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(
+                f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        except Exception:  # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        near = {i for i in range(os.cpu_count()) if (words[i // 64] >> (i % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = near & allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return f"bound to {len(cpus)} CPUs near GPU {index}"
+        return f"no binding needed ({len(allowed)} CPUs allowed, {len(near)} near GPU {index})"
+    except Exception as e:  # noqa: BLE001
+        return f"no NUMA binding ({e!r})"
+
+
 def host_cpu_info() -> dict:
     """Cores this process may actually use: the scheduler affinity mask capped by the cgroup CPU quota
     (os.cpu_count() reports the whole host, which a 1-GPU lease does not own)."""
@@ -293,6 +319,7 @@ def run_replicas(args, rank: int, local_rank: int, world: int) -> int:
     from libjxl_b200 import abi, pipeline
     from oracle import ref
     torch.cuda.set_device(local_rank)
+    log(f"rank {rank}: {bind_near_gpu(local_rank)}")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -460,7 +487,7 @@ def main() -> int:
                          "too and reported under \"variants\"")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="auto", choices=["auto", "ce", "multicast", "p2p", "nccl"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "ce", "sm", "multicast", "p2p", "nccl"],
                     help="N>1: how the bands are all-gathered into every rank's frame buffer (symmetric memory): "
                          "ce (= auto) finished row chunks travel to the peers through the copy engines while the next "
                          "chunk is filtered; p2p: peer stores fused into the filter kernel; multicast: multimem.st "
@@ -469,6 +496,8 @@ def main() -> int:
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.gather in ("p2p", "multicast"):
         os.environ["JXLGPU_GATHER"] = "kernel"   # (read when the context is created)
+    if args.gather == "sm":
+        os.environ["JXLGPU_GATHER"] = "sm"       # peer_copy_kernel per row chunk instead of copy-engine copies
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -488,6 +517,7 @@ def main() -> int:
         print(json.dumps({"error": "no CUDA device: the product path has no CPU fallback"}))
         return 2
     torch.cuda.set_device(local_rank)
+    log(f"rank {rank}: {bind_near_gpu(local_rank)}")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -549,7 +579,10 @@ def main() -> int:
         else:
             slot = max_rows * W * 3
             gathered = None
-            if args.gather != "nccl":
+            # auto: copy engines, except the f32 frame on 8 GPUs where NCCL measured 9 % faster (1.09 vs 1.19 ms:
+            # nothing left to overlap the gather with)
+            use_nccl = args.gather == "nccl" or (args.gather == "auto" and world >= 8 and kind == "f32")
+            if not use_nccl:
                 try:
                     # Fused compute + all-gather: the frame buffer of every rank is symmetric memory; a filter
                     # CTA writes its strip segment into the local slot and replays it to every peer with wide
@@ -569,6 +602,9 @@ def main() -> int:
                         pipe.set_output_replicas([int(hdl.buffer_ptrs[p]) + rank * slot * isz for p in range(world) if p != rank])
                         gather_mode = ("fused in the filter kernel: each CTA replays its finished region to the peers (NVLink P2P float2 stores)"
                                        if args.gather == "p2p" else
+                                       "SM copy kernel: every finished row chunk is stored to all peers' symmetric-memory frame buffers "
+                                       "by peer_copy_kernel (16-byte NVLink stores) on a side stream while the next chunk is filtered"
+                                       if args.gather == "sm" else
                                        "copy engines: every finished row chunk is copied to the peers' symmetric-memory frame buffers "
                                        "(NVLink, cudaMemcpyAsync on side streams) while the next chunk is filtered")
                 except Exception as e:  # noqa: BLE001

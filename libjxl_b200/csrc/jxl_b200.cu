@@ -92,6 +92,7 @@ struct jxlgpu_ctx {
   cudaStream_t rep_streams[8] = {};
   cudaEvent_t ev_chunk[8] = {}, ev_rep[8] = {};
   bool gather_in_kernel = false;
+  bool gather_sm = false;     // JXLGPU_GATHER=sm: peer_copy_kernel per row chunk instead of copy-engine copies
   DevBuf bmap;                // fused path: one 16-byte record per 8x8 block (plan kernel)
   // JXLGPU_FUSED=1 selects the fused decode kernel (jxl_fused.cuh).  Opt-in: on B200 it moves 2x fewer DRAM
   // bytes than the two-kernel path but is slower (1.33 ms vs 0.66 ms at 8K d1.0, profiles/r02_*fused*).
@@ -487,7 +488,10 @@ int jxlgpu_create(jxlgpu_ctx** out, const jxlgpu_config* cfg) {
     if (ea != cudaSuccess) return bail(ea, "cudaFuncSetAttribute(fused_tile_kernel)");
   if (const char* fe = getenv("JXLGPU_FUSED")) ctx->allow_fused = fe[0] == '1';
   if (const char* te = getenv("JXLGPU_IDCT8_TMA")) ctx->idct8_tma = te[0] != '0';
-  if (const char* ge = getenv("JXLGPU_GATHER")) ctx->gather_in_kernel = ge[0] == 'k';
+  if (const char* ge = getenv("JXLGPU_GATHER")) {
+    ctx->gather_in_kernel = ge[0] == 'k';
+    ctx->gather_sm = ge[0] == 's';
+  }
   {
     const char* env = getenv("JXLGPU_FORCE_GENERIC_FILTER");
     ctx->force_generic_filter = env && env[0] == '1';
@@ -1043,6 +1047,22 @@ static int render_device_on(jxlgpu_ctx* ctx, void* dev_out, size_t out_stride_by
     if (rc) break;
     cudaEvent_t ev = ctx->ev_chunk[chunk & 7];
     CU(cudaEventRecord(ev, s));
+    bool sm_ok = ctx->gather_sm && (uintptr_t)o % 16 == 0 && stride % 16 == 0;
+    for (uint32_t q = 0; q < nrep; q++) sm_ok = sm_ok && (uintptr_t)rep[q] % 16 == 0;
+    if (sm_ok) {  // one copy kernel per chunk and plane on a side stream: every peer at once, 16-byte stores
+      cudaStream_t cs = ctx->rep_streams[0];
+      CU(cudaStreamWaitEvent(cs, ev, 0));
+      for (size_t pl = 0; pl < planes; pl++) {
+        const size_t off = (pl * band_h + (y0 - P.band_y0)) * stride;
+        PeerDst dst{};
+        dst.n = nrep;
+        for (uint32_t q = 0; q < nrep; q++) dst.p[q] = rep[q] + off;
+        peer_copy_kernel<<<ctx->num_sms, 256, 0, cs>>>(o + off, dst, (size_t)(y1 - y0) * stride);
+        ctx->launches += 1;
+      }
+      CU(cudaGetLastError());
+      continue;
+    }
     for (uint32_t q = 0; q < nrep; q++) {
       const uint32_t peer = (q + (uint32_t)chunk) % nrep;  // (start every chunk at a different peer)
       CU(cudaStreamWaitEvent(ctx->rep_streams[peer], ev, 0));

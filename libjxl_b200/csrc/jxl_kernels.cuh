@@ -1463,6 +1463,36 @@ struct SparseBatch {
 };
 
 #ifndef JXLB_STRIP_TU
+// ---------------------------------------------------------------------------
+// Multi-GPU gather, SM variant (JXLGPU_GATHER=sm): one launch copies a finished row chunk of this rank's band to
+// the same offset of every peer's frame buffer (peer-mapped symmetric memory) with 16-byte loads and stores;
+// a warp writes 512 contiguous bytes per peer and instruction, CTAs start at different peers.
+// ---------------------------------------------------------------------------
+struct PeerDst {
+  char* p[8];
+  uint32_t n;
+};
+__global__ void __launch_bounds__(256) peer_copy_kernel(const char* __restrict__ src, const __grid_constant__ PeerDst dst,
+                                                        size_t bytes) {
+  const size_t n16 = bytes / 16;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  const uint32_t first = blockIdx.x % (dst.n ? dst.n : 1);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = s4[i];
+#pragma unroll 1
+    for (uint32_t k = 0; k < dst.n; k++) {
+      uint32_t q = first + k;
+      if (q >= dst.n) q -= dst.n;
+      reinterpret_cast<uint4*>(dst.p[q])[i] = v;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (bytes & 15)) {  // tail
+    const size_t i = n16 * 16 + threadIdx.x;
+    for (uint32_t q = 0; q < dst.n; q++) dst.p[q][i] = src[i];
+  }
+}
+
 template <bool I32>
 __global__ void __launch_bounds__(256) sparse_expand_kernel(const __grid_constant__ SparseBatch B,
                                                             const uint32_t* __restrict__ staging,

@@ -225,6 +225,46 @@ def test_emulated_fused_all_gather_replay(emu_pipe, fmt, srgb):
 
 
 @pytest.mark.timeout(900)
+@pytest.mark.parametrize("mode", ["ce", "sm", "kernel"])
+def test_emulated_gather_variants(emu_pipe, mode, monkeypatch):
+    """The three ways a band reaches the peers' frame buffers (JXLGPU_GATHER, read when a context is created):
+    copy-engine copies per row chunk (default), peer_copy_kernel per row chunk (`sm`, 16-byte stores), the replay
+    inside the filter kernel (`kernel`).  Same bytes everywhere, nothing outside the band."""
+    if mode != "ce":
+        monkeypatch.setenv("JXLGPU_GATHER", mode)
+    else:
+        monkeypatch.delenv("JXLGPU_GATHER", raising=False)
+    p = pipeline.TransformPipeline(device=0, num_host_threads=1)
+    try:
+        for fmt, srgb in ((abi.OUT_RGB_F32, 0), (abi.OUT_RGB_U8, abi.STAGE_SRGB), (abi.OUT_PLANAR_F32, 0)):
+            desc, coeffs = wl.synthetic_frame(304, 600, seed=70 + fmt, epf_iters=1)   # three row chunks
+            desc.out_format, desc.stage_mask = fmt, srgb
+            want = oracle(desc, coeffs).view(np.uint8).ravel()
+            dev = np.ascontiguousarray(coeffs)
+            p.set_device_coefficients([dev[c].ctypes.data for c in range(3)])
+            p.frame_begin(desc)
+            guard = 64
+            local = np.full(want.size + 2 * guard, 0xAB, np.uint8)
+            reps = [np.full(want.size + 2 * guard, 0xCD, np.uint8) for _ in range(3)]
+            base = lambda a: a.ctypes.data + (-a.ctypes.data) % 16 + 16
+            p.set_output_replicas([base(r) for r in reps])
+            try:
+                p.render_device(base(local), desc.out_row_bytes)
+                p.synchronize()
+            finally:
+                p.set_output_replicas([])
+                p.set_device_coefficients(None)
+            off = base(local) - local.ctypes.data
+            assert np.array_equal(local[off:off + want.size], want), (mode, fmt)
+            for r in reps:
+                o = base(r) - r.ctypes.data
+                assert np.array_equal(r[o:o + want.size], want), (mode, fmt)
+                assert (r[:o] == 0xCD).all() and (r[o + want.size:] == 0xCD).all()
+    finally:
+        p.close()
+
+
+@pytest.mark.timeout(900)
 def test_emulated_multicast_replay_and_its_limits(emu_pipe):
     """The multimem.st variant of the replay (emulated as a plain store to the one multicast address):
     4-byte granules for the f32 layouts; packed layouts are refused."""
