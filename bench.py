@@ -581,7 +581,14 @@ def main() -> int:
             gathered = None
             # auto: copy engines, except the f32 frame on 8 GPUs where NCCL measured 9 % faster (1.09 vs 1.19 ms:
             # nothing left to overlap the gather with)
-            use_nccl = args.gather == "nccl" or (args.gather == "auto" and world >= 8 and kind == "f32")
+            use_nccl = args.gather == "nccl"
+            if args.gather == "auto":
+                # measured: copy engines win while there is filter work to overlap with (N=2: 0.62 ms
+                # vs sm 0.73, nccl 0.89); the f32 frame on 8 GPUs is all gather: sm 1.04 ms, nccl 1.11, ce 1.17
+                if world >= 8 and kind == "f32":
+                    os.environ["JXLGPU_GATHER"] = "sm"     # (read again by jxlgpu_set_output_replicas)
+                else:
+                    os.environ.pop("JXLGPU_GATHER", None)
             if not use_nccl:
                 try:
                     # Fused compute + all-gather: the frame buffer of every rank is symmetric memory; a filter
@@ -604,7 +611,7 @@ def main() -> int:
                                        if args.gather == "p2p" else
                                        "SM copy kernel: every finished row chunk is stored to all peers' symmetric-memory frame buffers "
                                        "by peer_copy_kernel (16-byte NVLink stores) on a side stream while the next chunk is filtered"
-                                       if args.gather == "sm" else
+                                       if args.gather == "sm" or os.environ.get("JXLGPU_GATHER") == "sm" else
                                        "copy engines: every finished row chunk is copied to the peers' symmetric-memory frame buffers "
                                        "(NVLink, cudaMemcpyAsync on side streams) while the next chunk is filtered")
                 except Exception as e:  # noqa: BLE001

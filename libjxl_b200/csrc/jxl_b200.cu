@@ -1133,6 +1133,13 @@ int jxlgpu_set_output_replicas(jxlgpu_ctx* ctx, uint32_t n, void* const* dev_ptr
   ctx->P.nrep = multicast_ptr ? 0 : n;
   for (uint32_t i = 0; i < 8; i++) ctx->P.rep[i] = i < n ? (char*)dev_ptrs[i] : nullptr;
   ctx->P.mc = (char*)multicast_ptr;
+  // the gather mechanism can be chosen per set of replicas (JXLGPU_GATHER: unset/ce = copy engines, sm =
+  // peer_copy_kernel, kernel = replay inside the filter kernel); also read when the context is created
+  if (n) {
+    const char* ge = getenv("JXLGPU_GATHER");
+    ctx->gather_in_kernel = ge && ge[0] == 'k';
+    ctx->gather_sm = ge && ge[0] == 's';
+  }
   return JXLGPU_OK;
 }
 

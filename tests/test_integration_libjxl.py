@@ -113,8 +113,9 @@ def test_patched_decoder_through_the_emulated_library(sparse):
     import torch
     if torch.cuda.is_available():
         pytest.skip("a device is present: covered by the gpu test")
-    res = run_child("emu", [(300, 200, 1.0, -1, "f32"), (520, 264, 2.0, 2, "f32"), (300, 200, 1.0, -1, "u8"),
-                             (600, 300, 1.0, -1, "f32", 2)], sparse)   # the last: an upsampled frame (resampling 2)
+    cases = [(300, 200, 1.0, -1, "f32"), (520, 264, 2.0, 2, "f32"), (300, 200, 1.0, -1, "u8"),
+             (600, 300, 1.0, -1, "f32", 2)]   # the last: an upsampled frame (resampling 2)
+    res = run_child("emu", cases if sparse else cases[1:3], sparse)
     for k, v in res.items():
         assert v["taken"] == 1, (k, v)               # the frame really went through the backend
         if "-u8" in k:                         # the application's default: 8-bit sRGB, dithered
