@@ -586,7 +586,7 @@ def main() -> int:
                 # measured: copy engines win while there is filter work to overlap with (N=2: 0.62 ms
                 # vs sm 0.73, nccl 0.89); from 4 GPUs on the f32 frame is mostly gather: N=4 sm 0.85 / nccl 0.90 /
                 # ce 0.99 ms, N=8 sm 1.04 / nccl 1.11 / ce 1.17
-                if world >= 4 and kind == "f32":
+                if world >= int(os.environ.get("BENCH_AUTO_SM_MIN_WORLD", "4")) and kind == "f32":
                     os.environ["JXLGPU_GATHER"] = "sm"     # (read again by jxlgpu_set_output_replicas)
                 else:
                     os.environ.pop("JXLGPU_GATHER", None)

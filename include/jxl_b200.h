@@ -44,7 +44,7 @@ extern "C" {
 #define JXLGPU_API
 #endif
 
-#define JXLGPU_ABI_VERSION 4
+#define JXLGPU_ABI_VERSION 5
 
 enum {
   JXLGPU_OK = 0,
@@ -178,6 +178,16 @@ typedef struct jxlgpu_frame {
   uint32_t upsampling;
   uint32_t xsize_upsampled, ysize_upsampled;
   const float* upsampling_weights;
+
+  /* Noise: frame_header.flags & kNoise.  The library generates the three noise planes on
+   * the device (Random3Planes, lib/jxl/dec_noise.cc:45-152: Xorshift128Plus per 256x256 tile of the output image,
+   * seeded with the two frame indices of PassesDecoderState (dec_cache.h:127-128) and the tile origin), convolves
+   * them (ConvolveNoiseStage, stage_noise.cc:263-304) and mixes them into X, Y, B with the strength LUT
+   * (AddNoiseStage, :140-251; NoiseParams::lut, noise.h:27-43; the chroma factors are cfl_base_x / cfl_base_b)
+   * after the filters and the upsampling, before XYB -> RGB (dec_cache.cc:232-236).  Whole-frame contexts only. */
+  uint32_t noise;
+  float noise_lut[8];
+  uint32_t visible_frame_index, nonvisible_frame_index;
 } jxlgpu_frame;
 
 JXLGPU_API uint32_t jxlgpu_abi_version(void);

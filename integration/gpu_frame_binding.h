@@ -29,7 +29,7 @@ inline bool IsEligible(const jxl::FrameHeader& fh, const jxl::CodecMetadata& met
   return fh.encoding == jxl::FrameEncoding::kVarDCT && metadata.m.xyb_encoded &&
          fh.color_transform == jxl::ColorTransform::kXYB && fh.chroma_subsampling.Is444() &&
          (fh.upsampling == 1 || fh.upsampling == 2 || fh.upsampling == 4 || fh.upsampling == 8) &&
-         !(fh.flags & (FrameHeader::kPatches | FrameHeader::kSplines | FrameHeader::kNoise)) &&
+         !(fh.flags & (FrameHeader::kPatches | FrameHeader::kSplines)) &&   // (kNoise: generated and added on the device)
          metadata.m.num_extra_channels == 0;   // (several passes: accumulated in the dense pinned storage)
 }
 
@@ -119,6 +119,12 @@ inline bool BindGpuFrame(const jxl::PassesDecoderState& ds, const jxl::FrameHead
   }
   f.out_format = out_format;
   f.stage_mask = stage_mask;
+  if (fh.flags & jxl::FrameHeader::kNoise) {  // ConvolveNoise + AddNoise (dec_cache.cc:232-236), seeds: dec_cache.h:127-128
+    f.noise = 1;
+    for (size_t i = 0; i < 8; i++) f.noise_lut[i] = sh.image_features.noise_params.lut[i];
+    f.visible_frame_index = static_cast<uint32_t>(ds.visible_frame_index);
+    f.nonvisible_frame_index = static_cast<uint32_t>(ds.nonvisible_frame_index);
+  }
   if (fh.upsampling != 1) {  // UpsamplingStage of the colour channels (dec_cache.cc:216-227)
     const jxl::CustomTransformData& td = fh.nonserialized_metadata->transform_data;
     f.upsampling = fh.upsampling;

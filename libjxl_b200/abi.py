@@ -12,7 +12,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 NUM_STRATEGIES = 27
 GROUP_DIM = 256
 GROUP_COEFFS = 65536
@@ -70,6 +70,8 @@ class JxlGpuFrame(C.Structure):
         ("dc_group_mul", C.c_void_p), ("dc_smoothing", C.c_uint32),
         ("upsampling", C.c_uint32), ("xsize_upsampled", C.c_uint32), ("ysize_upsampled", C.c_uint32),
         ("upsampling_weights", C.c_void_p),
+        ("noise", C.c_uint32), ("noise_lut", C.c_float * 8),
+        ("visible_frame_index", C.c_uint32), ("nonvisible_frame_index", C.c_uint32),
     ]
 
 
@@ -149,6 +151,11 @@ class FrameDesc:
     upsampling_weights: np.ndarray | None = None
     xsize_upsampled: int = 0
     ysize_upsampled: int = 0
+    # noise (frame flag kNoise): NoiseParams::lut and the frame indices that seed the generator
+    noise: int = 0
+    noise_lut: tuple = (0.0,) * 8
+    visible_frame_index: int = 1
+    nonvisible_frame_index: int = 0
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -267,6 +274,10 @@ class FrameDesc:
             s.upsampling = int(self.upsampling)
             s.xsize_upsampled, s.ysize_upsampled = self.out_xsize, self.out_ysize
             s.upsampling_weights = pin(np.asarray(self.upsampling_weights, np.float32).ravel()[:nw], np.float32, (nw,))
+        if self.noise:
+            s.noise = 1
+            s.noise_lut[:] = list(_f32(self.noise_lut, 8))
+            s.visible_frame_index, s.nonvisible_frame_index = int(self.visible_frame_index), int(self.nonvisible_frame_index)
         s.dequant_table = pin(self.dequant, np.float32)
         s.dequant_table_floats = int(np.asarray(self.dequant).size)
         offs = np.asarray(self.dequant_offsets, np.uint32).reshape(NUM_STRATEGIES * 3)

@@ -98,7 +98,8 @@ struct jxlgpu_ctx {
   // bytes than the two-kernel path but is slower (1.33 ms vs 0.66 ms at 8K d1.0, profiles/r02_*fused*).
   bool allow_fused = false;
   bool idct8_tma = true;      // JXLGPU_IDCT8_TMA=0: the round-1 idct8_kernel (ordinary loads) for A/B runs
-  DevBuf ups_in, ups_kern;    // upsampling: filtered XYB planes at the coded size, the N*N x 25 tap table
+  DevBuf ups_in, ups_kern;    // upsampling / noise: filtered XYB planes at the coded size, the N*N x 25 tap table
+  DevBuf noise_buf;           // noise: the generator's three planes at the output size
   DevBuf qdc, dc_deq;         // DC stage on the device: quantised planes (+ per-group mul), dequantised planes
   DevBuf sparse;              // staging for the non-zero lists of jxlgpu_submit_groups_sparse
   size_t sparse_used = 0;     // words handed out this frame (bump allocation, guarded by mu)
@@ -188,7 +189,7 @@ bool fused_chain(uint32_t mask) {
 }
 bool use_fused(const jxlgpu_ctx* ctx) {
   const FrameDev& P = ctx->P;
-  if (!ctx->allow_fused || ctx->force_generic_filter || !fused_chain(P.stage_mask) || P.mc || P.ups) return false;
+  if (!ctx->allow_fused || ctx->force_generic_filter || !fused_chain(P.stage_mask) || P.mc || P.ups || P.noise) return false;
   for (int c = 0; c < 3; c++)
     if ((uintptr_t)P.coeff[c] % 16) return false;
   return true;
@@ -291,7 +292,7 @@ int launch_filter(jxlgpu_ctx* ctx, uint32_t y0, uint32_t y1, uint32_t out_y0, ui
   P.band_y1 = y1;
   P.out_y0 = out_y0;
   P.out_h = out_h;
-  if (P.ups) {
+  if (P.ups || P.noise) {
     // the filters run at the coded size into planar XYB; upsample_kernel (launch_upsample) carries the
     // stages behind the upsampling: XYB -> RGB, transfer function, packing
     P.stage_mask &= 15u;
@@ -304,7 +305,7 @@ int launch_filter(jxlgpu_ctx* ctx, uint32_t y0, uint32_t y1, uint32_t out_y0, ui
     out_row_stride = (size_t)P.xsize * 4;
   }
   cudaError_t strip_err = cudaSuccess;
-  if (!P.ups && use_fused(ctx)) {
+  if (!(P.ups || P.noise) && use_fused(ctx)) {
     // coefficients -> pixels in one kernel; finished rows leave through the TMA unit when every row
     // segment is 16-byte aligned (the kernel checks the per-strip size)
     bool aligned = (uintptr_t)dev_out % 16 == 0 && out_row_stride % 16 == 0;
@@ -336,7 +337,7 @@ int launch_upsample(jxlgpu_ctx* ctx, char* dev_out, size_t out_row_stride, cudaS
 }
 
 int ensure_out(jxlgpu_ctx* ctx) {
-  const uint32_t band_h = ctx->P.ups ? ctx->P.out_hh : ctx->P.band_y1 - ctx->P.band_y0;
+  const uint32_t band_h = (ctx->P.ups || ctx->P.noise) ? ctx->P.out_hh : ctx->P.band_y1 - ctx->P.band_y0;
   CU(ctx->out.ensure(out_planes(ctx->P.out_format) * band_h * ctx->out_row_bytes));
   return JXLGPU_OK;
 }
@@ -402,7 +403,7 @@ int pump(jxlgpu_ctx* ctx, bool force) {
     rc = launch_filter(ctx, y0, y1, P.band_y0, band_h, (char*)ctx->out.p, ctx->out_row_bytes, s);
     if (rc) return rc;
     for (uint32_t r = g; r < h; r++) ctx->row_filtered[r] = 1;
-    if (ctx->host_out && y1 > y0 && !P.ups) {  // copy the finished rows back while later rows still arrive
+    if (ctx->host_out && y1 > y0 && !(P.ups || P.noise)) {  // copy the finished rows back while later rows still arrive
       CU(cudaEventRecord(ctx->ev_filter, s));
       CU(cudaStreamWaitEvent(ctx->s_down, ctx->ev_filter, 0));
       const size_t row_bytes = ctx->out_row_bytes;
@@ -715,6 +716,21 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   P.out_w = out_w;
   P.out_hh = out_hh;
   P.ups_kernel = nullptr;
+  P.noise = f->noise ? 1u : 0u;
+  P.noise_planes = nullptr;
+  if (P.noise) {
+    if (f->band_ny_groups) return JXLGPU_ERR_UNSUPPORTED;  // whole-frame contexts only
+    memcpy(P.noise_lut, f->noise_lut, sizeof(P.noise_lut));
+    CU(ctx->noise_buf.ensure((size_t)3 * out_w * out_hh * 4));
+    CU(ctx->ups_in.ensure((size_t)3 * f->xsize * f->ysize * 4));
+    P.noise_planes = (const float*)ctx->noise_buf.p;
+    // the planes depend on the frame indices and the output size only: generated while the side information uploads
+    const uint32_t tiles = ((out_w + 255) / 256) * ((out_hh + 255) / 256);
+    float* const np_ = (float*)ctx->noise_buf.p;
+    noise_gen_kernel<<<(tiles + 3) / 4, 32, 0, s>>>(np_, out_w, out_hh, f->visible_frame_index, f->nonvisible_frame_index);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+  }
   if (ups) {
     // the stage's constructor (stage_upsampling.cc:61-86): N/2 x N/2 x 25 symmetric weights -> N*N kernels of 25 taps
     const uint32_t N = ups, H = N / 2;
@@ -1018,7 +1034,7 @@ static int render_device_on(jxlgpu_ctx* ctx, void* dev_out, size_t out_stride_by
   }
   int rc = launch_idct(ctx, ctx->need_row0, ctx->need_row1, P.need_y0, P.need_y1, s);
   if (rc) return rc;
-  if (P.ups) {
+  if (P.ups || P.noise) {
     rc = launch_filter(ctx, P.band_y0, P.band_y1, P.band_y0, band_h, o, stride, s);
     return rc ? rc : launch_upsample(ctx, o, stride, s);
   }
@@ -1102,7 +1118,7 @@ int jxlgpu_frame_finish(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes) {
         return JXLGPU_ERR_STATE;
       }
   }
-  if (ctx->P.ups) {  // every row is filtered: upsample the frame, then the whole output travels
+  if (ctx->P.ups || ctx->P.noise) {  // every row is filtered: upsample / add noise, then the whole output travels
     int rc = launch_upsample(ctx, (char*)ctx->out.p, ctx->out_row_bytes, ctx->stream);
     if (rc) return rc;
     if (!out && ctx->host_out) {
@@ -1112,7 +1128,7 @@ int jxlgpu_frame_finish(jxlgpu_ctx* ctx, void* out, size_t out_stride_bytes) {
     ctx->host_out = nullptr;
   }
   if (out && out != ctx->host_out) {
-    const uint32_t band_h = ctx->P.ups ? ctx->P.out_hh : ctx->P.band_y1 - ctx->P.band_y0;
+    const uint32_t band_h = (ctx->P.ups || ctx->P.noise) ? ctx->P.out_hh : ctx->P.band_y1 - ctx->P.band_y0;
     const size_t row_bytes = ctx->out_row_bytes;
     if (out_stride_bytes < row_bytes) return JXLGPU_ERR_INVALID_ARGUMENT;
     const size_t planes = out_planes(ctx->P.out_format);

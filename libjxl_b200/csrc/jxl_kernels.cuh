@@ -16,14 +16,20 @@
 //
 // Thread mapping (B200: 148 SMs, 32-wide warps):
 //   plan kernel   one CTA (1024 thr) per 256x256 AC group: block-scan of varblock sizes ->
-//                 per-block coefficient offsets, per-strategy work lists, sigma plane.
-//   small IDCT    one warp per "warp item" = 32/W varblocks of one strategy (W = 8,16,32 lanes
-//                 per varblock); lane = vertical frequency in pass 1, pixel column in pass 2;
-//                 1-D transforms live entirely in registers, one smem transpose in between.
-//   large IDCT    one CTA per varblock with a 64..256 side: pass 1 row transforms, pass 2
-//                 column transforms through the (exclusively owned) output plane region.
-//   filter        one CTA per 64x32 output tile (+halo), all enabled stages fused through two
-//                 shared-memory ping-pong tiles, XYB->RGB in the epilogue.
+//                 per-block coefficient offsets, per-strategy work lists, sigma plane (one block per thread).
+//   8x8 IDCT      idct8_tma_kernel: 8 lanes per block, 4 blocks per warp, coefficients staged one item ahead
+//                 with cp.async.bulk + mbarrier (idct8_kernel: the same with ordinary loads).
+//   mid IDCT      one warp per "warp item" = 32/W varblocks of one strategy (W = 16, 32 lanes per varblock);
+//                 lane = vertical frequency in pass 1, pixel column in pass 2; 1-D transforms live entirely
+//                 in registers, one smem transpose in between.
+//   large IDCT    64..256 sides: two launches (rows, columns) over slabs of a varblock; 128/256-point
+//                 transforms warp-cooperative, column tiles through shared memory.
+//   filter        filter_strip_kernel: a CTA owns 256 columns x a row segment and streams the rows through
+//                 per-stage rings in shared memory (Gaborish -> EPF0/1/2 -> XYB->RGB -> packing), the EPF
+//                 passes on a permutation of the strip's block columns (engaged blocks first).
+//                 filter_kernel: generic 64x32 tile + halo version for arbitrary stage masks.
+//   upsampling    upsample_kernel: one thread per output pixel, fused with XYB->RGB and the packing.
+//   fused         jxl_fused.cuh (opt-in): everything above for the 8x8 class in one persistent kernel.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -118,6 +124,10 @@ struct FrameDev {
   // upsampling after the filters (stage_upsampling.cc): factor (0/1 = none), output size, the N*N x 25 tap table
   uint32_t ups, out_w, out_hh;
   const float* ups_kernel;
+  // noise (stage_noise.cc): three planes [out_hh][out_w] of generator output in [1, 2), the strength LUT
+  uint32_t noise;
+  const float* noise_planes;
+  float noise_lut[8];
 };
 
 // ---------------------------------------------------------------------------
@@ -1712,6 +1722,126 @@ __device__ __forceinline__ float epf_weight(float sad, float inv_sigma) {
 }
 
 #ifndef JXLB_STRIP_TU
+// What PreparePipeline puts behind the filters / the upsampling (dec_cache.cc:232-330), for one output pixel:
+// [ConvolveNoise + AddNoise] -> XYB -> linear RGB [-> sRGB] -> output packing.
+__device__ __forceinline__ float noise_strength(const FrameDev& P, float x) {  // StrengthEvalLut, stage_noise.cc:72-139
+  float scaled = x * 6.0f;
+  scaled = scaled > 0.0f ? scaled : 0.0f;
+  float fl = floorf(scaled);
+  float frac = scaled - fl;
+  if (scaled >= 7.0f) {
+    fl = 6.0f;
+    frac = 1.0f;
+  }
+  const int i = (int)fl;
+  float v = fmaf(P.noise_lut[i + 1] - P.noise_lut[i], frac, P.noise_lut[i]);
+  v = v < 1.0f ? v : 1.0f;
+  return v < 0.0f ? 0.0f : v;
+}
+__device__ __forceinline__ void finish_px(const FrameDev& P, char* __restrict__ out, size_t out_row_stride, int X, int Y,
+                                          float a, float b, float c3) {
+  if (P.noise) {
+    const int OW = (int)P.out_w, OH = (int)P.out_hh;
+    int cx[5], ry[5];
+#pragma unroll
+    for (int d = 0; d < 5; d++) {
+      cx[d] = mirror_i(X + d - 2, OW);
+      ry[d] = mirror_i(Y + d - 2, OH) * OW;
+    }
+    float rnd[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {  // ConvolveNoiseStage (stage_noise.cc:263-304), the reference's summation order
+      const float* p = P.noise_planes + (size_t)c * OW * OH;
+      float others = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 5; i++) {
+        others = others + __ldg(p + ry[0] + cx[i]);
+        others = others + __ldg(p + ry[1] + cx[i]);
+        others = others + __ldg(p + ry[3] + cx[i]);
+        others = others + __ldg(p + ry[4] + cx[i]);
+      }
+      others = others + __ldg(p + ry[2] + cx[0]);
+      others = others + __ldg(p + ry[2] + cx[1]);
+      others = others + __ldg(p + ry[2] + cx[3]);
+      others = others + __ldg(p + ry[2] + cx[4]);
+      rnd[c] = fmaf(others, 0.16f, __ldg(p + ry[2] + cx[2]) * -3.84f) * 0.22f;
+    }
+    // AddNoiseStage (stage_noise.cc:140-251)
+    const float in_g = b - a, in_r = b + a;
+    const float sg = noise_strength(P, in_g * 0.5f), sr = noise_strength(P, in_r * 0.5f);
+    const float red = sr * fmaf(0.0078125f, rnd[0], 0.9921875f * rnd[2]);
+    const float green = sg * fmaf(0.0078125f, rnd[1], 0.9921875f * rnd[2]);
+    const float sum = red + green;
+    a = fmaf(P.cfl_base_x, sum, red - green) + a;
+    b = b + sum;
+    c3 = fmaf(P.cfl_base_b, sum, c3);
+  }
+  if (P.stage_mask & 16u) {  // XYB -> linear RGB (dec_xyb-inl.h:38-86)
+    float gr = b + a, gg = b - a, gb = c3;
+    gr = gr - P.opsin_cbrt[0];
+    gg = gg - P.opsin_cbrt[1];
+    gb = gb - P.opsin_cbrt[2];
+    const float r2 = gr * gr, g2 = gg * gg, b2 = gb * gb;
+    const float mr = fmaf(r2, gr, P.opsin_bias[0]);
+    const float mg = fmaf(g2, gg, P.opsin_bias[1]);
+    const float mb = fmaf(b2, gb, P.opsin_bias[2]);
+    float lr = P.opsin_m[0] * mr, lg = P.opsin_m[3] * mr, lb = P.opsin_m[6] * mr;
+    lr = fmaf(P.opsin_m[1], mg, lr); lg = fmaf(P.opsin_m[4], mg, lg); lb = fmaf(P.opsin_m[7], mg, lb);
+    lr = fmaf(P.opsin_m[2], mb, lr); lg = fmaf(P.opsin_m[5], mb, lg); lb = fmaf(P.opsin_m[8], mb, lb);
+    a = lr; b = lg; c3 = lb;
+  }
+  store_px<1>(P, out, out_row_stride, Y, X, (int)P.out_hh, a, b, c3);
+}
+
+// Noise planes (Random3Planes, lib/jxl/dec_noise.cc:45-110): per 256x256 tile of the output image a
+// Xorshift128Plus with eight 128-bit states (lib/jxl/xorshift128plus-inl.h:31-91), seeded with the two frame
+// indices and the tile origin, fills plane 0, then 1, then 2, row by row, 16 floats (eight 64-bit outputs) per
+// step, "1.0 + 23 random mantissa bits".  The generator is sequential per tile: eight lanes carry the eight
+// states of one tile, four tiles per warp.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(32) noise_gen_kernel(float* __restrict__ planes, uint32_t W, uint32_t H, uint32_t visible,
+                                                       uint32_t nonvisible) {
+  const uint32_t lane = threadIdx.x & 7u;
+  const uint32_t tiles_x = (W + 255u) / 256u, tiles_y = (H + 255u) / 256u;
+  const uint32_t tile = blockIdx.x * 4u + (threadIdx.x >> 3);
+  if (tile >= tiles_x * tiles_y) return;
+  const uint32_t x0 = (tile % tiles_x) * 256u, y0 = (tile / tiles_x) * 256u;
+  const uint32_t xs = min(256u, W - x0), ys = min(256u, H - y0);
+  // state `lane` of the generator: s0[i] = SplitMix64^i(s0[0]), s1[i] likewise
+  uint64_t s0 = splitmix64((((uint64_t)visible << 32) + nonvisible) + 0x9E3779B97F4A7C15ull);
+  uint64_t s1 = splitmix64((((uint64_t)x0 << 32) + y0) + 0x9E3779B97F4A7C15ull);
+  for (uint32_t i = 0; i < lane; i++) {
+    s0 = splitmix64(s0);
+    s1 = splitmix64(s1);
+  }
+  const size_t plane = (size_t)W * H;
+#pragma unroll 1
+  for (int p = 0; p < 3; p++)
+#pragma unroll 1
+    for (uint32_t y = 0; y < ys; y++) {
+      float* row = planes + (size_t)p * plane + (size_t)(y0 + y) * W + x0;
+      // entire batches while x + 16 < xs, then one more batch for the remaining (at most 16) pixels
+#pragma unroll 1
+      for (uint32_t x = 0;; x += 16) {
+        uint64_t a = s0;
+        const uint64_t b = s1;
+        const uint64_t bits = a + b;
+        s0 = b;
+        a ^= a << 23;
+        a ^= b ^ (a >> 18) ^ (b >> 5);
+        s1 = a;
+        const uint32_t xa = x + 2u * lane;
+        if (xa < xs) row[xa] = __uint_as_float(((uint32_t)bits >> 9) | 0x3F800000u);
+        if (xa + 1 < xs) row[xa + 1] = __uint_as_float(((uint32_t)(bits >> 32) >> 9) | 0x3F800000u);
+        if (!(x + 16 < xs)) break;
+      }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // UpsamplingStage (lib/jxl/render_pipeline/stage_upsampling.cc:51-271) fused with the
 // stages PreparePipeline puts behind it (dec_cache.cc:216-330): XYB -> linear RGB [-> sRGB] -> output packing.
@@ -1724,7 +1854,13 @@ __global__ void __launch_bounds__(256) upsample_kernel(const __grid_constant__ F
                                                        char* __restrict__ out, size_t out_row_stride) {
   const int X = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (X >= (int)P.out_w || Y >= (int)P.out_hh) return;
-  const int N = (int)P.ups, W = (int)P.xsize, H = (int)P.ysize;
+  const int N = P.ups ? (int)P.ups : 1, W = (int)P.xsize, H = (int)P.ysize;
+  if (N == 1) {  // no upsampling: the filtered planes are the stage's input as they are (noise-only frames)
+    float a = __ldg(in + (size_t)Y * W + X), b = __ldg(in + (size_t)W * H + (size_t)Y * W + X),
+          c3 = __ldg(in + 2 * (size_t)W * H + (size_t)Y * W + X);
+    finish_px(P, out, out_row_stride, X, Y, a, b, c3);
+    return;
+  }
   const int x = X / N, y = Y / N;
   const float* k = P.ups_kernel + (N * (Y - y * N) + (X - x * N)) * 25;
   int cx[5], ry[5];
@@ -1764,22 +1900,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(const __grid_constant__ F
     r = r > mx ? mx : r;
     res[c] = r;
   }
-  float a = res[0], b = res[1], c3 = res[2];
-  if (P.stage_mask & 16u) {  // XYB -> linear RGB (dec_xyb-inl.h:38-86)
-    float gr = b + a, gg = b - a, gb = c3;
-    gr = gr - P.opsin_cbrt[0];
-    gg = gg - P.opsin_cbrt[1];
-    gb = gb - P.opsin_cbrt[2];
-    const float r2 = gr * gr, g2 = gg * gg, b2 = gb * gb;
-    const float mr = fmaf(r2, gr, P.opsin_bias[0]);
-    const float mg = fmaf(g2, gg, P.opsin_bias[1]);
-    const float mb = fmaf(b2, gb, P.opsin_bias[2]);
-    float lr = P.opsin_m[0] * mr, lg = P.opsin_m[3] * mr, lb = P.opsin_m[6] * mr;
-    lr = fmaf(P.opsin_m[1], mg, lr); lg = fmaf(P.opsin_m[4], mg, lg); lb = fmaf(P.opsin_m[7], mg, lb);
-    lr = fmaf(P.opsin_m[2], mb, lr); lg = fmaf(P.opsin_m[5], mb, lg); lb = fmaf(P.opsin_m[8], mb, lb);
-    a = lr; b = lg; c3 = lb;
-  }
-  store_px<1>(P, out, out_row_stride, Y, X, (int)P.out_hh, a, b, c3);
+  finish_px(P, out, out_row_stride, X, Y, res[0], res[1], res[2]);
 }
 
 __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_constant__ FrameDev P,

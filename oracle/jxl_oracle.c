@@ -926,6 +926,126 @@ void jxo_upsample_plane(int N, const float* kernel, const float* in, size_t w, s
     }
 }
 
+/* ---- noise: Random3Planes + ConvolveNoiseStage + AddNoiseStage ----
+ * lib/jxl/dec_noise.cc:45-110,120-152 (generation per 256x256 tile of the OUTPUT image, Xorshift128Plus seeded with
+ * (visible_frame_index, nonvisible_frame_index, x0, y0), lib/jxl/xorshift128plus-inl.h:31-91),
+ * lib/jxl/render_pipeline/stage_noise.cc:263-304 (convolution) and :140-251 (strength LUT, mixing into X, Y, B). */
+typedef struct { uint64_t s0[8], s1[8]; } jxo_rng;
+static uint64_t splitmix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static void rng_init(jxo_rng* r, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  r->s0[0] = splitmix64((((uint64_t)a << 32) + b) + 0x9E3779B97F4A7C15ull);
+  r->s1[0] = splitmix64((((uint64_t)c << 32) + d) + 0x9E3779B97F4A7C15ull);
+  for (int i = 1; i < 8; i++) {
+    r->s0[i] = splitmix64(r->s0[i - 1]);
+    r->s1[i] = splitmix64(r->s1[i - 1]);
+  }
+}
+static void rng_fill(jxo_rng* r, uint64_t* bits) {
+  for (int i = 0; i < 8; i++) {
+    uint64_t s1 = r->s0[i];
+    const uint64_t s0 = r->s1[i];
+    bits[i] = s1 + s0;
+    r->s0[i] = s0;
+    s1 ^= s1 << 23;
+    s1 ^= s0 ^ (s1 >> 18) ^ (s0 >> 5);
+    r->s1[i] = s1;
+  }
+}
+/* three planes W x H of floats in [1, 2) (row stride W) */
+void jxo_noise_planes(uint32_t visible, uint32_t nonvisible, size_t W, size_t H, float* planes) {
+  for (size_t y0 = 0; y0 < H; y0 += 256)
+    for (size_t x0 = 0; x0 < W; x0 += 256) {
+      const size_t xs = W - x0 < 256 ? W - x0 : 256, ys = H - y0 < 256 ? H - y0 : 256;
+      jxo_rng rng;
+      rng_init(&rng, visible, nonvisible, (uint32_t)x0, (uint32_t)y0);
+      for (int p = 0; p < 3; p++)
+        for (size_t y = 0; y < ys; y++) {
+          float* row = planes + (size_t)p * W * H + (y0 + y) * W + x0;
+          uint64_t b64[8];
+          uint32_t b32[16];
+          size_t x = 0;
+          for (; x + 16 < xs; x += 16) {  /* only entire batches */
+            rng_fill(&rng, b64);
+            memcpy(b32, b64, sizeof(b32));
+            for (int i = 0; i < 16; i++) {
+              const uint32_t u = (b32[i] >> 9) | 0x3F800000u;
+              memcpy(&row[x + i], &u, 4);
+            }
+          }
+          rng_fill(&rng, b64);             /* the remaining pixels (<= 16) */
+          memcpy(b32, b64, sizeof(b32));
+          for (int i = 0; x < xs; x++, i++) {
+            const uint32_t u = (b32[i] >> 9) | 0x3F800000u;
+            memcpy(&row[x], &u, 4);
+          }
+        }
+    }
+}
+/* ConvolveNoiseStage on one plane (mirrored borders), out-of-place */
+static void noise_convolve(const float* in, float* out, size_t W, size_t H) {
+#pragma omp parallel for schedule(static)
+  for (int64_t y = 0; y < (int64_t)H; y++) {
+    const float* rows[5];
+    for (int i = 0; i < 5; i++) rows[i] = in + mirror_sz(y + i - 2, (int64_t)H) * W;
+    for (size_t x = 0; x < W; x++) {
+      size_t xi[5];
+      for (int i = 0; i < 5; i++) xi[i] = mirror_sz((int64_t)x + i - 2, (int64_t)W);
+      float others = 0.0f;
+      for (int i = 0; i < 5; i++) {
+        others = others + rows[0][xi[i]];
+        others = others + rows[1][xi[i]];
+        others = others + rows[3][xi[i]];
+        others = others + rows[4][xi[i]];
+      }
+      others = others + rows[2][xi[0]];
+      others = others + rows[2][xi[1]];
+      others = others + rows[2][xi[3]];
+      others = others + rows[2][xi[4]];
+      out[(size_t)y * W + x] = fmaf(others, 0.16f, rows[2][xi[2]] * -3.84f);
+    }
+  }
+}
+static float noise_strength(const float* lut, float x) {
+  float scaled = x * 6.0f;   /* kNumNoisePoints - 2 */
+  scaled = scaled > 0.0f ? scaled : 0.0f;
+  float fl = floorf(scaled);
+  float frac = scaled - fl;
+  if (scaled >= 7.0f) { fl = 6.0f; frac = 1.0f; }
+  const int i = (int)fl;
+  float v = fmaf(lut[i + 1] - lut[i], frac, lut[i]);
+  v = v < 1.0f ? v : 1.0f;   /* Clamp0ToMax: Min(x, 1) then ZeroIfNegative */
+  return v < 0.0f ? 0.0f : v;
+}
+/* p[3]: X, Y, B planes W x H (row stride ps), in place */
+void jxo_add_noise(const float* lut, float ytox, float ytob, uint32_t visible, uint32_t nonvisible, float* const p[3],
+                   size_t W, size_t H, size_t ps) {
+  float* raw = (float*)malloc(3 * W * H * sizeof(float));
+  float* conv = (float*)malloc(3 * W * H * sizeof(float));
+  if (!raw || !conv) { free(raw); free(conv); return; }
+  jxo_noise_planes(visible, nonvisible, W, H, raw);
+  for (int c = 0; c < 3; c++) noise_convolve(raw + (size_t)c * W * H, conv + (size_t)c * W * H, W, H);
+#pragma omp parallel for schedule(static)
+  for (int64_t y = 0; y < (int64_t)H; y++)
+    for (size_t x = 0; x < W; x++) {
+      const size_t i = (size_t)y * ps + x, n = (size_t)y * W + x;
+      const float vx = p[0][i], vy = p[1][i];
+      const float in_g = vy - vx, in_r = vy + vx;
+      const float sg = noise_strength(lut, in_g * 0.5f), sr = noise_strength(lut, in_r * 0.5f);
+      const float rr = conv[n] * 0.22f, rg = conv[W * H + n] * 0.22f, rc = conv[2 * W * H + n] * 0.22f;
+      const float red = sr * fmaf(0.0078125f, rr, 0.9921875f * rc);
+      const float green = sg * fmaf(0.0078125f, rg, 0.9921875f * rc);
+      const float sum = red + green;
+      p[0][i] = fmaf(ytox, sum, red - green) + vx;
+      p[1][i] = vy + sum;
+      p[2][i] = fmaf(ytob, sum, p[2][i]);
+    }
+  free(raw); free(conv);
+}
+
 int jxo_render_frame(const jxlgpu_frame* f_in, const void* const coeff[3], int rcp_mode, void* out_v) {
   float* out = (float*)out_v;
   /* optional DC stage (quant_dc given): DequantDC per DC group + AdaptiveDCSmoothing, then as usual */
@@ -1007,6 +1127,11 @@ int jxo_render_frame(const jxlgpu_frame* f_in, const void* const coeff[3], int r
     f_up.xsize = (uint32_t)ow;
     f_up.ysize = (uint32_t)oh;
     fo = &f_up;
+  }
+  if (f->noise) {  /* ConvolveNoise + AddNoise at the output resolution, before the colour transform (dec_cache.cc:232-236) */
+    float* N[3] = {cur[0], cur[1], cur[2]};
+    jxo_add_noise(f->noise_lut, f->cfl_base_x, f->cfl_base_b, f->visible_frame_index, f->nonvisible_frame_index, N,
+                  fo->xsize, fo->ysize, ps_out);
   }
   if (mask & JXLGPU_STAGE_XYB) xyb_to_linear(fo, cur, ps_out);
   if (mask & JXLGPU_STAGE_SRGB) srgb_from_linear(fo, cur, ps_out);

@@ -47,6 +47,8 @@ class RefFrameInfo(C.Structure):
         ("dequant_offsets", C.c_int32 * 81),
         ("upsampling", C.c_int32), ("xsize_upsampled", C.c_int32), ("ysize_upsampled", C.c_int32),
         ("upsampling_weights", C.c_float * 210),
+        ("noise", C.c_int32), ("noise_lut", C.c_float * 8),
+        ("visible_frame_index", C.c_uint32), ("nonvisible_frame_index", C.c_uint32),
     ]
 
 
@@ -55,6 +57,7 @@ PLANE_DC, PLANE_SIGMA, PLANE_DEQUANT, PLANE_COEFFS, PLANE_DECODED = 5, 6, 7, 8, 
 
 STAGE_GAB, STAGE_EPF0, STAGE_EPF1, STAGE_EPF2, STAGE_XYB = 1, 2, 4, 8, 16
 STAGE_UPSAMPLING = 64   # ref_frame_render: the frame's own UpsamplingStage (before XYB)
+STAGE_NOISE = 128        # ref_frame_render: ConvolveNoise + AddNoise of a frame with the kNoise flag
 
 _libs: dict = {}
 _variant = "default"

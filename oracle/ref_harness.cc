@@ -66,7 +66,9 @@
 #include "lib/jxl/render_pipeline/render_pipeline.h"
 #include "lib/jxl/render_pipeline/stage_epf.h"
 #include "lib/jxl/render_pipeline/stage_from_linear.h"
+#include "lib/jxl/dec_noise.h"
 #include "lib/jxl/render_pipeline/stage_gaborish.h"
+#include "lib/jxl/render_pipeline/stage_noise.h"
 #include "lib/jxl/render_pipeline/stage_upsampling.h"
 #include "lib/jxl/render_pipeline/stage_write.h"
 #include "lib/jxl/render_pipeline/stage_xyb.h"
@@ -105,7 +107,7 @@ REF_API int ref_encode_rgb8(const uint8_t* rgb, int w, int h, float distance,
   return ref_encode_rgb8_ex(rgb, w, h, distance, effort, gaborish, epf, -1, threads, out, out_size);
 }
 // resampling: -1 = encoder default, 1/2/4/8 = JXL_ENC_FRAME_SETTING_RESAMPLING (frame_header.upsampling);
-// + 256: JXL_ENC_FRAME_SETTING_PROGRESSIVE_AC (multi-pass frame)
+// + 256: JXL_ENC_FRAME_SETTING_PROGRESSIVE_AC (multi-pass frame); + (iso / 100) << 16: JXL_ENC_FRAME_SETTING_PHOTON_NOISE
 REF_API int ref_encode_rgb8_ex(const uint8_t* rgb, int w, int h, float distance, int effort, int gaborish, int epf,
                                int resampling, int threads, uint8_t** out, size_t* out_size) {
   Runner runner(threads);
@@ -142,6 +144,8 @@ REF_API int ref_encode_rgb8_ex(const uint8_t* rgb, int w, int h, float distance,
       JxlEncoderFrameSettingsSetOption(fs, JXL_ENC_FRAME_SETTING_RESAMPLING, resampling & 15);
     if (resampling > 0 && (resampling & 256))  // bit 8: progressive AC (several passes per group)
       JxlEncoderFrameSettingsSetOption(fs, JXL_ENC_FRAME_SETTING_PROGRESSIVE_AC, 1);
+    if (resampling > 0 && (resampling >> 16))  // bits 16..: photon noise ISO / 100 (frame flag kNoise)
+      JxlEncoderFrameSettingsSetFloatOption(fs, JXL_ENC_FRAME_SETTING_PHOTON_NOISE, 100.0f * (resampling >> 16));
     JxlPixelFormat pf = {3, JXL_TYPE_UINT8, JXL_NATIVE_ENDIAN, 0};
     if (JxlEncoderAddImageFrame(fs, &pf, rgb, static_cast<size_t>(w) * h * 3) !=
         JXL_ENC_SUCCESS) { rc = 5; break; }
@@ -337,7 +341,7 @@ Status OpenImpl(RefFrame* f, const uint8_t* data, size_t n) {
   if (fh.encoding != FrameEncoding::kVarDCT) return JXL_FAILURE("not VarDCT");
   if (!fh.chroma_subsampling.Is444()) return JXL_FAILURE("not 444");
   // (fh.upsampling != 1 is fine: UpsamplingStage, SURVEY.md §8f rank 4, follows the filters)
-  if (fh.flags & (FrameHeader::kPatches | FrameHeader::kSplines | FrameHeader::kNoise))
+  if (fh.flags & (FrameHeader::kPatches | FrameHeader::kSplines))  // (kNoise: the noise stages follow the filters)
     return JXL_FAILURE("image features present");
   if (fh.passes.num_passes != 1) return JXL_FAILURE("multi-pass");
   const FrameDimensions fdim = fh.ToFrameDimensions();
@@ -448,6 +452,9 @@ struct RefFrameInfo {
   int32_t upsampling;                       // frame_header.upsampling (1, 2, 4, 8)
   int32_t xsize_upsampled, ysize_upsampled; // FrameDimensions (frame_dimensions.h:34-60)
   float upsampling_weights[210];            // CustomTransformData::upsampling{2,4,8}_weights of that factor (15 / 55 / 210 used)
+  int32_t noise;                            // frame_header.flags & kNoise
+  float noise_lut[8];                       // NoiseParams::lut (noise.h:27-43)
+  uint32_t visible_frame_index, nonvisible_frame_index;  // PassesDecoderState, seeds of the noise generator
 };
 
 REF_API void* ref_frame_open_storage(const uint8_t* jxl, size_t n, int threads, int storage);
@@ -542,6 +549,10 @@ REF_API int ref_frame_info(void* h, RefFrameInfo* o) {
     const size_t n = o->upsampling == 2 ? 15 : o->upsampling == 4 ? 55 : 210;
     memcpy(o->upsampling_weights, w, n * sizeof(float));
   }
+  o->noise = (f->frame_header->flags & FrameHeader::kNoise) ? 1 : 0;
+  for (int i = 0; i < 8; i++) o->noise_lut[i] = sh.image_features.noise_params.lut[i];
+  o->visible_frame_index = static_cast<uint32_t>(f->dec_state->visible_frame_index);
+  o->nonvisible_frame_index = static_cast<uint32_t>(f->dec_state->nonvisible_frame_index);
   o->dequant_table_floats = DequantMatrices::kSumRequiredXy * kDCTBlockSize * 3;
   for (int k = 0; k < 27; k++)
     for (int c = 0; c < 3; c++)
@@ -679,6 +690,7 @@ REF_API int ref_frame_render(void* h, int stage_mask, float* out, int reps, doub
   }
   if ((stage_mask & 14) && lf.epf_iters == 0) return 7;  // no sigma image
   if (reps < 1) reps = 1;
+  const bool with_noise = (stage_mask & 128) && (fh.flags & FrameHeader::kNoise);
   // The pipeline, the per-thread scratch and the output image are set up once and reused by
   // every timed repetition (ClearDone() re-arms the groups, as progressive passes do,
   // dec_frame.cc:700-705): the timed region is the hot path only, no allocation, no page faults.
@@ -696,11 +708,12 @@ REF_API int ref_frame_render(void* h, int stage_mask, float* out, int reps, doub
     RenderPipelineInput input = ds->render_pipeline->GetInputBuffers(g, thread);
     JXL_RETURN_IF_ERROR(DecodeGroupForRoundtrip(fh, f->ac32, g, ds, &caches[thread], thread, input,
                                                 nullptr, nullptr));
+    if (with_noise) PrepareNoiseInput(*ds, d, fh, g, thread);  // as ProcessACGroup does (dec_frame.cc:545-548)
     JXL_RETURN_IF_ERROR(input.Done());
     return true;
   };
   Status st = [&]() -> Status {
-    RenderPipeline::Builder builder(&f->mm, 3);
+    RenderPipeline::Builder builder(&f->mm, with_noise ? 6 : 3);
     if (stage_mask & 1) JXL_RETURN_IF_ERROR(builder.AddStage(GetGaborishStage(lf)));
     if (stage_mask & 2)
       JXL_RETURN_IF_ERROR(builder.AddStage(GetEPFStage(lf, ds->sigma, EpfStage::Zero)));
@@ -712,6 +725,11 @@ REF_API int ref_frame_render(void* h, int stage_mask, float* out, int reps, doub
       for (size_t c = 0; c < 3; c++)
         JXL_RETURN_IF_ERROR(builder.AddStage(GetUpsamplingStage(&f->mm, fh.nonserialized_metadata->transform_data, c,
                                                                 CeilLog2Nonzero(fh.upsampling))));
+    }
+    if (with_noise) {  // ConvolveNoise + AddNoise on three extra channels (dec_cache.cc:232-236)
+      JXL_RETURN_IF_ERROR(builder.AddStage(GetConvolveNoiseStage(3)));
+      JXL_RETURN_IF_ERROR(builder.AddStage(GetAddNoiseStage(ds->shared->image_features.noise_params,
+                                                            ds->shared->cmap.base(), 3)));
     }
     if (stage_mask & 16)
       JXL_RETURN_IF_ERROR(builder.AddStage(GetXYBStage(ds->output_encoding_info)));

@@ -111,6 +111,7 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
   return m;
 }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 template <typename T>

@@ -496,3 +496,25 @@ def test_emulated_upsampling(emu_pipe, n, w, h, fmt, srgb):
     desc.band_y0_groups, desc.band_ny_groups = 0, 1       # bands and upsampling do not combine (yet)
     with pytest.raises(pipeline.JxlGpuError):
         emu_pipe.frame_begin(desc)
+
+
+NOISE_LUT = (0.001, 0.0068, 0.0039, 0.0049, 0.0059, 0.0078, 0.0088, 0.0107)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("n,w,h", [(1, 301, 260), (2, 140, 131), (1, 17, 9)])
+@pytest.mark.parametrize("fmt,srgb", [(abi.OUT_RGB_F32, 0), (abi.OUT_RGB_U8, abi.STAGE_SRGB)])
+def test_emulated_noise(emu_pipe, n, w, h, fmt, srgb):
+    """the noise generator (Xorshift128Plus per 256x256 output tile, noise_gen_kernel), the
+    convolution and AddNoise fused with XYB -> RGB and the packing (finish_px), alone and behind the upsampling."""
+    if n > 1:
+        desc, coeffs = upsampled_frame(n, w, h, seed=5 + n, fmt=fmt, srgb=srgb)
+    else:
+        desc, coeffs = wl.synthetic_frame(w, h, seed=5 + n, epf_iters=1)
+        desc.out_format, desc.stage_mask = fmt, srgb
+    desc.noise, desc.noise_lut = 1, NOISE_LUT
+    desc.visible_frame_index, desc.nonvisible_frame_index = 3, 1
+    want = oracle(desc, coeffs)
+    assert same(emu_pipe.decode_frame(desc, coeffs), want)
+    desc.noise = 0
+    assert not same(oracle(desc, coeffs), want)

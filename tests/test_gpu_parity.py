@@ -366,3 +366,20 @@ def test_upsampled_reference_frames(pipe, rs):
     assert got.shape == d.decoded.shape
     assert_same(got, oracle(desc, d.coeffs), f"resampling {rs} vs oracle")
     assert np.abs(got - d.decoded).max() <= 2e-5       # vs the reference decoder (rcpps in AdjustQuantBias)
+
+
+@pytest.mark.parametrize("n,w,h", [(1, 1201, 531), (2, 600, 270)])
+@pytest.mark.parametrize("fmt,srgb", [(abi.OUT_RGB_F32, 0), (abi.OUT_RGB_U8, abi.STAGE_SRGB)])
+def test_noise_bit_exact(pipe, n, w, h, fmt, srgb):
+    """noise generation + ConvolveNoise + AddNoise on the device (noise_gen_kernel, finish_px),
+    alone and behind the upsampling; the restatement is pinned bit-exactly against the reference's stages
+    (tests/test_oracle_vs_reference.py::test_noise_stages_bit_exact)."""
+    from tests.test_emulated_cuda import NOISE_LUT, upsampled_frame
+    if n > 1:
+        desc, coeffs = upsampled_frame(n, w, h, seed=21 + n, fmt=fmt, srgb=srgb)
+    else:
+        desc, coeffs = wl.synthetic_frame(w, h, seed=21, epf_iters=1)
+        desc.out_format, desc.stage_mask = fmt, srgb
+    desc.noise, desc.noise_lut = 1, NOISE_LUT
+    desc.visible_frame_index, desc.nonvisible_frame_index = 2, 5
+    assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), f"noise, upsampling {n}")

@@ -114,8 +114,9 @@ def test_patched_decoder_through_the_emulated_library(sparse):
     if torch.cuda.is_available():
         pytest.skip("a device is present: covered by the gpu test")
     cases = [(300, 200, 1.0, -1, "f32"), (520, 264, 2.0, 2, "f32"), (300, 200, 1.0, -1, "u8"),
-             (600, 300, 1.0, -1, "f32", 2)]   # the last: an upsampled frame (resampling 2)
-    res = run_child("emu", cases if sparse else cases[1:3], sparse)
+             (600, 300, 1.0, -1, "f32", 2),               # an upsampled frame (resampling 2)
+             (300, 200, 1.0, -1, "f32", 1 + (32 << 16))]  # photon noise ISO 3200 (frame flag kNoise)
+    res = run_child("emu", cases if sparse else cases[1:3] + cases[4:], sparse)
     for k, v in res.items():
         assert v["taken"] == 1, (k, v)               # the frame really went through the backend
         if "-u8" in k:                         # the application's default: 8-bit sRGB, dithered
@@ -148,7 +149,9 @@ def test_patched_decoder_on_the_gpu(sparse):
     need_gpu_variant()
     res = run_child("gpu", [(1000, 700, 1.0, -1, "f32"), (2048, 1100, 2.0, 2, "f32"), (777, 333, 0.5, 0, "f32"),
                             (1500, 900, 4.0, 3, "f32"), (1000, 700, 1.0, -1, "u8"),
-                            (1400, 900, 1.0, -1, "f32", 2), (2200, 1100, 1.0, -1, "u8", 4)], sparse)   # upsampled frames
+                            (1400, 900, 1.0, -1, "f32", 2), (2200, 1100, 1.0, -1, "u8", 4),   # upsampled frames
+                            (1000, 700, 1.0, -1, "f32", 1 + (32 << 16)), (1400, 900, 1.0, -1, "f32", 2 + (64 << 16))],   # noise
+                           sparse)
     for k, v in res.items():
         assert v["taken"] == 1, (k, v)
         if "-u8" in k:

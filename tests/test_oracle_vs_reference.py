@@ -243,3 +243,28 @@ def test_upsampling_stage_bit_exact(rs, w, h, refmod):
     fr.close()
     full = refmod.decode_linear_f32(data, 2)              # the decoder's real pipeline
     assert np.array_equal(np.moveaxis(want, 0, 2), full)
+
+
+@pytest.mark.parametrize("rs,w,h,iso", [(1, 600, 300, 3200), (2, 600, 299, 6400), (1, 523, 260, 1600)])
+def test_noise_stages_bit_exact(rs, w, h, iso, refmod):
+    """SURVEY.md §8f rank 4, noise: frames the reference encoder made with photon noise (frame flag kNoise).
+    Random3Planes (dec_noise.cc:45-152) + ConvolveNoiseStage + AddNoiseStage (stage_noise.cc) restated in
+    oracle/jxl_oracle.c: bit-exact against the reference's own stages, alone and behind the upsampling, and the
+    reference's hot path + stages equals its public decode."""
+    from oracle import cpu
+    img = wl.synth_image(w, h, seed=rs + iso)
+    data = refmod.encode_rgb8(img, 1.0, 7, -1, -1, 4, resampling=rs | ((iso // 100) << 16))
+    fr = refmod.Frame(data, 2)
+    i = fr.info
+    assert i.noise == 1 and max(i.noise_lut) > 1e-3 and i.upsampling == rs
+    d = fr.dump()
+    desc = cpu.desc_from_dump(d)
+    assert desc.noise == 1 and (desc.visible_frame_index, desc.nonvisible_frame_index) == (1, 0)
+    desc.out_format = abi.OUT_PLANAR_F32
+    chain = (1 if i.gab else 0) | (2 if i.epf_iters >= 3 else 0) | (4 if i.epf_iters >= 1 else 0) | (8 if i.epf_iters >= 2 else 0)
+    want, _ = fr.render(chain | refmod.STAGE_XYB | refmod.STAGE_UPSAMPLING | refmod.STAGE_NOISE)
+    assert np.array_equal(cpu.render_frame(desc, d.coeffs, rcp_mode=1), want)
+    without, _ = fr.render(chain | refmod.STAGE_XYB | refmod.STAGE_UPSAMPLING)
+    assert not np.array_equal(without, want)
+    fr.close()
+    assert np.array_equal(np.moveaxis(want, 0, 2), refmod.decode_linear_f32(data, 2))
