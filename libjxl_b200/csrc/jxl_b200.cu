@@ -329,8 +329,16 @@ int launch_upsample(jxlgpu_ctx* ctx, char* dev_out, size_t out_row_stride, cudaS
   FrameDev P = ctx->P;
   P.out_y0 = 0;
   P.out_h = P.out_hh;
-  const dim3 grid((P.out_w + 31) / 32, (P.out_hh + 7) / 8);
-  upsample_kernel<<<grid, 256, 0, s>>>(P, (const float*)ctx->ups_in.p, dev_out, out_row_stride);
+  const float* src = (const float*)ctx->ups_in.p;
+  if (P.ups) {  // one thread per input pixel (window loaded once for its N x N outputs)
+    const dim3 gi((P.xsize + 31) / 32, (P.ysize + 7) / 8);
+    if (P.ups == 2) upsample_in_kernel<2><<<gi, 256, 0, s>>>(P, src, dev_out, out_row_stride);
+    else if (P.ups == 4) upsample_in_kernel<4><<<gi, 256, 0, s>>>(P, src, dev_out, out_row_stride);
+    else upsample_in_kernel<8><<<gi, 256, 0, s>>>(P, src, dev_out, out_row_stride);
+  } else {      // noise only: one thread per output (= input) pixel
+    const dim3 grid((P.out_w + 31) / 32, (P.out_hh + 7) / 8);
+    upsample_kernel<<<grid, 256, 0, s>>>(P, src, dev_out, out_row_stride);
+  }
   ctx->launches += 1;
   CU(cudaGetLastError());
   return JXLGPU_OK;

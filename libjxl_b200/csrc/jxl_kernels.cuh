@@ -1903,6 +1903,69 @@ __global__ void __launch_bounds__(256) upsample_kernel(const __grid_constant__ F
   finish_px(P, out, out_row_stride, X, Y, res[0], res[1], res[2]);
 }
 
+// The same stage with one thread per INPUT pixel: the 5x5 window of the three channels is loaded once (75 values
+// in registers, plus its minima / maxima) and reused for the N x N outputs of the pixel, whose taps come from a
+// shared-memory copy of the table -- upsample_kernel reloads the window for every output pixel (N^2 times).
+template <int N>
+__global__ void __launch_bounds__(256) upsample_in_kernel(const __grid_constant__ FrameDev P, const float* __restrict__ in,
+                                                          char* __restrict__ out, size_t out_row_stride) {
+  __shared__ float taps[N * N * 25];
+  for (int i = threadIdx.x; i < N * N * 25; i += 256) taps[i] = __ldg(P.ups_kernel + i);
+  __syncthreads();
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int W = (int)P.xsize, H = (int)P.ysize;
+  if (x >= W || y >= H) return;
+  int cx[5], ry[5];
+#pragma unroll
+  for (int d = 0; d < 5; d++) {
+    cx[d] = mirror_i(x + d - 2, W);
+    ry[d] = mirror_i(y + d - 2, H) * W;
+  }
+  float v[3][25], mn[3], mx[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const float* p = in + (size_t)c * W * H;
+#pragma unroll
+    for (int iy = 0; iy < 5; iy++)
+#pragma unroll
+      for (int ix = 0; ix < 5; ix++) v[c][5 * iy + ix] = __ldg(p + ry[iy] + cx[ix]);
+    mn[c] = mx[c] = v[c][0];
+#pragma unroll
+    for (int i = 1; i < 25; i++) {
+      mn[c] = fminf(mn[c], v[c][i]);
+      mx[c] = fmaxf(mx[c], v[c][i]);
+    }
+  }
+#pragma unroll 1
+  for (int oy = 0; oy < N; oy++) {
+    const int Y = y * N + oy;
+    if (Y >= (int)P.out_hh) break;
+#pragma unroll 1
+    for (int ox = 0; ox < N; ox++) {
+      const int X = x * N + ox;
+      if (X >= (int)P.out_w) break;
+      const float* kw = taps + (N * oy + ox) * 25;
+      float res[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        float a0 = v[c][0] * kw[0], a1 = v[c][1] * kw[1], a2 = v[c][2] * kw[2];
+#pragma unroll
+        for (int i = 3; i < 24; i += 3) {
+          a0 = fmaf(v[c][i], kw[i], a0);
+          a1 = fmaf(v[c][i + 1], kw[i + 1], a1);
+          a2 = fmaf(v[c][i + 2], kw[i + 2], a2);
+        }
+        a0 = fmaf(v[c][24], kw[24], a0);
+        float r = (a1 + a2) + a0;
+        r = r < mn[c] ? mn[c] : r;
+        r = r > mx[c] ? mx[c] : r;
+        res[c] = r;
+      }
+      finish_px(P, out, out_row_stride, X, Y, res[0], res[1], res[2]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_constant__ FrameDev P,
                                                                char* __restrict__ out,
                                                                size_t out_row_stride /*bytes*/) {
