@@ -99,7 +99,7 @@ struct jxlgpu_ctx {
   bool allow_fused = false;
   bool idct8_tma = true;      // JXLGPU_IDCT8_TMA=0: the round-1 idct8_kernel (ordinary loads) for A/B runs
   DevBuf ups_in, ups_kern;    // upsampling / noise: filtered XYB planes at the coded size, the N*N x 25 tap table
-  DevBuf noise_buf;           // noise: the generator's three planes at the output size
+  DevBuf noise_buf, noise_raw; // noise at the output size: the convolved planes the finish kernels read / the generator's output
   DevBuf qdc, dc_deq;         // DC stage on the device: quantised planes (+ per-group mul), dequantised planes
   DevBuf sparse;              // staging for the non-zero lists of jxlgpu_submit_groups_sparse
   size_t sparse_used = 0;     // words handed out this frame (bump allocation, guarded by mu)
@@ -730,14 +730,18 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
     if (f->band_ny_groups) return JXLGPU_ERR_UNSUPPORTED;  // whole-frame contexts only
     memcpy(P.noise_lut, f->noise_lut, sizeof(P.noise_lut));
     CU(ctx->noise_buf.ensure((size_t)3 * out_w * out_hh * 4));
+    CU(ctx->noise_raw.ensure((size_t)3 * out_w * out_hh * 4));
     CU(ctx->ups_in.ensure((size_t)3 * f->xsize * f->ysize * 4));
     P.noise_planes = (const float*)ctx->noise_buf.p;
     // the planes depend on the frame indices and the output size only: generated while the side information uploads
     const uint32_t tiles = ((out_w + 255) / 256) * ((out_hh + 255) / 256);
-    float* const np_ = (float*)ctx->noise_buf.p;
-    noise_gen_kernel<<<(tiles + 3) / 4, 32, 0, s>>>(np_, out_w, out_hh, f->visible_frame_index, f->nonvisible_frame_index);
+    float* const nraw = (float*)ctx->noise_raw.p;
+    float* const nconv = (float*)ctx->noise_buf.p;
+    noise_gen_kernel<<<(tiles + 3) / 4, 32, 0, s>>>(nraw, out_w, out_hh, f->visible_frame_index, f->nonvisible_frame_index);
+    const dim3 cgrid((out_w + 31) / 32, (out_hh + 7) / 8, 3);
+    noise_conv_kernel<<<cgrid, 256, 0, s>>>(nraw, nconv, (int)out_w, (int)out_hh);
     CU(cudaGetLastError());
-    ctx->launches += 1;
+    ctx->launches += 2;
   }
   if (ups) {
     // the stage's constructor (stage_upsampling.cc:61-86): N/2 x N/2 x 25 symmetric weights -> N*N kernels of 25 taps

@@ -1742,30 +1742,10 @@ __device__ __forceinline__ void finish_px(const FrameDev& P, char* __restrict__ 
                                           float a, float b, float c3) {
   if (P.noise) {
     const int OW = (int)P.out_w, OH = (int)P.out_hh;
-    int cx[5], ry[5];
-#pragma unroll
-    for (int d = 0; d < 5; d++) {
-      cx[d] = mirror_i(X + d - 2, OW);
-      ry[d] = mirror_i(Y + d - 2, OH) * OW;
-    }
+    // (the planes hold the CONVOLVED noise: noise_conv_kernel ran once per frame, behind the generator)
     float rnd[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) {  // ConvolveNoiseStage (stage_noise.cc:263-304), the reference's summation order
-      const float* p = P.noise_planes + (size_t)c * OW * OH;
-      float others = 0.0f;
-#pragma unroll
-      for (int i = 0; i < 5; i++) {
-        others = others + __ldg(p + ry[0] + cx[i]);
-        others = others + __ldg(p + ry[1] + cx[i]);
-        others = others + __ldg(p + ry[3] + cx[i]);
-        others = others + __ldg(p + ry[4] + cx[i]);
-      }
-      others = others + __ldg(p + ry[2] + cx[0]);
-      others = others + __ldg(p + ry[2] + cx[1]);
-      others = others + __ldg(p + ry[2] + cx[3]);
-      others = others + __ldg(p + ry[2] + cx[4]);
-      rnd[c] = fmaf(others, 0.16f, __ldg(p + ry[2] + cx[2]) * -3.84f) * 0.22f;
-    }
+    for (int c = 0; c < 3; c++) rnd[c] = __ldg(P.noise_planes + ((size_t)c * OH + Y) * OW + X) * 0.22f;
     // AddNoiseStage (stage_noise.cc:140-251)
     const float in_g = b - a, in_r = b + a;
     const float sg = noise_strength(P, in_g * 0.5f), sr = noise_strength(P, in_r * 0.5f);
@@ -1850,6 +1830,33 @@ __global__ void __launch_bounds__(32) noise_gen_kernel(float* __restrict__ plane
 // (X/N, Y/N); 25 taps of the 5x5 window (mirrored about the coded size) in three accumulators in the
 // reference's order (:246-262), clamped to the window's minimum / maximum (:152-206).
 // ---------------------------------------------------------------------------
+// ConvolveNoiseStage (stage_noise.cc:263-304) over the three generated planes, once per frame: 24 neighbours summed
+// in the reference's order, 0.16 * sum - 3.84 * centre; borders mirrored about the output size.
+__global__ void __launch_bounds__(256) noise_conv_kernel(const float* __restrict__ raw, float* __restrict__ conv, int OW, int OH) {
+  const int X = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (X >= OW || Y >= OH) return;
+  int cx[5], ry[5];
+#pragma unroll
+  for (int d = 0; d < 5; d++) {
+    cx[d] = mirror_i(X + d - 2, OW);
+    ry[d] = mirror_i(Y + d - 2, OH) * OW;
+  }
+  const float* p = raw + (size_t)blockIdx.z * OW * OH;
+  float others = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    others = others + __ldg(p + ry[0] + cx[i]);
+    others = others + __ldg(p + ry[1] + cx[i]);
+    others = others + __ldg(p + ry[3] + cx[i]);
+    others = others + __ldg(p + ry[4] + cx[i]);
+  }
+  others = others + __ldg(p + ry[2] + cx[0]);
+  others = others + __ldg(p + ry[2] + cx[1]);
+  others = others + __ldg(p + ry[2] + cx[3]);
+  others = others + __ldg(p + ry[2] + cx[4]);
+  conv[((size_t)blockIdx.z * OH + Y) * OW + X] = fmaf(others, 0.16f, __ldg(p + ry[2] + cx[2]) * -3.84f);
+}
+
 __global__ void __launch_bounds__(256) upsample_kernel(const __grid_constant__ FrameDev P, const float* __restrict__ in,
                                                        char* __restrict__ out, size_t out_row_stride) {
   const int X = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
