@@ -81,6 +81,8 @@ int main(int argc, char** argv) {
   fr.dequant_table = dq.data();
   fr.quant_dc[0] = fr.quant_dc[1] = fr.quant_dc[2] = nullptr;
   fr.dc_group_mul = nullptr;
+  if (fr.upsampling > 1) Reader::die("this example does not carry the upsampling weights of the dump");
+  fr.upsampling_weights = nullptr;
 
   const size_t es = fr.ac_type == JXLGPU_AC_INT16 ? 2 : 4;
   const uint32_t xg = (fr.xsize + 255) / 256, yg = (fr.ysize + 255) / 256, num_groups = xg * yg;
