@@ -295,7 +295,11 @@ int launch_filter(jxlgpu_ctx* ctx, uint32_t y0, uint32_t y1, uint32_t out_y0, ui
   if (P.ups || P.noise) {
     // the filters run at the coded size into planar XYB; upsample_kernel (launch_upsample) carries the
     // stages behind the upsampling: XYB -> RGB, transfer function, packing
-    P.stage_mask &= 15u;
+    // (the production chains keep their strip-kernel instantiation: the XYB bit stays in the mask, the kernel
+    //  skips the conversion at run time; other masks fall to the generic tile kernel without the bit)
+    const bool strip_chain = !ctx->force_generic_filter && (P.stage_mask & 16u);
+    P.skip_xyb = strip_chain ? 1u : 0u;
+    P.stage_mask &= strip_chain ? 31u : 15u;
     P.out_format = 1;
     P.out_y0 = 0;
     P.out_h = P.ysize;
@@ -694,6 +698,7 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   P.sigma = (float*)ctx->sigma.p;
   P.bmap = (uint4*)ctx->bmap.p;
   P.fused = 0;
+  P.skip_xyb = 0;
   P.list = (uint4*)ctx->list.p;
   P.counts = (uint32_t*)ctx->counts.p;
   P.xyb = (float*)ctx->xyb.p;

@@ -128,6 +128,7 @@ struct FrameDev {
   uint32_t noise;
   const float* noise_planes;
   float noise_lut[8];
+  uint32_t skip_xyb;   // frames with upsampling / noise: the strip kernel stops before XYB -> RGB (planar XYB out)
 };
 
 // ---------------------------------------------------------------------------
@@ -2302,7 +2303,7 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
   auto emit = [&](int r, int col, float a, float b, float c3) {
     const int xe = xs0 + col;
     if (!(col >= LEAD && col < kStripThreads - LEAD && xe < W)) return;
-    if constexpr (C::XYB) {
+    if (C::XYB && !P.skip_xyb) {
       float gr = b + a, gg = b - a, gb = c3;
       gr = gr - P.opsin_cbrt[0];
       gg = gg - P.opsin_cbrt[1];
