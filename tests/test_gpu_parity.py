@@ -383,3 +383,36 @@ def test_noise_bit_exact(pipe, n, w, h, fmt, srgb):
     desc.noise, desc.noise_lut = 1, NOISE_LUT
     desc.visible_frame_index, desc.nonvisible_frame_index = 2, 5
     assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), f"noise, upsampling {n}")
+
+
+@pytest.mark.parametrize("mode", ["ce", "sm", "kernel"])
+def test_gather_mechanisms_on_one_device(mode, monkeypatch):
+    """The multi-GPU gather with the "peers" being three more buffers on this GPU: copy-engine copies
+    per row chunk (default), peer_copy_kernel per row chunk (JXLGPU_GATHER=sm), replay inside the filter kernel
+    (=kernel).  Every replica ends up identical to the local band, in an f32 and an 8-bit layout."""
+    import torch
+    if mode == "ce":
+        monkeypatch.delenv("JXLGPU_GATHER", raising=False)
+    else:
+        monkeypatch.setenv("JXLGPU_GATHER", mode)
+    p = pipeline.TransformPipeline(device=0, num_host_threads=1)
+    try:
+        for fmt, srgb, dt in ((abi.OUT_RGB_F32, 0, torch.float32), (abi.OUT_RGB_U8, abi.STAGE_SRGB, torch.uint8)):
+            desc, coeffs = wl.synthetic_frame(1200, 1100, seed=40 + fmt, epf_iters=1)
+            desc.out_format, desc.stage_mask = fmt, srgb
+            want = oracle(desc, coeffs)
+            dev = torch.from_numpy(coeffs).cuda()
+            p.set_device_coefficients([dev[c].data_ptr() for c in range(3)])
+            p.frame_begin(desc)
+            bufs = [torch.zeros((desc.ysize, desc.xsize, 3), dtype=dt, device="cuda") for _ in range(4)]
+            p.set_output_replicas([b.data_ptr() for b in bufs[1:]])
+            try:
+                p.render_device(bufs[0].data_ptr(), desc.out_row_bytes, torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+            finally:
+                p.set_output_replicas([])
+                p.set_device_coefficients(None)
+            for i, b in enumerate(bufs):
+                assert_same(b.cpu().numpy(), want, f"{mode}: buffer {i}")
+    finally:
+        p.close()
