@@ -367,6 +367,15 @@ def test_emulated_argument_validation(emu_pipe):
     assert begin_rc(lambda s: (setattr(s, "band_y0_groups", 1), setattr(s, "band_ny_groups", 1))) == abi.ERR_INVALID_ARGUMENT
     assert begin_rc(lambda s: setattr(s, "epf_sharpness", None)) == abi.ERR_INVALID_ARGUMENT   # epf_iters = 3
     assert begin_rc(lambda s: s.dc.__setitem__(1, None)) == abi.ERR_INVALID_ARGUMENT
+    # upsampling: factor 2/4/8 only, weights required, upsampled size consistent with the coded size; noise and
+    # upsampling are whole-frame features (no band)
+    w2 = np.zeros(15, np.float32)
+    assert begin_rc(lambda s: setattr(s, "upsampling", 3)) == abi.ERR_INVALID_ARGUMENT
+    assert begin_rc(lambda s: setattr(s, "upsampling", 2)) == abi.ERR_INVALID_ARGUMENT          # no weights
+    assert begin_rc(lambda s: (setattr(s, "upsampling", 2), setattr(s, "upsampling_weights", w2.ctypes.data),
+                               setattr(s, "xsize_upsampled", 2 * s.xsize + 1))) == abi.ERR_INVALID_ARGUMENT
+    assert begin_rc(lambda s: (setattr(s, "upsampling", 2), setattr(s, "upsampling_weights", w2.ctypes.data))) == abi.OK
+    assert begin_rc(lambda s: (setattr(s, "noise", 1), setattr(s, "band_ny_groups", 1))) == abi.ERR_UNSUPPORTED
     assert begin_rc(lambda s: None) == abi.OK
     # submit: thread id beyond num_host_threads, null channel pointer, too many coefficients
     ptrs = (C.c_void_p * 3)(*[coeffs[c, 0].ctypes.data for c in range(3)])
