@@ -488,10 +488,11 @@ def main() -> int:
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="auto", choices=["auto", "ce", "sm", "multicast", "p2p", "nccl"],
-                    help="N>1: how the bands are all-gathered into every rank's frame buffer (symmetric memory): "
-                         "ce (= auto) finished row chunks travel to the peers through the copy engines while the next "
-                         "chunk is filtered; p2p: peer stores fused into the filter kernel; multicast: multimem.st "
-                         "through the NVSwitch; nccl: all_gather_into_tensor after the kernels")
+                    help="N>1: how the bands are all-gathered into every rank's frame buffer (symmetric memory): ce = finished "
+                         "row chunks travel to the peers through the copy engines while the next chunk is filtered; sm = the same "
+                         "chunks stored to all peers by a copy kernel; p2p: peer stores fused into the filter kernel; multicast: "
+                         "multimem.st through the NVSwitch; nccl: all_gather_into_tensor after the kernels; auto (default) = ce, "
+                         "except sm for the f32 frame on 4 and more GPUs (DESIGN.md section 6)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.gather in ("p2p", "multicast"):

@@ -6,7 +6,8 @@
 Random frame size (1..700 px), strategy subset, Gaborish/EPF setting, coefficient type, output format,
 transfer function, stage chain (incl. odd ones -> tile kernel) and hand-off (dense / sparse / shuffled /
 streamed / band by band); every frame is compared bit for bit with the oracle.  End of round 1: 872
-frames over four seeds, no mismatch."""
+frames over four seeds, no mismatch.  Round 2 adds: EPF engaged on a random subset of the blocks (sharpness 0 / 7,
+quantiser 1: the strip kernel's block permutation), upsampling 2/4/8 with ragged output sizes, noise."""
 import sys, time, ctypes as C
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
@@ -17,6 +18,7 @@ from tests.emu import build_emu
 from oracle import cpu
 pipeline._lib = pipeline.bind(C.CDLL(str(build_emu.build())))
 pipe = pipeline.TransformPipeline(device=0, num_host_threads=2)
+WTS = np.load(Path(__file__).resolve().parents[1] / "golden" / "upsampling_weights.npz")
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv)>1 else 0)
 t_end = time.time() + float(sys.argv[2]) if len(sys.argv)>2 else time.time()+300
 n=0; bad=0
@@ -34,12 +36,26 @@ while time.time() < t_end:
     except Exception as e:
         desc, coeffs = wl.synthetic_frame(w, h, seed=int(rng.integers(1<<30)), gab=gab, epf_iters=epf, ac_type=ac)
     desc.out_format, desc.stage_mask = fmt, srgb
-    if rng.random()<0.2:  # explicit odd chain -> tile kernel
+    post = False
+    if epf and rng.random() < 0.5:   # EPF really engaged on part of the blocks
+        desc.raw_quant = np.where(desc.raw_quant > 0, 1, 0).astype(np.int32)
+        desc.epf_sharpness = np.where(rng.random(desc.epf_sharpness.shape) < rng.random(), 7, 0).astype(np.uint8)
+        coeffs = np.clip(coeffs, -2, 2)
+    if rng.random() < 0.25 and w * h < 40000:   # upsampling and / or noise (whole-frame features)
+        post = True
+        if rng.random() < 0.7:
+            nn = int(rng.choice([2, 4, 8]))
+            desc.upsampling, desc.upsampling_weights = nn, WTS[f"weights{nn}"]
+            desc.xsize_upsampled = nn * w - int(rng.integers(0, nn)); desc.ysize_upsampled = nn * h - int(rng.integers(0, nn))
+        if desc.upsampling == 1 or rng.random() < 0.5:
+            desc.noise, desc.noise_lut = 1, tuple(float(x) for x in rng.random(8) * 0.02)
+            desc.visible_frame_index, desc.nonvisible_frame_index = int(rng.integers(0, 5)), int(rng.integers(0, 3))
+    if not post and rng.random()<0.2:  # explicit odd chain -> tile kernel
         desc.stage_mask = abi.STAGE_EXPLICIT | int(rng.integers(0,32)) | srgb
         if (desc.stage_mask & 14) and epf==0: desc.stage_mask &= ~14
     want = cpu.render_frame(desc, coeffs, rcp_mode=0)
-    mode = rng.integers(0,4)
-    cfg = dict(w=w,h=h,gab=gab,epf=epf,ac=ac,fmt=fmt,mask=hex(desc.stage_mask),mode=int(mode))
+    mode = rng.integers(0,3) if post else rng.integers(0,4)
+    cfg = dict(w=w,h=h,gab=gab,epf=epf,ac=ac,fmt=fmt,mask=hex(desc.stage_mask),mode=int(mode),ups=desc.upsampling,noise=desc.noise)
     try:
         if mode==0: got = pipe.decode_frame(desc, coeffs)
         elif mode==1: got = pipe.decode_frame(desc, coeffs, sparse=True, order=rng.permutation(desc.num_groups).tolist(), stream_output=True)
