@@ -44,7 +44,7 @@ extern "C" {
 #define JXLGPU_API
 #endif
 
-#define JXLGPU_ABI_VERSION 5
+#define JXLGPU_ABI_VERSION 6
 
 enum {
   JXLGPU_OK = 0,
@@ -188,6 +188,13 @@ typedef struct jxlgpu_frame {
   uint32_t noise;
   float noise_lut[8];
   uint32_t visible_frame_index, nonvisible_frame_index;
+
+  /* Colour transform of the frame (frame_header.color_transform): 0 = XYB (everything above), 1 = YCbCr --
+   * JPEG-origin frames without chroma subsampling (4:4:4): the colour stage (JXLGPU_STAGE_XYB position) is then
+   * kYCbCrStage (lib/jxl/render_pipeline/stage_ycbcr.cc:33-71, full-range BT.601; channel 0 = Cb, 1 = Y, 2 = Cr) and
+   * its output is already in the image's own (non-linear) encoding: no JXLGPU_STAGE_SRGB. */
+  uint32_t color_transform;
+  uint32_t reserved1;
 } jxlgpu_frame;
 
 JXLGPU_API uint32_t jxlgpu_abi_version(void);

@@ -26,8 +26,10 @@ namespace jxlb_integration {
 // Frames the GPU path takes; everything else stays on libjxl's CPU path.
 inline bool IsEligible(const jxl::FrameHeader& fh, const jxl::CodecMetadata& metadata) {
   using jxl::FrameHeader;
-  return fh.encoding == jxl::FrameEncoding::kVarDCT && metadata.m.xyb_encoded &&
-         fh.color_transform == jxl::ColorTransform::kXYB && fh.chroma_subsampling.Is444() &&
+  // XYB frames, or JPEG-origin frames (YCbCr colour transform on a non-XYB image) without chroma subsampling
+  const bool xyb = metadata.m.xyb_encoded && fh.color_transform == jxl::ColorTransform::kXYB;
+  const bool ycbcr = !metadata.m.xyb_encoded && fh.color_transform == jxl::ColorTransform::kYCbCr;
+  return fh.encoding == jxl::FrameEncoding::kVarDCT && (xyb || ycbcr) && fh.chroma_subsampling.Is444() &&
          (fh.upsampling == 1 || fh.upsampling == 2 || fh.upsampling == 4 || fh.upsampling == 8) &&
          !(fh.flags & (FrameHeader::kPatches | FrameHeader::kSplines)) &&   // (kNoise: generated and added on the device)
          metadata.m.num_extra_channels == 0;   // (several passes: accumulated in the dense pinned storage)
@@ -119,6 +121,7 @@ inline bool BindGpuFrame(const jxl::PassesDecoderState& ds, const jxl::FrameHead
   }
   f.out_format = out_format;
   f.stage_mask = stage_mask;
+  f.color_transform = fh.color_transform == jxl::ColorTransform::kYCbCr ? 1u : 0u;   // kYCbCrStage instead of XYBStage
   if (fh.flags & jxl::FrameHeader::kNoise) {  // ConvolveNoise + AddNoise (dec_cache.cc:232-236), seeds: dec_cache.h:127-128
     f.noise = 1;
     for (size_t i = 0; i < 8; i++) f.noise_lut[i] = sh.image_features.noise_params.lut[i];

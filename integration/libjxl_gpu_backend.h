@@ -235,7 +235,12 @@ inline bool FrameIsOurs(const jxl::FrameHeader& fh, const jxl::PassesDecoderStat
   if (ce.GetColorSpace() != jxl::ColorSpace::kRGB) return false;
   if (!(oei.color_encoding_is_original || !oei.cms_set)) return false;   // a CMS stage would follow
   if (jxl::GetToneMappingStage(oei)) return false;
-  if (ce.Tf().IsLinear()) *stage_mask = 0;
+  if (fh.color_transform == jxl::ColorTransform::kYCbCr) {
+    // a non-XYB image: kYCbCrStage leaves the pixels in the image's own encoding, nothing follows it unless the
+    // application asked for another colour space (then a CMS stage would: dec_cache.cc:355-360)
+    if (!oei.color_encoding_is_original) return false;
+    *stage_mask = 0;
+  } else if (ce.Tf().IsLinear()) *stage_mask = 0;
   else if (ce.Tf().IsSRGB()) *stage_mask = JXLGPU_STAGE_SRGB;
   else return false;
   if (ds.width != ds.shared->frame_dim.xsize_upsampled || ds.height != ds.shared->frame_dim.ysize_upsampled) return false;

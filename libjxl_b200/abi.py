@@ -12,7 +12,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 NUM_STRATEGIES = 27
 GROUP_DIM = 256
 GROUP_COEFFS = 65536
@@ -72,6 +72,7 @@ class JxlGpuFrame(C.Structure):
         ("upsampling_weights", C.c_void_p),
         ("noise", C.c_uint32), ("noise_lut", C.c_float * 8),
         ("visible_frame_index", C.c_uint32), ("nonvisible_frame_index", C.c_uint32),
+        ("color_transform", C.c_uint32), ("reserved1", C.c_uint32),
     ]
 
 
@@ -156,6 +157,7 @@ class FrameDesc:
     noise_lut: tuple = (0.0,) * 8
     visible_frame_index: int = 1
     nonvisible_frame_index: int = 0
+    color_transform: int = 0     # 0 = XYB, 1 = YCbCr (JPEG-origin 4:4:4 frames)
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -274,6 +276,7 @@ class FrameDesc:
             s.upsampling = int(self.upsampling)
             s.xsize_upsampled, s.ysize_upsampled = self.out_xsize, self.out_ysize
             s.upsampling_weights = pin(np.asarray(self.upsampling_weights, np.float32).ravel()[:nw], np.float32, (nw,))
+        s.color_transform = int(self.color_transform)
         if self.noise:
             s.noise = 1
             s.noise_lut[:] = list(_f32(self.noise_lut, 8))

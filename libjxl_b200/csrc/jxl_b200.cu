@@ -189,7 +189,7 @@ bool fused_chain(uint32_t mask) {
 }
 bool use_fused(const jxlgpu_ctx* ctx) {
   const FrameDev& P = ctx->P;
-  if (!ctx->allow_fused || ctx->force_generic_filter || !fused_chain(P.stage_mask) || P.mc || P.ups || P.noise) return false;
+  if (!ctx->allow_fused || ctx->force_generic_filter || !fused_chain(P.stage_mask) || P.mc || P.ups || P.noise || P.ycbcr) return false;
   for (int c = 0; c < 3; c++)
     if ((uintptr_t)P.coeff[c] % 16) return false;
   return true;
@@ -559,6 +559,7 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
                    : (!f->dc[0] || !f->dc[1] || !f->dc[2]))
     return JXLGPU_ERR_INVALID_ARGUMENT;
   if (f->ac_type > JXLGPU_AC_INT32 || f->out_format > JXLGPU_OUT_RGB_F16) return JXLGPU_ERR_INVALID_ARGUMENT;
+  if (f->color_transform > 1) return JXLGPU_ERR_INVALID_ARGUMENT;
   const uint32_t ups = f->upsampling <= 1 ? 0 : f->upsampling;
   uint32_t out_w = f->xsize, out_hh = f->ysize;
   if (ups) {
@@ -699,6 +700,7 @@ int jxlgpu_frame_begin(jxlgpu_ctx* ctx, const jxlgpu_frame* f) {
   P.bmap = (uint4*)ctx->bmap.p;
   P.fused = 0;
   P.skip_xyb = 0;
+  P.ycbcr = f->color_transform == 1 ? 1u : 0u;
   P.list = (uint4*)ctx->list.p;
   P.counts = (uint32_t*)ctx->counts.p;
   P.xyb = (float*)ctx->xyb.p;

@@ -129,6 +129,7 @@ struct FrameDev {
   const float* noise_planes;
   float noise_lut[8];
   uint32_t skip_xyb;   // frames with upsampling / noise: the strip kernel stops before XYB -> RGB (planar XYB out)
+  uint32_t ycbcr;      // colour transform of the frame: 0 = XYB, 1 = YCbCr (kYCbCrStage instead of the opsin inverse)
 };
 
 // ---------------------------------------------------------------------------
@@ -1601,6 +1602,16 @@ __host__ __device__ constexpr int out_pixel_bytes(uint32_t fmt) {
 // TF_SRGB::EncodedFromDisplay (cms/transfer_functions-inl.h:244-267): what FromLinearStage<OpRgb>
 // applies with JXL_HIGH_PRECISION (stage_from_linear.cc:42-53).  IEEE sqrt and division, Horner
 // with FMAs (rational_polynomial-inl.h:59-97) -- bit-exact against the CPU.
+// kYCbCrStage (lib/jxl/render_pipeline/stage_ycbcr.cc:33-71): full-range BT.601; a = Cb, b = Y, c3 = Cr in, R, G, B out
+__device__ __forceinline__ void ycbcr_px(float& a, float& b, float& c3) {
+  const float c128 = 128.0f / 255, crcr = 1.402f, cgcb = -0.114f * 1.772f / 0.587f, cgcr = -0.299f * 1.402f / 0.587f,
+              cbcb = 1.772f;
+  const float yv = b + c128, cb = a, cr = c3;
+  a = fmaf(crcr, cr, yv);
+  b = fmaf(cgcr, cr, fmaf(cgcb, cb, yv));
+  c3 = fmaf(cbcb, cb, yv);
+}
+
 __device__ __forceinline__ float srgb_from_linear(float v) {
   const float x = fabsf(v);
   const float s = __fsqrt_rn(x);
@@ -1757,7 +1768,9 @@ __device__ __forceinline__ void finish_px(const FrameDev& P, char* __restrict__ 
     b = b + sum;
     c3 = fmaf(P.cfl_base_b, sum, c3);
   }
-  if (P.stage_mask & 16u) {  // XYB -> linear RGB (dec_xyb-inl.h:38-86)
+  if ((P.stage_mask & 16u) && P.ycbcr) {
+    ycbcr_px(a, b, c3);
+  } else if (P.stage_mask & 16u) {  // XYB -> linear RGB (dec_xyb-inl.h:38-86)
     float gr = b + a, gg = b - a, gb = c3;
     gr = gr - P.opsin_cbrt[0];
     gg = gg - P.opsin_cbrt[1];
@@ -2177,7 +2190,9 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const __grid_con
     if (y >= (int)P.band_y1 || x >= W) continue;
     const int o_c = ty * kSP + tx;
     float a = cur[o_c], b = cur[kTilePlane + o_c], c3 = cur[2 * kTilePlane + o_c];
-    if (mask & 16) {
+    if ((mask & 16) && P.ycbcr) {
+      ycbcr_px(a, b, c3);
+    } else if (mask & 16) {
       float gr = b + a, gg = b - a, gb = c3;
       gr = gr - P.opsin_cbrt[0];
       gg = gg - P.opsin_cbrt[1];
@@ -2303,7 +2318,9 @@ __device__ __forceinline__ void filter_strip_body(const FrameDev& P, char* __res
   auto emit = [&](int r, int col, float a, float b, float c3) {
     const int xe = xs0 + col;
     if (!(col >= LEAD && col < kStripThreads - LEAD && xe < W)) return;
-    if (C::XYB && !P.skip_xyb) {
+    if (C::XYB && !P.skip_xyb && P.ycbcr) {
+      ycbcr_px(a, b, c3);
+    } else if (C::XYB && !P.skip_xyb) {
       float gr = b + a, gg = b - a, gb = c3;
       gr = gr - P.opsin_cbrt[0];
       gg = gg - P.opsin_cbrt[1];

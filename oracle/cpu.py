@@ -161,6 +161,8 @@ def desc_from_dump(d, **overrides) -> abi.FrameDesc:
         opsin_biases=tuple(i.opsin_biases)[:3], opsin_biases_cbrt=tuple(i.opsin_biases_cbrt)[:3],
         ac_type=abi.AC_INT16 if i.ac_is16 else abi.AC_INT32,
     )
+    if getattr(i, "ycbcr", 0):
+        desc.color_transform = 1
     if getattr(i, "noise", 0):
         desc.noise, desc.noise_lut = 1, tuple(i.noise_lut)
         desc.visible_frame_index, desc.nonvisible_frame_index = int(i.visible_frame_index), int(i.nonvisible_frame_index)

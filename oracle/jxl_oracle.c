@@ -703,7 +703,23 @@ static void epf(const jxlgpu_frame* f, int which, const float* sigma, float* con
 }
 
 /* XybToRgb (lib/jxl/dec_xyb-inl.h:38-86), in place */
+/* kYCbCrStage (lib/jxl/render_pipeline/stage_ycbcr.cc:33-71): full-range BT.601, planes 0 = Cb, 1 = Y, 2 = Cr */
+static void ycbcr_to_rgb(const jxlgpu_frame* f, float* const p[3], size_t ps) {
+  const float c128 = 128.0f / 255, crcr = 1.402f, cgcb = -0.114f * 1.772f / 0.587f, cgcr = -0.299f * 1.402f / 0.587f,
+              cbcb = 1.772f;
+#pragma omp parallel for schedule(static)
+  for (int64_t y = 0; y < (int64_t)f->ysize; y++)
+    for (size_t x = 0; x < f->xsize; x++) {
+      const size_t i = (size_t)y * ps + x;
+      const float yv = p[1][i] + c128, cb = p[0][i], cr = p[2][i];
+      p[0][i] = fmaf(crcr, cr, yv);
+      p[1][i] = fmaf(cgcr, cr, fmaf(cgcb, cb, yv));
+      p[2][i] = fmaf(cbcb, cb, yv);
+    }
+}
+
 static void xyb_to_linear(const jxlgpu_frame* f, float* const p[3], size_t ps) {
+  if (f->color_transform == 1) { ycbcr_to_rgb(f, p, ps); return; }
   const float* m = f->inverse_opsin_matrix;
 #pragma omp parallel for schedule(static)
   for (int64_t y = 0; y < (int64_t)f->ysize; y++)

@@ -47,6 +47,7 @@ class RefFrameInfo(C.Structure):
         ("dequant_offsets", C.c_int32 * 81),
         ("upsampling", C.c_int32), ("xsize_upsampled", C.c_int32), ("ysize_upsampled", C.c_int32),
         ("upsampling_weights", C.c_float * 210),
+        ("ycbcr", C.c_int32),
         ("noise", C.c_int32), ("noise_lut", C.c_float * 8),
         ("visible_frame_index", C.c_uint32), ("nonvisible_frame_index", C.c_uint32),
     ]
@@ -132,6 +133,20 @@ def encode_rgb8(img: np.ndarray, distance: float = 1.0, effort: int = 7, gaboris
         raise RuntimeError(f"ref_encode_rgb8 failed rc={rc}")
     data = C.string_at(out, n.value)
     lib().ref_free(out)
+    return data
+
+
+def encode_jpeg(jpeg: bytes, threads: int | None = None) -> bytes:
+    """Lossless JPEG recompression through JxlEncoderAddJPEGFrame (YCbCr VarDCT frame); bare codestream."""
+    out = C.POINTER(C.c_uint8)()
+    n = C.c_size_t()
+    L = lib()
+    L.ref_encode_jpeg.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
+    rc = L.ref_encode_jpeg(jpeg, len(jpeg), threads or os.cpu_count() or 1, C.byref(out), C.byref(n))
+    if rc:
+        raise RuntimeError(f"ref_encode_jpeg failed rc={rc}")
+    data = C.string_at(out, n.value)
+    L.ref_free(out)
     return data
 
 

@@ -72,6 +72,7 @@
 #include "lib/jxl/render_pipeline/stage_upsampling.h"
 #include "lib/jxl/render_pipeline/stage_write.h"
 #include "lib/jxl/render_pipeline/stage_xyb.h"
+#include "lib/jxl/render_pipeline/stage_ycbcr.h"
 
 #define REF_API extern "C" __attribute__((visibility("default")))
 
@@ -149,6 +150,40 @@ REF_API int ref_encode_rgb8_ex(const uint8_t* rgb, int w, int h, float distance,
     JxlPixelFormat pf = {3, JXL_TYPE_UINT8, JXL_NATIVE_ENDIAN, 0};
     if (JxlEncoderAddImageFrame(fs, &pf, rgb, static_cast<size_t>(w) * h * 3) !=
         JXL_ENC_SUCCESS) { rc = 5; break; }
+    JxlEncoderCloseInput(enc);
+    size_t pos = 0;
+    for (;;) {
+      uint8_t* next = buf.data() + pos;
+      size_t avail = buf.size() - pos;
+      JxlEncoderStatus st = JxlEncoderProcessOutput(enc, &next, &avail);
+      pos = next - buf.data();
+      if (st == JXL_ENC_NEED_MORE_OUTPUT) { buf.resize(buf.size() * 2); continue; }
+      if (st != JXL_ENC_SUCCESS) rc = 6;
+      break;
+    }
+    if (rc) break;
+    *out = static_cast<uint8_t*>(malloc(pos));
+    memcpy(*out, buf.data(), pos);
+    *out_size = pos;
+  } while (false);
+  JxlEncoderDestroy(enc);
+  return rc;
+}
+
+// (1b) lossless JPEG recompression (JxlEncoderAddJPEGFrame): a VarDCT frame with the YCbCr colour transform whose
+// coefficients are the JPEG's own.  No reconstruction metadata is stored (pixels only).
+REF_API int ref_encode_jpeg(const uint8_t* jpeg, size_t n, int threads, uint8_t** out, size_t* out_size) {
+  Runner runner(threads);
+  JxlEncoder* enc = JxlEncoderCreate(nullptr);
+  if (!enc) return 1;
+  int rc = 0;
+  std::vector<uint8_t> buf(1 << 20);
+  do {
+    if (JxlEncoderSetParallelRunner(enc, JxlThreadParallelRunner, runner.opaque) != JXL_ENC_SUCCESS) { rc = 2; break; }
+    JxlEncoderUseContainer(enc, JXL_FALSE);
+    JxlEncoderStoreJPEGMetadata(enc, JXL_FALSE);
+    JxlEncoderFrameSettings* fs = JxlEncoderFrameSettingsCreate(enc, nullptr);
+    if (JxlEncoderAddJPEGFrame(fs, jpeg, n) != JXL_ENC_SUCCESS) { rc = 5; break; }
     JxlEncoderCloseInput(enc);
     size_t pos = 0;
     for (;;) {
@@ -452,6 +487,7 @@ struct RefFrameInfo {
   int32_t upsampling;                       // frame_header.upsampling (1, 2, 4, 8)
   int32_t xsize_upsampled, ysize_upsampled; // FrameDimensions (frame_dimensions.h:34-60)
   float upsampling_weights[210];            // CustomTransformData::upsampling{2,4,8}_weights of that factor (15 / 55 / 210 used)
+  int32_t ycbcr;                            // frame_header.color_transform == kYCbCr (JPEG-origin frames)
   int32_t noise;                            // frame_header.flags & kNoise
   float noise_lut[8];                       // NoiseParams::lut (noise.h:27-43)
   uint32_t visible_frame_index, nonvisible_frame_index;  // PassesDecoderState, seeds of the noise generator
@@ -549,6 +585,7 @@ REF_API int ref_frame_info(void* h, RefFrameInfo* o) {
     const size_t n = o->upsampling == 2 ? 15 : o->upsampling == 4 ? 55 : 210;
     memcpy(o->upsampling_weights, w, n * sizeof(float));
   }
+  o->ycbcr = f->frame_header->color_transform == ColorTransform::kYCbCr ? 1 : 0;
   o->noise = (f->frame_header->flags & FrameHeader::kNoise) ? 1 : 0;
   for (int i = 0; i < 8; i++) o->noise_lut[i] = sh.image_features.noise_params.lut[i];
   o->visible_frame_index = static_cast<uint32_t>(f->dec_state->visible_frame_index);
@@ -731,8 +768,10 @@ REF_API int ref_frame_render(void* h, int stage_mask, float* out, int reps, doub
       JXL_RETURN_IF_ERROR(builder.AddStage(GetAddNoiseStage(ds->shared->image_features.noise_params,
                                                             ds->shared->cmap.base(), 3)));
     }
-    if (stage_mask & 16)
-      JXL_RETURN_IF_ERROR(builder.AddStage(GetXYBStage(ds->output_encoding_info)));
+    if (stage_mask & 16) {  // the frame's colour transform (dec_cache.cc:259-267)
+      if (fh.color_transform == ColorTransform::kYCbCr) JXL_RETURN_IF_ERROR(builder.AddStage(GetYCbCrStage()));
+      else JXL_RETURN_IF_ERROR(builder.AddStage(GetXYBStage(ds->output_encoding_info)));
+    }
     JXL_RETURN_IF_ERROR(builder.AddStage(GetWriteToImage3FStage(&f->mm, &result)));
     JXL_ASSIGN_OR_RETURN(ds->render_pipeline, std::move(builder).Finalize(d));
     // warm-up pass (untimed): allocates and touches everything
@@ -837,8 +876,10 @@ REF_API int ref_frame_render_out(void* h, int stage_mask, int out_format, void* 
       JXL_RETURN_IF_ERROR(builder.AddStage(GetEPFStage(lf, ds->sigma, EpfStage::One)));
     if (stage_mask & 8)
       JXL_RETURN_IF_ERROR(builder.AddStage(GetEPFStage(lf, ds->sigma, EpfStage::Two)));
-    if (stage_mask & 16)
-      JXL_RETURN_IF_ERROR(builder.AddStage(GetXYBStage(ds->output_encoding_info)));
+    if (stage_mask & 16) {  // the frame's colour transform (dec_cache.cc:259-267)
+      if (fh.color_transform == ColorTransform::kYCbCr) JXL_RETURN_IF_ERROR(builder.AddStage(GetYCbCrStage()));
+      else JXL_RETURN_IF_ERROR(builder.AddStage(GetXYBStage(ds->output_encoding_info)));
+    }
     if (stage_mask & 32) {
       OutputEncodingInfo info = ds->output_encoding_info;
       info.color_encoding = ColorEncoding::SRGB(/*is_gray=*/false);

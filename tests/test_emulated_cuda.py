@@ -527,3 +527,17 @@ def test_emulated_noise(emu_pipe, n, w, h, fmt, srgb):
     assert same(emu_pipe.decode_frame(desc, coeffs), want)
     desc.noise = 0
     assert not same(oracle(desc, coeffs), want)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("fmt", [abi.OUT_RGB_F32, abi.OUT_RGB_U8])
+@pytest.mark.parametrize("w,h,filters", [(301, 260, 0), (301, 260, 1), (17, 9, 0)])
+def test_emulated_ycbcr_colour_transform(emu_pipe, w, h, filters, fmt):
+    """JPEG-origin frames (frame_header.color_transform = YCbCr, 4:4:4): kYCbCrStage in the place of the opsin inverse,
+    in the strip kernel's epilogue and in the tile kernel."""
+    desc, coeffs = wl.synthetic_frame(w, h, seed=5, gab=filters, epf_iters=filters, strategies="0")
+    desc.color_transform, desc.out_format = 1, fmt
+    assert same(emu_pipe.decode_frame(desc, coeffs), oracle(desc, coeffs))
+    desc.stage_mask = abi.STAGE_EXPLICIT | abi.STAGE_EPF2 | abi.STAGE_XYB     # tile kernel
+    if filters:
+        assert same(emu_pipe.decode_frame(desc, coeffs), oracle(desc, coeffs))

@@ -416,3 +416,34 @@ def test_gather_mechanisms_on_one_device(mode, monkeypatch):
                 assert_same(b.cpu().numpy(), want, f"{mode}: buffer {i}")
     finally:
         p.close()
+
+
+@pytest.mark.parametrize("fmt", [abi.OUT_RGB_F32, abi.OUT_RGB_U8])
+def test_ycbcr_colour_transform_bit_exact(pipe, fmt):
+    """JPEG-origin 4:4:4 frames -- kYCbCrStage (stage_ycbcr.cc:33-71) in the place of the opsin
+    inverse; the restatement is pinned against the reference's stage and public decoder
+    (tests/test_oracle_vs_reference.py::test_jpeg_origin_ycbcr_frames)."""
+    desc, coeffs = wl.synthetic_frame(1201, 531, seed=31, gab=0, epf_iters=0, strategies="0")
+    desc.color_transform, desc.out_format = 1, fmt
+    assert_same(pipe.decode_frame(desc, coeffs), oracle(desc, coeffs), "ycbcr")
+
+
+def test_jpeg_origin_frame_against_the_reference_decoder(pipe):
+    """A 4:4:4 JPEG, recompressed by the reference encoder, entropy-decoded by the reference, rendered here: the 8-bit
+    pixels are the reference decoder's."""
+    pytest.importorskip("PIL")
+    from oracle import cpu, ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    from tests.test_oracle_vs_reference import make_jpeg
+    data = ref.encode_jpeg(make_jpeg(1000, 700, 85), 4)
+    fr = ref.Frame(data, 2)
+    d = fr.dump()
+    fr.close()
+    desc = cpu.desc_from_dump(d)
+    assert desc.color_transform == 1
+    desc.out_format = abi.OUT_RGB_U8
+    got = pipe.decode_frame(desc, d.coeffs)
+    want = ref.decode_native(data, (700, 1000, 3), np.uint8, 2)
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3      # (rcpps in AdjustQuantBias may cross a rounding boundary)

@@ -52,7 +52,15 @@ for case in {cases!r}:
     w, h, dist, epf, fmt = case[:5]
     rs = case[5] if len(case) > 5 else -1          # frame_header.upsampling (JXL_ENC_FRAME_SETTING_RESAMPLING)
     img = wl.synth_image(w, h, seed=w + h)
-    data = ref.encode_rgb8(img, dist, 7, -1, epf, 4, resampling=rs)
+    if fmt == "jpeg":      # a 4:4:4 JPEG recompressed losslessly: YCbCr frame, the application gets 8-bit pixels
+        import io
+        from PIL import Image
+        b = io.BytesIO()
+        Image.fromarray(img).save(b, format="JPEG", quality=int(dist), subsampling=0)
+        data = ref.encode_jpeg(b.getvalue(), 4)
+        fmt = "u8"
+    else:
+        data = ref.encode_rgb8(img, dist, 7, -1, epf, 4, resampling=rs)
     ref.use_variant("default")
     dec = (lambda: ref.decode_linear_f32(data, 4)) if fmt == "f32" else (lambda: ref.decode_native(data, (h, w, 3), np.uint8, 4))
     want = dec()
@@ -61,7 +69,7 @@ for case in {cases!r}:
     got = dec()
     taken = ref.gpu_frames_taken() - before
     d = np.abs(got.astype(np.float64) - want.astype(np.float64))
-    res[f"{{w}}x{{h}}-d{{dist}}-epf{{epf}}-{{fmt}}" + (f"-rs{{rs}}" if rs > 0 else "")] = dict(taken=int(taken), peak=float(d.max()), differing=float((d != 0).mean()))
+    res[f"{{w}}x{{h}}-d{{dist}}-epf{{epf}}-{{case[4]}}-{{fmt}}" + (f"-rs{{rs}}" if rs > 0 else "")] = dict(taken=int(taken), peak=float(d.max()), differing=float((d != 0).mean()))
 print("RESULT " + json.dumps(res))
 """
 
@@ -115,8 +123,9 @@ def test_patched_decoder_through_the_emulated_library(sparse):
         pytest.skip("a device is present: covered by the gpu test")
     cases = [(300, 200, 1.0, -1, "f32"), (520, 264, 2.0, 2, "f32"), (300, 200, 1.0, -1, "u8"),
              (600, 300, 1.0, -1, "f32", 2),               # an upsampled frame (resampling 2)
-             (300, 200, 1.0, -1, "f32", 1 + (32 << 16))]  # photon noise ISO 3200 (frame flag kNoise)
-    res = run_child("emu", cases if sparse else cases[1:3] + cases[4:], sparse)
+             (300, 200, 1.0, -1, "f32", 1 + (32 << 16)),  # photon noise ISO 3200 (frame flag kNoise)
+             (300, 200, 90, -1, "jpeg")]                  # JPEG-origin frame (YCbCr colour transform), quality 90
+    res = run_child("emu", cases if sparse else cases[1:3] + cases[4:5], sparse)
     for k, v in res.items():
         assert v["taken"] == 1, (k, v)               # the frame really went through the backend
         if "-u8" in k:                         # the application's default: 8-bit sRGB, dithered
@@ -150,7 +159,8 @@ def test_patched_decoder_on_the_gpu(sparse):
     res = run_child("gpu", [(1000, 700, 1.0, -1, "f32"), (2048, 1100, 2.0, 2, "f32"), (777, 333, 0.5, 0, "f32"),
                             (1500, 900, 4.0, 3, "f32"), (1000, 700, 1.0, -1, "u8"),
                             (1400, 900, 1.0, -1, "f32", 2), (2200, 1100, 1.0, -1, "u8", 4),   # upsampled frames
-                            (1000, 700, 1.0, -1, "f32", 1 + (32 << 16)), (1400, 900, 1.0, -1, "f32", 2 + (64 << 16))],   # noise
+                            (1000, 700, 1.0, -1, "f32", 1 + (32 << 16)), (1400, 900, 1.0, -1, "f32", 2 + (64 << 16)),   # noise
+                            (1000, 700, 85, -1, "jpeg")],   # JPEG-origin
                            sparse)
     for k, v in res.items():
         assert v["taken"] == 1, (k, v)

@@ -268,3 +268,35 @@ def test_noise_stages_bit_exact(rs, w, h, iso, refmod):
     assert not np.array_equal(without, want)
     fr.close()
     assert np.array_equal(np.moveaxis(want, 0, 2), refmod.decode_linear_f32(data, 2))
+
+
+def make_jpeg(w, h, quality, seed=5):
+    """A baseline 4:4:4 JPEG of the seeded test image (Pillow)."""
+    import io
+    from PIL import Image
+    b = io.BytesIO()
+    Image.fromarray(wl.synth_image(w, h, seed)).save(b, format="JPEG", quality=quality, subsampling=0)
+    return b.getvalue()
+
+
+@pytest.mark.parametrize("w,h,q", [(600, 300, 90), (517, 331, 75)])
+def test_jpeg_origin_ycbcr_frames(w, h, q, refmod):
+    """SURVEY.md §8f rank 4, YCbCr: a 4:4:4 JPEG recompressed by the reference encoder (JxlEncoderAddJPEGFrame) is a
+    VarDCT frame with the YCbCr colour transform.  Dequantisation + IDCT are the XYB path's; the colour stage is
+    kYCbCrStage (stage_ycbcr.cc:33-71).  Restatement bit-exact against the reference's stages, and its 8-bit output
+    identical to the reference's PUBLIC decoder (no transfer function follows: the image is not XYB-encoded)."""
+    pytest.importorskip("PIL")
+    from oracle import cpu
+    data = refmod.encode_jpeg(make_jpeg(w, h, q), 4)
+    fr = refmod.Frame(data, 2)
+    i = fr.info
+    assert i.ycbcr == 1 and i.gab == 0 and i.epf_iters == 0
+    d = fr.dump()
+    desc = cpu.desc_from_dump(d)
+    assert desc.color_transform == 1
+    desc.out_format = abi.OUT_PLANAR_F32
+    want, _ = fr.render(refmod.STAGE_XYB)          # bit 16 = the frame's colour transform
+    fr.close()
+    assert np.array_equal(cpu.render_frame(desc, d.coeffs, rcp_mode=1), want)
+    desc.out_format = abi.OUT_RGB_U8
+    assert np.array_equal(cpu.render_frame(desc, d.coeffs, rcp_mode=1), refmod.decode_native(data, (h, w, 3), np.uint8, 2))
